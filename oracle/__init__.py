@@ -1,0 +1,222 @@
+"""CPU oracle for the WSOVOD region-scoring path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  ``wsovod_b200`` (the product) never does: it has no CPU path at all.
+
+The functions here wrap ``oracle/oracle.c`` (a plain-C restatement; each C function cites the
+reference lines it follows) with CPU ``torch`` tensors in / out.  ``oracle.pins`` documents what the
+restatement was checked against (torchvision's compiled CPU ops, ``oracle/_ref`` built from the
+reference's own C++ sources, and the goldens in ``tests/golden`` produced by importing the reference
+Python verbatim through ``oracle/d2_shim.py``).
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    """Compile oracle.c with gcc (seconds)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.orc_batched_nms.restype = ctypes.c_int64
+        _lib.orc_detections_image.restype = ctypes.c_int64
+    return _lib
+
+
+def _f(t):
+    t = t.detach().to("cpu", torch.float32).contiguous()
+    return t, ctypes.c_void_p(t.data_ptr())
+
+
+def _i64(t):
+    t = t.detach().to("cpu", torch.int64).contiguous()
+    return t, ctypes.c_void_p(t.data_ptr())
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+_c64 = ctypes.c_int64
+_cf = ctypes.c_float
+_ci = ctypes.c_int
+
+
+def roi_pool(input, rois, spatial_scale, output_size, with_argmax=True):
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    x, xp = _f(input)
+    r, rp = _f(rois)
+    N, C, H, W = x.shape
+    R = r.shape[0]
+    out = torch.empty(R, C, ph, pw, dtype=torch.float32)
+    arg = torch.empty(R, C, ph, pw, dtype=torch.int32) if with_argmax else None
+    lib().orc_roi_pool_fwd(xp, _c64(N), _c64(C), _c64(H), _c64(W), rp, _c64(R), _cf(spatial_scale),
+                           _ci(ph), _ci(pw), _p(out), _p(arg))
+    return out, arg
+
+
+def roi_pool_backward(grad_out, rois, argmax, input_shape, num_rois=None):
+    g, gp = _f(grad_out)
+    r, rp = _f(rois)
+    a = argmax.detach().to("cpu", torch.int32).contiguous()
+    N, C, H, W = input_shape
+    rows, _, ph, pw = g.shape
+    R = r.shape[0] if num_rois is None else num_rois
+    gi = torch.empty(N, C, H, W, dtype=torch.float32)
+    lib().orc_roi_pool_bwd(gp, rp, _p(a), _c64(rows), _c64(R), _c64(N), _c64(C), _c64(H), _c64(W),
+                           _ci(ph), _ci(pw), _p(gi))
+    return gi
+
+
+def roi_loop_pool(input, rois, spatial_scale, output_size):
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    x, xp = _f(input)
+    r, rp = _f(rois)
+    N, C, H, W = x.shape
+    R = r.shape[0]
+    out = torch.empty(3 * R, C, ph, pw, dtype=torch.float32)
+    arg = torch.empty(3 * R, C, ph, pw, dtype=torch.int32)
+    lib().orc_roi_loop_pool_fwd(xp, _c64(N), _c64(C), _c64(H), _c64(W), rp, _c64(R),
+                                _cf(spatial_scale), _ci(ph), _ci(pw), _p(out), _p(arg))
+    return out, arg
+
+
+def roi_align(input, rois, spatial_scale, output_size, sampling_ratio=0, aligned=False):
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    x, xp = _f(input)
+    r, rp = _f(rois)
+    N, C, H, W = x.shape
+    R = r.shape[0]
+    out = torch.empty(R, C, ph, pw, dtype=torch.float32)
+    lib().orc_roi_align_fwd(xp, _c64(N), _c64(C), _c64(H), _c64(W), rp, _c64(R), _cf(spatial_scale),
+                            _ci(ph), _ci(pw), _ci(int(sampling_ratio)), _ci(int(bool(aligned))), _p(out))
+    return out
+
+
+def align(x, classifier, temperature=50.0, norm_weight=True, append_background=True, bias=None,
+          want_probs=True):
+    xx, xp = _f(x)
+    cc, cp = _f(classifier)
+    M, D = xx.shape
+    K = cc.shape[0]
+    KO = K + (1 if append_background else 0)
+    logits = torch.empty(M, KO, dtype=torch.float32)
+    probs = torch.empty(M, KO, dtype=torch.float32) if want_probs else None
+    b = None if bias is None else torch.as_tensor([float(bias)], dtype=torch.float32)
+    lib().orc_align_fwd(xp, cp, _c64(M), _c64(D), _c64(K), _cf(temperature), _ci(int(norm_weight)),
+                        _ci(int(append_background)), _p(b), _p(logits), _p(probs))
+    return logits, probs
+
+
+def mil(cls, det, offsets):
+    c, cp = _f(cls)
+    d, dp = _f(det)
+    o, op = _i64(torch.as_tensor(offsets))
+    M, K = c.shape
+    N = o.numel() - 1
+    scores = torch.empty(M, K, dtype=torch.float32)
+    img = torch.empty(N, K, dtype=torch.float32)
+    lib().orc_mil_fwd(cp, dp, op, _c64(M), _c64(N), _c64(K), _p(scores), _p(img))
+    return scores, img
+
+
+def pgt_top1(scores, boxes, offsets, gt_classes, gt_offsets, img_scores):
+    s, sp = _f(scores)
+    b, bp = _f(boxes)
+    o, op = _i64(torch.as_tensor(offsets))
+    gc, gcp = _i64(torch.as_tensor(gt_classes))
+    go, gop = _i64(torch.as_tensor(gt_offsets))
+    im, imp = _f(img_scores)
+    N = o.numel() - 1
+    K = im.shape[1]
+    G = gc.numel()
+    sb = torch.zeros(G, 4)
+    sc = torch.zeros(G, dtype=torch.int64)
+    ss = torch.zeros(G)
+    sw = torch.zeros(G)
+    sr = torch.zeros(G, dtype=torch.int64)
+    cnt = torch.zeros(N, dtype=torch.int64)
+    lib().orc_pgt_top1(sp, _c64(s.shape[1]), bp, op, gcp, gop, imp, _c64(N), _c64(K), _p(sb), _p(sc),
+                       _p(ss), _p(sw), _p(sr), _p(cnt))
+    return dict(seed_boxes=sb, seed_classes=sc, seed_scores=ss, seed_weights=sw, seed_rows=sr,
+                seed_count=cnt)
+
+
+def refine_assign(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_weights, seed_offsets,
+                  seed_count, num_classes, iou_thresh=0.5):
+    b, bp = _f(boxes)
+    o, op = _i64(torch.as_tensor(offsets))
+    sb, sbp = _f(seed_boxes)
+    sc, scp = _i64(seed_classes)
+    ss, ssp = _f(seed_scores)
+    sw, swp = _f(seed_weights)
+    so, sop = _i64(torch.as_tensor(seed_offsets))
+    cnt = None if seed_count is None else _i64(torch.as_tensor(seed_count))[0]
+    M = b.shape[0]
+    N = o.numel() - 1
+    midx = torch.zeros(M, dtype=torch.int64)
+    mlab = torch.zeros(M, dtype=torch.int8)
+    miou = torch.zeros(M)
+    gcls = torch.zeros(M, dtype=torch.int64)
+    gbox = torch.zeros(M, 4)
+    gsc = torch.zeros(M)
+    gw = torch.zeros(M)
+    lib().orc_refine_assign(bp, op, sbp, scp, ssp, swp, sop, _p(cnt), _c64(N), _c64(num_classes),
+                            _cf(iou_thresh), _p(midx), _p(mlab), _p(miou), _p(gcls), _p(gbox),
+                            _p(gsc), _p(gw))
+    return dict(matched_idx=midx, matched_label=mlab, matched_iou=miou, gt_classes=gcls,
+                gt_boxes=gbox, gt_scores=gsc, gt_weights=gw)
+
+
+IOU_TV_CPU = 0
+IOU_TV_CUDA = 1
+
+
+def batched_nms(boxes, scores, groups, iou_thresh, iou_mode=IOU_TV_CPU):
+    b, bp = _f(boxes)
+    s, sp = _f(scores)
+    g, gp = _i64(groups)
+    M = b.shape[0]
+    keep = torch.empty(max(M, 1), dtype=torch.int64)
+    n = lib().orc_batched_nms(bp, sp, gp, _c64(M), ctypes.c_double(iou_thresh), _ci(iou_mode), _p(keep))
+    return keep[:n].clone()
+
+
+def detections(probs, boxes, offsets, image_sizes, score_thresh, nms_thresh, topk,
+               iou_mode=IOU_TV_CPU):
+    """fast_rcnn_inference for class-agnostic boxes; returns padded [N,topk,...] tensors + counts."""
+    p, _ = _f(probs)
+    b, _ = _f(boxes)
+    offsets = [int(v) for v in offsets]
+    N = len(offsets) - 1
+    K = p.shape[1] - 1
+    db = torch.zeros(N, topk, 4)
+    ds = torch.zeros(N, topk)
+    dc = torch.full((N, topk), -1, dtype=torch.int64)
+    dr = torch.full((N, topk), -1, dtype=torch.int64)
+    cnt = torch.zeros(N, dtype=torch.int64)
+    for n in range(N):
+        r0, r1 = offsets[n], offsets[n + 1]
+        pn = p[r0:r1].contiguous()
+        bn = b[r0:r1].contiguous()
+        h, w = float(image_sizes[n][0]), float(image_sizes[n][1])
+        k = lib().orc_detections_image(_p(pn), _p(bn), _c64(r1 - r0), _c64(K), _cf(h), _cf(w),
+                                       _cf(score_thresh), ctypes.c_double(nms_thresh), _c64(topk), _ci(iou_mode),
+                                       _p(db[n]), _p(ds[n]), _p(dc[n]), _p(dr[n]))
+        cnt[n] = k
+    return dict(det_boxes=db, det_scores=ds, det_classes=dc, det_rows=dr, det_count=cnt)

@@ -1,0 +1,185 @@
+"""Generate tests/golden/*.pt by running the REFERENCE code on seeded synthetic inputs.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden            # rewrites tests/golden/*.pt
+
+What runs verbatim from /root/reference (through oracle/d2_shim.py):
+  * wsovod/modeling/class_heads/open_vocabulary_classifier.py  OpenVocabularyClassifier.forward
+    (projection replaced by nn.Identity(): the MLP is out of scope, the contraction is what we pin)
+  * wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py  ObjectMiningOutputLayers.forward /
+    predict_probs_img / predict_probs, InstanceRefinementOutputLayers.predict_probs,
+    fast_rcnn_inference
+  * wsovod/modeling/roi_heads/roi_heads.py  WSOVODROIHeads.get_pgt_top_k,
+    label_and_sample_proposals_wsl, _sample_proposals_wsl, get_image_level_gt
+and from the installed torchvision 0.26 (the reference's un-vendored dependency):
+  * torch.ops.torchvision.roi_pool / roi_align (CPU), torchvision.ops.boxes._batched_nms_vanilla
+The reference's ROILoopPool has no CPU path (ROILoopPool.h:62); its 3-way golden comes from the
+compiled reference CUDA extension on the GPU box (oracle/_ref, see oracle/build_ref.py).
+"""
+import math
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+REF = os.environ.get("WSOVOD_REFERENCE", "/root/reference")
+
+
+def make_rois(R, N, img_h, img_w, g, stress=True):
+    """SURVEY 8d proposal generator: LogU sizes, clipped, 5% duplicates, 1% degenerate."""
+    x1 = torch.rand(R, generator=g) * 0.85 * img_w
+    y1 = torch.rand(R, generator=g) * 0.85 * img_h
+    w = torch.exp(torch.rand(R, generator=g) * (math.log(0.6 * img_w) - math.log(16)) + math.log(16))
+    h = torch.exp(torch.rand(R, generator=g) * (math.log(0.6 * img_h) - math.log(16)) + math.log(16))
+    x2 = (x1 + w).clamp(max=img_w)
+    y2 = (y1 + h).clamp(max=img_h)
+    boxes = torch.stack([x1, y1, x2, y2], 1)
+    if stress and R >= 40:
+        nd = max(R // 20, 1)
+        src = torch.randint(0, R, (nd,), generator=g)
+        dst = torch.randint(0, R, (nd,), generator=g)
+        boxes[dst] = boxes[src]
+        nz = max(R // 100, 1)
+        z = torch.randint(0, R, (nz,), generator=g)
+        boxes[z, 2] = boxes[z, 0]
+    b = torch.randint(0, N, (R,), generator=g).sort().values.float()
+    return torch.cat([b[:, None], boxes], 1)
+
+
+def main():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import d2_shim
+    d2_shim.install(REF)
+    import wsovod.modeling.roi_heads.fast_rcnn_open_vocabulary as fr
+    import wsovod.modeling.roi_heads.roi_heads as rh
+    from wsovod.modeling.class_heads import OpenVocabularyClassifier
+    from oracle.d2_shim import Boxes, Instances, Matcher, ShapeSpec, Box2BoxTransform
+
+    os.makedirs(GOLD, exist_ok=True)
+    g = torch.Generator().manual_seed(20261017)
+
+    # ---- (1) pooling: torchvision CPU ops (what POOLER_TYPE "ROIPool"/"ROIAlign" run) -----------
+    N, C, H, W = 2, 6, 30, 40
+    feat = torch.randn(N, C, H, W, generator=g)          # negatives included (tv semantics)
+    rois = make_rois(100, N, H * 8, W * 8, g)
+    rois[:6, 1:] += torch.randn(6, 4, generator=g) * 150  # out-of-image / malformed boxes
+    out, arg = torch.ops.torchvision.roi_pool(feat, rois, 1 / 8, 7, 7)
+    rois_ok = make_rois(100, N, H * 8, W * 8, g, stress=False)
+    rois_ok[:8, 1:] += 120.0                              # partly outside the map, well formed
+    al = {}
+    for sr in (0, 2):
+        for aligned in (False, True):
+            al[(sr, aligned)] = torch.ops.torchvision.roi_align(feat, rois_ok, 1 / 8, 7, 7, sr, aligned)
+    torch.save(dict(feat=feat, rois=rois, scale=1 / 8, out=out, argmax=arg.int(),
+                    rois_align=rois_ok, align=al), os.path.join(GOLD, "pool.pt"))
+
+    # ---- (2a) alignment + row softmax ----------------------------------------------------------
+    cases = {}
+    for name, (M, D, K) in dict(small=(70, 96, 20), wide=(40, 64, 300)).items():
+        x = torch.relu(torch.randn(M, D, generator=g))
+        x[::17] = 0                                      # all-zero rows (eps path of F.normalize)
+        text = torch.randn(K, D, generator=g)
+        m = OpenVocabularyClassifier(ShapeSpec(channels=D), num_classes=K, weight_path="rand",
+                                     weight_dim=D, norm_temperature=50.0)
+        m.projection = nn.Identity()
+        with torch.no_grad():
+            logits = m(x, text, append_background=True)
+            logits_nobg = m(x, text, append_background=False)
+        head = types.SimpleNamespace()
+        props = [list(range(M))]                         # len() only
+        probs = fr.InstanceRefinementOutputLayers.predict_probs(head, (logits, None), props)[0]
+        cases[name] = dict(x=x, text=text, T=50.0, logits=logits, logits_nobg=logits_nobg, probs=probs)
+    torch.save(cases, os.path.join(GOLD, "align.pt"))
+
+    # ---- (2b) MIL two-stream ---------------------------------------------------------------------
+    cases = {}
+    for name, (sizes, K) in dict(multi=((50, 1, 77), 20), single=((64,), 20), k1=((33, 9), 1)).items():
+        Fdim = 16
+        om = fr.ObjectMiningOutputLayers(ShapeSpec(channels=Fdim), box2box_transform=Box2BoxTransform((10, 10, 5, 5)),
+                                         num_classes=K, loss_weight={})
+        x = torch.randn(sum(sizes), Fdim, generator=g) * 4
+        props = [list(range(s)) for s in sizes]
+        with torch.no_grad():
+            Cl, Dl = om.cls(x), om.det(x)
+            scores, _ = om(x, props)
+            img = om.predict_probs_img((scores, None), props)
+            pb = om.predict_probs((scores, None), props)
+        cases[name] = dict(cls=Cl, det=Dl, sizes=list(sizes), scores=scores, img=img,
+                           probs_bg=torch.cat(pb, 0))
+    torch.save(cases, os.path.join(GOLD, "mil.pt"))
+
+    # ---- (4) fast_rcnn_inference (filter + clip + batched_nms + top-k) -----------------------------
+    sizes, K = (300, 260), 20
+    img_shapes = [(240, 320), (200, 304)]
+    boxes, probs = [], []
+    for s, (ih, iw) in zip(sizes, img_shapes):
+        b = make_rois(s, 1, ih, iw, g)[:, 1:]
+        b[:10] += torch.randn(10, 4, generator=g) * 40       # boxes leaving the image -> clip matters
+        lg = torch.randn(s, K + 1, generator=g) * 2.5
+        boxes.append(b)
+        probs.append(torch.softmax(lg, -1))
+    probs[0][5, 3] = float("nan")                            # non-finite row is dropped (:178-182)
+    for p, b in zip(probs, boxes):
+        valid = torch.isfinite(b).all(1) & torch.isfinite(p).all(1)
+        ncand = int((p[valid][:, :-1] > 1e-5).sum())
+        assert ncand * 4 > 4000, "must exercise torchvision's vanilla batched_nms branch"
+    inst, kept, _, _ = fr.fast_rcnn_inference(boxes, probs, img_shapes, 1e-5, 0.3, 100)
+    torch.save(dict(boxes=boxes, probs=probs, image_shapes=img_shapes, score_thresh=1e-5,
+                    nms_thresh=0.3, topk=100,
+                    det_boxes=[i.pred_boxes.tensor for i in inst], det_scores=[i.scores for i in inst],
+                    det_classes=[i.pred_classes for i in inst], kept_indices=kept,
+                    det_rows=[i.pred_inds for i in inst]),
+               os.path.join(GOLD, "detections.pt"))
+
+    # ---- (3) refinement: get_pgt_top_k + label_and_sample_proposals_wsl ----------------------------
+    K = 20
+    sizes = (180, 90, 40)
+    img_shapes = [(240, 320), (200, 304), (120, 160)]
+    self = types.SimpleNamespace()
+    self.num_classes = K
+    self.images = [None] * len(sizes)
+    gt_inst = [types.SimpleNamespace(gt_classes=torch.tensor(c)) for c in ([7, 2, 7, 15], [0], [19, 3])]
+    _, self.gt_classes_img_int, oh = rh.get_image_level_gt(gt_inst, K)
+    proposals, scores_l, boxes_l = [], [], []
+    for i, (s, (ih, iw)) in enumerate(zip(sizes, img_shapes)):
+        b = make_rois(s, 1, ih, iw, g)[:, 1:]
+        if i == 2:
+            b[:, 2] = b[:, 0] + 3.0
+            b[:, 3] = b[:, 1] + 3.0                          # every box has area 9 <= 20 -> fallback seed
+        inst = Instances((ih, iw))
+        inst.proposal_boxes = Boxes(b)
+        inst.objectness_logits = torch.rand(s, generator=g)
+        proposals.append(inst)
+        boxes_l.append(b)
+        sc = torch.rand(s, K, generator=g) * 0.01
+        scores_l.append(torch.cat([sc, torch.zeros(s, 1)], 1))   # predict_probs appends a bg column
+    self.pred_class_img_logits = torch.rand(len(sizes), K, generator=g).clamp(1e-6, 1 - 1e-6)
+    self.proposal_matchers = [Matcher([0.5], [0, 1], allow_low_quality_matches=False)]
+    self.batch_size_per_images = [4096]
+    self.positive_sample_fractions = [1.0]
+    self.proposal_append_gt = False
+    self.cls_agnostic_bbox_known = False
+    self._sample_proposals_wsl = types.MethodType(rh.WSOVODROIHeads._sample_proposals_wsl, self)
+    targets = rh.WSOVODROIHeads.get_pgt_top_k(self, boxes_l, scores_l, proposals)
+    labelled = rh.WSOVODROIHeads.label_and_sample_proposals_wsl(self, 0, proposals, targets)
+    torch.save(dict(
+        boxes=boxes_l, scores=scores_l, sizes=list(sizes), num_classes=K,
+        gt_classes_img=[t.clone() for t in self.gt_classes_img_int],
+        img_scores=self.pred_class_img_logits,
+        seed_boxes=[t.gt_boxes.tensor for t in targets], seed_classes=[t.gt_classes for t in targets],
+        seed_scores=[t.gt_scores for t in targets], seed_weights=[t.gt_weights for t in targets],
+        gt_classes=[p.gt_classes for p in labelled], gt_boxes=[p.gt_boxes.tensor for p in labelled],
+        gt_scores=[p.gt_scores for p in labelled], gt_weights=[p.gt_weights for p in labelled],
+    ), os.path.join(GOLD, "refine.pt"))
+
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()
