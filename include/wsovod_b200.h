@@ -108,6 +108,7 @@ int wsovod_b200_align_fwd(const float* x, const float* classifier, int64_t M, in
                           const float* bias, int precision,
                           float* logits, float* probs,
                           void* workspace, size_t workspace_bytes, void* stream);
+size_t wsovod_b200_align_bwd_workspace(int64_t M, int64_t D, int64_t K);
 /* backward of align_fwd w.r.t. x (grad_x [M,D]) and optionally the classifier (grad_classifier [K,D],
  * may be NULL -- a buffer in every shipped config) given grad_logits [M,K+bg]. fp32. */
 int wsovod_b200_align_bwd(const float* grad_logits, const float* x, const float* classifier,
@@ -199,10 +200,14 @@ int wsovod_b200_batched_nms(const float* boxes, const float* scores, const int64
  * probs [M,K+1], boxes [M,4], offsets device int64 [N+1], image_sizes device fp32 [N,2].
  * Outputs are padded to topk per image: det_boxes [N,topk,4] (clipped), det_scores [N,topk],
  * det_classes [N,topk] int64, det_rows [N,topk] int64 (row local to the image = the reference's
- * kept_indices / pred_inds), det_count [N] int64.  Unused slots: score 0, class/row -1, box 0. */
+ * pred_inds; equal to its kept_indices whenever no row was dropped as non-finite), det_count [N]
+ * int64.  Unused slots: score 0, class/row -1, box 0.  max_rows_per_image: host-known upper bound of
+ * offsets[n+1]-offsets[n] (sizes the per-class shared-memory candidate list; <= ~9400).  topk must
+ * be in [1,4096]; for "keep everything" filter on the host side and call batched_nms. */
 size_t wsovod_b200_detections_workspace(int64_t M, int64_t N, int64_t K, int64_t topk);
 int wsovod_b200_detections(const float* probs, const float* boxes, const int64_t* offsets,
                            const float* image_sizes, int64_t M, int64_t N, int64_t K,
+                           int64_t max_rows_per_image,
                            float score_thresh, double nms_thresh, int64_t topk, int iou_mode,
                            float* det_boxes, float* det_scores, int64_t* det_classes,
                            int64_t* det_rows, int64_t* det_count,

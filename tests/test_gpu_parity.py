@@ -1,0 +1,329 @@
+"""GPU parity tests: every CUDA kernel (called through the C ABI via wsovod_b200.ops) against the CPU
+oracle on the same seeded inputs, against the reference-generated goldens in tests/golden, and --
+where torchvision's CUDA ops are the reference's own GPU path -- against those.
+
+Bars (north star): bit-exact for ROIPool values+argmax, refinement assignments and NMS keep-lists;
+1e-5 relative for fp32 pooling (ROIAlign) and softmax; stated TF32 tolerance |dlogit| <= 5e-2 for the
+tensor-core similarity logits.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402  (CPU checker)
+from wsovod_b200 import ops, synth  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _offs(sizes):
+    o = [0]
+    for s in sizes:
+        o.append(o[-1] + int(s))
+    return o
+
+
+# ------------------------------------------------------------------------------------------------ (1)
+def _pool_case(N, C, H, W, R, seed, relu=False, wild=True):
+    g = synth.gen(seed)
+    feat = synth.features(N, C, H, W, g, relu=relu)
+    boxes = [synth.proposals(R, H * 8, W * 8, g) for _ in range(N)]
+    rois, _ = synth.rois_from(boxes)
+    if wild:   # out-of-image, inverted and huge boxes
+        k = max(R // 10, 1)
+        rois[:k, 1:] += torch.randn(k, 4, generator=g) * 200
+    perm = torch.randperm(rois.size(0), generator=g)     # arbitrary batch order
+    return feat, rois[perm].contiguous()
+
+
+@pytest.mark.parametrize("N,C,H,W,R", [(1, 4, 30, 40, 300), (3, 5, 23, 37, 200), (2, 1, 16, 16, 64),
+                                         (2, 2, 60, 80, 500), (1, 7, 9, 11, 50), (2, 64, 60, 80, 700)])
+def test_roi_pool_bit_exact(N, C, H, W, R):
+    feat, rois = _pool_case(N, C, H, W, R, seed=N * 1000 + C)
+    out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)
+    o_ref, a_ref = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    assert torch.equal(out.cpu(), o_ref)
+    assert torch.equal(arg.cpu(), a_ref)
+    out2, arg2 = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
+    assert torch.equal(out2.cpu(), o_ref) and arg2.numel() == 0
+
+
+def test_roi_pool_vs_torchvision_cuda_and_golden(golden):
+    import torchvision  # noqa: F401
+    g = golden("pool")
+    out, arg = ops.roi_pool(g["feat"].to(DEV), g["rois"].to(DEV), g["scale"], 7, with_argmax=True)
+    assert torch.equal(out.cpu(), g["out"]) and torch.equal(arg.cpu(), g["argmax"])
+    feat, rois = _pool_case(2, 32, 60, 80, 1000, seed=5)
+    tv_out, tv_arg = torch.ops.torchvision.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, 7)
+    out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)
+    assert torch.equal(out, tv_out) and torch.equal(arg, tv_arg.int())
+
+
+def test_roi_pool_scale_epilogue_and_sizes():
+    feat, rois = _pool_case(2, 6, 30, 40, 200, seed=9, relu=True, wild=False)
+    obj = torch.rand(rois.size(0))
+    out, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0)
+    ref, _ = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    ref = ref * (obj + 1).view(-1, 1, 1, 1)               # roi_heads.py:733-739
+    assert torch.equal(out.cpu(), ref)
+    for ps in [(3, 5), (14, 14), (1, 1)]:
+        o, a = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, ps, with_argmax=True)
+        r, ra = oracle.roi_pool(feat, rois, 1 / 8, ps)
+        assert torch.equal(o.cpu(), r) and torch.equal(a.cpu(), ra)
+    # empty inputs
+    o, a = ops.roi_pool(feat.to(DEV), rois[:0].to(DEV), 1 / 8, 7, with_argmax=True)
+    assert o.shape == (0, 6, 7, 7)
+
+
+def test_roi_pool_large_map_fallback():
+    # a plane that does not fit shared memory (H*W*4 > 227 KB) takes the global-memory variant
+    g = synth.gen(3)
+    feat = torch.randn(1, 2, 250, 260, generator=g)
+    boxes = synth.proposals(150, 250 * 8, 260 * 8, g)
+    rois, _ = synth.rois_from([boxes])
+    o, a = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)
+    r, ra = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    assert torch.equal(o.cpu(), r) and torch.equal(a.cpu(), ra)
+
+
+def test_roi_pool_backward():
+    feat, rois = _pool_case(2, 3, 20, 24, 120, seed=11, wild=False)
+    x = feat.to(DEV).requires_grad_(True)
+    out, arg = ops.roi_pool(x, rois.to(DEV), 1 / 8, 7)
+    assert arg.numel() == out.numel()
+    go = torch.randn_like(out)
+    out.backward(go)
+    ref = oracle.roi_pool_backward(go.cpu(), rois, arg.cpu(), feat.shape)
+    torch.testing.assert_close(x.grad.cpu(), ref, rtol=1e-5, atol=1e-5)   # atomics: order differs
+
+
+@pytest.mark.parametrize("N,C,H,W,R", [(1, 4, 30, 40, 300), (2, 3, 23, 37, 200), (2, 1, 16, 16, 64)])
+def test_roi_loop_pool_vs_oracle(N, C, H, W, R):
+    feat, rois = _pool_case(N, C, H, W, R, seed=77 + C, relu=True, wild=False)
+    out, arg = ops.roi_loop_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7)
+    o_ref, a_ref = oracle.roi_loop_pool(feat, rois, 1 / 8, 7)
+    assert out.shape == (3 * rois.size(0), C, 7, 7)
+    assert torch.equal(out.cpu(), o_ref)
+    assert torch.equal(arg.cpu(), a_ref)
+
+
+@pytest.mark.parametrize("sr,aligned", [(0, False), (0, True), (2, False), (2, True)])
+def test_roi_align(sr, aligned, golden):
+    g = golden("pool")
+    out = ops.roi_align(g["feat"].to(DEV), g["rois_align"].to(DEV), g["scale"], 7, sr, aligned)
+    torch.testing.assert_close(out.cpu(), g["align"][(sr, aligned)], rtol=1e-5, atol=1e-5)
+    feat, rois = _pool_case(2, 5, 30, 40, 300, seed=21, wild=False)
+    out = ops.roi_align(feat.to(DEV), rois.to(DEV), 1 / 8, 7, sr, aligned)
+    ref = oracle.roi_align(feat, rois, 1 / 8, 7, sr, aligned)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ (2)
+TF32_LOGIT_TOL = 5e-2      # stated tolerance: T*2*2^-11 worst case at T=50
+
+
+@pytest.mark.parametrize("precision,tol", [(ops.ALIGN_FP32, 5e-5), (ops.ALIGN_TF32, TF32_LOGIT_TOL)])
+def test_align_golden(precision, tol, golden):
+    for name, c in golden("align").items():
+        lg, pr = ops.align(c["x"].to(DEV), c["text"].to(DEV), c["T"], True, True, None, precision, True, True)
+        assert (lg.cpu() - c["logits"]).abs().max().item() <= tol, name
+        # softmax itself is fp32: compare against softmax of OUR logits at 1e-5 relative
+        torch.testing.assert_close(pr, torch.softmax(lg, -1), rtol=1e-5, atol=1e-9)
+        if precision == ops.ALIGN_FP32:
+            torch.testing.assert_close(pr.cpu(), c["probs"], rtol=2e-4, atol=1e-7)
+        lg2, _ = ops.align(c["x"].to(DEV), c["text"].to(DEV), c["T"], True, False, None, precision, True, False)
+        assert (lg2.cpu() - c["logits_nobg"]).abs().max().item() <= tol, name
+
+
+@pytest.mark.parametrize("M,D,K", [(1000, 768, 20), (300, 512, 80), (257, 768, 1203), (64, 64, 5), (129, 100, 33)])
+@pytest.mark.parametrize("precision", [ops.ALIGN_FP32, ops.ALIGN_TF32])
+def test_align_vs_oracle(M, D, K, precision):
+    g = synth.gen(M + K)
+    x = synth.region_embeddings(M, D, g)
+    x[3] = 0
+    t = synth.text_embeddings(K, D, g)
+    bias = torch.tensor([0.25])
+    lo, po = oracle.align(x, t, 50.0, True, True, bias=0.25)
+    lg, pr = ops.align(x.to(DEV), t.to(DEV), 50.0, True, True, bias.to(DEV), precision, True, True)
+    tol = 5e-5 if precision == ops.ALIGN_FP32 else TF32_LOGIT_TOL
+    assert (lg.cpu() - lo).abs().max().item() <= tol
+    torch.testing.assert_close(pr, torch.softmax(lg, -1), rtol=1e-5, atol=1e-9)
+    # probs-only call (logits staged in the probs buffer)
+    _, pr2 = ops.align(x.to(DEV), t.to(DEV), 50.0, True, True, bias.to(DEV), precision, False, True)
+    torch.testing.assert_close(pr2, pr, rtol=1e-6, atol=1e-9)
+    # no normalisation branch (:94 skipped when norm_weight is False)
+    lo3, _ = oracle.align(x, t, 50.0, False, False, want_probs=False)
+    lg3, _ = ops.align(x.to(DEV), t.to(DEV), 50.0, False, False, None, precision, True, False)
+    scale = lo3.abs().max().item()
+    assert (lg3.cpu() - lo3).abs().max().item() <= (1e-5 if precision == ops.ALIGN_FP32 else 4e-3) * scale
+
+
+def test_align_backward():
+    g = synth.gen(5)
+    x = synth.region_embeddings(200, 96, g).add_(0.01)
+    t = synth.text_embeddings(20, 96, g)
+    xg = x.to(DEV).requires_grad_(True)
+    lg, _ = ops.align(xg, t.to(DEV), 50.0, True, True, None, ops.ALIGN_FP32, True, False)
+    go = torch.randn_like(lg)
+    lg.backward(go)
+    xr = x.clone().requires_grad_(True)
+    w = torch.nn.functional.normalize(t.t().contiguous(), p=2, dim=0)
+    w = torch.cat([w, w.new_zeros(96, 1)], 1)
+    ref = torch.mm(50.0 * torch.nn.functional.normalize(xr, p=2, dim=1), w)   # open_vocabulary_classifier.py:94-102
+    ref.backward(go.cpu())
+    torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_mil_golden_and_oracle(golden):
+    for name, c in golden("mil").items():
+        off = torch.tensor(_offs(c["sizes"]), dtype=torch.int64, device=DEV)
+        s, img = ops.mil(c["cls"].to(DEV), c["det"].to(DEV), off)
+        torch.testing.assert_close(s.cpu(), c["scores"], rtol=1e-5, atol=1e-10)
+        torch.testing.assert_close(img.cpu(), c["img"], rtol=1e-5, atol=1e-8)
+    g = synth.gen(8)
+    sizes = [4000, 1, 2500, 0, 333]
+    for K in (20, 80, 300):
+        C, D = synth.mil_logits(sum(sizes), K, g)
+        off = _offs(sizes)
+        s, img = ops.mil(C.to(DEV), D.to(DEV), torch.tensor(off, device=DEV))
+        so, io = oracle.mil(C, D, off)
+        torch.testing.assert_close(s.cpu(), so, rtol=1e-5, atol=1e-12)
+        keep = [i for i, n in enumerate(sizes) if n > 0]
+        torch.testing.assert_close(img.cpu()[keep], io[keep], rtol=1e-5, atol=1e-8)
+
+
+def test_mil_backward():
+    g = synth.gen(12)
+    sizes = [70, 33]
+    C, D = synth.mil_logits(sum(sizes), 20, g)
+    off = _offs(sizes)
+    Cg, Dg = C.to(DEV).requires_grad_(True), D.to(DEV).requires_grad_(True)
+    s, img = ops.mil(Cg, Dg, torch.tensor(off, device=DEV))
+    gs, gi = torch.randn_like(s), torch.randn_like(img)
+    (s * gs).sum().add((img * gi).sum()).backward()
+    Cr, Dr = C.clone().requires_grad_(True), D.clone().requires_grad_(True)
+    parts = [torch.softmax(c, 1) * torch.softmax(d, 0) for c, d in zip(Cr.split(sizes), Dr.split(sizes))]
+    sr = torch.cat(parts)
+    ir = torch.stack([p.sum(0) for p in parts]).clamp(1e-6, 1 - 1e-6)
+    (sr * gs.cpu()).sum().add((ir * gi.cpu()).sum()).backward()
+    torch.testing.assert_close(Cg.grad.cpu(), Cr.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(Dg.grad.cpu(), Dr.grad, rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ (3)
+def _refine_run(boxes_l, scores_l, gt_l, img_scores, K):
+    off = _offs([len(b) for b in boxes_l])
+    goff = _offs([len(gc) for gc in gt_l])
+    d = lambda t, dt=None: (t if dt is None else t.to(dt)).to(DEV)
+    offd, goffd = d(torch.tensor(off)), d(torch.tensor(goff))
+    seeds = ops.pgt_top1(d(torch.cat(scores_l)), d(torch.cat(boxes_l)), offd, d(torch.cat(gt_l)), goffd, d(img_scores))
+    asg = ops.refine_assign(d(torch.cat(boxes_l)), offd, seeds["seed_boxes"], seeds["seed_classes"],
+                            seeds["seed_scores"], seeds["seed_weights"], goffd, seeds["seed_count"], K, 0.5)
+    so = oracle.pgt_top1(torch.cat(scores_l), torch.cat(boxes_l), off, torch.cat(gt_l), goff, img_scores)
+    ao = oracle.refine_assign(torch.cat(boxes_l), off, so["seed_boxes"], so["seed_classes"], so["seed_scores"],
+                              so["seed_weights"], goff, so["seed_count"], K, 0.5)
+    return seeds, asg, so, ao, off, goff
+
+
+def test_refine_golden(golden):
+    f = golden("refine")
+    seeds, asg, so, ao, off, goff = _refine_run(f["boxes"], f["scores"], f["gt_classes_img"], f["img_scores"],
+                                                f["num_classes"])
+    for n in range(len(f["sizes"])):
+        g0, c = goff[n], int(seeds["seed_count"][n])
+        assert c == len(f["seed_classes"][n])
+        assert torch.equal(seeds["seed_boxes"][g0:g0 + c].cpu(), f["seed_boxes"][n])
+        assert torch.equal(seeds["seed_classes"][g0:g0 + c].cpu(), f["seed_classes"][n])
+        assert torch.equal(seeds["seed_scores"][g0:g0 + c].cpu(), f["seed_scores"][n])
+        assert torch.equal(seeds["seed_weights"][g0:g0 + c].cpu(), f["seed_weights"][n])
+        sl = slice(off[n], off[n + 1])
+        assert torch.equal(asg["gt_classes"][sl].cpu(), f["gt_classes"][n])
+        assert torch.equal(asg["gt_boxes"][sl].cpu(), f["gt_boxes"][n])
+        assert torch.equal(asg["gt_scores"][sl].cpu(), f["gt_scores"][n])
+        assert torch.equal(asg["gt_weights"][sl].cpu(), f["gt_weights"][n])
+
+
+def test_refine_vs_oracle_full_size():
+    g = synth.gen(31)
+    K, sizes = 80, [5024, 4000, 1, 3000]
+    boxes = [synth.proposals(s, 800, 1216, g) if s > 1 else torch.tensor([[10., 10., 200., 300.]]) for s in sizes]
+    boxes[1] = (boxes[1] / 16).round() * 16            # integer grid: exact IoU ties and IoU == 0.5 cases
+    scores = [torch.rand(s, K + 1, generator=g) for s in sizes]
+    scores[0][:, 5] = 0.25                              # all-equal column: first index must win
+    gts = synth.image_labels(len(sizes), K, g, max_labels=8)
+    gts[0] = torch.unique(torch.cat([gts[0], torch.tensor([5])]))
+    img = torch.rand(len(sizes), K, generator=g)
+    seeds, asg, so, ao, _, _ = _refine_run(boxes, scores, gts, img, K)
+    for k in so:
+        assert torch.equal(seeds[k].cpu(), so[k]), k
+    for k in ao:
+        assert torch.equal(asg[k].cpu(), ao[k]), k
+    assert (ao["gt_classes"] < K).sum() > 50           # the test actually has foreground
+
+
+# ------------------------------------------------------------------------------------------------ (4)
+def _nms_case(M, ngroups, seed, grid=None):
+    g = synth.gen(seed)
+    b = synth.proposals(M, 480, 640, g)
+    if grid:
+        b = (b / grid).round() * grid
+    s = torch.rand(M, generator=g)
+    idx = torch.randint(0, ngroups, (M,), generator=g)
+    return b, s, idx
+
+
+@pytest.mark.parametrize("M,G,grid", [(3000, 20, None), (3000, 20, 4), (5000, 3, 16), (17, 4, None), (9000, 1, 8),
+                                        (20000, 80, None)])
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
+def test_batched_nms_vs_oracle(M, G, grid, mode):
+    b, s, idx = _nms_case(M, G, M + G, grid)
+    keep = ops.batched_nms(b.to(DEV), s.to(DEV), (idx * 7 + 3).to(DEV), 0.3, mode)   # non-dense ids
+    ref = oracle.batched_nms(b, s, idx, 0.3, mode)
+    assert torch.equal(keep.cpu(), ref)
+
+
+def test_batched_nms_vs_torchvision():
+    from torchvision.ops.boxes import _batched_nms_vanilla
+    for grid in (None, 4, 16):
+        b, s, idx = _nms_case(4000, 20, 99, grid)
+        # CPU arithmetic mode == torchvision CPU kernel
+        keep = ops.batched_nms(b.to(DEV), s.to(DEV), idx.to(DEV), 0.3, ops.IOU_TV_CPU)
+        assert torch.equal(keep.cpu(), _batched_nms_vanilla(b, s, idx, 0.3))
+        # CUDA arithmetic mode == torchvision CUDA kernel (the reference's own GPU path)
+        keep = ops.batched_nms(b.to(DEV), s.to(DEV), idx.to(DEV), 0.3, ops.IOU_TV_CUDA)
+        tv = _batched_nms_vanilla(b.to(DEV), s.to(DEV), idx.to(DEV), 0.3)
+        assert torch.equal(keep, tv)
+
+
+def test_detections_golden(golden):
+    d = golden("detections")
+    off = _offs([len(b) for b in d["boxes"]])
+    r = ops.detections(torch.cat(d["probs"]).to(DEV), torch.cat(d["boxes"]).to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(d["image_shapes"], dtype=torch.float32, device=DEV), max(len(b) for b in d["boxes"]),
+                       d["score_thresh"], d["nms_thresh"], d["topk"], ops.IOU_TV_CPU)
+    for n in range(len(d["boxes"])):
+        c = int(r["det_count"][n])
+        assert c == len(d["det_scores"][n])
+        assert torch.equal(r["det_rows"][n, :c].cpu(), d["det_rows"][n])
+        assert torch.equal(r["det_classes"][n, :c].cpu(), d["det_classes"][n])
+        assert torch.equal(r["det_scores"][n, :c].cpu(), d["det_scores"][n])
+        assert torch.equal(r["det_boxes"][n, :c].cpu(), d["det_boxes"][n])
+
+
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
+def test_detections_vs_oracle(mode):
+    g = synth.gen(41)
+    K, sizes = 20, [2000, 1500, 3]
+    shapes = [(480, 640), (400, 600), (100, 100)]
+    boxes = [synth.proposals(s, h, w, g) for s, (h, w) in zip(sizes, shapes)]
+    boxes[1] = (boxes[1] / 8).round() * 8
+    boxes[0][:20] += torch.randn(20, 4, generator=g) * 60
+    probs = [torch.softmax(torch.randn(s, K + 1, generator=g) * 2.0, -1) for s in sizes]
+    probs[0][7, 2] = float("inf")
+    off = _offs(sizes)
+    r = ops.detections(torch.cat(probs).to(DEV), torch.cat(boxes).to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(shapes, dtype=torch.float32, device=DEV), max(sizes), 1e-5, 0.3, 100, mode)
+    o = oracle.detections(torch.cat(probs), torch.cat(boxes), off, shapes, 1e-5, 0.3, 100, mode)
+    for k in o:
+        assert torch.equal(r[k].cpu(), o[k]), k

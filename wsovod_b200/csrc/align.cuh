@@ -1,0 +1,22 @@
+// align.cuh -- shared declarations of the alignment kernels (align.cu, align_tc.cu)
+#pragma once
+#include "common.cuh"
+
+namespace wsovod {
+
+struct AlignWs {
+  size_t what, wt, dy, tmaps, bytes;
+  int64_t Dp, Kp;   // padded reduction length / padded number of weight rows (TF32 path)
+};
+AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward);
+
+__global__ void align_wnorm_kernel(const float* __restrict__ w, int K, int D, int Dp, int norm,
+                                   float* __restrict__ out);
+__global__ void row_softmax_kernel(const float* __restrict__ logits, int64_t M, int KO,
+                                   float* __restrict__ probs);
+
+int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D, int64_t K,
+                   float temperature, int norm_weight, int append_background, const float* bias,
+                   float* logits, float* probs, const AlignWs& w, char* ws, cudaStream_t st);
+
+}  // namespace wsovod

@@ -1,0 +1,342 @@
+// align_tc.cu -- the tensor-core path of kernel (2a): tcgen05.mma kind::tf32, operands fed by TMA into
+// 128B-swizzled shared memory, fp32 accumulators in TMEM, fused normalise / temperature / bias /
+// row-softmax epilogue read back with tcgen05.ld.
+//
+// Persistent, warp-specialised, one CTA per SM (grid = min(#row tiles, 148)):
+//   warp 0   TMA producer : x tile [128 rows x 32 fp32] + W^ tile [BN rows x 32 fp32] per pipeline stage
+//   warp 1   MMA issuer   : one elected thread, 4 x (M=128, N=BN, K=8) tcgen05.mma per stage,
+//                           tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2   TMEM allocator (2 accumulator buffers so the epilogue of tile t overlaps the MMAs of t+1)
+//   warps 4-7 epilogue    : thread == accumulator row (TMEM lane); ||x_r|| from the (L2-hot) rows of x,
+//                           logits = acc * T/||x_r|| (+bias), online softmax across N chunks.
+// x is consumed as fp32 straight from HBM (the tensor core truncates the low 13 mantissa bits: TF32),
+// no conversion pass, no extra copy.  K (classes) > 256 is processed in chunks of 256 accumulator
+// columns with a running (max, sum) per row.
+#include <cuda.h>
+
+#include "align.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace wsovod {
+
+constexpr int TC_BM = 128;          // rows per tile (UMMA M)
+constexpr int TC_BK = 32;           // fp32 elements per stage row = 128 B = one swizzle atom
+constexpr int TC_THREADS = 256;
+constexpr int TC_SPIN_LIMIT = 1 << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (spin > TC_SPIN_LIMIT) __trap();   // a protocol bug must abort the launch, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128B swizzle, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                              // leading byte offset (unused: one atom along K)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+  return d;
+}
+
+struct TcParams {
+  const float* x;
+  const float* bias;
+  float* logits;      // [M, KO] (never null inside the kernel: falls back to `probs` storage)
+  float* probs;       // [M, KO] or null
+  int64_t M;
+  int D, KO, Kp;      // Kp: padded weight rows (multiple of 32)
+  int BN;             // accumulator columns per chunk (multiple of 32, <= 256)
+  int nchunks, kblocks, stages, ntiles;
+  int norm;
+  float temperature;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 128B-swizzled operand stages must start on a 1024-byte boundary of the shared window
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (uint32_t)p.BN * TC_BK * 4;
+  unsigned char* sa = smem;                                   // [stages][16 KB]
+  unsigned char* sb = smem + (size_t)p.stages * a_bytes;      // [stages][BN*128 B]   (1024-aligned: BN % 16 == 0 -> multiple of 2 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + (size_t)p.stages * b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tfull = bars + 2 * p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int c = 0; c < p.nchunks; ++c)
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], a_bytes + b_bytes);
+            tma_load_2d(&map_x, sa + (size_t)stage * a_bytes, &full[stage], kb * TC_BK, tile * TC_BM);
+            tma_load_2d(&map_w, sb + (size_t)stage * b_bytes, &full[stage], kb * TC_BK, c * p.BN);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+          mbar_wait(&tempty[buf], aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.BN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(sa + (size_t)stage * a_bytes));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sb + (size_t)stage * b_bytes));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k)   // UMMA_K = 8 tf32 = 32 B: advance the start address inside the atom
+              tc_mma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            tc_commit(&empty[stage]);            // frees the smem stage once these MMAs have read it
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&tfull[buf]);                // accumulator complete
+        }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp - 4;                     // TMEM lane quarter this warp may access (warp % 4)
+    const int row_in_tile = wq * 32 + lane;
+    const float bias = p.bias ? __ldg(p.bias) : 0.f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int64_t m0 = (int64_t)tile * TC_BM;
+      const int64_t row = m0 + row_in_tile;
+      // ||x_r||^2 for this warp's 32 rows: coalesced 128-bit loads of rows the TMA just pulled into L2
+      float scale = 1.f;
+      if (p.norm) {
+        float myss = 0.f;
+        for (int i = 0; i < 32; ++i) {
+          const int64_t r = m0 + wq * 32 + i;
+          float ss = 0.f;
+          if (r < p.M) {
+            const float4* xr = reinterpret_cast<const float4*>(p.x + r * p.D);
+            for (int d = lane; d < (p.D >> 2); d += 32) {
+              const float4 v = __ldg(xr + d);
+              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+          }
+          ss = warp_sum(ss);
+          if (lane == i) myss = ss;
+        }
+        scale = p.temperature / fmaxf(sqrtf(myss), 1e-12f);
+      }
+      float run_m = -FLT_MAX, run_s = 0.f;
+      float* lrow = p.logits + row * p.KO;
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&tfull[buf], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)p.BN;
+        const int col0 = c * p.BN;
+        const int ncols = min(p.BN, p.KO - col0);        // valid output columns in this chunk
+        float v[32];
+        // sweep A: chunk maximum
+        float cm = -FLT_MAX;
+        for (int j = 0; j < ncols; j += 32) {
+          tmem_ld32(taddr + j, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (j + i < ncols) cm = fmaxf(cm, fmaf(v[i], scale, bias));
+        }
+        const float new_m = fmaxf(run_m, cm);
+        run_s *= expf(run_m - new_m);
+        run_m = new_m;
+        // sweep B: logits out, running sum of exp
+        for (int j = 0; j < ncols; j += 32) {
+          tmem_ld32(taddr + j, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (j + i < ncols) {
+              const float l = fmaf(v[i], scale, bias);
+              run_s += expf(l - run_m);
+              if (row < p.M) lrow[col0 + j + i] = l;
+            }
+        }
+        if (p.probs && p.nchunks == 1) {
+          // sweep C (single chunk): probabilities straight from TMEM
+          const float inv = 1.f / run_s;
+          float* prow = p.probs + row * p.KO;
+          for (int j = 0; j < ncols; j += 32) {
+            tmem_ld32(taddr + j, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (j + i < ncols && row < p.M) prow[j + i] = expf(fmaf(v[i], scale, bias) - run_m) * inv;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);               // accumulator buffer may be overwritten
+      }
+      if (p.probs && p.nchunks > 1 && row < p.M) {
+        // multi-chunk: the row's logits were written by this very thread; normalise them
+        const float inv = 1.f / run_s;
+        float* prow = p.probs + row * p.KO;
+        for (int k = 0; k < p.KO; ++k) prow[k] = expf(lrow[k] - run_m) * inv;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                    uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return WSOVOD_B200_EUNSUPPORTED;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_elems * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : WSOVOD_B200_EINVAL;
+}
+
+int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D, int64_t K, float temperature,
+                   int norm_weight, int append_background, const float* bias, float* logits, float* probs,
+                   const AlignWs& w, char* ws, cudaStream_t st) {
+  if ((D & 3) || ((uintptr_t)x & 15)) return WSOVOD_B200_EALIGN;   // TMA: 16-byte rows
+  if (M > 0x7fffffffLL - TC_BM) return WSOVOD_B200_ETOOBIG;
+  const int64_t KO = K + (append_background ? 1 : 0);
+  float* what = (float*)(ws + w.what);                              // [Kp, Dp], rows >= K and cols >= D are zero
+  cudaError_t e = cudaMemsetAsync(what, 0, sizeof(float) * (size_t)(w.Kp * w.Dp), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  if (K > 0) {
+    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)w.Dp, norm_weight, what);
+    if ((rc = after_launch())) return rc;
+  }
+  TcParams p;
+  p.x = x; p.bias = bias; p.logits = logits ? logits : probs; p.probs = probs;
+  p.M = M; p.D = (int)D; p.KO = (int)KO; p.Kp = (int)w.Kp;
+  p.BN = (int)std::min<int64_t>(w.Kp, 256);
+  p.nchunks = (int)ceil_div(KO, p.BN);
+  p.kblocks = (int)ceil_div(D, TC_BK);
+  p.ntiles = (int)ceil_div(M, TC_BM);
+  p.norm = norm_weight; p.temperature = temperature;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4;
+  p.stages = (int)std::max<size_t>(2, std::min<size_t>(8, ((size_t)kMaxSmemOptin - 4096) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 2048;   // + alignment slack + barriers
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
+  p.tmem_cols = cols;                                               // <= 512
+  CUtensorMap mx, mw;
+  if ((rc = make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
+  if ((rc = make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
+  e = cudaFuncSetAttribute(align_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = std::min(p.ntiles, kNumSMs);
+  align_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
+  if ((rc = after_launch())) return rc;
+  if (!logits && probs && p.nchunks > 1) return 0;   // probs were normalised in place by the kernel
+  return 0;
+}
+
+}  // namespace wsovod

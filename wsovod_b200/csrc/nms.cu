@@ -1,0 +1,523 @@
+// nms.cu -- kernel (4): per-class NMS and the fused fast_rcnn_inference tail.
+//
+// Greedy NMS keeps a box iff no higher-scoring KEPT box of its class overlaps it by more than thr, so
+// only (candidates x kept) IoUs matter, not the (candidates^2)/2 bitmask torchvision's kernel fills.
+// One CTA owns one (image, class) segment, holds its candidates (key, box) in shared memory and
+// iterates:  [suppress everything the last kept box covers  +  block arg-max of what is still alive]
+// in ONE pass over shared memory per kept box, with one __syncthreads per pass.  No sort is needed:
+// the arg-max sequence IS the score-descending kept list.  The inference tail needs only the
+// DETECTIONS_PER_IMAGE best survivors of an image, and no class can contribute more than that many,
+// so every segment stops after `topk` kept boxes (exact, see DESIGN.md "Kernel 4").
+//
+// Keys: 64 bit = (order-inverted score bits << 32) | candidate id, so "smaller key" == "higher score,
+// then lower id" -- torchvision's stable descending sort.  IoU arithmetic is bit-exact to either
+// torchvision kernel (WSOVOD_B200_IOU_TV_CPU / _TV_CUDA), see suppresses().
+#include "common.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace wsovod {
+
+constexpr int kNmsThreads = 512;
+constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr unsigned long long kDead = ~0ull;
+
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t id) {
+  uint32_t u = __float_as_uint(score);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);     // ascending float order as unsigned
+  return ((unsigned long long)(~u) << 32) | id;        // ascending key = descending score
+}
+__device__ __forceinline__ float key_score(unsigned long long key) {
+  uint32_t u = ~(uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+// does kept box i (area ai precomputed) suppress candidate j ?
+//   MODE 0 (torchvision cpu/nms_kernel.cpp): ovr = inter / ((ai + aj) - inter); (double)ovr > thr
+//   MODE 1 (torchvision cuda/nms_kernel.cu as compiled for sm_100): den = fma(wj, hj, ai) - inter;
+//           ovr > (float)thr
+// `thr` arrives pre-converted so that both are a single fp32 compare (see cmp_threshold()).
+template <int MODE>
+__device__ __forceinline__ bool suppresses(const float4 bi, const float ai, const float4 bj,
+                                           const float thr) {
+  float w = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+  float h = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+  w = fmaxf(w, 0.f);
+  h = fmaxf(h, 0.f);
+  const float inter = __fmul_rn(w, h);
+  float den;
+  if (MODE == 0) {
+    const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+    den = __fsub_rn(__fadd_rn(ai, aj), inter);
+  } else {
+    den = __fsub_rn(__fmaf_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y), ai), inter);
+  }
+  return __fdiv_rn(inter, den) > thr;
+}
+__device__ __forceinline__ float area_rn(const float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// fp32 threshold t such that the reference's comparison equals `ovr > t` for every fp32 ovr
+static float cmp_threshold(double thr, int mode) {
+  if (mode == WSOVOD_B200_IOU_TV_CUDA) return (float)thr;       // F2F.F32.F64 (round to nearest)
+  float f = (float)thr;                                         // (double)ovr > thr
+  if ((double)f > thr) f = nextafterf(f, -INFINITY);            // largest float <= thr
+  return f;
+}
+
+// block arg-min over (key) with the owning position; double-buffered slots -> one barrier per call
+struct ArgMinSlots {
+  unsigned long long key[2][kNmsWarps];
+  int pos[2][kNmsWarps];
+};
+
+__device__ __forceinline__ void block_argmin(unsigned long long& key, int& pos, ArgMinSlots& s, int buf) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+    const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+    if (ok < key) { key = ok; pos = op; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s.key[buf][wid] = key; s.pos[buf][wid] = pos; }
+  __syncthreads();
+  key = s.key[buf][0];
+  pos = s.pos[buf][0];
+#pragma unroll
+  for (int w = 1; w < kNmsWarps; ++w) {
+    const unsigned long long ok = s.key[buf][w];
+    if (ok < key) { key = ok; pos = s.pos[buf][w]; }
+  }
+}
+
+// Greedy selection over n candidates (keys[], boxes[] in shared or global memory).  Writes the kept
+// keys in score-descending order to kept_keys[0..ret).  SUPPRESS=false degenerates to "top-limit".
+template <int MODE, bool SUPPRESS>
+__device__ int select_greedy(unsigned long long* keys, const float4* boxes, int n, float thr, int limit,
+                             unsigned long long* kept_keys, ArgMinSlots& slots) {
+  int kept = 0, last = -1, buf = 0;
+  float4 kb = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ka = 0.f;
+  while (limit < 0 || kept < limit) {
+    unsigned long long best = kDead;
+    int bpos = -1;
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+      const unsigned long long key = keys[i];
+      if (key == kDead) continue;
+      if (i == last) { keys[i] = kDead; continue; }
+      if (SUPPRESS && last >= 0 && suppresses<MODE>(kb, ka, boxes[i], thr)) { keys[i] = kDead; continue; }
+      if (key < best) { best = key; bpos = i; }
+    }
+    block_argmin(best, bpos, slots, buf);
+    buf ^= 1;
+    if (bpos < 0) break;
+    if (threadIdx.x == 0) kept_keys[kept] = best;
+    ++kept;
+    last = bpos;
+    if (SUPPRESS) { kb = boxes[bpos]; ka = area_rn(kb); }
+  }
+  return kept;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused inference tail (fast_rcnn_inference_single_image, fast_rcnn_open_vocabulary.py:149-217)
+// ------------------------------------------------------------------------------------------------
+// rows: finite filter (:178-182) + Boxes.clip (:187-188)
+__global__ void det_rows_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                const int64_t* __restrict__ offsets, const float* __restrict__ image_sizes,
+                                int64_t M, int N, int K1, uint8_t* __restrict__ valid,
+                                float4* __restrict__ cboxes) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per row
+  const int lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + r);
+  bool ok = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w);
+  for (int k = lane; k < K1; k += 32) ok &= isfinite(__ldg(probs + r * K1 + k));
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    int lo = 0, hi = N - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= r) lo = mid; else hi = mid - 1; }
+    const float ih = image_sizes[2 * lo], iw = image_sizes[2 * lo + 1];
+    valid[r] = ok ? 1 : 0;
+    cboxes[r] = make_float4(fminf(fmaxf(b.x, 0.f), iw), fminf(fmaxf(b.y, 0.f), ih),
+                            fminf(fmaxf(b.z, 0.f), iw), fminf(fmaxf(b.w, 0.f), ih));
+  }
+}
+
+// one CTA per (class, image): gather the column's candidates, greedy NMS up to `limit` kept,
+// append (score, row*K+class) keys to the image's kept list
+template <int MODE>
+__global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
+    const float* __restrict__ probs, const int64_t* __restrict__ offsets, const uint8_t* __restrict__ valid,
+    const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int cap,
+    int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ ArgMinSlots slots;
+  __shared__ int s_n, s_base;
+  float4* sbox = reinterpret_cast<float4*>(sm);
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm + (size_t)cap * sizeof(float4));
+  unsigned long long* skept = skey + cap;                       // [limit]
+  const int k = blockIdx.x, n = blockIdx.y;
+  const int64_t r0 = offsets[n], r1 = offsets[n + 1];
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int K1 = K + 1;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += kNmsThreads) {
+    if (!valid[r]) continue;
+    const float s = __ldg(probs + r * K1 + k);
+    if (s > score_thr) {                                         // :194
+      const int p = atomicAdd(&s_n, 1);
+      sbox[p] = cboxes[r];
+      skey[p] = make_key(s, (uint32_t)(r - r0));
+    }
+  }
+  __syncthreads();
+  const int nc = s_n;
+  const int kept = select_greedy<MODE, true>(skey, sbox, nc, thr, limit, skept, slots);
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = atomicAdd(&img_cnt[n], kept);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
+    const unsigned long long key = skept[i];
+    const uint32_t row = (uint32_t)key;
+    img_kept[(int64_t)n * kept_stride + s_base + i] =
+        (key & 0xffffffff00000000ull) | (uint32_t)(row * (uint32_t)K + (uint32_t)k);
+  }
+}
+
+// one CTA per image: the topk best kept candidates, in order (:207-208), and the output gather
+__global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
+    const int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
+    const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk,
+    float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
+    int64_t* __restrict__ det_rows, int64_t* __restrict__ det_count) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ ArgMinSlots slots;
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(sm);   // [topk]
+  const int n = blockIdx.x;
+  const int cnt = img_cnt[n];
+  unsigned long long* keys = img_kept + (int64_t)n * kept_stride;
+  const int got = select_greedy<0, false>(keys, nullptr, cnt, 0.f, topk, sel, slots);
+  __syncthreads();
+  const int64_t r0 = offsets[n];
+  for (int i = threadIdx.x; i < topk; i += kNmsThreads) {
+    const int64_t o = (int64_t)n * topk + i;
+    float4* db = reinterpret_cast<float4*>(det_boxes) + o;
+    if (i < got) {
+      const unsigned long long key = sel[i];
+      const uint32_t id = (uint32_t)key;
+      const uint32_t row = id / (uint32_t)K, cls = id - row * (uint32_t)K;
+      *db = cboxes[r0 + row];
+      det_scores[o] = key_score(key);
+      det_classes[o] = cls;
+      det_rows[o] = row;
+    } else {
+      *db = make_float4(0.f, 0.f, 0.f, 0.f);
+      det_scores[o] = 0.f;
+      det_classes[o] = -1;
+      det_rows[o] = -1;
+    }
+  }
+  if (threadIdx.x == 0) det_count[n] = got;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic batched_nms (vanilla strategy of torchvision/ops/boxes.py:97-120)
+// ------------------------------------------------------------------------------------------------
+__global__ void nms_hist_kernel(const int64_t* __restrict__ groups, int64_t M, int G, int32_t* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int64_t g = groups[i];
+  if (g >= 0 && g < G) atomicAdd(&counts[g], 1);
+}
+
+__global__ void nms_scan_kernel(const int32_t* __restrict__ counts, int G, int32_t* __restrict__ starts) {
+  // single CTA exclusive scan (G is the number of classes / levels: small)
+  __shared__ int s_part[1024];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < G; g0 += 1024) {
+    const int g = g0 + threadIdx.x;
+    const int v = g < G ? counts[g] : 0;
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_part[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (g < G) starts[g] = s_carry + s_part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry += s_part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) starts[G] = s_carry;
+}
+
+__global__ void nms_scatter_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                   const int64_t* __restrict__ groups, int64_t M, int G,
+                                   const int32_t* __restrict__ starts, int32_t* __restrict__ cursor,
+                                   unsigned long long* __restrict__ keys, float4* __restrict__ segboxes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int64_t g = groups[i];
+  if (g < 0 || g >= G) return;
+  const int p = starts[g] + atomicAdd(&cursor[g], 1);
+  keys[p] = make_key(scores[i], (uint32_t)i);
+  segboxes[p] = __ldg(reinterpret_cast<const float4*>(boxes) + i);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(
+    const int32_t* __restrict__ starts, unsigned long long* __restrict__ keys,
+    const float4* __restrict__ segboxes, unsigned long long* __restrict__ tmp, float thr, int cap,
+    int32_t* __restrict__ total, unsigned long long* __restrict__ kept_all) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  __shared__ ArgMinSlots slots;
+  __shared__ int s_base;
+  const int g = blockIdx.x;
+  const int s0 = starts[g], n = starts[g + 1] - s0;
+  if (n <= 0) return;
+  unsigned long long* k = keys + s0;
+  const float4* b = segboxes + s0;
+  if (n <= cap) {   // stage the segment in shared memory
+    float4* sbox = reinterpret_cast<float4*>(sm);
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm + (size_t)cap * sizeof(float4));
+    for (int i = threadIdx.x; i < n; i += kNmsThreads) { sbox[i] = b[i]; skey[i] = k[i]; }
+    __syncthreads();
+    k = skey;
+    b = sbox;
+  }
+  const int kept = select_greedy<MODE, true>(k, b, n, thr, -1, tmp + s0, slots);
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = atomicAdd(total, kept);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kept; i += kNmsThreads) kept_all[s_base + i] = tmp[s0 + i];
+}
+
+// --- global bitonic sort of kept_all[0..npad) (unused slots hold kDead and sort to the end) -------
+constexpr int kSortTile = 4096;
+constexpr int kSortThreads = 512;
+
+__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b, bool asc) {
+  if ((a > b) == asc) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// all stages with j < kSortTile for level k (k <= tile: full local sort when first==1)
+__global__ void __launch_bounds__(kSortThreads) bitonic_local_kernel(unsigned long long* data, int64_t npad,
+                                                                    int64_t k_lo, int64_t k_hi) {
+  __shared__ unsigned long long s[kSortTile];
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  const int tile = (int)std::min<int64_t>(kSortTile, npad);
+  for (int i = threadIdx.x; i < tile; i += kSortThreads) s[i] = data[base + i];
+  __syncthreads();
+  for (int64_t k = k_lo; k <= k_hi; k <<= 1) {
+    for (int64_t j = std::min<int64_t>(k >> 1, tile >> 1); j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < tile; i += kSortThreads) {
+        const int ixj = i ^ (int)j;
+        if (ixj > i) {
+          const bool asc = ((base + i) & k) == 0;
+          unsigned long long a = s[i], b = s[ixj];
+          cmpxchg(a, b, asc);
+          s[i] = a; s[ixj] = b;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < tile; i += kSortThreads) data[base + i] = s[i];
+}
+
+__global__ void bitonic_global_kernel(unsigned long long* data, int64_t npad, int64_t k, int64_t j) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  const int64_t ixj = i ^ j;
+  if (ixj > i) {
+    const bool asc = (i & k) == 0;
+    unsigned long long a = data[i], b = data[ixj];
+    cmpxchg(a, b, asc);
+    data[i] = a; data[ixj] = b;
+  }
+}
+
+__global__ void nms_emit_kernel(const unsigned long long* __restrict__ kept_all, const int32_t* __restrict__ total,
+                                int64_t M, int64_t* __restrict__ keep, int64_t* __restrict__ num_keep) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *num_keep = *total;
+  if (i >= M) return;
+  keep[i] = i < *total ? (int64_t)(uint32_t)kept_all[i] : -1;
+}
+
+static int64_t next_pow2(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
+
+struct NmsWs {
+  size_t counts, starts, cursor, total, keys, segboxes, tmp, kept_all, bytes;
+  int64_t npad;
+};
+static NmsWs nms_plan(int64_t M, int64_t G) {
+  NmsWs w;
+  size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+  w.npad = next_pow2(std::max<int64_t>(M, 1));
+  w.counts = take(sizeof(int32_t) * (size_t)(G + 1));
+  w.cursor = take(sizeof(int32_t) * (size_t)(G + 1));
+  w.total = take(sizeof(int32_t) * 4);
+  w.starts = take(sizeof(int32_t) * (size_t)(G + 1));
+  w.keys = take(sizeof(unsigned long long) * (size_t)M);
+  w.segboxes = take(sizeof(float4) * (size_t)M);
+  w.tmp = take(sizeof(unsigned long long) * (size_t)M);
+  w.kept_all = take(sizeof(unsigned long long) * (size_t)w.npad);
+  w.bytes = o;
+  return w;
+}
+
+struct DetWs { size_t valid, cboxes, img_cnt, img_kept, bytes; int64_t kept_stride; };
+static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
+  DetWs w;
+  size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
+  w.kept_stride = K * std::max<int64_t>(topk, 0);
+  w.valid = take((size_t)M);
+  w.cboxes = take(sizeof(float4) * (size_t)M);
+  w.img_cnt = take(sizeof(int32_t) * (size_t)(N + 1));
+  w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
+  w.bytes = o;
+  return w;
+}
+
+}  // namespace wsovod
+
+using namespace wsovod;
+
+static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+WSOVOD_API size_t wsovod_b200_batched_nms_workspace(int64_t M, int64_t num_groups) {
+  if (M < 0 || num_groups < 0) return 0;
+  return nms_plan(M, num_groups).bytes;
+}
+
+WSOVOD_API int wsovod_b200_batched_nms(const float* boxes, const float* scores, const int64_t* groups,
+                                       int64_t M, int64_t num_groups, double iou_thresh, int iou_mode,
+                                       int64_t* keep, int64_t* num_keep, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (M < 0 || num_groups < 0 || !num_keep || (iou_mode != 0 && iou_mode != 1)) return WSOVOD_B200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0 || num_groups == 0) {
+    cudaError_t e = cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st);
+    if (e == cudaSuccess && M > 0 && keep) e = cudaMemsetAsync(keep, 0xff, sizeof(int64_t) * (size_t)M, st);
+    return (int)e;
+  }
+  if (!boxes || !scores || !groups || !keep) return WSOVOD_B200_EINVAL;
+  if (!al16(boxes)) return WSOVOD_B200_EALIGN;
+  if (M >= (1LL << 31) || num_groups >= (1LL << 30)) return WSOVOD_B200_ETOOBIG;
+  const NmsWs w = nms_plan(M, num_groups);
+  if (!workspace || workspace_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
+  char* ws = (char*)workspace;
+  int32_t* counts = (int32_t*)(ws + w.counts);
+  int32_t* cursor = (int32_t*)(ws + w.cursor);
+  int32_t* total = (int32_t*)(ws + w.total);
+  int32_t* starts = (int32_t*)(ws + w.starts);
+  unsigned long long* keys = (unsigned long long*)(ws + w.keys);
+  float4* segboxes = (float4*)(ws + w.segboxes);
+  unsigned long long* tmp = (unsigned long long*)(ws + w.tmp);
+  unsigned long long* kept_all = (unsigned long long*)(ws + w.kept_all);
+  cudaError_t e = cudaMemsetAsync(ws + w.counts, 0, w.starts - w.counts, st);   // counts, cursor, total
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(kept_all, 0xff, sizeof(unsigned long long) * (size_t)w.npad, st);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  const int G = (int)num_groups;
+  nms_hist_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(groups, M, G, counts);
+  if ((rc = after_launch())) return rc;
+  nms_scan_kernel<<<1, 1024, 0, st>>>(counts, G, starts);
+  if ((rc = after_launch())) return rc;
+  nms_scatter_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(boxes, scores, groups, M, G, starts, cursor, keys, segboxes);
+  if ((rc = after_launch())) return rc;
+  const float thr = cmp_threshold(iou_thresh, iou_mode);
+  const int cap = (int)std::min<int64_t>(M, 8192);
+  const size_t smem = (size_t)cap * (sizeof(float4) + sizeof(unsigned long long));
+  auto kern = iou_mode == 0 ? nms_segment_kernel<0> : nms_segment_kernel<1>;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(unsigned)G, kNmsThreads, smem, st>>>(starts, keys, segboxes, tmp, thr, cap, total, kept_all);
+  if ((rc = after_launch())) return rc;
+  // order all survivors by (score desc, index asc)
+  const int64_t npad = w.npad;
+  const unsigned tiles = (unsigned)std::max<int64_t>(1, npad / kSortTile);
+  bitonic_local_kernel<<<tiles, kSortThreads, 0, st>>>(kept_all, npad, 2, std::min<int64_t>(npad, kSortTile));
+  if ((rc = after_launch())) return rc;
+  for (int64_t k = 2 * (int64_t)kSortTile; k <= npad; k <<= 1) {
+    for (int64_t j = k >> 1; j >= kSortTile; j >>= 1) {
+      bitonic_global_kernel<<<(unsigned)ceil_div(npad, 256), 256, 0, st>>>(kept_all, npad, k, j);
+      if ((rc = after_launch())) return rc;
+    }
+    bitonic_local_kernel<<<tiles, kSortThreads, 0, st>>>(kept_all, npad, k, k);
+    if ((rc = after_launch())) return rc;
+  }
+  nms_emit_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(kept_all, total, M, keep, num_keep);
+  return after_launch();
+}
+
+WSOVOD_API size_t wsovod_b200_detections_workspace(int64_t M, int64_t N, int64_t K, int64_t topk) {
+  if (M < 0 || N < 0 || K < 0) return 0;
+  return det_plan(M, N, K, topk).bytes;
+}
+
+WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, const int64_t* offsets,
+                                      const float* image_sizes, int64_t M, int64_t N, int64_t K,
+                                      int64_t max_rows_per_image, float score_thresh, double nms_thresh,
+                                      int64_t topk, int iou_mode, float* det_boxes, float* det_scores,
+                                      int64_t* det_classes, int64_t* det_rows, int64_t* det_count,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (M < 0 || N < 0 || K < 0 || max_rows_per_image < 0 || (iou_mode != 0 && iou_mode != 1))
+    return WSOVOD_B200_EINVAL;
+  if (N == 0) return 0;
+  if (topk <= 0) return WSOVOD_B200_EUNSUPPORTED;   // "return all": use batched_nms on the filtered set
+  if (!offsets || !image_sizes || !det_boxes || !det_scores || !det_classes || !det_rows || !det_count ||
+      (M > 0 && (!probs || !boxes)))
+    return WSOVOD_B200_EINVAL;
+  if (!al16(boxes) || !al16(det_boxes)) return WSOVOD_B200_EALIGN;
+  if (M >= (1LL << 31) || K >= 65535 || N >= 65535 || max_rows_per_image * std::max<int64_t>(K, 1) >= (1LL << 32) ||
+      topk > 4096)
+    return WSOVOD_B200_ETOOBIG;
+  const DetWs w = det_plan(M, N, K, topk);
+  if (!workspace || workspace_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
+  const int cap = (int)std::max<int64_t>(max_rows_per_image, 1);
+  const int limit = (int)std::min<int64_t>(topk, cap);
+  const size_t smem = (size_t)cap * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(unsigned long long) * (size_t)limit;
+  if (smem > (size_t)kMaxSmemOptin - 1024) return WSOVOD_B200_EUNSUPPORTED;   // > ~9.4k proposals per image
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  uint8_t* valid = (uint8_t*)(ws + w.valid);
+  float4* cboxes = (float4*)(ws + w.cboxes);
+  int32_t* img_cnt = (int32_t*)(ws + w.img_cnt);
+  unsigned long long* img_kept = (unsigned long long*)(ws + w.img_kept);
+  cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(N + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  if (M > 0 && K > 0) {
+    det_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, valid, cboxes);
+    if ((rc = after_launch())) return rc;
+    auto kern = iou_mode == 0 ? det_class_kernel<0> : det_class_kernel<1>;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)K, (unsigned)N);
+    kern<<<grid, kNmsThreads, smem, st>>>(probs, offsets, valid, cboxes, (int)K, score_thresh,
+                                         cmp_threshold(nms_thresh, iou_mode), limit, cap, img_cnt, img_kept, w.kept_stride);
+    if ((rc = after_launch())) return rc;
+  }
+  det_topk_kernel<<<(unsigned)N, kNmsThreads, sizeof(unsigned long long) * (size_t)topk, st>>>(
+      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, det_boxes, det_scores,
+      det_classes, det_rows, det_count);
+  return after_launch();
+}

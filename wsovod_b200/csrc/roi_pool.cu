@@ -1,0 +1,573 @@
+// roi_pool.cu -- kernel family (1): ROI max-pool (+argmax), the 3-way ROILoopPool and bilinear ROIAlign.
+//
+// Design (DESIGN.md "Kernel 1"): a proposal's window is read ~50x less often than it is re-read by
+// the 100+ other proposals covering the same cells, so the unit of work is NOT a proposal.  A CTA
+// owns (image n, a group of CB<=4 channels): it stages those CB feature planes ONCE into shared memory,
+// channel-interleaved ([cell][CB] -> one LDS.128 fetches a cell for 4 channels), and then walks every
+// proposal of that image.  Lanes map to consecutive flattened (proposal, bin) outputs, so a warp store
+// is 32 consecutive floats of the (R,C,7,7) output (coalesced with no staging buffer) and all lanes of a
+// warp share at most two proposals (no trip-count divergence to speak of).  Feature maps cross
+// L2->SM exactly once per channel group; the only HBM stream left is the output itself.
+//
+// Bin edges are integer data shared by all channel groups, so a tiny prologue kernel computes them
+// once per proposal (exact fp32 sequence of ROILoopPool_cpu.cpp:29-51) into an int16 table and
+// builds a stable per-image ordering of the proposals (rois may arrive in any batch order).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace wsovod {
+
+enum { MODE_POOL = 0, MODE_LOOP = 1, MODE_ALIGN = 2 };
+
+struct PoolParams {
+  const float* input;
+  const float* rois;
+  const float* row_scale;
+  float row_scale_bias;
+  float* output;
+  int32_t* argmax;
+  // workspace
+  const int32_t* counts;   // [N]   proposals per image
+  const int32_t* order;    // [R]   proposal ids grouped by image (stable)
+  const int16_t* edges;    // [R, EW] bin edge table
+  const float* alignp;     // [R, 8] ROIAlign parameters
+  int32_t N, C, H, W;
+  int64_t R;
+  int32_t PH, PW;
+  int32_t CG;              // channel groups  = ceil(C / CB)
+  int32_t S;               // proposal chunks per image
+  int32_t sampling_ratio, aligned;
+};
+
+// ------------------------------------------------------------------------------------------------
+// prologue 1: per-proposal geometry (one thread per proposal)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_edges(int16_t* e, int rsh, int rsw, int reh, int rew, int PH,
+                                            int PW, int H, int W) {
+  // ROILoopPool_cpu.cpp:35-51
+  int rw = max(rew - rsw + 1, 1);
+  int rh = max(reh - rsh + 1, 1);
+  float bh = __fdiv_rn((float)rh, (float)PH);
+  float bw = __fdiv_rn((float)rw, (float)PW);
+  for (int ph = 0; ph < PH; ++ph) {
+    int hs = (int)floorf(__fmul_rn((float)ph, bh));
+    int he = (int)ceilf(__fmul_rn((float)(ph + 1), bh));
+    e[ph] = (int16_t)min(max(hs + rsh, 0), H);
+    e[PH + ph] = (int16_t)min(max(he + rsh, 0), H);
+  }
+  for (int pw = 0; pw < PW; ++pw) {
+    int ws = (int)floorf(__fmul_rn((float)pw, bw));
+    int we = (int)ceilf(__fmul_rn((float)(pw + 1), bw));
+    e[2 * PH + pw] = (int16_t)min(max(ws + rsw, 0), W);
+    e[2 * PH + PW + pw] = (int16_t)min(max(we + rsw, 0), W);
+  }
+}
+
+// saturating float->int like the reference's `int x = round(float)` on sane inputs; huge values clamp
+__device__ __forceinline__ int round_i(float v) {
+  v = roundf(v);
+  v = fminf(fmaxf(v, -1.0e6f), 1.0e6f);
+  return (int)v;
+}
+
+template <int MODE>
+__global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W,
+                                   float scale, int PH, int PW, int sampling_ratio, int aligned,
+                                   int32_t* __restrict__ bidx, int32_t* __restrict__ counts,
+                                   int16_t* __restrict__ edges, float* __restrict__ alignp) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* roi = rois + r * 5;
+  int b = (int)roi[0];
+  b = min(max(b, 0), N - 1);
+  bidx[r] = b;
+  atomicAdd(&counts[b], 1);
+  const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
+  if (MODE == MODE_POOL) {
+    int16_t* e = edges + r * (2 * (PH + PW));
+    write_edges(e, round_i(__fmul_rn(y1, scale)), round_i(__fmul_rn(x1, scale)),
+                round_i(__fmul_rn(y2, scale)), round_i(__fmul_rn(x2, scale)), PH, PW, H, W);
+  } else if (MODE == MODE_LOOP) {
+    // ROILoopPool_cuda.cu:34-74: inner (/1.8) and outer (x1.8) boxes in image space, clamped.
+    // The expressions are kept in the reference's own form and compiled with the same default
+    // contraction rules (nvcc -fmad=true) the reference build uses.
+    const float ratio = 1.8f;
+    float rw_ = x2 - x1, rh_ = y2 - y1;
+    float iw = rw_ / ratio, ih = rh_ / ratio;
+    float ow = rw_ * ratio, oh = rh_ * ratio;
+    float irw = rw_ - iw, irh = rh_ - ih;
+    float orw = ow - rw_, orh = oh - rh_;
+    float x1i = x1 + irw / 2, y1i = y1 + irh / 2, x2i = x2 - irw / 2, y2i = y2 - irh / 2;
+    float x1o = x1 - orw / 2, y1o = y1 - orh / 2, x2o = x2 + orw / 2, y2o = y2 + orh / 2;
+    const float xmax = (float)(1.0 * W / scale), ymax = (float)(1.0 * H / scale);
+    x1i = fminf(fmaxf(x1i, 0.f), xmax); y1i = fminf(fmaxf(y1i, 0.f), ymax);
+    x2i = fminf(fmaxf(x2i, 0.f), xmax); y2i = fminf(fmaxf(y2i, 0.f), ymax);
+    x1o = fminf(fmaxf(x1o, 0.f), xmax); y1o = fminf(fmaxf(y1o, 0.f), ymax);
+    x2o = fminf(fmaxf(x2o, 0.f), xmax); y2o = fminf(fmaxf(y2o, 0.f), ymax);
+    const int EW = 4 * (PH + PW) + 8;
+    int16_t* e = edges + r * EW;
+    int rsw = round_i(x1 * scale), rsh = round_i(y1 * scale);
+    int rew = round_i(x2 * scale), reh = round_i(y2 * scale);
+    write_edges(e, rsh, rsw, reh, rew, PH, PW, H, W);                        // grid of the ROI
+    int osw = round_i(x1o * scale), osh = round_i(y1o * scale);
+    int oew = round_i(x2o * scale), oeh = round_i(y2o * scale);
+    write_edges(e + 2 * (PH + PW), osh, osw, oeh, oew, PH, PW, H, W);        // grid of the outer box
+    int16_t* q = e + 4 * (PH + PW);
+    auto sat = [](int v) { return (int16_t)min(max(v, -32768), 32767); };
+    q[0] = sat(round_i(y1i * scale)); q[1] = sat(round_i(y2i * scale));      // inner box (h range)
+    q[2] = sat(round_i(x1i * scale)); q[3] = sat(round_i(x2i * scale));      // inner box (w range)
+    q[4] = sat(rsh); q[5] = sat(reh); q[6] = sat(rsw); q[7] = sat(rew);      // the ROI itself
+  } else {
+    // torchvision roi_align
+    float off = aligned ? 0.5f : 0.f;
+    float sw = x1 * scale - off, sh = y1 * scale - off;
+    float ew = x2 * scale - off, eh = y2 * scale - off;
+    float rw = ew - sw, rh = eh - sh;
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    float bh = rh / (float)PH, bw = rw / (float)PW;
+    int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
+    int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+    float* a = alignp + r * 8;
+    a[0] = sw; a[1] = sh; a[2] = bw; a[3] = bh;
+    a[4] = __int_as_float(gh); a[5] = __int_as_float(gw);
+    a[6] = (float)max(gh * gw, 1); a[7] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue 2: stable grouping of proposal ids by image (one CTA per image)
+// ------------------------------------------------------------------------------------------------
+__global__ void roi_order_kernel(const int32_t* __restrict__ bidx, const int32_t* __restrict__ counts,
+                                 int64_t R, int32_t* __restrict__ order) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nw = blockDim.x >> 5;
+  if (tid == 0) {
+    int s = 0;
+    for (int m = 0; m < n; ++m) s += counts[m];
+    s_base = s;
+  }
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < R; c0 += blockDim.x) {
+    int64_t r = c0 + tid;
+    bool f = r < R && bidx[r] == n;
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+      int c = s_warp[w];
+      if (w < wid) pre += c;
+      tot += c;
+    }
+    if (f) order[s_base + pre + __popc(bal & ((1u << lane) - 1))] = (int32_t)r;
+    __syncthreads();
+    if (tid == 0) s_base += tot;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+template <int CB> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+template <int CB> __device__ __forceinline__ void unpack(const typename Vec<CB>::T& v, float* f);
+template <> __device__ __forceinline__ void unpack<4>(const float4& v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+template <> __device__ __forceinline__ void unpack<2>(const float2& v, float* f) { f[0] = v.x; f[1] = v.y; }
+template <> __device__ __forceinline__ void unpack<1>(const float& v, float* f) { f[0] = v; }
+template <int CB> __device__ __forceinline__ typename Vec<CB>::T pack(const float* f);
+template <> __device__ __forceinline__ float4 pack<4>(const float* f) { return make_float4(f[0], f[1], f[2], f[3]); }
+template <> __device__ __forceinline__ float2 pack<2>(const float* f) { return make_float2(f[0], f[1]); }
+template <> __device__ __forceinline__ float pack<1>(const float* f) { return f[0]; }
+
+// CB: channels per CTA (interleaved in smem); SMEM=false reads the (single) plane from global memory
+// (fallback for maps that do not fit shared memory); ARG: track/emit argmax.
+template <int CB, int MODE, bool SMEM, bool ARG>
+__global__ void __launch_bounds__(1024, 1) roi_plane_kernel(const PoolParams p) {
+  using V = typename Vec<CB>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = p.H, W = p.W, HW = H * W;
+  const int PH = p.PH, PW = p.PW, BINS = PH * PW;
+  const int bid = blockIdx.x;
+  const int cg = bid % p.CG;
+  const int s = (bid / p.CG) % p.S;
+  const int n = bid / (p.CG * p.S);
+  const int c0 = cg * CB;
+  const int nc = min(CB, p.C - c0);
+
+  // proposals of image n handled by this CTA: positions [pos0, pos0 + nroi) of `order`
+  int start = 0;
+  for (int m = 0; m < n; ++m) start += p.counts[m];
+  const int cnt = p.counts[n];
+  const int per = (cnt + p.S - 1) / p.S;
+  const int pos0 = s * per;
+  const int nroi = min(cnt, pos0 + per) - pos0;
+  if (nroi <= 0) return;
+
+  const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+  const V* plane;
+  if (SMEM) {
+    V* sp = reinterpret_cast<V*>(smem_raw);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float f[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
+      sp[i] = pack<CB>(f);
+    }
+    __syncthreads();
+    plane = sp;
+  } else {
+    plane = reinterpret_cast<const V*>(src);   // CB == 1
+  }
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = nroi * BINS;
+  const int EW = MODE == MODE_LOOP ? 4 * (PH + PW) + 8 : 2 * (PH + PW);
+  const int64_t block_stride = p.R * (int64_t)p.C * BINS;   // ROILoopPool: roi | frame | context
+
+  for (int flat0 = wid * 32; flat0 < total; flat0 += nw * 32) {
+    const int flat = flat0 + lane;
+    if (flat >= total) break;
+    const int rpos = flat / BINS;
+    const int bin = flat - rpos * BINS;
+    const int ph = bin / PW, pw = bin - ph * PW;
+    const int r = __ldg(p.order + start + pos0 + rpos);
+    float scale = 1.f;
+    if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
+    const int64_t obase = ((int64_t)r * p.C + c0) * BINS + bin;
+
+    if (MODE == MODE_POOL) {
+      const int16_t* e = p.edges + (int64_t)r * EW;
+      const int hs = e[ph], he = e[PH + ph], ws = e[2 * PH + pw], we = e[2 * PH + PW + pw];
+      const bool empty = (he <= hs) || (we <= ws);
+      float m[CB];
+      int mi[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) { m[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
+      for (int h = hs; h < he; ++h) {
+        const V* row = plane + h * W;
+#pragma unroll 2
+        for (int w = ws; w < we; ++w) {
+          float f[CB];
+          unpack<CB>(row[w], f);
+#pragma unroll
+          for (int k = 0; k < CB; ++k)
+            if (f[k] > m[k]) { m[k] = f[k]; if (ARG) mi[k] = h * W + w; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CB; ++k)
+        if (k < nc) {
+          p.output[obase + (int64_t)k * BINS] = p.row_scale ? __fmul_rn(m[k], scale) : m[k];
+          if (ARG) p.argmax[obase + (int64_t)k * BINS] = mi[k];
+        }
+    } else if (MODE == MODE_LOOP) {
+      const int16_t* e = p.edges + (int64_t)r * EW;
+      const int16_t* q = e + 4 * (PH + PW);
+      {  // roi + frame on the ROI's own grid (ROILoopPool_cuda.cu:76-142)
+        const int hs = e[ph], he = e[PH + ph], ws = e[2 * PH + pw], we = e[2 * PH + PW + pw];
+        const int ish = q[0], ieh = q[1], isw = q[2], iew = q[3];
+        float m[CB], mf[CB];
+        int mi[CB], mfi[CB];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) { m[k] = 0.f; mf[k] = 0.f; mi[k] = -1; mfi[k] = -1; }
+        for (int h = hs; h < he; ++h) {
+          const V* row = plane + h * W;
+          const bool in_h = h > ish && h < ieh;
+          for (int w = ws; w < we; ++w) {
+            float f[CB];
+            unpack<CB>(row[w], f);
+            const bool inside = in_h && (w > isw && w < iew);
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+              if (f[k] > m[k]) { m[k] = f[k]; mi[k] = h * W + w; }
+              if (!inside && f[k] > mf[k]) { mf[k] = f[k]; mfi[k] = h * W + w; }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CB; ++k)
+          if (k < nc) {
+            const int64_t o = obase + (int64_t)k * BINS;
+            p.output[o] = p.row_scale ? __fmul_rn(m[k], scale) : m[k];
+            p.output[o + block_stride] = p.row_scale ? __fmul_rn(mf[k], scale) : mf[k];
+            if (ARG) { p.argmax[o] = mi[k]; p.argmax[o + block_stride] = mfi[k]; }
+          }
+      }
+      {  // context on the outer box's grid, excluding the ROI (ROILoopPool_cuda.cu:144-202)
+        const int16_t* e2 = e + 2 * (PH + PW);
+        const int hs = e2[ph], he = e2[PH + ph], ws = e2[2 * PH + pw], we = e2[2 * PH + PW + pw];
+        const int ish = q[4], ieh = q[5], isw = q[6], iew = q[7];
+        float mc[CB];
+        int mci[CB];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) { mc[k] = 0.f; mci[k] = -1; }
+        for (int h = hs; h < he; ++h) {
+          const V* row = plane + h * W;
+          const bool in_h = h > ish && h < ieh;
+          for (int w = ws; w < we; ++w) {
+            if (in_h && (w > isw && w < iew)) continue;
+            float f[CB];
+            unpack<CB>(row[w], f);
+#pragma unroll
+            for (int k = 0; k < CB; ++k)
+              if (f[k] > mc[k]) { mc[k] = f[k]; mci[k] = h * W + w; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CB; ++k)
+          if (k < nc) {
+            const int64_t o = obase + (int64_t)k * BINS + 2 * block_stride;
+            p.output[o] = p.row_scale ? __fmul_rn(mc[k], scale) : mc[k];
+            if (ARG) p.argmax[o] = mci[k];
+          }
+      }
+    } else {  // MODE_ALIGN
+      const float* a = p.alignp + (int64_t)r * 8;
+      const float sw = a[0], sh = a[1], bw = a[2], bh = a[3], count = a[6];
+      const int gh = __float_as_int(a[4]), gw = __float_as_int(a[5]);
+      float acc[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) acc[k] = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        const float yy = sh + ph * bh + ((float)iy + .5f) * bh / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          const float xx = sw + pw * bw + ((float)ix + .5f) * bw / (float)gw;
+          float y = yy, x = xx;
+          if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+          if (y <= 0) y = 0;
+          if (x <= 0) x = 0;
+          int yl = (int)y, xl = (int)x, yh, xh;
+          if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+          if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+          const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          float f1[CB], f2[CB], f3[CB], f4[CB];
+          unpack<CB>(plane[yl * W + xl], f1);
+          unpack<CB>(plane[yl * W + xh], f2);
+          unpack<CB>(plane[yh * W + xl], f3);
+          unpack<CB>(plane[yh * W + xh], f4);
+#pragma unroll
+          for (int k = 0; k < CB; ++k) acc[k] += w1 * f1[k] + w2 * f2[k] + w3 * f3[k] + w4 * f4[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CB; ++k)
+        if (k < nc) {
+          float v = acc[k] / count;
+          p.output[obase + (int64_t)k * BINS] = p.row_scale ? __fmul_rn(v, scale) : v;
+        }
+    }
+  }
+}
+
+// backward: grad_input[b, c, argmax] += grad_output (ROILoopPool_cuda.cu:206-248)
+__global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
+                                    const int32_t* __restrict__ argmax, int64_t total, int64_t R, int N,
+                                    int C, int HW, int BINS, float* __restrict__ grad_in) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = argmax[i];
+    if (a < 0) continue;
+    const int64_t nc = i / BINS;
+    const int c = (int)(nc % C);
+    const int64_t row = nc / C;
+    int b = (int)rois[(row % R) * 5];
+    b = min(max(b, 0), N - 1);
+    atomicAdd(grad_in + ((int64_t)b * C + c) * HW + a, grad_out[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct PoolWs {
+  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; size_t bytes;
+};
+
+static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
+  PoolWs w;
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
+  char* base = (char*)ws;
+  size_t o_counts = take(sizeof(int32_t) * (size_t)(N + 1));
+  size_t o_bidx = take(sizeof(int32_t) * (size_t)R);
+  size_t o_order = take(sizeof(int32_t) * (size_t)R);
+  size_t ew = mode == MODE_LOOP ? 4 * (PH + PW) + 8 : 2 * (PH + PW);
+  size_t o_edges = take(mode == MODE_ALIGN ? 0 : sizeof(int16_t) * ew * (size_t)R);
+  size_t o_align = take(mode == MODE_ALIGN ? sizeof(float) * 8 * (size_t)R : 0);
+  w.counts = (int32_t*)(base + o_counts);
+  w.bidx = (int32_t*)(base + o_bidx);
+  w.order = (int32_t*)(base + o_order);
+  w.edges = (int16_t*)(base + o_edges);
+  w.alignp = (float*)(base + o_align);
+  w.bytes = off;
+  return w;
+}
+
+template <int CB, int MODE, bool SMEM, bool ARG>
+static int launch_plane(const PoolParams& p, int threads, size_t smem, cudaStream_t st) {
+  auto kern = roi_plane_kernel<CB, MODE, SMEM, ARG>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int64_t grid = (int64_t)p.N * p.S * p.CG;
+  kern<<<(unsigned)grid, threads, smem, st>>>(p);
+  return after_launch();
+}
+
+template <int MODE, bool ARG>
+static int dispatch_plane(PoolParams& p, int64_t R, cudaStream_t st) {
+  const size_t plane = (size_t)p.H * p.W * sizeof(float);
+  int cb = 0;
+  if (MODE == MODE_LOOP) {
+    // three accumulator sets: two channels per lane keep the kernel at 64 registers
+    if (2 * plane <= (size_t)kMaxSmemOptin && p.C >= 2) cb = 2;
+    else if (plane <= (size_t)kMaxSmemOptin) cb = 1;
+  } else {
+    if (4 * plane <= (size_t)kMaxSmemOptin && p.C >= 3) cb = 4;
+    else if (2 * plane <= (size_t)kMaxSmemOptin && p.C >= 2) cb = 2;
+    else if (plane <= (size_t)kMaxSmemOptin) cb = 1;
+  }
+  const int cbe = cb ? cb : 1;
+  p.CG = (int)ceil_div(p.C, cbe);
+  const size_t smem = cb ? cbe * plane : 0;
+  // CTAs per SM the shared-memory footprint allows (<=4), threads so that one SM holds <=2048
+  int per_sm = cb ? (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / std::max<size_t>(smem + 1024, 1)) : 2;
+  per_sm = max(per_sm, 1);
+  const int threads = per_sm == 1 ? 1024 : 512;
+  // proposal chunks per image: aim for >= 4 waves of CTAs, each with a few hundred outputs at least
+  const int64_t slots = (int64_t)kNumSMs * per_sm;
+  const int64_t base = (int64_t)p.N * p.CG;
+  int64_t S = ceil_div(4 * slots, base);
+  const int64_t avg = std::max<int64_t>(R / max(p.N, 1), 1);
+  S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 96)));
+  p.S = (int)S;
+  if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
+  switch (cb) {
+    case 4: return launch_plane<4, MODE == MODE_LOOP ? MODE_POOL : MODE, true, ARG>(p, threads, smem, st);
+    case 2: return launch_plane<2, MODE, true, ARG>(p, threads, smem, st);
+    case 1: return launch_plane<1, MODE, true, ARG>(p, threads, smem, st);
+    default: return launch_plane<1, MODE, false, ARG>(p, 512, 0, st);
+  }
+}
+
+static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
+                       const float* rois, int64_t R, float scale, int PH, int PW, int sampling_ratio,
+                       int aligned, const float* row_scale, float row_scale_bias, float* output,
+                       int32_t* argmax, void* workspace, size_t ws_bytes, void* stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || R < 0 || PH <= 0 || PW <= 0) return WSOVOD_B200_EINVAL;
+  if (R == 0 || C == 0) return 0;
+  if (!input || !rois || !output || N == 0 || H == 0 || W == 0) return WSOVOD_B200_EINVAL;
+  if (H > 32767 || W > 32767 || H * W >= (1LL << 31) || PH > 64 || PW > 64 || N > 65535 ||
+      R >= (1LL << 31) / (PH * PW) || C >= (1 << 30))
+    return WSOVOD_B200_ETOOBIG;
+  PoolWs w = carve(nullptr, mode, N, R, PH, PW);
+  if (!workspace || ws_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
+  w = carve(workspace, mode, N, R, PH, PW);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)(N + 1), st);
+  if (e != cudaSuccess) return (int)e;
+  const int pt = 128;
+  const unsigned pg = (unsigned)ceil_div(R, pt);
+  if (mode == MODE_POOL)
+    roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp);
+  else if (mode == MODE_LOOP)
+    roi_prepare_kernel<MODE_LOOP><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp);
+  else
+    roi_prepare_kernel<MODE_ALIGN><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, sampling_ratio, aligned, w.bidx, w.counts, w.edges, w.alignp);
+  int rc = after_launch();
+  if (rc) return rc;
+  roi_order_kernel<<<(unsigned)N, 256, 0, st>>>(w.bidx, w.counts, R, w.order);
+  rc = after_launch();
+  if (rc) return rc;
+
+  PoolParams p;
+  p.input = input; p.rois = rois; p.row_scale = row_scale; p.row_scale_bias = row_scale_bias;
+  p.output = output; p.argmax = argmax;
+  p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
+  p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
+  p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+  if (mode == MODE_POOL) return argmax ? dispatch_plane<MODE_POOL, true>(p, R, st) : dispatch_plane<MODE_POOL, false>(p, R, st);
+  if (mode == MODE_LOOP) return argmax ? dispatch_plane<MODE_LOOP, true>(p, R, st) : dispatch_plane<MODE_LOOP, false>(p, R, st);
+  return dispatch_plane<MODE_ALIGN, false>(p, R, st);
+}
+
+static int bwd_common(const float* grad_output, const float* rois, const int32_t* argmax, int64_t rows,
+                      int64_t R, int64_t N, int64_t C, int64_t H, int64_t W, int PH, int PW,
+                      float* grad_input, void* stream) {
+  if (rows < 0 || R < 0 || N <= 0 || C < 0 || H <= 0 || W <= 0 || PH <= 0 || PW <= 0) return WSOVOD_B200_EINVAL;
+  if (rows == 0 || C == 0) return 0;
+  if (!grad_output || !rois || !argmax || !grad_input) return WSOVOD_B200_EINVAL;
+  if (H * W >= (1LL << 31)) return WSOVOD_B200_ETOOBIG;
+  const int64_t total = rows * C * PH * PW;
+  const int threads = 256;
+  const int64_t grid = std::min<int64_t>(ceil_div(total, threads), (int64_t)kNumSMs * 32);
+  roi_pool_bwd_kernel<<<(unsigned)grid, threads, 0, (cudaStream_t)stream>>>(
+      grad_output, rois, argmax, total, R, (int)N, (int)C, (int)(H * W), PH * PW, grad_input);
+  return after_launch();
+}
+
+}  // namespace wsovod
+
+using namespace wsovod;
+
+WSOVOD_API size_t wsovod_b200_roi_pool_workspace(int64_t N, int64_t R, int PH, int PW) {
+  return carve(nullptr, MODE_POOL, N, R, PH, PW).bytes;
+}
+WSOVOD_API size_t wsovod_b200_roi_loop_pool_workspace(int64_t N, int64_t R, int PH, int PW) {
+  return carve(nullptr, MODE_LOOP, N, R, PH, PW).bytes;
+}
+WSOVOD_API size_t wsovod_b200_roi_align_workspace(int64_t N, int64_t R, int PH, int PW) {
+  return carve(nullptr, MODE_ALIGN, N, R, PH, PW).bytes;
+}
+
+WSOVOD_API int wsovod_b200_roi_pool_fwd(const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
+                                        const float* rois, int64_t R, float spatial_scale, int PH,
+                                        int PW, const float* row_scale, float row_scale_bias,
+                                        float* output, int32_t* argmax, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return pool_common(MODE_POOL, input, N, C, H, W, rois, R, spatial_scale, PH, PW, 0, 0, row_scale,
+                     row_scale_bias, output, argmax, workspace, workspace_bytes, stream);
+}
+
+WSOVOD_API int wsovod_b200_roi_loop_pool_fwd(const float* input, int64_t N, int64_t C, int64_t H,
+                                             int64_t W, const float* rois, int64_t R,
+                                             float spatial_scale, int PH, int PW,
+                                             const float* row_scale, float row_scale_bias,
+                                             float* output, int32_t* argmax, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  return pool_common(MODE_LOOP, input, N, C, H, W, rois, R, spatial_scale, PH, PW, 0, 0, row_scale,
+                     row_scale_bias, output, argmax, workspace, workspace_bytes, stream);
+}
+
+WSOVOD_API int wsovod_b200_roi_align_fwd(const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
+                                         const float* rois, int64_t R, float spatial_scale, int PH,
+                                         int PW, int sampling_ratio, int aligned,
+                                         const float* row_scale, float row_scale_bias, float* output,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  return pool_common(MODE_ALIGN, input, N, C, H, W, rois, R, spatial_scale, PH, PW, sampling_ratio,
+                     aligned, row_scale, row_scale_bias, output, nullptr, workspace, workspace_bytes,
+                     stream);
+}
+
+WSOVOD_API int wsovod_b200_roi_pool_bwd(const float* grad_output, const float* rois,
+                                        const int32_t* argmax, int64_t R, int64_t N, int64_t C,
+                                        int64_t H, int64_t W, int PH, int PW, float* grad_input,
+                                        void* stream) {
+  return bwd_common(grad_output, rois, argmax, R, R, N, C, H, W, PH, PW, grad_input, stream);
+}
+
+WSOVOD_API int wsovod_b200_roi_loop_pool_bwd(const float* grad_output, const float* rois,
+                                             const int32_t* argmax, int64_t R, int64_t N, int64_t C,
+                                             int64_t H, int64_t W, int PH, int PW, float* grad_input,
+                                             void* stream) {
+  return bwd_common(grad_output, rois, argmax, 3 * R, R, N, C, H, W, PH, PW, grad_input, stream);
+}
