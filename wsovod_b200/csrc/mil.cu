@@ -220,7 +220,7 @@ WSOVOD_API int wsovod_b200_mil_fwd(const float* cls, const float* det, const int
   (void)KT;
   if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)K * (2 + kMilWarps);
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mil_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
@@ -254,7 +254,7 @@ WSOVOD_API int wsovod_b200_mil_bwd(const float* grad_scores, const float* grad_i
   mil_colstats_kernel<<<grid, kMilThreads, sizeof(float2) * kMilThreads, st>>>(det, offsets, (int)K, pl.chunks, stats);
   if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)K * (2 + kMilWarps);
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mil_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }

@@ -443,7 +443,7 @@ WSOVOD_API int wsovod_b200_batched_nms(const float* boxes, const float* scores, 
   const int cap = (int)std::min<int64_t>(M, 8192);
   const size_t smem = (size_t)cap * (sizeof(float4) + sizeof(unsigned long long));
   auto kern = iou_mode == 0 ? nms_segment_kernel<0> : nms_segment_kernel<1>;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {   // static slots + dynamic may cross the 48 KB default limit
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
@@ -507,7 +507,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     det_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, valid, cboxes);
     if ((rc = after_launch())) return rc;
     auto kern = iou_mode == 0 ? det_class_kernel<0> : det_class_kernel<1>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static slots + dynamic may cross the 48 KB default limit
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }

@@ -121,13 +121,13 @@ __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, in
   } else {
     // torchvision roi_align
     float off = aligned ? 0.5f : 0.f;
-    float sw = x1 * scale - off, sh = y1 * scale - off;
-    float ew = x2 * scale - off, eh = y2 * scale - off;
-    float rw = ew - sw, rh = eh - sh;
+    float sw = __fsub_rn(__fmul_rn(x1, scale), off), sh = __fsub_rn(__fmul_rn(y1, scale), off);
+    float ew = __fsub_rn(__fmul_rn(x2, scale), off), eh = __fsub_rn(__fmul_rn(y2, scale), off);
+    float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
     if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
-    float bh = rh / (float)PH, bw = rw / (float)PW;
-    int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rh / (float)PH);
-    int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(rw / (float)PW);
+    float bh = __fdiv_rn(rh, (float)PH), bw = __fdiv_rn(rw, (float)PW);
+    int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)PH));
+    int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)PW));
     float* a = alignp + r * 8;
     a[0] = sw; a[1] = sh; a[2] = bw; a[3] = bh;
     a[4] = __int_as_float(gh); a[5] = __int_as_float(gw);
@@ -335,10 +335,14 @@ __global__ void __launch_bounds__(1024, 1) roi_plane_kernel(const PoolParams p) 
       float acc[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) acc[k] = 0.f;
+      // every operation individually rounded, in torchvision's CPU order (roi_align_common.h), so the
+      // result does not depend on FMA contraction
       for (int iy = 0; iy < gh; ++iy) {
-        const float yy = sh + ph * bh + ((float)iy + .5f) * bh / (float)gh;
+        const float yy = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)),
+                                   __fdiv_rn(__fmul_rn((float)iy + .5f, bh), (float)gh));
         for (int ix = 0; ix < gw; ++ix) {
-          const float xx = sw + pw * bw + ((float)ix + .5f) * bw / (float)gw;
+          const float xx = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)),
+                                     __fdiv_rn(__fmul_rn((float)ix + .5f, bw), (float)gw));
           float y = yy, x = xx;
           if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
           if (y <= 0) y = 0;
@@ -346,21 +350,26 @@ __global__ void __launch_bounds__(1024, 1) roi_plane_kernel(const PoolParams p) 
           int yl = (int)y, xl = (int)x, yh, xh;
           if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
           if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-          const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
-          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+          const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+          const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
           float f1[CB], f2[CB], f3[CB], f4[CB];
           unpack<CB>(plane[yl * W + xl], f1);
           unpack<CB>(plane[yl * W + xh], f2);
           unpack<CB>(plane[yh * W + xl], f3);
           unpack<CB>(plane[yh * W + xh], f4);
 #pragma unroll
-          for (int k = 0; k < CB; ++k) acc[k] += w1 * f1[k] + w2 * f2[k] + w3 * f3[k] + w4 * f4[k];
+          for (int k = 0; k < CB; ++k) {
+            const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, f1[k]), __fmul_rn(w2, f2[k])),
+                                                  __fmul_rn(w3, f3[k])), __fmul_rn(w4, f4[k]));
+            acc[k] = __fadd_rn(acc[k], val);
+          }
         }
       }
 #pragma unroll
       for (int k = 0; k < CB; ++k)
         if (k < nc) {
-          float v = acc[k] / count;
+          float v = __fdiv_rn(acc[k], count);
           p.output[obase + (int64_t)k * BINS] = p.row_scale ? __fmul_rn(v, scale) : v;
         }
     }
