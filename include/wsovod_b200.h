@@ -95,8 +95,10 @@ int wsovod_b200_roi_align_fwd(const float* input, int64_t N, int64_t C, int64_t 
 /* replaces the contraction part of OpenVocabularyClassifier.forward
  * (wsovod/modeling/class_heads/open_vocabulary_classifier.py:85-104) plus the row softmax of
  * InstanceRefinementOutputLayers.predict_probs (roi_heads/fast_rcnn_open_vocabulary.py:1019-1036):
- *   w_k   = norm_weight ? classifier[k] / max(||classifier[k]||, 1e-12) : classifier[k]
- *   x_r   = norm_weight ? temperature * x[r] / max(||x[r]||, 1e-12)     : x[r]
+ *   w_k   = norm_weight==1 ? classifier[k] / max(||classifier[k]||, 1e-12) : classifier[k]
+ *   x_r   = norm_weight!=0 ? temperature * x[r] / max(||x[r]||, 1e-12)     : x[r]
+ *   (norm_weight: 0 = NORM_WEIGHT False; 1 = True with a classifier passed in, :87-90; 2 = True with the
+ *    module's stored weights, which the reference does NOT re-normalise, :91-92)
  *   logits[r,k] = <x_r, w_k> (+ bias[0] if bias != NULL);  background column (all-zero weight) appended
  *   when append_background != 0;  probs = softmax(logits, dim=1) when probs != NULL.
  * x [M,D], classifier [K,D] (the (K,D) text-embedding matrix, as loaded at

@@ -1,0 +1,71 @@
+"""Compile the reference's OWN native sources, where they lie under /root/reference, into oracle/_ref/
+(TEST INFRASTRUCTURE; outputs are git-ignored but travel to the GPU box).
+
+  wsovod_ref_C.so   the reference extension exactly as its setup.py builds it (wsovod/layers/vision.cpp,
+                    ROILoopPool/*.cpp|.cu, csc/*.cu; flags of setup.py:70-81) for sm_100a: the GPU-only
+                    oracle of ROILoopPool forward/backward (its dispatcher rejects CPU tensors,
+                    ROILoopPool.h:62).
+  wsovod_ref_cpu.so a 12-line pybind shim (written here, not reference code) that exposes the
+                    reference's ROILoopPool_forward_cpu / _backward_cpu (ROILoopPool_cpu.cpp:125-232),
+                    which the reference compiles but never dispatches to: the CPU oracle of ROIPool.
+No reference source is copied into the repository; the compiler reads the files in place.
+"""
+import argparse
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+
+SHIM = r'''
+#include <torch/extension.h>
+#include "ROILoopPool/ROILoopPool.h"
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("roi_pool_forward_cpu", &wsovod::ROILoopPool_forward_cpu);
+  m.def("roi_pool_backward_cpu", &wsovod::ROILoopPool_backward_cpu);
+}
+'''
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--cpu-only", action="store_true")
+    a = ap.parse_args()
+    layers = os.path.join(a.reference, "wsovod", "layers")
+    if not os.path.isdir(layers):
+        print("reference not present; nothing to build")
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    build = os.path.join("/tmp", "wsovod_ref_build")
+    os.makedirs(build, exist_ok=True)
+    shim = os.path.join(build, "cpu_shim.cpp")
+    with open(shim, "w") as f:
+        f.write(SHIM)
+    os.makedirs(os.path.join(build, "cpu"), exist_ok=True)
+    load(name="wsovod_ref_cpu", sources=[shim, os.path.join(layers, "ROILoopPool", "ROILoopPool_cpu.cpp")],
+         extra_include_paths=[layers], extra_cflags=["-O2"], build_directory=os.path.join(build, "cpu"),
+         is_python_module=False, verbose=False)
+    shutil.copy(os.path.join(build, "cpu", "wsovod_ref_cpu.so"), os.path.join(OUT, "wsovod_ref_cpu.so"))
+    print("built", os.path.join(OUT, "wsovod_ref_cpu.so"))
+    if not a.cpu_only:
+        os.makedirs(os.path.join(build, "cuda"), exist_ok=True)
+        srcs = [os.path.join(layers, "vision.cpp"),
+                os.path.join(layers, "ROILoopPool", "ROILoopPool_cpu.cpp"),
+                os.path.join(layers, "ROILoopPool", "ROILoopPool_cuda.cu"),
+                os.path.join(layers, "csc", "csc_cuda.cu")]
+        load(name="wsovod_ref_C", sources=srcs, extra_include_paths=[layers], with_cuda=True,
+             extra_cflags=["-DWITH_CUDA"],
+             extra_cuda_cflags=["-O3", "-DCUDA_HAS_FP16=1", "-D__CUDA_NO_HALF_OPERATORS__",
+                                "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__", "-DWITH_CUDA"],
+             build_directory=os.path.join(build, "cuda"), is_python_module=False, verbose=False)
+        shutil.copy(os.path.join(build, "cuda", "wsovod_ref_C.so"), os.path.join(OUT, "wsovod_ref_C.so"))
+        print("built", os.path.join(OUT, "wsovod_ref_C.so"))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,151 @@
+"""CPU tests: the oracle against (a) goldens produced by the reference code itself (tests/golden, see
+oracle/make_golden.py), (b) torchvision's compiled CPU ops, (c) the reference's own C++ in oracle/_ref."""
+import pytest
+import torch
+
+import oracle
+from oracle import ref
+from wsovod_b200 import synth
+
+
+def _offs(sizes):
+    o = [0]
+    for s in sizes:
+        o.append(o[-1] + int(s))
+    return o
+
+
+def test_pool_golden(golden):
+    p = golden("pool")
+    o, a = oracle.roi_pool(p["feat"], p["rois"], p["scale"], 7)
+    assert torch.equal(o, p["out"]) and torch.equal(a, p["argmax"])
+    for (sr, al), v in p["align"].items():
+        assert torch.equal(oracle.roi_align(p["feat"], p["rois_align"], p["scale"], 7, sr, al), v)
+
+
+def test_pool_vs_torchvision_cpu():
+    import torchvision  # noqa: F401
+    g = synth.gen(1)
+    for trial in range(3):
+        feat = synth.features(2, 9, 30, 40, g, relu=False)
+        rois, _ = synth.rois_from([synth.proposals(200, 240, 320, g) for _ in range(2)])
+        rois[:20, 1:] += torch.randn(20, 4, generator=g) * 150
+        o, a = oracle.roi_pool(feat, rois, 1 / 8, 7)
+        to, ta = torch.ops.torchvision.roi_pool(feat, rois, 1 / 8, 7, 7)
+        assert torch.equal(o, to) and torch.equal(a, ta.int())
+        assert (a == -1).any()          # empty bins are exercised
+
+
+def test_pool_vs_reference_cpp():
+    m = ref.cpu()
+    if m is None:
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py)")
+    g = synth.gen(2)
+    feat = synth.features(2, 6, 30, 40, g, relu=False)
+    rois, _ = synth.rois_from([synth.proposals(200, 240, 320, g) for _ in range(2)])
+    rois[:20, 1:] += torch.randn(20, 4, generator=g) * 150
+    o, a = m.roi_pool_forward_cpu(feat, rois, 1 / 8, 7, 7)          # ROILoopPool_cpu.cpp:125
+    oo, aa = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    assert torch.equal(o, oo) and torch.equal(a, aa)
+    go = torch.randn_like(o)
+    gi = m.roi_pool_backward_cpu(go, rois, a, 1 / 8, 7, 7, 2, 6, 30, 40)
+    torch.testing.assert_close(gi, oracle.roi_pool_backward(go, rois, aa, feat.shape), rtol=1e-6, atol=1e-6)
+
+
+def test_loop_pool_first_block_is_relu_pool():
+    # ROILoopPool's first R rows equal ROIPool clamped at 0 (ROILoopPool_cuda.cu:107-113)
+    g = synth.gen(4)
+    feat = synth.features(1, 3, 30, 40, g, relu=False)
+    rois, _ = synth.rois_from([synth.proposals(100, 240, 320, g)])
+    o3, a3 = oracle.roi_loop_pool(feat, rois, 1 / 8, 7)
+    o1, a1 = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    R = rois.size(0)
+    assert torch.equal(o3[:R], o1.clamp(min=0))
+    pos = o1 > 0
+    assert torch.equal(a3[:R][pos], a1[pos]) and (a3[:R][~pos] == -1).all()
+    # frame <= roi (subset of cells), context is pooled over a larger box
+    assert (o3[R:2 * R] <= o3[:R]).all()
+
+
+def test_align_golden(golden):
+    for name, c in golden("align").items():
+        lg, pr = oracle.align(c["x"], c["text"], c["T"], True, True)
+        torch.testing.assert_close(lg, c["logits"], rtol=0, atol=5e-5)
+        torch.testing.assert_close(pr, c["probs"], rtol=1e-4, atol=1e-9)
+        lg2, _ = oracle.align(c["x"], c["text"], c["T"], True, False, want_probs=False)
+        torch.testing.assert_close(lg2, c["logits_nobg"], rtol=0, atol=5e-5)
+
+
+def test_mil_golden(golden):
+    for name, c in golden("mil").items():
+        s, i = oracle.mil(c["cls"], c["det"], _offs(c["sizes"]))
+        torch.testing.assert_close(s, c["scores"], rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(i, c["img"], rtol=1e-5, atol=1e-8)
+        assert torch.equal(c["probs_bg"][:, :-1], c["scores"]) and (c["probs_bg"][:, -1] == 0).all()
+
+
+def test_refine_golden(golden):
+    f = golden("refine")
+    off = _offs(f["sizes"])
+    goff = _offs([len(x) for x in f["gt_classes_img"]])
+    sd = oracle.pgt_top1(torch.cat(f["scores"]), torch.cat(f["boxes"]), off, torch.cat(f["gt_classes_img"]), goff,
+                         f["img_scores"])
+    ra = oracle.refine_assign(torch.cat(f["boxes"]), off, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"],
+                              sd["seed_weights"], goff, sd["seed_count"], f["num_classes"], 0.5)
+    for n in range(len(f["sizes"])):
+        g0, c = goff[n], int(sd["seed_count"][n])
+        for k in ("seed_boxes", "seed_classes", "seed_scores", "seed_weights"):
+            assert torch.equal(sd[k][g0:g0 + c], f[k][n]), (n, k)
+        sl = slice(off[n], off[n + 1])
+        for k in ("gt_classes", "gt_boxes", "gt_scores", "gt_weights"):
+            assert torch.equal(ra[k][sl], f[k][n]), (n, k)
+    assert int(sd["seed_count"][2]) == 1 and sd["seed_boxes"][goff[2]].tolist() == [-10000, -10000, 10000, 10000]
+
+
+def test_detections_golden(golden):
+    d = golden("detections")
+    off = _offs([len(b) for b in d["boxes"]])
+    r = oracle.detections(torch.cat(d["probs"]), torch.cat(d["boxes"]), off, d["image_shapes"], d["score_thresh"],
+                          d["nms_thresh"], d["topk"], oracle.IOU_TV_CPU)
+    for n in range(len(d["boxes"])):
+        c = int(r["det_count"][n])
+        assert c == len(d["det_scores"][n])
+        assert torch.equal(r["det_rows"][n, :c], d["det_rows"][n])          # == Instances.pred_inds
+        assert torch.equal(r["det_classes"][n, :c], d["det_classes"][n])
+        assert torch.equal(r["det_scores"][n, :c], d["det_scores"][n])
+        assert torch.equal(r["det_boxes"][n, :c], d["det_boxes"][n])
+
+
+@pytest.mark.parametrize("grid", [None, 4, 16])
+def test_nms_vs_torchvision_cpu(grid):
+    from torchvision.ops.boxes import _batched_nms_vanilla
+    g = synth.gen(7)
+    for trial in range(3):
+        b = synth.proposals(2500, 480, 640, g)
+        if grid:
+            b = (b / grid).round() * grid      # exact IoU == threshold pairs, duplicates, zero-area boxes
+        s = torch.rand(2500, generator=g)
+        idx = torch.randint(0, 20, (2500,), generator=g)
+        assert torch.equal(oracle.batched_nms(b, s, idx, 0.3, oracle.IOU_TV_CPU), _batched_nms_vanilla(b, s, idx, 0.3))
+    # the double-vs-float threshold probe of SURVEY C-9
+    b = torch.tensor([[0., 0., 13., 1.], [7., 0., 20., 1.]])
+    s = torch.tensor([0.9, 0.8])
+    z = torch.zeros(2, dtype=torch.int64)
+    assert oracle.batched_nms(b, s, z, 0.3, oracle.IOU_TV_CPU).tolist() == [0]
+    assert oracle.batched_nms(b, s, z, 0.3, oracle.IOU_TV_CUDA).tolist() == [0, 1]
+
+
+def test_cpu_path_matches_oracle():
+    """bench's CPU baseline (oracle/cpu_path.py: the reference's library calls) agrees with the C oracle."""
+    from oracle import cpu_path
+    w = synth.workload("c1")
+    w = dict(w)
+    dt, n, pooled, probs, dets = cpu_path.run_slice(w, images=1, proposals=300)
+    rois = w["rois"][:300]
+    o, _ = oracle.roi_pool(w["features"], rois, w["spatial_scale"], 7)
+    assert torch.equal(pooled, o * (w["objectness"][:300] + 1).view(-1, 1, 1, 1))
+    lg, pr = oracle.align(w["region_emb"][:300], w["text_emb"], 50.0, True, True)
+    torch.testing.assert_close(probs, pr, rtol=1e-4, atol=1e-9)
+    r = oracle.detections(probs, rois[:, 1:], [0, 300], [(480, 640)], 1e-5, 0.3, 100, oracle.IOU_TV_CPU)
+    c = int(r["det_count"][0])
+    assert torch.equal(r["det_rows"][0, :c], dets[0][3]) and torch.equal(r["det_classes"][0, :c], dets[0][2])

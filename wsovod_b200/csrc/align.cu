@@ -191,7 +191,7 @@ WSOVOD_API int wsovod_b200_align_fwd(const float* x, const float* classifier, in
     return align_fwd_tf32(x, classifier, M, D, K, temperature, norm_weight, append_background, bias, logits,
                           probs, w, ws, st);
   if (K > 0) {
-    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)D, norm_weight, what);
+    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)D, norm_weight == 1, what);
     if ((rc = after_launch())) return rc;
   }
   // logits go to `logits` when given, else straight into `probs` and are normalised in place
@@ -228,7 +228,7 @@ WSOVOD_API int wsovod_b200_align_bwd(const float* grad_logits, const float* x, c
   const int64_t KO = K + (append_background ? 1 : 0);
   int rc;
   if (K == 0) return (int)cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)(M * D), st);
-  align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)D, norm_weight, what);
+  align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)D, norm_weight == 1, what);
   if ((rc = after_launch())) return rc;
   transpose_kernel<<<(unsigned)ceil_div(K * D, 256), 256, 0, st>>>(what, (int)K, (int)D, (int)D, wt);   // wt [D,K]
   if ((rc = after_launch())) return rc;

@@ -310,7 +310,7 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   if (e != cudaSuccess) return (int)e;
   int rc;
   if (K > 0) {
-    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)w.Dp, norm_weight, what);
+    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)w.Dp, norm_weight == 1, what);
     if ((rc = after_launch())) return rc;
   }
   TcParams p;

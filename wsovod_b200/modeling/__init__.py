@@ -1,0 +1,10 @@
+"""Host-side mirror of the reference's ROI-head interfaces for the region-scoring path."""
+from .poolers import ROIPooler, convert_boxes_to_pooler_format
+from .class_heads import OpenVocabularyClassifier
+from .roi_heads import (InstanceRefinementOutputLayers, ObjectMiningOutputLayers, fast_rcnn_inference,
+                        fast_rcnn_inference_single_image, get_image_level_gt, get_pgt_top_k,
+                        label_proposals_wsl)
+
+__all__ = ["ROIPooler", "convert_boxes_to_pooler_format", "OpenVocabularyClassifier", "ObjectMiningOutputLayers",
+           "InstanceRefinementOutputLayers", "fast_rcnn_inference", "fast_rcnn_inference_single_image",
+           "get_image_level_gt", "get_pgt_top_k", "label_proposals_wsl"]

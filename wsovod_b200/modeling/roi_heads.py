@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's output-layer / ROI-head methods on the region-scoring path.
+
+Same names, argument meaning and return structure as
+wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py (``ObjectMiningOutputLayers``,
+``InstanceRefinementOutputLayers``, ``fast_rcnn_inference``) and the pseudo-label methods of
+``WSOVODROIHeads`` in wsovod/modeling/roi_heads/roi_heads.py (``get_image_level_gt``, ``get_pgt_top_k``,
+``label_and_sample_proposals_wsl``) -- but each per-image Python loop of the reference is ONE batched
+kernel call here.  The Linear layers (cls/det/bbox_pred, projection) stay PyTorch (out of scope).
+Proposals are duck-typed: anything with ``len()``, ``.proposal_boxes.tensor`` and ``.image_size``.
+"""
+from typing import List, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..structures import Boxes, Instances
+
+
+def _offsets(proposals, device):
+    sizes = [len(p) for p in proposals]
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    return torch.tensor(off, dtype=torch.int64, device=device), sizes
+
+
+# ------------------------------------------------------------------------------------------------
+class ObjectMiningOutputLayers(nn.Module):
+    """MIL head (fast_rcnn_open_vocabulary.py:220-618).  ``cls``/``det`` are Linear layers unless a
+    ``class_head`` (an OpenVocabularyClassifier) is supplied -- the fused "alignment + MIL" variant of
+    the commented-out line roi_heads.py:588-589."""
+
+    def __init__(self, input_size, num_classes, class_head=None):
+        super().__init__()
+        self.num_classes = num_classes
+        self.det = nn.Linear(input_size, num_classes)
+        nn.init.xavier_uniform_(self.det.weight)
+        nn.init.constant_(self.det.bias, 0)
+        if class_head is None:
+            self.cls = nn.Linear(input_size, num_classes)
+            nn.init.xavier_uniform_(self.cls.weight)
+            nn.init.constant_(self.cls.bias, 0)
+        else:
+            self.cls = class_head
+
+    def forward(self, x, proposals=None, context=False):
+        """-> (scores (M,K), proposal_deltas (M,4) zeros); scores = softmax(C,1) * per-image softmax(D,0)"""
+        if context:                                           # ContextLocNet variant (:369-390)
+            xr, xf, xc = x[:]
+            C = self.cls(torch.flatten(xr, 1))
+            D = self.det(torch.flatten(xf, 1)) - self.det(torch.flatten(xc, 1))
+        else:
+            if x.dim() > 2:
+                x = torch.flatten(x, start_dim=1)
+            C, D = self.cls(x), self.det(x)
+        scores, img = self.score(C, D, proposals)
+        self._last = (scores, img)          # the image-level scores come out of the same kernel pass
+        deltas = torch.zeros(scores.shape[0], 4, dtype=scores.dtype, device=scores.device)
+        return scores, deltas
+
+    @staticmethod
+    def score(C, D, proposals=None):
+        if proposals is None:
+            off = torch.tensor([0, C.shape[0]], dtype=torch.int64, device=C.device)
+        else:
+            off, _ = _offsets(proposals, C.device)
+        return ops.mil(C, D, off)                             # (scores, clamped image-level scores)
+
+    def predict_probs_img(self, predictions, proposals):
+        """:604-618 -- clamp(sum over the image's proposals of scores, 1e-6, 1-1e-6)"""
+        scores, _ = predictions
+        last = getattr(self, "_last", None)
+        if last is not None and last[0] is scores:
+            return last[1]
+        sizes = [len(p) for p in proposals]                   # scores edited by the caller: plain reduction
+        sums = torch.cat([s.sum(dim=0, keepdim=True) for s in scores.split(sizes, dim=0)], dim=0)
+        return torch.clamp(sums, min=1e-6, max=1.0 - 1e-6)
+
+    def predict_probs(self, predictions, proposals):
+        """:580-602 -- scores with a zero background column, split per image"""
+        scores, _ = predictions
+        probs = torch.cat((scores, scores.new_zeros(scores.shape[0], 1)), 1)
+        return probs.split([len(p) for p in proposals], dim=0)
+
+    def predict_boxes(self, predictions, proposals):
+        return [p.proposal_boxes.tensor for p in proposals]    # :567 (early return of the reference)
+
+
+class InstanceRefinementOutputLayers(nn.Module):
+    """Refinement head (fast_rcnn_open_vocabulary.py:621-1058): class_head logits (+ optional bbox_pred)."""
+
+    def __init__(self, input_size, num_classes, class_head, test_score_thresh=0.0, test_nms_thresh=0.5,
+                 test_topk_per_image=100, refine_reg=False, box_dim=4, iou_mode=ops.IOU_TV_CUDA):
+        super().__init__()
+        self.num_classes = num_classes
+        self.cls = class_head
+        self.refine_reg = refine_reg
+        if refine_reg:
+            self.bbox_pred = nn.Linear(input_size, box_dim)
+            nn.init.normal_(self.bbox_pred.weight, std=0.001)
+            nn.init.constant_(self.bbox_pred.bias, 0)
+        self.test_score_thresh, self.test_nms_thresh = test_score_thresh, test_nms_thresh
+        self.test_topk_per_image = test_topk_per_image
+        self.iou_mode = iou_mode
+
+    def forward(self, x, classifier=None, append_background=True):
+        if x.dim() > 2:
+            x = torch.flatten(x, start_dim=1)
+        scores = self.cls(x, classifier, append_background=append_background)
+        deltas = self.bbox_pred(x) if self.refine_reg else torch.zeros(scores.shape[0], 4, dtype=scores.dtype,
+                                                                       device=scores.device)
+        return scores, deltas
+
+    def predict_probs(self, predictions, proposals):
+        scores, _ = predictions
+        return torch.softmax(scores, dim=-1).split([len(p) for p in proposals], dim=0)    # :1034-1036
+
+    def predict_probs_K(self, predictions, proposals):
+        probs = torch.zeros_like(predictions[0][0])
+        for s, _ in predictions:
+            probs += torch.softmax(s, dim=-1)
+        return (probs / len(predictions)).split([len(p) for p in proposals], dim=0)       # :1052-1058
+
+    def predict_boxes(self, predictions, proposals):
+        return [p.proposal_boxes.tensor for p in proposals]    # class-agnostic, deltas applied by the caller
+
+    def inference(self, predictions, proposals):
+        """:894-924 -- predictions: (scores, deltas) or a list of them (one per refinement head)"""
+        if isinstance(predictions[0], tuple):
+            scores = self.predict_probs_K(predictions, proposals)
+        else:
+            scores = self.predict_probs(predictions, proposals)
+        boxes = self.predict_boxes(predictions, proposals)
+        shapes = [p.image_size for p in proposals]
+        return fast_rcnn_inference(boxes, scores, shapes, self.test_score_thresh, self.test_nms_thresh,
+                                   self.test_topk_per_image, iou_mode=self.iou_mode)
+
+
+# ------------------------------------------------------------------------------------------------
+def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], image_shapes: List[Tuple[int, int]],
+                        score_thresh: float, nms_thresh: float, topk_per_image: int, iou_mode=ops.IOU_TV_CUDA):
+    """fast_rcnn_open_vocabulary.py:52-96: -> (instances, kept_indices, all_scores, all_boxes), all images in
+    three kernel launches.  One device->host read (the per-image detection counts) sizes the outputs,
+    as the reference's boolean indexing does implicitly."""
+    if len(boxes) == 0:
+        return [], [], [], []
+    if boxes[0].shape[1] != 4:
+        raise NotImplementedError("class-specific box regression is not used by WSOVOD (CLS_AGNOSTIC boxes)")
+    if topk_per_image < 0:
+        raise NotImplementedError("topk_per_image < 0: filter, then call wsovod_b200.ops.batched_nms")
+    dev = scores[0].device
+    sizes = [int(s.shape[0]) for s in scores]
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    probs = scores[0] if len(scores) == 1 else torch.cat(list(scores), 0)
+    bx = boxes[0] if len(boxes) == 1 else torch.cat(list(boxes), 0)
+    r = ops.detections(probs, bx, torch.tensor(off, dtype=torch.int64, device=dev),
+                       torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev),
+                       max(sizes), score_thresh, nms_thresh, topk_per_image, iou_mode)
+    counts = r["det_count"].tolist()
+    instances, kept = [], []
+    for n, c in enumerate(counts):
+        inst = Instances(tuple(image_shapes[n]))
+        inst.pred_boxes = Boxes(r["det_boxes"][n, :c])
+        inst.scores = r["det_scores"][n, :c]
+        inst.pred_classes = r["det_classes"][n, :c]
+        inst.pred_inds = r["det_rows"][n, :c]
+        instances.append(inst)
+        rows = r["det_rows"][n, :c]
+        # the reference's kept index counts only rows that survive the finite filter (:178-182)
+        valid = torch.isfinite(boxes[n]).all(1) & torch.isfinite(scores[n]).all(1)
+        if not bool(valid.all()):
+            rows = (torch.cumsum(valid.to(torch.int64), 0) - 1)[rows]
+        kept.append(rows)
+    return instances, kept, [s.unsqueeze(0) for s in scores], [b.unsqueeze(0) for b in boxes]
+
+
+def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image,
+                                     iou_mode=ops.IOU_TV_CUDA):
+    """:149-217"""
+    inst, kept, s, b = fast_rcnn_inference([boxes], [scores], [image_shape], score_thresh, nms_thresh,
+                                           topk_per_image, iou_mode)
+    return inst[0], kept[0], s[0], b[0]
+
+
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def get_image_level_gt(targets, num_classes):
+    """roi_heads.py:159-174 (tiny host-side op, kept in PyTorch): sorted unique classes + one-hot"""
+    if targets is None:
+        return None, None, None
+    gt = [torch.unique(t.gt_classes, sorted=True) for t in targets]
+    gt_int = [g.to(torch.int64) for g in gt]
+    oh = torch.cat([torch.zeros((1, num_classes), dtype=torch.float, device=g.device).scatter_(1, g.unsqueeze(0), 1)
+                    for g in gt_int], dim=0)
+    return gt, gt_int, oh
+
+
+@torch.no_grad()
+def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits,
+                  num_classes):
+    """roi_heads.py:1043-1343 with top_k=1, thres=0, need_weight=True, sam=None: one seed per image-level
+    class.  Returns (targets: list[Instances{gt_boxes, gt_classes, gt_scores, gt_weights}], flat seeds)."""
+    dev = prev_pred_boxes[0].device
+    off, sizes = _offsets(proposals, dev)
+    scores = prev_pred_scores if isinstance(prev_pred_scores, torch.Tensor) else torch.cat(list(prev_pred_scores), 0)
+    boxes = torch.cat([b.reshape(-1, 4) for b in prev_pred_boxes], 0)
+    gsz = [int(g.numel()) for g in gt_classes_img_int]
+    goff = [0]
+    for s in gsz:
+        goff.append(goff[-1] + s)
+    goff_t = torch.tensor(goff, dtype=torch.int64, device=dev)
+    seeds = ops.pgt_top1(scores, boxes, off, torch.cat(list(gt_classes_img_int)).to(dev), goff_t,
+                         pred_class_img_logits)
+    seeds["seed_offsets"] = goff_t
+    counts = seeds["seed_count"].tolist()
+    targets = []
+    for n, p in enumerate(proposals):
+        a, c = goff[n], counts[n]
+        targets.append(Instances(p.image_size, gt_boxes=Boxes(seeds["seed_boxes"][a:a + c]),
+                                 gt_classes=seeds["seed_classes"][a:a + c], gt_scores=seeds["seed_scores"][a:a + c],
+                                 gt_weights=seeds["seed_weights"][a:a + c]))
+    return targets, seeds
+
+
+@torch.no_grad()
+def label_proposals_wsl(proposals, seeds, num_classes, iou_threshold=0.5, batch_size_per_image=4096,
+                        positive_fraction=1.0):
+    """label_and_sample_proposals_wsl + _sample_proposals_wsl (roi_heads.py:1566-1610,1722-1825): IoU ->
+    argmax -> label -> class / gathered seed box, score, loss weight in one kernel for all images; the
+    random subsampling to BATCH_SIZE_PER_IMAGE stays in PyTorch (torch RNG, :1597-1610) and only runs
+    when an image has more candidates than the budget."""
+    dev = seeds["seed_boxes"].device
+    off, sizes = _offsets(proposals, dev)
+    boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], 0)
+    a = ops.refine_assign(boxes, off, seeds["seed_boxes"], seeds["seed_classes"], seeds["seed_scores"],
+                          seeds["seed_weights"], seeds["seed_offsets"], seeds["seed_count"], num_classes, iou_threshold)
+    out = []
+    o = off.tolist()
+    for n, p in enumerate(proposals):
+        sl = slice(o[n], o[n + 1])
+        cls = a["gt_classes"][sl]
+        if sizes[n] > batch_size_per_image:                    # subsample_labels semantics
+            pos = torch.nonzero((cls != -1) & (cls != num_classes), as_tuple=True)[0]
+            neg = torch.nonzero(cls == num_classes, as_tuple=True)[0]
+            num_pos = min(pos.numel(), int(batch_size_per_image * positive_fraction))
+            num_neg = min(neg.numel(), batch_size_per_image - num_pos)
+            keep = torch.cat([pos[torch.randperm(pos.numel(), device=dev)[:num_pos]],
+                              neg[torch.randperm(neg.numel(), device=dev)[:num_neg]]])
+            sampled = torch.full_like(cls, -1)
+            sampled[keep] = cls[keep]
+            cls = sampled
+        q = Instances(p.image_size, proposal_boxes=p.proposal_boxes, gt_classes=cls,
+                      gt_boxes=Boxes(a["gt_boxes"][sl]), gt_scores=a["gt_scores"][sl], gt_weights=a["gt_weights"][sl])
+        if hasattr(p, "has") and p.has("objectness_logits"):
+            q.objectness_logits = p.objectness_logits
+        out.append(q)
+    return out, a

@@ -239,7 +239,7 @@ def roi_align(input, rois, spatial_scale, output_size, sampling_ratio=0, aligned
 # (2) alignment + MIL
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("wsovod_b200::align", mutates_args=())
-def _align(x: torch.Tensor, classifier: torch.Tensor, temperature: float, norm_weight: bool,
+def _align(x: torch.Tensor, classifier: torch.Tensor, temperature: float, norm_weight: int,
            append_background: bool, bias: Optional[torch.Tensor], precision: int,
            want_logits: bool, want_probs: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     _need_cuda(x, classifier, bias)
@@ -274,7 +274,7 @@ def _(x, classifier, temperature, norm_weight, append_background, bias, precisio
 
 @torch.library.custom_op("wsovod_b200::align_backward", mutates_args=())
 def _align_backward(grad_logits: torch.Tensor, x: torch.Tensor, classifier: torch.Tensor,
-                    temperature: float, norm_weight: bool, append_background: bool) -> torch.Tensor:
+                    temperature: float, norm_weight: int, append_background: bool) -> torch.Tensor:
     _need_cuda(grad_logits, x, classifier)
     grad_logits, x, classifier = _f32c(grad_logits), _f32c(x), _f32c(classifier)
     M, D = x.shape
@@ -322,7 +322,7 @@ def align(x, classifier, temperature=50.0, norm_weight=True, append_background=T
           precision=ALIGN_TF32, want_logits=True, want_probs=False):
     """Contraction part of OpenVocabularyClassifier.forward (+ optional fused row softmax).
     Returns (logits, probs); a tensor that was not requested is empty."""
-    return torch.ops.wsovod_b200.align(x, classifier, float(temperature), bool(norm_weight),
+    return torch.ops.wsovod_b200.align(x, classifier, float(temperature), int(norm_weight),
                                        bool(append_background), bias, int(precision), bool(want_logits),
                                        bool(want_probs))
 
