@@ -204,7 +204,7 @@ int wsovod_b200_batched_nms(const float* boxes, const float* scores, const int64
  * det_classes [N,topk] int64, det_rows [N,topk] int64 (row local to the image = the reference's
  * pred_inds; equal to its kept_indices whenever no row was dropped as non-finite), det_count [N]
  * int64.  Unused slots: score 0, class/row -1, box 0.  max_rows_per_image: host-known upper bound of
- * offsets[n+1]-offsets[n] (sizes the per-class shared-memory candidate list; <= ~9400).  topk must
+ * offsets[n+1]-offsets[n] (sizes the per-class shared-memory candidate list; <= 16384).  topk must
  * be in [1,4096]; for "keep everything" filter on the host side and call batched_nms. */
 size_t wsovod_b200_detections_workspace(int64_t M, int64_t N, int64_t K, int64_t topk);
 int wsovod_b200_detections(const float* probs, const float* boxes, const int64_t* offsets,

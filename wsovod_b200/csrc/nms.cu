@@ -148,41 +148,110 @@ __global__ void det_rows_kernel(const float* __restrict__ probs, const float* __
   }
 }
 
-// one CTA per (class, image): gather the column's candidates, greedy NMS up to `limit` kept,
-// append (score, row*K+class) keys to the image's kept list
+// in-place bitonic sort (ascending) of npad = 2^k keys in shared memory by the whole CTA
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int npad) {
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += kNmsThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool asc = (i & k) == 0;
+          if ((a > b) == asc) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct FirstSlots {     // per-warp "lowest alive candidate" of the current chunk, double buffered
+  int tid[2][kNmsWarps];
+  float4 box[2][kNmsWarps];
+};
+
+// one CTA per (class, image):
+//   1. gather the column's candidates (score > thr, finite row) as 64-bit keys in shared memory
+//   2. bitonic-sort them once (score descending, row ascending)
+//   3. greedy NMS over the sorted list in chunks of one candidate per thread: a chunk is first tested
+//      against the boxes kept so far, then resolved with "lowest alive thread is kept, suppresses the
+//      rest" rounds (one barrier per kept box); stops at `limit` kept boxes
+//   4. append (score, row*K+class) keys to the image's kept list
 template <int MODE>
 __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
     const float* __restrict__ probs, const int64_t* __restrict__ offsets, const uint8_t* __restrict__ valid,
-    const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int cap,
+    const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap,
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride) {
   extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ ArgMinSlots slots;
+  __shared__ FirstSlots slots;
   __shared__ int s_n, s_base;
-  float4* sbox = reinterpret_cast<float4*>(sm);
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm + (size_t)cap * sizeof(float4));
-  unsigned long long* skept = skey + cap;                       // [limit]
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);                 // [npad_cap]
+  float4* kbox = reinterpret_cast<float4*>(sm + (size_t)npad_cap * sizeof(unsigned long long));   // [limit]
+  float* karea = reinterpret_cast<float*>(kbox + limit);                                 // [limit]
+  unsigned long long* kkey = reinterpret_cast<unsigned long long*>(karea + ((limit + 1) & ~1));   // [limit]
   const int k = blockIdx.x, n = blockIdx.y;
   const int64_t r0 = offsets[n], r1 = offsets[n + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const int K1 = K + 1;
   for (int64_t r = r0 + threadIdx.x; r < r1; r += kNmsThreads) {
     if (!valid[r]) continue;
     const float s = __ldg(probs + r * K1 + k);
-    if (s > score_thr) {                                         // :194
-      const int p = atomicAdd(&s_n, 1);
-      sbox[p] = cboxes[r];
-      skey[p] = make_key(s, (uint32_t)(r - r0));
-    }
+    if (s > score_thr) skey[atomicAdd(&s_n, 1)] = make_key(s, (uint32_t)(r - r0));   // :194
   }
   __syncthreads();
   const int nc = s_n;
-  const int kept = select_greedy<MODE, true>(skey, sbox, nc, thr, limit, skept, slots);
+  if (nc == 0) return;
+  int npad = 1;
+  while (npad < nc) npad <<= 1;
+  for (int i = nc + threadIdx.x; i < npad; i += kNmsThreads) skey[i] = kDead;
+  __syncthreads();
+  bitonic_sort_smem(skey, npad);
+
+  int kept = 0, buf = 0;
+  for (int base = 0; base < nc && kept < limit; base += kNmsThreads) {
+    const int i = base + threadIdx.x;
+    bool alive = i < nc;
+    unsigned long long key = 0;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (alive) {
+      key = skey[i];
+      box = __ldg(cboxes + r0 + (uint32_t)key);
+      for (int j = 0; j < kept && alive; ++j)
+        if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
+    }
+    // rounds: the lowest alive thread of the chunk is the next kept box
+    while (kept < limit) {
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) slots.tid[buf][wid] = bal ? (wid * 32 + __ffs(bal) - 1) : 0x7fffffff;
+      if (bal && lane == __ffs(bal) - 1) slots.box[buf][wid] = box;
+      __syncthreads();
+      int first = 0x7fffffff, fw = 0;
+#pragma unroll
+      for (int w = 0; w < kNmsWarps; ++w) {
+        const int t = slots.tid[buf][w];
+        if (t < first) { first = t; fw = w; }
+      }
+      if (first == 0x7fffffff) { buf ^= 1; break; }
+      const float4 kb = slots.box[buf][fw];
+      const float ka = area_rn(kb);
+      buf ^= 1;
+      if ((int)threadIdx.x == first) {
+        kbox[kept] = kb; karea[kept] = ka; kkey[kept] = key;
+        alive = false;
+      } else if (alive && (int)threadIdx.x > first && suppresses<MODE>(kb, ka, box, thr)) {
+        alive = false;
+      }
+      ++kept;
+    }
+    __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
+  }
   __syncthreads();
   if (threadIdx.x == 0) s_base = atomicAdd(&img_cnt[n], kept);
   __syncthreads();
   for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
-    const unsigned long long key = skept[i];
+    const unsigned long long key = kkey[i];
     const uint32_t row = (uint32_t)key;
     img_kept[(int64_t)n * kept_stride + s_base + i] =
         (key & 0xffffffff00000000ull) | (uint32_t)(row * (uint32_t)K + (uint32_t)k);
@@ -490,10 +559,12 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     return WSOVOD_B200_ETOOBIG;
   const DetWs w = det_plan(M, N, K, topk);
   if (!workspace || workspace_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
-  const int cap = (int)std::max<int64_t>(max_rows_per_image, 1);
-  const int limit = (int)std::min<int64_t>(topk, cap);
-  const size_t smem = (size_t)cap * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(unsigned long long) * (size_t)limit;
-  if (smem > (size_t)kMaxSmemOptin - 1024) return WSOVOD_B200_EUNSUPPORTED;   // > ~9.4k proposals per image
+  int npad_cap = 2;
+  while (npad_cap < max_rows_per_image) npad_cap <<= 1;
+  const int limit = (int)std::min<int64_t>(topk, std::max<int64_t>(max_rows_per_image, 1));
+  const size_t smem = (size_t)npad_cap * sizeof(unsigned long long) +
+                      (size_t)limit * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(float) * (size_t)(limit + 2);
+  if (smem > (size_t)kMaxSmemOptin - 2048) return WSOVOD_B200_EUNSUPPORTED;   // > 16384 proposals per image
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   uint8_t* valid = (uint8_t*)(ws + w.valid);
@@ -513,7 +584,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     }
     dim3 grid((unsigned)K, (unsigned)N);
     kern<<<grid, kNmsThreads, smem, st>>>(probs, offsets, valid, cboxes, (int)K, score_thresh,
-                                         cmp_threshold(nms_thresh, iou_mode), limit, cap, img_cnt, img_kept, w.kept_stride);
+                                         cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, img_cnt, img_kept, w.kept_stride);
     if ((rc = after_launch())) return rc;
   }
   det_topk_kernel<<<(unsigned)N, kNmsThreads, sizeof(unsigned long long) * (size_t)topk, st>>>(

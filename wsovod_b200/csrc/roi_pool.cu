@@ -75,7 +75,8 @@ template <int MODE>
 __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W,
                                    float scale, int PH, int PW, int sampling_ratio, int aligned,
                                    int32_t* __restrict__ bidx, int32_t* __restrict__ counts,
-                                   int16_t* __restrict__ edges, float* __restrict__ alignp) {
+                                   int16_t* __restrict__ edges, float* __restrict__ alignp,
+                                   uint2* __restrict__ bins) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float* roi = rois + r * 5;
@@ -88,6 +89,13 @@ __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, in
     int16_t* e = edges + r * (2 * (PH + PW));
     write_edges(e, round_i(__fmul_rn(y1, scale)), round_i(__fmul_rn(x1, scale)),
                 round_i(__fmul_rn(y2, scale)), round_i(__fmul_rn(x2, scale)), PH, PW, H, W);
+    if (bins) {   // one 8-byte word per output bin: (hs | he << 16, ws | we << 16) -- coalesced per-lane fetch
+      uint2* b = bins + r * (PH * PW);
+      for (int ph = 0; ph < PH; ++ph)
+        for (int pw = 0; pw < PW; ++pw)
+          b[ph * PW + pw] = make_uint2((uint32_t)(uint16_t)e[ph] | ((uint32_t)(uint16_t)e[PH + ph] << 16),
+                                       (uint32_t)(uint16_t)e[2 * PH + pw] | ((uint32_t)(uint16_t)e[2 * PH + PW + pw] << 16));
+    }
   } else if (MODE == MODE_LOOP) {
     // ROILoopPool_cuda.cu:34-74: inner (/1.8) and outer (x1.8) boxes in image space, clamped.
     // The expressions are kept in the reference's own form and compiled with the same default
@@ -376,6 +384,149 @@ __global__ void __launch_bounds__(1024, 1) roi_plane_kernel(const PoolParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast path: ROIPool 7x7, four channels per CTA (the shape every shipped WSOVOD config uses)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Lanes own consecutive flattened (proposal, bin) outputs.  Per pass a lane fetches ONE 8-byte bin word
+// (coalesced), scans its bin in shared memory and stores 4 (+4) scalars that are contiguous across the
+// warp.  ARG=false: max only (FMNMX3) and, because max is order independent, each lane starts its
+// column scan at an offset that puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
+// (the interleaved plane has a pitch of W cells and every shipped W is a multiple of 8, so the bank
+// group of a cell is its column mod 8): the 128-bit loads are conflict-free for bins >= 8 wide and
+// half-conflicting at worst for bins of 4..7.  ARG=true keeps torchvision's h-major scan (strict >,
+// first maximum wins).
+template <bool ARG>
+__global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, const uint2* __restrict__ bins) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int BINS = 49;
+  const int H = p.H, W = p.W, HW = H * W;
+  const int bid = blockIdx.x;
+  const int cg = bid % p.CG;
+  const int sidx = (bid / p.CG) % p.S;
+  const int n = bid / (p.CG * p.S);
+  const int c0 = cg * 4;
+  const int nc = min(4, p.C - c0);
+  int start = 0;
+  for (int m = 0; m < n; ++m) start += __ldg(p.counts + m);
+  const int cnt = __ldg(p.counts + n);
+  const int per = (cnt + p.S - 1) / p.S;
+  const int pos0 = sidx * per;
+  const int nroi = min(cnt, pos0 + per) - pos0;
+  if (nroi <= 0) return;
+  {
+    const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+    float4* sp = reinterpret_cast<float4*>(smem_raw);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float4 v;
+      v.x = __ldg(src + i);
+      v.y = nc > 1 ? __ldg(src + (int64_t)HW + i) : 0.f;
+      v.z = nc > 2 ? __ldg(src + 2 * (int64_t)HW + i) : 0.f;
+      v.w = nc > 3 ? __ldg(src + 3 * (int64_t)HW + i) : 0.f;
+      sp[i] = v;
+    }
+  }
+  __syncthreads();
+  uint32_t sbase;
+  {  // volatile: computed once, never re-materialised inside the loops
+    unsigned long long s64;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
+    sbase = (uint32_t)s64;
+  }
+  const uint32_t pitch = (uint32_t)W * 16u;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = nroi * BINS;
+  const int32_t* order = p.order + start + pos0;
+  const int stride = nw * 32;
+
+  // software pipeline: the (proposal id, bin word, scale) of the NEXT pass are fetched while this one runs
+  int flat = wid * 32 + lane;
+  int r_n = 0, bin_n = 0;
+  uint2 e_n = make_uint2(0, 0);
+  float sc_n = 1.f;
+  auto fetch = [&](int f) {
+    if (f < total) {
+      const int rpos = f / BINS;
+      bin_n = f - rpos * BINS;
+      r_n = __ldg(order + rpos);
+      e_n = __ldg(bins + (int64_t)r_n * BINS + bin_n);
+      if (p.row_scale) sc_n = __fadd_rn(__ldg(p.row_scale + r_n), p.row_scale_bias);
+    }
+  };
+  fetch(flat);
+  for (; flat < total; flat += stride) {
+    const int r = r_n, bin = bin_n;
+    const uint2 e = e_n;
+    const float scale = sc_n;
+    fetch(flat + stride);
+    const int hs = e.x & 0xffff, he = e.x >> 16, ws = e.y & 0xffff, we = e.y >> 16;
+    const int bw = we - ws;
+    const bool empty = (he <= hs) || (bw <= 0);
+    float m0, m1, m2, m3;
+    m0 = m1 = m2 = m3 = empty ? 0.f : -FLT_MAX;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    if (!empty) {
+      if (!ARG) {
+        // start offset of this lane's column scan: wide bins aim at bank group == lane % 8; narrow bins
+        // spread the lanes of the quarter-warp that would start on the same group
+        int rot = ((lane & 7) - ws) & 7;
+        if (bw < 8) {
+          const unsigned grp = __match_any_sync(__activemask(), ((lane >> 3) << 3) | (ws & 7));
+          rot = __popc(grp & ((1u << lane) - 1));
+          rot = rot < bw ? rot : rot % bw;
+        }
+        uint32_t lo = sbase + (uint32_t)(hs * W + ws) * 16u;     // first cell of the bin row
+        const uint32_t span = (uint32_t)bw * 16u;
+        for (int h = hs; h < he; ++h, lo += pitch) {
+          const uint32_t hi = lo + span;
+          uint32_t a = lo + (uint32_t)rot * 16u;
+#pragma unroll 2
+          for (int t = 0; t < bw; ++t) {
+            const float4 v = lds128(a);
+            m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y); m2 = fmaxf(m2, v.z); m3 = fmaxf(m3, v.w);
+            a += 16u;
+            a = a == hi ? lo : a;
+          }
+        }
+      } else {
+        int rowi = hs * W + ws;
+        uint32_t lo = sbase + (uint32_t)rowi * 16u;
+        for (int h = hs; h < he; ++h, lo += pitch, rowi += W) {
+          uint32_t a = lo;
+          int idx = rowi;
+#pragma unroll 2
+          for (int t = 0; t < bw; ++t, a += 16u, ++idx) {
+            const float4 v = lds128(a);
+            if (v.x > m0) { m0 = v.x; i0 = idx; }
+            if (v.y > m1) { m1 = v.y; i1 = idx; }
+            if (v.z > m2) { m2 = v.z; i2 = idx; }
+            if (v.w > m3) { m3 = v.w; i3 = idx; }
+          }
+        }
+      }
+    }
+    const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin;
+    if (p.row_scale) {
+      m0 = __fmul_rn(m0, scale); m1 = __fmul_rn(m1, scale); m2 = __fmul_rn(m2, scale); m3 = __fmul_rn(m3, scale);
+    }
+    __stcs(p.output + o, m0);
+    if (nc > 1) __stcs(p.output + o + BINS, m1);
+    if (nc > 2) __stcs(p.output + o + 2 * BINS, m2);
+    if (nc > 3) __stcs(p.output + o + 3 * BINS, m3);
+    if (ARG) {
+      __stcs(p.argmax + o, i0);
+      if (nc > 1) __stcs(p.argmax + o + BINS, i1);
+      if (nc > 2) __stcs(p.argmax + o + 2 * BINS, i2);
+      if (nc > 3) __stcs(p.argmax + o + 3 * BINS, i3);
+    }
+  }
+}
+
 // backward: grad_input[b, c, argmax] += grad_output (ROILoopPool_cuda.cu:206-248)
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
                                     const int32_t* __restrict__ argmax, int64_t total, int64_t R, int N,
@@ -397,7 +548,7 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // host side
 // ------------------------------------------------------------------------------------------------
 struct PoolWs {
-  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; size_t bytes;
+  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; size_t bytes;
 };
 
 static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
@@ -411,11 +562,13 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
   size_t ew = mode == MODE_LOOP ? 4 * (PH + PW) + 8 : 2 * (PH + PW);
   size_t o_edges = take(mode == MODE_ALIGN ? 0 : sizeof(int16_t) * ew * (size_t)R);
   size_t o_align = take(mode == MODE_ALIGN ? sizeof(float) * 8 * (size_t)R : 0);
+  size_t o_bins = take(mode == MODE_POOL && PH == 7 && PW == 7 ? sizeof(uint2) * 49 * (size_t)R : 0);
   w.counts = (int32_t*)(base + o_counts);
   w.bidx = (int32_t*)(base + o_bidx);
   w.order = (int32_t*)(base + o_order);
   w.edges = (int16_t*)(base + o_edges);
   w.alignp = (float*)(base + o_align);
+  w.bins = (uint2*)(base + o_bins);
   w.bytes = off;
   return w;
 }
@@ -468,6 +621,28 @@ static int dispatch_plane(PoolParams& p, int64_t R, cudaStream_t st) {
   }
 }
 
+static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, cudaStream_t st) {
+  const size_t smem = 4 * (size_t)p.H * p.W * sizeof(float);
+  p.CG = (int)ceil_div(p.C, 4);
+  int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
+  per_sm = std::max(per_sm, 1);
+  const int threads = per_sm == 1 ? 1024 : 512;
+  const int64_t slots = (int64_t)kNumSMs * per_sm;
+  const int64_t base = (int64_t)p.N * p.CG;
+  int64_t S = ceil_div(4 * slots, base);
+  const int64_t avg = std::max<int64_t>(R / std::max(p.N, 1), 1);
+  S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 96)));
+  p.S = (int)S;
+  if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
+  auto kern = arg ? roi_pool7_kernel<true> : roi_pool7_kernel<false>;
+  if (smem > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(unsigned)((int64_t)p.N * p.S * p.CG), threads, smem, st>>>(p, bins);
+  return after_launch();
+}
+
 static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
                        const float* rois, int64_t R, float scale, int PH, int PW, int sampling_ratio,
                        int aligned, const float* row_scale, float row_scale_bias, float* output,
@@ -486,12 +661,15 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   if (e != cudaSuccess) return (int)e;
   const int pt = 128;
   const unsigned pg = (unsigned)ceil_div(R, pt);
+  // specialised kernel: 7x7 bins, four interleaved planes fit shared memory, at least 3 channels
+  const bool fast7 = mode == MODE_POOL && PH == 7 && PW == 7 && C >= 3 &&
+                     4 * (size_t)H * W * sizeof(float) <= (size_t)kMaxSmemOptin;
   if (mode == MODE_POOL)
-    roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp);
+    roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, fast7 ? w.bins : nullptr);
   else if (mode == MODE_LOOP)
-    roi_prepare_kernel<MODE_LOOP><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp);
+    roi_prepare_kernel<MODE_LOOP><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, nullptr);
   else
-    roi_prepare_kernel<MODE_ALIGN><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, sampling_ratio, aligned, w.bidx, w.counts, w.edges, w.alignp);
+    roi_prepare_kernel<MODE_ALIGN><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, sampling_ratio, aligned, w.bidx, w.counts, w.edges, w.alignp, nullptr);
   int rc = after_launch();
   if (rc) return rc;
   roi_order_kernel<<<(unsigned)N, 256, 0, st>>>(w.bidx, w.counts, R, w.order);
@@ -504,6 +682,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
   p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+  if (fast7) return launch_pool7(p, w.bins, R, argmax != nullptr, st);
   if (mode == MODE_POOL) return argmax ? dispatch_plane<MODE_POOL, true>(p, R, st) : dispatch_plane<MODE_POOL, false>(p, R, st);
   if (mode == MODE_LOOP) return argmax ? dispatch_plane<MODE_LOOP, true>(p, R, st) : dispatch_plane<MODE_LOOP, false>(p, R, st);
   return dispatch_plane<MODE_ALIGN, false>(p, R, st);
