@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,7 +71,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -82,7 +85,12 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
+        # a short timed region can fall between two nvidia-smi samples: then use every sample taken while
+        # the GPU was running this benchmark's steps (warm-up + timed region + per-kernel timing)
+        rows = inside if len(inside) >= 3 else [r for _, r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -93,7 +101,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    samples=len(sm), reasons=sorted(reasons))
+                    samples=len(sm), samples_in_timed_region=len(inside), reasons=sorted(reasons))
 
 
 def cpu_reference_leg(w, budget_s=20.0):
@@ -180,30 +188,33 @@ def main():
                              ops.IOU_TV_CUDA)
         return pooled, det
 
-    for _ in range(args.warmup):
-        out = step()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
     # ---- timed region: exactly `steps` steps, device time, barrier + synchronize on both sides ------
     shard.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.window(t_wall0, time.time())
     shard.barrier()
     ms_total = shard.max_over_ranks(e0.elapsed_time(e1), dev)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     value = world * M * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel device times (CUDA events on the launching stream), same inputs ----------------
     def ktime(fn, iters):
+        for _ in range(2):
+            fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -220,6 +231,7 @@ def main():
     t_align = ktime(lambda: ops.align(emb, text, w["temperature"], 1, True, None, ops.ALIGN_TF32, False, True), it)
     t_det = ktime(lambda: ops.detections(probs, boxes, off, sizes, R, w["score_thresh"], w["nms_thresh"], w["topk"],
                                          ops.IOU_TV_CUDA), it)
+    clocks = sampler.stop() if rank == 0 else None
     peaks = load_peaks()
     out_bytes = M * C * 49 * 4
     pool_bytes = out_bytes * (2 if with_arg else 1) + feat.numel() * 4 + M * 20      # DESIGN.md "Kernel 1"
@@ -299,7 +311,7 @@ def main():
                        "global_proposals_per_step": world * M, "pool_argmax": with_arg,
                        "l2": "inputs+outputs per step (3.5 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "roofline": {"bound": "hbm", "kernel": "roi_plane_kernel (ROI pool)", "achieved": pool_gbs,
+            "roofline": {"bound": "hbm", "kernel": "roi_pool7_kernel (ROI pool)", "achieved": pool_gbs,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
                          "peak_source": peaks["source"], "traffic": load_traffic(with_arg),
                          "share_of_step": t_pool / (ms_total / args.steps)},

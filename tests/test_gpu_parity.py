@@ -38,7 +38,7 @@ def _pool_case(N, C, H, W, R, seed, relu=False, wild=True):
 
 
 @pytest.mark.parametrize("N,C,H,W,R", [(1, 4, 30, 40, 300), (3, 5, 23, 37, 200), (2, 1, 16, 16, 64),
-                                         (2, 2, 60, 80, 500), (1, 7, 9, 11, 50), (2, 64, 60, 80, 700)])
+                                         (2, 2, 60, 80, 500), (1, 7, 9, 11, 50), (2, 64, 60, 80, 700), (1, 6, 100, 152, 400), (2, 3, 100, 167, 300)])
 def test_roi_pool_bit_exact(N, C, H, W, R):
     feat, rois = _pool_case(N, C, H, W, R, seed=N * 1000 + C)
     out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)

@@ -98,11 +98,13 @@ struct TcParams {
   const float* bias;
   float* logits;      // [M, KO] (never null inside the kernel: falls back to `probs` storage)
   float* probs;       // [M, KO] or null
+  float* rowstat;     // [M, 2] (row max, 1/sum exp) when the softmax is finished by normalize_rows_kernel
   int64_t M;
   int D, KO, Kp;      // Kp: padded weight rows (multiple of 32)
   int BN;             // accumulator columns per chunk (multiple of 32, <= 256)
   int nchunks, kblocks, stages, ntiles;
   int norm;
+  int write_logits;   // 0: only probabilities are wanted and they come straight from TMEM
   float temperature;
   uint32_t tmem_cols;
 };
@@ -115,21 +117,29 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (uint32_t)p.BN * TC_BK * 4;
   unsigned char* sa = smem;                                   // [stages][16 KB]
-  unsigned char* sb = smem + (size_t)p.stages * a_bytes;      // [stages][BN*128 B]   (1024-aligned: BN % 16 == 0 -> multiple of 2 KB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + (size_t)p.stages * b_bytes);
+  unsigned char* sb = smem + (size_t)p.stages * a_bytes;      // [stages][BN*128 B]
+  float* stage_out = reinterpret_cast<float*>(sb + (size_t)p.stages * b_bytes);   // [4 warps][32][33] epilogue staging
+  float* snorm = stage_out + 4 * 32 * 33;                     // [2][128] sum of squares per row, per tile parity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(snorm + 2 * TC_BM);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* nfull = tempty + 2;
+  uint64_t* nempty = nfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nempty + 2);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    // a stage is released by the MMA commit and by the two norm warps that read it
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128);
+      mbar_init(&nfull[b], 2); mbar_init(&nempty[b], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -179,35 +189,58 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           tc_commit(&tfull[buf]);                // accumulator complete
         }
     }
-  } else if (warp >= 4) {
-    const int wq = warp - 4;                     // TMEM lane quarter this warp may access (warp % 4)
-    const int row_in_tile = wq * 32 + lane;
-    const float bias = p.bias ? __ldg(p.bias) : 0.f;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const int64_t m0 = (int64_t)tile * TC_BM;
-      const int64_t row = m0 + row_in_tile;
-      // ||x_r||^2 for this warp's 32 rows: coalesced 128-bit loads of rows the TMA just pulled into L2
-      float scale = 1.f;
-      if (p.norm) {
-        float myss = 0.f;
-        for (int i = 0; i < 32; ++i) {
-          const int64_t r = m0 + wq * 32 + i;
-          float ss = 0.f;
-          if (r < p.M) {
-            const float4* xr = reinterpret_cast<const float4*>(p.x + r * p.D);
-            for (int d = lane; d < (p.D >> 2); d += 32) {
-              const float4 v = __ldg(xr + d);
-              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  } else if (warp < 4) {
+    // ===== norm warps: ||x_r||^2 from the very stages the MMA consumes (x crosses HBM once) =====
+    const int t = (warp - 2) * 32 + lane;        // 0..63, rows t and t + 64 of the tile
+    int stage = 0; uint32_t phase = 0; uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+      float ss0 = 0.f, ss1 = 0.f;
+      for (int c = 0; c < p.nchunks; ++c) {
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (c == 0 && p.norm) {
+            // a row is 128 B = 8 chunks of 16 B (swizzled among themselves: irrelevant for a sum);
+            // lane l starts at chunk l & 7 so a quarter-warp touches 8 different bank groups
+            const unsigned char* base = sa + (size_t)stage * a_bytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int ch = (j + lane) & 7;
+              const float4 v0 = *reinterpret_cast<const float4*>(base + t * 128 + ch * 16);
+              const float4 v1 = *reinterpret_cast<const float4*>(base + (t + 64) * 128 + ch * 16);
+              ss0 += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+              ss1 += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
             }
           }
-          ss = warp_sum(ss);
-          if (lane == i) myss = ss;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        scale = p.temperature / fmaxf(sqrtf(myss), 1e-12f);
+        if (c == 0) {
+          // publish as soon as the first N chunk has streamed all of x's tile: the epilogue needs the
+          // norms to drain accumulator 0 while the MMA warp is already on the next chunks
+          const uint32_t nb = tcount & 1, nphase = (tcount >> 1) & 1;
+          mbar_wait(&nempty[nb], nphase ^ 1);    // the epilogue has read the previous use of this buffer
+          snorm[nb * TC_BM + t] = ss0;
+          snorm[nb * TC_BM + t + 64] = ss1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&nfull[nb]);
+        }
       }
+    }
+  } else {
+    // ===== epilogue warps: thread == accumulator row; stores staged per warp for coalescing =====
+    const int wq = warp - 4;                     // TMEM lane quarter this warp may access (warp % 4)
+    float* st = stage_out + wq * 32 * 33;        // [32 rows][33]
+    const float bias = p.bias ? __ldg(p.bias) : 0.f;
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+      const int64_t wrow0 = (int64_t)tile * TC_BM + wq * 32;     // first row of this warp
+      const uint32_t nb = tcount & 1, nphase = (tcount >> 1) & 1;
+      mbar_wait(&nfull[nb], nphase);
+      float scale = 1.f;
+      if (p.norm) scale = p.temperature / fmaxf(sqrtf(snorm[nb * TC_BM + wq * 32 + lane]), 1e-12f);
+      mbar_arrive(&nempty[nb]);
       float run_m = -FLT_MAX, run_s = 0.f;
-      float* lrow = p.logits + row * p.KO;
       for (int c = 0; c < p.nchunks; ++c, ++it) {
         const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(&tfull[buf], aphase);
@@ -226,36 +259,44 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const float new_m = fmaxf(run_m, cm);
         run_s *= expf(run_m - new_m);
         run_m = new_m;
-        // sweep B: logits out, running sum of exp
+        // sweep B: logits (staged, then written as 128-byte row segments), running sum of exp
         for (int j = 0; j < ncols; j += 32) {
           tmem_ld32(taddr + j, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (j + i < ncols) {
-              const float l = fmaf(v[i], scale, bias);
-              run_s += expf(l - run_m);
-              if (row < p.M) lrow[col0 + j + i] = l;
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float l = fmaf(v[i], scale, bias);
+            if (j + i < ncols) run_s += expf(l - run_m);
+            st[lane * 33 + i] = l;
+          }
+          __syncwarp();
+          const int cc = col0 + j + lane;
+          if (p.write_logits && cc < p.KO)
+            for (int rr = 0; rr < 32; ++rr)
+              if (wrow0 + rr < p.M) p.logits[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+          __syncwarp();
         }
         if (p.probs && p.nchunks == 1) {
           // sweep C (single chunk): probabilities straight from TMEM
           const float inv = 1.f / run_s;
-          float* prow = p.probs + row * p.KO;
           for (int j = 0; j < ncols; j += 32) {
             tmem_ld32(taddr + j, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (j + i < ncols && row < p.M) prow[j + i] = expf(fmaf(v[i], scale, bias) - run_m) * inv;
+            for (int i = 0; i < 32; ++i) st[lane * 33 + i] = expf(fmaf(v[i], scale, bias) - run_m) * inv;
+            __syncwarp();
+            const int cc = j + lane;
+            if (cc < p.KO)
+              for (int rr = 0; rr < 32; ++rr)
+                if (wrow0 + rr < p.M) p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+            __syncwarp();
           }
         }
         tc_fence_before();
         mbar_arrive(&tempty[buf]);               // accumulator buffer may be overwritten
       }
-      if (p.probs && p.nchunks > 1 && row < p.M) {
-        // multi-chunk: the row's logits were written by this very thread; normalise them
-        const float inv = 1.f / run_s;
-        float* prow = p.probs + row * p.KO;
-        for (int k = 0; k < p.KO; ++k) prow[k] = expf(lrow[k] - run_m) * inv;
+      if (p.rowstat && wrow0 + lane < p.M) {
+        // multi-chunk: (max, 1/sum) per row for the streaming normalisation kernel that follows
+        p.rowstat[2 * (wrow0 + lane)] = run_m;
+        p.rowstat[2 * (wrow0 + lane) + 1] = 1.f / run_s;
       }
     }
   }
@@ -264,6 +305,23 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// probs[r, :] = exp(logits[r, :] - max_r) * inv_r   (K > 256: the row spans several accumulator chunks)
+__global__ void normalize_rows_kernel(const float* __restrict__ logits, const float* __restrict__ rowstat, int64_t M,
+                                      int KO, float* __restrict__ probs) {
+  const int64_t total = M * KO;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total;
+       i += (int64_t)gridDim.x * blockDim.x * 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = i + j;
+      if (e < total) {
+        const int64_t r = e / KO;
+        probs[e] = expf(logits[e] - __ldg(rowstat + 2 * r)) * __ldg(rowstat + 2 * r + 1);
+      }
+    }
   }
 }
 
@@ -315,15 +373,19 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   }
   TcParams p;
   p.x = x; p.bias = bias; p.logits = logits ? logits : probs; p.probs = probs;
+  p.rowstat = nullptr;
   p.M = M; p.D = (int)D; p.KO = (int)KO; p.Kp = (int)w.Kp;
   p.BN = (int)std::min<int64_t>(w.Kp, 256);
   p.nchunks = (int)ceil_div(KO, p.BN);
   p.kblocks = (int)ceil_div(D, TC_BK);
   p.ntiles = (int)ceil_div(M, TC_BM);
   p.norm = norm_weight; p.temperature = temperature;
+  p.write_logits = (logits != nullptr || p.nchunks > 1) ? 1 : 0;
+  if (probs && p.nchunks > 1) p.rowstat = (float*)(ws + w.rowstat);
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 4 + (size_t)p.BN * TC_BK * 4;
-  p.stages = (int)std::max<size_t>(2, std::min<size_t>(8, ((size_t)kMaxSmemOptin - 4096) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + 2048;   // + alignment slack + barriers
+  const size_t extra = 4 * 32 * 33 * sizeof(float) + 2 * TC_BM * sizeof(float) + 512;   // staging, norms, barriers
+  p.stages = (int)std::max<size_t>(2, std::min<size_t>(8, ((size_t)kMaxSmemOptin - 1024 - extra) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + extra + 1024;                   // + alignment slack
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;                                               // <= 512
@@ -335,7 +397,10 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   const int grid = std::min(p.ntiles, kNumSMs);
   align_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   if ((rc = after_launch())) return rc;
-  if (!logits && probs && p.nchunks > 1) return 0;   // probs were normalised in place by the kernel
+  if (p.rowstat) {   // in place when the caller did not ask for logits (p.logits aliases probs)
+    normalize_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(p.logits, p.rowstat, M, (int)KO, probs);
+    if ((rc = after_launch())) return rc;
+  }
   return 0;
 }
 

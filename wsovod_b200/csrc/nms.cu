@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
 // one CTA per image: the topk best kept candidates, in order (:207-208), and the output gather
 __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
     const int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
-    const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk,
+    const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk, int sort_cap,
     float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
     int64_t* __restrict__ det_rows, int64_t* __restrict__ det_count) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -270,7 +270,20 @@ __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
   const int n = blockIdx.x;
   const int cnt = img_cnt[n];
   unsigned long long* keys = img_kept + (int64_t)n * kept_stride;
-  const int got = select_greedy<0, false>(keys, nullptr, cnt, 0.f, topk, sel, slots);
+  int got;
+  if (sort_cap > 0) {
+    // the image's kept list fits shared memory: one bitonic sort, the first topk keys are the answer
+    unsigned long long* sk = sel + topk;
+    int npad = 2;
+    while (npad < cnt) npad <<= 1;
+    for (int i = threadIdx.x; i < npad; i += kNmsThreads) sk[i] = i < cnt ? keys[i] : kDead;
+    __syncthreads();
+    bitonic_sort_smem(sk, npad);
+    got = min(cnt, topk);
+    for (int i = threadIdx.x; i < got; i += kNmsThreads) sel[i] = sk[i];
+  } else {
+    got = select_greedy<0, false>(keys, nullptr, cnt, 0.f, topk, sel, slots);
+  }
   __syncthreads();
   const int64_t r0 = offsets[n];
   for (int i = threadIdx.x; i < topk; i += kNmsThreads) {
@@ -587,8 +600,17 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
                                          cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, img_cnt, img_kept, w.kept_stride);
     if ((rc = after_launch())) return rc;
   }
-  det_topk_kernel<<<(unsigned)N, kNmsThreads, sizeof(unsigned long long) * (size_t)topk, st>>>(
-      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, det_boxes, det_scores,
-      det_classes, det_rows, det_count);
+  // final ordering: sort the image's kept list in shared memory when it fits (K * topk <= 16384 keys)
+  int sort_cap = 2;
+  while (sort_cap < w.kept_stride) sort_cap <<= 1;
+  if (w.kept_stride > 16384) sort_cap = 0;
+  const size_t tsmem = sizeof(unsigned long long) * ((size_t)topk + (size_t)sort_cap);
+  if (tsmem > 32 * 1024) {
+    e = cudaFuncSetAttribute(det_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  det_topk_kernel<<<(unsigned)N, kNmsThreads, tsmem, st>>>(
+      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap, det_boxes,
+      det_scores, det_classes, det_rows, det_count);
   return after_launch();
 }

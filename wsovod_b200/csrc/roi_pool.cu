@@ -84,6 +84,11 @@ __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, in
   b = min(max(b, 0), N - 1);
   bidx[r] = b;
   atomicAdd(&counts[b], 1);
+  if (r > 0) {   // counts[N] doubles as the "rois are not grouped by image" flag
+    int pb = (int)rois[(r - 1) * 5];
+    pb = min(max(pb, 0), N - 1);
+    if (pb > b) atomicOr(&counts[N], 1);
+  }
   const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
   if (MODE == MODE_POOL) {
     int16_t* e = edges + r * (2 * (PH + PW));
@@ -143,15 +148,55 @@ __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, in
   }
 }
 
+// prologue of the 7x7 fast path: one thread per (proposal, bin) -> coalesced 8-byte bin words.
+// Same fp32 sequence as write_edges(); thread 0 of a proposal also does the per-image bookkeeping.
+__global__ void roi_bins7_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W, float scale,
+                                 int32_t* __restrict__ bidx, int32_t* __restrict__ counts,
+                                 uint2* __restrict__ bins) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 49) return;
+  const int64_t r = i / 49;
+  const int bin = (int)(i - r * 49);
+  const int ph = bin / 7, pw = bin - ph * 7;
+  const float* roi = rois + r * 5;
+  const int rsw = round_i(__fmul_rn(roi[1], scale)), rsh = round_i(__fmul_rn(roi[2], scale));
+  const int rew = round_i(__fmul_rn(roi[3], scale)), reh = round_i(__fmul_rn(roi[4], scale));
+  const float bh = __fdiv_rn((float)max(reh - rsh + 1, 1), 7.f);
+  const float bw = __fdiv_rn((float)max(rew - rsw + 1, 1), 7.f);
+  const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + rsh, 0), H);
+  const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + rsh, 0), H);
+  const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + rsw, 0), W);
+  const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + rsw, 0), W);
+  bins[i] = make_uint2((uint32_t)hs | ((uint32_t)he << 16), (uint32_t)ws | ((uint32_t)we << 16));
+  if (bin == 0) {
+    int b = (int)roi[0];
+    b = min(max(b, 0), N - 1);
+    bidx[r] = b;
+    atomicAdd(&counts[b], 1);
+    if (r > 0) {
+      int pb = (int)rois[(r - 1) * 5];
+      pb = min(max(pb, 0), N - 1);
+      if (pb > b) atomicOr(&counts[N], 1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // prologue 2: stable grouping of proposal ids by image (one CTA per image)
 // ------------------------------------------------------------------------------------------------
 __global__ void roi_order_kernel(const int32_t* __restrict__ bidx, const int32_t* __restrict__ counts,
-                                 int64_t R, int32_t* __restrict__ order) {
+                                 int64_t R, int N, int32_t* __restrict__ order) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nw = blockDim.x >> 5;
+  if (counts[N] == 0) {   // already grouped by image (what ROIPooler produces): the order is the identity
+    int s = 0;
+    for (int m = 0; m < n; ++m) s += counts[m];
+    const int c = counts[n];
+    for (int i = tid; i < c; i += blockDim.x) order[s + i] = s + i;
+    return;
+  }
   if (tid == 0) {
     int s = 0;
     for (int m = 0; m < n; ++m) s += counts[m];
@@ -387,31 +432,36 @@ __global__ void __launch_bounds__(1024, 1) roi_plane_kernel(const PoolParams p) 
 // ------------------------------------------------------------------------------------------------
 // fast path: ROIPool 7x7, four channels per CTA (the shape every shipped WSOVOD config uses)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+template <int CB> __device__ __forceinline__ void lds_cell(uint32_t addr, float* f);
+template <> __device__ __forceinline__ void lds_cell<4>(uint32_t addr, float* f) {
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_cell<2>(uint32_t addr, float* f) {
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f[0]), "=f"(f[1]) : "r"(addr));
 }
 
 // Lanes own consecutive flattened (proposal, bin) outputs.  Per pass a lane fetches ONE 8-byte bin word
-// (coalesced), scans its bin in shared memory and stores 4 (+4) scalars that are contiguous across the
-// warp.  ARG=false: max only (FMNMX3) and, because max is order independent, each lane starts its
-// column scan at an offset that puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
-// (the interleaved plane has a pitch of W cells and every shipped W is a multiple of 8, so the bank
-// group of a cell is its column mod 8): the 128-bit loads are conflict-free for bins >= 8 wide and
-// half-conflicting at worst for bins of 4..7.  ARG=true keeps torchvision's h-major scan (strict >,
-// first maximum wins).
-template <bool ARG>
+// (coalesced), scans its bin in shared memory and stores CB (+CB) scalars that are contiguous across the
+// warp.  CB = 4 channels per CTA (16-byte cells, LDS.128) when four planes fit shared memory, else 2
+// (8-byte cells, LDS.64).  ARG=false: max only (FMNMX3) and, because max is order independent, each
+// lane starts its column scan at an offset that puts the G = 32/CB lanes sharing a shared-memory phase
+// on G different bank groups (bank group of a cell = cell index mod G): conflict-free for bins >= G
+// wide; narrower bins spread the lanes that would start on the same group.  ARG=true keeps
+// torchvision's h-major scan (strict >, first maximum wins).
+template <int CB, bool ARG>
 __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, const uint2* __restrict__ bins) {
+  using V = typename Vec<CB>::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int BINS = 49;
+  constexpr uint32_t CS = 4u * CB;          // bytes per interleaved cell
+  constexpr int G = 32 / CB;                // lanes per shared-memory phase == bank groups
   const int H = p.H, W = p.W, HW = H * W;
   const int bid = blockIdx.x;
   const int cg = bid % p.CG;
   const int sidx = (bid / p.CG) % p.S;
   const int n = bid / (p.CG * p.S);
-  const int c0 = cg * 4;
-  const int nc = min(4, p.C - c0);
+  const int c0 = cg * CB;
+  const int nc = min(CB, p.C - c0);
   int start = 0;
   for (int m = 0; m < n; ++m) start += __ldg(p.counts + m);
   const int cnt = __ldg(p.counts + n);
@@ -421,14 +471,12 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
   if (nroi <= 0) return;
   {
     const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
-    float4* sp = reinterpret_cast<float4*>(smem_raw);
+    V* sp = reinterpret_cast<V*>(smem_raw);
     for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      float4 v;
-      v.x = __ldg(src + i);
-      v.y = nc > 1 ? __ldg(src + (int64_t)HW + i) : 0.f;
-      v.z = nc > 2 ? __ldg(src + 2 * (int64_t)HW + i) : 0.f;
-      v.w = nc > 3 ? __ldg(src + 3 * (int64_t)HW + i) : 0.f;
-      sp[i] = v;
+      float f[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
+      sp[i] = pack<CB>(f);
     }
   }
   __syncthreads();
@@ -438,7 +486,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  const uint32_t pitch = (uint32_t)W * 16u;
+  const uint32_t pitch = (uint32_t)W * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
@@ -467,63 +515,58 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
     const int hs = e.x & 0xffff, he = e.x >> 16, ws = e.y & 0xffff, we = e.y >> 16;
     const int bw = we - ws;
     const bool empty = (he <= hs) || (bw <= 0);
-    float m0, m1, m2, m3;
-    m0 = m1 = m2 = m3 = empty ? 0.f : -FLT_MAX;
-    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    float m[CB];
+    int mi[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) { m[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
     if (!empty) {
+      const int cell0 = hs * W + ws;
       if (!ARG) {
-        // start offset of this lane's column scan: wide bins aim at bank group == lane % 8; narrow bins
-        // spread the lanes of the quarter-warp that would start on the same group
-        int rot = ((lane & 7) - ws) & 7;
-        if (bw < 8) {
-          const unsigned grp = __match_any_sync(__activemask(), ((lane >> 3) << 3) | (ws & 7));
+        int rot = ((lane & (G - 1)) - cell0) & (G - 1);
+        if (bw < G) {
+          const unsigned grp = __match_any_sync(__activemask(), ((lane / G) * G) | (cell0 & (G - 1)));
           rot = __popc(grp & ((1u << lane) - 1));
           rot = rot < bw ? rot : rot % bw;
         }
-        uint32_t lo = sbase + (uint32_t)(hs * W + ws) * 16u;     // first cell of the bin row
-        const uint32_t span = (uint32_t)bw * 16u;
+        uint32_t lo = sbase + (uint32_t)cell0 * CS;              // first cell of the bin row
+        const uint32_t span = (uint32_t)bw * CS;
         for (int h = hs; h < he; ++h, lo += pitch) {
           const uint32_t hi = lo + span;
-          uint32_t a = lo + (uint32_t)rot * 16u;
+          uint32_t a = lo + (uint32_t)rot * CS;
 #pragma unroll 2
           for (int t = 0; t < bw; ++t) {
-            const float4 v = lds128(a);
-            m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y); m2 = fmaxf(m2, v.z); m3 = fmaxf(m3, v.w);
-            a += 16u;
+            float f[CB];
+            lds_cell<CB>(a, f);
+#pragma unroll
+            for (int k = 0; k < CB; ++k) m[k] = fmaxf(m[k], f[k]);
+            a += CS;
             a = a == hi ? lo : a;
           }
         }
       } else {
-        int rowi = hs * W + ws;
-        uint32_t lo = sbase + (uint32_t)rowi * 16u;
+        int rowi = cell0;
+        uint32_t lo = sbase + (uint32_t)rowi * CS;
         for (int h = hs; h < he; ++h, lo += pitch, rowi += W) {
           uint32_t a = lo;
           int idx = rowi;
 #pragma unroll 2
-          for (int t = 0; t < bw; ++t, a += 16u, ++idx) {
-            const float4 v = lds128(a);
-            if (v.x > m0) { m0 = v.x; i0 = idx; }
-            if (v.y > m1) { m1 = v.y; i1 = idx; }
-            if (v.z > m2) { m2 = v.z; i2 = idx; }
-            if (v.w > m3) { m3 = v.w; i3 = idx; }
+          for (int t = 0; t < bw; ++t, a += CS, ++idx) {
+            float f[CB];
+            lds_cell<CB>(a, f);
+#pragma unroll
+            for (int k = 0; k < CB; ++k)
+              if (f[k] > m[k]) { m[k] = f[k]; mi[k] = idx; }
           }
         }
       }
     }
     const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin;
-    if (p.row_scale) {
-      m0 = __fmul_rn(m0, scale); m1 = __fmul_rn(m1, scale); m2 = __fmul_rn(m2, scale); m3 = __fmul_rn(m3, scale);
-    }
-    __stcs(p.output + o, m0);
-    if (nc > 1) __stcs(p.output + o + BINS, m1);
-    if (nc > 2) __stcs(p.output + o + 2 * BINS, m2);
-    if (nc > 3) __stcs(p.output + o + 3 * BINS, m3);
-    if (ARG) {
-      __stcs(p.argmax + o, i0);
-      if (nc > 1) __stcs(p.argmax + o + BINS, i1);
-      if (nc > 2) __stcs(p.argmax + o + 2 * BINS, i2);
-      if (nc > 3) __stcs(p.argmax + o + 3 * BINS, i3);
-    }
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+      if (k < nc) {
+        __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(m[k], scale) : m[k]);
+        if (ARG) __stcs(p.argmax + o + k * BINS, mi[k]);
+      }
   }
 }
 
@@ -621,9 +664,10 @@ static int dispatch_plane(PoolParams& p, int64_t R, cudaStream_t st) {
   }
 }
 
+template <int CB>
 static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, cudaStream_t st) {
-  const size_t smem = 4 * (size_t)p.H * p.W * sizeof(float);
-  p.CG = (int)ceil_div(p.C, 4);
+  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float);
+  p.CG = (int)ceil_div(p.C, CB);
   int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
   per_sm = std::max(per_sm, 1);
   const int threads = per_sm == 1 ? 1024 : 512;
@@ -634,7 +678,7 @@ static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, c
   S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 96)));
   p.S = (int)S;
   if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
-  auto kern = arg ? roi_pool7_kernel<true> : roi_pool7_kernel<false>;
+  auto kern = arg ? roi_pool7_kernel<CB, true> : roi_pool7_kernel<CB, false>;
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -662,9 +706,12 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   const int pt = 128;
   const unsigned pg = (unsigned)ceil_div(R, pt);
   // specialised kernel: 7x7 bins, four interleaved planes fit shared memory, at least 3 channels
-  const bool fast7 = mode == MODE_POOL && PH == 7 && PW == 7 && C >= 3 &&
-                     4 * (size_t)H * W * sizeof(float) <= (size_t)kMaxSmemOptin;
-  if (mode == MODE_POOL)
+  const size_t plane_bytes = (size_t)H * W * sizeof(float);
+  const bool fast7 = mode == MODE_POOL && PH == 7 && PW == 7 && C >= 2 && 2 * plane_bytes <= (size_t)kMaxSmemOptin;
+  const bool fast7_cb4 = fast7 && C >= 3 && 4 * plane_bytes <= (size_t)kMaxSmemOptin;
+  if (fast7)
+    roi_bins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins);
+  else if (mode == MODE_POOL)
     roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, fast7 ? w.bins : nullptr);
   else if (mode == MODE_LOOP)
     roi_prepare_kernel<MODE_LOOP><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, nullptr);
@@ -672,7 +719,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
     roi_prepare_kernel<MODE_ALIGN><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, sampling_ratio, aligned, w.bidx, w.counts, w.edges, w.alignp, nullptr);
   int rc = after_launch();
   if (rc) return rc;
-  roi_order_kernel<<<(unsigned)N, 256, 0, st>>>(w.bidx, w.counts, R, w.order);
+  roi_order_kernel<<<(unsigned)N, 256, 0, st>>>(w.bidx, w.counts, R, (int)N, w.order);
   rc = after_launch();
   if (rc) return rc;
 
@@ -682,7 +729,8 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
   p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
-  if (fast7) return launch_pool7(p, w.bins, R, argmax != nullptr, st);
+  if (fast7) return fast7_cb4 ? launch_pool7<4>(p, w.bins, R, argmax != nullptr, st)
+                             : launch_pool7<2>(p, w.bins, R, argmax != nullptr, st);
   if (mode == MODE_POOL) return argmax ? dispatch_plane<MODE_POOL, true>(p, R, st) : dispatch_plane<MODE_POOL, false>(p, R, st);
   if (mode == MODE_LOOP) return argmax ? dispatch_plane<MODE_LOOP, true>(p, R, st) : dispatch_plane<MODE_LOOP, false>(p, R, st);
   return dispatch_plane<MODE_ALIGN, false>(p, R, st);
