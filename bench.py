@@ -265,12 +265,14 @@ def main():
     arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    copy_s = torch.cuda.Stream(dev)
+    copy_stream = ctypes.c_void_p(copy_s.cuda_stream)
 
     def e2e_step():
         rc = L.wsovod_b200_infer_host(P(h_feat), N, C, H, W, P(h_rois), P(h_obj), M, P(h_off), P(h_sizes), P(h_emb),
                                       P(h_text), D, K, w["spatial_scale"], 7, w["temperature"], w["score_thresh"],
                                       w["nms_thresh"], topk, 1, 1, int(with_arg), P(h_db), P(h_ds), P(h_dc), P(h_dr),
-                                      P(h_cnt), P(arena), arena_bytes, None, stream)
+                                      P(h_cnt), P(arena), arena_bytes, None, stream, copy_stream)
         _lib.check(rc, "infer_host")
         torch.cuda.current_stream(dev).synchronize()      # the host reads the step's detections
         return int(h_cnt.sum())

@@ -221,6 +221,10 @@ int wsovod_b200_detections(const float* probs, const float* boxes, const int64_t
  * detections out on `stream`.  `dev_arena` is a caller-owned device buffer of at least
  * wsovod_b200_infer_host_arena() bytes.  The pooled tensor stays on the device (it feeds the
  * box-head FCs there); a pointer to it inside the arena is returned through pooled_dev when non-NULL.
+ * copy_stream (may be NULL): a second caller-owned stream; when given, the per-image host->device copies
+ * are issued there and overlap the kernels of the previous image (events order the two streams; the
+ * caller only synchronises `stream`).  The embedding area of the arena is reused for packed boxes, so a
+ * new call must not start on another stream before this one has finished.
  * ---------------------------------------------------------------------------------------------- */
 size_t wsovod_b200_infer_host_arena(int64_t N, int64_t C, int64_t H, int64_t W, int64_t R_total,
                                     int64_t D, int64_t K, int pooled, int64_t topk, int with_argmax);
@@ -233,7 +237,8 @@ int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_t C, int64_
                            int precision, int iou_mode, int with_argmax,
                            float* h_det_boxes, float* h_det_scores, int64_t* h_det_classes,
                            int64_t* h_det_rows, int64_t* h_det_count,
-                           void* dev_arena, size_t arena_bytes, float** pooled_dev, void* stream);
+                           void* dev_arena, size_t arena_bytes, float** pooled_dev, void* stream,
+                           void* copy_stream);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,7 @@ SIGNATURES = {
                                             c_i64, c_int]),
     "wsovod_b200_infer_host": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p,
                                        c_p, c_i64, c_i64, c_f, c_int, c_f, c_f, c_d, c_i64, c_int, c_int,
-                                       c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
+                                       c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p]),
 }
 
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace wsovod {
 struct Arena {
@@ -59,7 +60,7 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
                                       int iou_mode, int with_argmax, float* h_det_boxes,
                                       float* h_det_scores, int64_t* h_det_classes, int64_t* h_det_rows,
                                       int64_t* h_det_count, void* dev_arena, size_t arena_bytes,
-                                      float** pooled_dev, void* stream) {
+                                      float** pooled_dev, void* stream, void* copy_stream) {
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || R < 0 || D <= 0 || K <= 0 || pooled <= 0 || topk <= 0)
     return WSOVOD_B200_EINVAL;
   if (!h_features || !h_rois || !h_offsets || !h_image_sizes || !h_region_emb || !h_text_emb ||
@@ -68,50 +69,97 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
   const Arena a = arena_plan(N, C, H, W, R, D, K, pooled, topk, with_argmax, WSOVOD_B200_ALIGN_TF32);
   if (arena_bytes < a.bytes) return WSOVOD_B200_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
+  // With a second stream the per-image host->device copies run ahead of the kernels of the previous
+  // image (PCIe and SMs busy at the same time); without one everything is serial on `stream`.
+  cudaStream_t cs = copy_stream ? (cudaStream_t)copy_stream : st;
+  const bool piped = copy_stream != nullptr && copy_stream != stream;
   char* d = (char*)dev_arena;
   int64_t max_rows = 0;
-  for (int64_t n = 0; n < N; ++n) max_rows = std::max(max_rows, h_offsets[n + 1] - h_offsets[n]);
-  auto h2d = [&](size_t off, const void* src, size_t bytes) {
-    return bytes ? cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  for (int64_t n = 0; n < N; ++n) {
+    if (h_offsets[n + 1] < h_offsets[n]) return WSOVOD_B200_EINVAL;
+    max_rows = std::max(max_rows, h_offsets[n + 1] - h_offsets[n]);
+  }
+  if (h_offsets[0] != 0 || h_offsets[N] != R) return WSOVOD_B200_EINVAL;
+  cudaError_t e = cudaSuccess;
+  int rc = 0;
+  cudaEvent_t ev_start = nullptr, ev_small = nullptr;
+  std::vector<cudaEvent_t> ev((size_t)N, nullptr);
+  auto cleanup = [&]() {
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_small) cudaEventDestroy(ev_small);
+    for (auto x : ev) if (x) cudaEventDestroy(x);
   };
-  cudaError_t e;
-  if ((e = h2d(a.feat, h_features, sizeof(float) * (size_t)(N * C * H * W))) != cudaSuccess) return (int)e;
-  if ((e = h2d(a.rois, h_rois, sizeof(float) * 5 * (size_t)R)) != cudaSuccess) return (int)e;
-  if (h_objectness && (e = h2d(a.obj, h_objectness, sizeof(float) * (size_t)R)) != cudaSuccess) return (int)e;
-  if ((e = h2d(a.offs, h_offsets, sizeof(int64_t) * (size_t)(N + 1))) != cudaSuccess) return (int)e;
-  if ((e = h2d(a.sizes, h_image_sizes, sizeof(float) * 2 * (size_t)N)) != cudaSuccess) return (int)e;
-  if ((e = h2d(a.emb, h_region_emb, sizeof(float) * (size_t)(R * D))) != cudaSuccess) return (int)e;
-  if ((e = h2d(a.text, h_text_emb, sizeof(float) * (size_t)(K * D))) != cudaSuccess) return (int)e;
-  int rc = wsovod_b200_roi_pool_fwd((const float*)(d + a.feat), N, C, H, W, (const float*)(d + a.rois), R,
-                                    spatial_scale, pooled, pooled,
-                                    h_objectness ? (const float*)(d + a.obj) : nullptr, 1.0f,
-                                    (float*)(d + a.pooled), with_argmax ? (int32_t*)(d + a.argmax) : nullptr,
-                                    d + a.ws_pool, a.ws_align - a.ws_pool, st);
-  if (rc) return rc;
-  rc = wsovod_b200_align_fwd((const float*)(d + a.emb), (const float*)(d + a.text), R, D, K, temperature, 1, 1,
-                             nullptr, precision, nullptr, (float*)(d + a.probs), d + a.ws_align,
-                             a.ws_det - a.ws_align, st);
-  if (rc) return rc;
-  // class-agnostic boxes = the proposal boxes (columns 1..4 of rois) -> need a packed [R,4] copy
-  // (rois rows are 20 B apart): reuse the first 16R bytes of the detections' output area? No: pack
-  // with a strided 2D copy into the emb buffer, which align_fwd has finished reading on this stream.
+#define CK(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return (int)e; } } while (0)
+#define RC(call) do { rc = (call); if (rc) { cleanup(); return rc; } } while (0)
+  auto h2d = [&](size_t off, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
+  };
+  if (piped) {   // the copy stream must not overwrite the arena before earlier work on `stream` is done
+    CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_start, st));
+    CK(cudaStreamWaitEvent(cs, ev_start, 0));
+  }
+  // small tensors first
+  CK(h2d(a.rois, h_rois, sizeof(float) * 5 * (size_t)R));
+  if (h_objectness) CK(h2d(a.obj, h_objectness, sizeof(float) * (size_t)R));
+  CK(h2d(a.offs, h_offsets, sizeof(int64_t) * (size_t)(N + 1)));
+  CK(h2d(a.sizes, h_image_sizes, sizeof(float) * 2 * (size_t)N));
+  CK(h2d(a.text, h_text_emb, sizeof(float) * (size_t)(K * D)));
+  if (piped) {
+    CK(cudaEventCreateWithFlags(&ev_small, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_small, cs));
+    CK(cudaStreamWaitEvent(st, ev_small, 0));
+  }
+  const size_t plane = sizeof(float) * (size_t)(C * H * W);
+  const int64_t out_row = C * (int64_t)pooled * pooled;
+  const size_t ws_pool_bytes = a.ws_align - a.ws_pool, ws_align_bytes = a.ws_det - a.ws_align;
+  // per image: copy (features, embeddings) -> pool -> align; image n+1's copies overlap image n's kernels
+  for (int64_t n = 0; n < N; ++n) {
+    const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
+    CK(h2d(a.feat + plane * (size_t)n, h_features + (size_t)n * (size_t)(C * H * W), plane));
+    CK(h2d(a.emb + sizeof(float) * (size_t)(r0 * D), h_region_emb + r0 * D, sizeof(float) * (size_t)(rn * D)));
+    if (piped) {
+      CK(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
+      CK(cudaEventRecord(ev[n], cs));
+    }
+  }
+  // One pooling launch per image (N = 1, that image's plane and rois) so it can start as soon as the
+  // image has landed.  The rois keep their global batch index; with N = 1 the kernel clamps it to 0.
+  for (int64_t n = 0; n < N; ++n) {
+    const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
+    if (piped) CK(cudaStreamWaitEvent(st, ev[n], 0));
+    if (rn == 0) continue;
+    RC(wsovod_b200_roi_pool_fwd((const float*)(d + a.feat + plane * (size_t)n), 1, C, H, W,
+                                (const float*)(d + a.rois) + 5 * r0, rn,
+                                spatial_scale, pooled, pooled,
+                                h_objectness ? (const float*)(d + a.obj) + r0 : nullptr, 1.0f,
+                                (float*)(d + a.pooled) + r0 * out_row,
+                                with_argmax ? (int32_t*)(d + a.argmax) + r0 * out_row : nullptr,
+                                d + a.ws_pool, ws_pool_bytes, st));
+    RC(wsovod_b200_align_fwd((const float*)(d + a.emb) + r0 * D, (const float*)(d + a.text), rn, D, K, temperature,
+                             1, 1, nullptr, precision, nullptr, (float*)(d + a.probs) + r0 * (K + 1),
+                             d + a.ws_align, ws_align_bytes, st));
+  }
+  // class-agnostic boxes = the proposal boxes (columns 1..4 of rois) -> packed [R,4] copy (rois rows are
+  // 20 B apart) into the embedding buffer, which align_fwd has finished reading on this stream
   float* dboxes = (float*)(d + a.emb);
-  e = cudaMemcpy2DAsync(dboxes, 16, (const char*)(d + a.rois) + 4, 20, 16, (size_t)R, cudaMemcpyDeviceToDevice, st);
-  if (e != cudaSuccess) return (int)e;
-  rc = wsovod_b200_detections((const float*)(d + a.probs), dboxes, (const int64_t*)(d + a.offs),
-                              (const float*)(d + a.sizes), R, N, K, max_rows, score_thresh, nms_thresh, topk,
-                              iou_mode, (float*)(d + a.det_boxes), (float*)(d + a.det_scores),
-                              (int64_t*)(d + a.det_classes), (int64_t*)(d + a.det_rows),
-                              (int64_t*)(d + a.det_count), d + a.ws_det, a.det_boxes - a.ws_det, st);
-  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(dboxes, 16, (const char*)(d + a.rois) + 4, 20, 16, (size_t)R, cudaMemcpyDeviceToDevice, st));
+  RC(wsovod_b200_detections((const float*)(d + a.probs), dboxes, (const int64_t*)(d + a.offs),
+                            (const float*)(d + a.sizes), R, N, K, max_rows, score_thresh, nms_thresh, topk,
+                            iou_mode, (float*)(d + a.det_boxes), (float*)(d + a.det_scores),
+                            (int64_t*)(d + a.det_classes), (int64_t*)(d + a.det_rows),
+                            (int64_t*)(d + a.det_count), d + a.ws_det, a.det_boxes - a.ws_det, st));
   auto d2h = [&](void* dst, size_t off, size_t bytes) {
     return cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, st);
   };
-  if ((e = d2h(h_det_boxes, a.det_boxes, sizeof(float) * 4 * (size_t)(N * topk))) != cudaSuccess) return (int)e;
-  if ((e = d2h(h_det_scores, a.det_scores, sizeof(float) * (size_t)(N * topk))) != cudaSuccess) return (int)e;
-  if ((e = d2h(h_det_classes, a.det_classes, sizeof(int64_t) * (size_t)(N * topk))) != cudaSuccess) return (int)e;
-  if ((e = d2h(h_det_rows, a.det_rows, sizeof(int64_t) * (size_t)(N * topk))) != cudaSuccess) return (int)e;
-  if ((e = d2h(h_det_count, a.det_count, sizeof(int64_t) * (size_t)N)) != cudaSuccess) return (int)e;
+  CK(d2h(h_det_boxes, a.det_boxes, sizeof(float) * 4 * (size_t)(N * topk)));
+  CK(d2h(h_det_scores, a.det_scores, sizeof(float) * (size_t)(N * topk)));
+  CK(d2h(h_det_classes, a.det_classes, sizeof(int64_t) * (size_t)(N * topk)));
+  CK(d2h(h_det_rows, a.det_rows, sizeof(int64_t) * (size_t)(N * topk)));
+  CK(d2h(h_det_count, a.det_count, sizeof(int64_t) * (size_t)N));
+#undef CK
+#undef RC
+  cleanup();
   if (pooled_dev) *pooled_dev = (float*)(d + a.pooled);
   return 0;
 }
