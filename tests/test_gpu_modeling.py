@@ -1,0 +1,167 @@
+"""GPU tests of the host-side mirror (wsovod_b200.modeling / .layers): the reference's interfaces, driven
+the way wsovod/modeling/roi_heads/roi_heads.py:696-907 drives them, against the reference-generated
+goldens and a plain-PyTorch restatement of the training slice."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from wsovod_b200 import ops, synth  # noqa: E402
+from wsovod_b200.modeling import (InstanceRefinementOutputLayers, ObjectMiningOutputLayers, OpenVocabularyClassifier,  # noqa: E402
+                                  ROIPooler, fast_rcnn_inference, get_image_level_gt, get_pgt_top_k,
+                                  label_proposals_wsl)
+from wsovod_b200.structures import Boxes, Instances  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _proposals(boxes_l, shapes, obj_l=None):
+    out = []
+    for i, (b, s) in enumerate(zip(boxes_l, shapes)):
+        p = Instances(tuple(s), proposal_boxes=Boxes(b.to(DEV)))
+        if obj_l is not None:
+            p.objectness_logits = obj_l[i].to(DEV)
+        out.append(p)
+    return out
+
+
+@pytest.mark.parametrize("ptype", ["ROIPool", "ROILoopPool", "ROIAlign", "ROIAlignV2"])
+def test_roi_pooler_single_level(ptype):
+    g = synth.gen(17)
+    feat = synth.features(2, 6, 30, 40, g)
+    boxes = [synth.proposals(120, 240, 320, g, stress=False) for _ in range(2)]
+    obj = [synth.objectness(120, g) for _ in range(2)]
+    pooler = ROIPooler(7, (1 / 8,), 0, ptype)
+    out = pooler([feat.to(DEV)], [Boxes(b.to(DEV)) for b in boxes])
+    rois, _ = synth.rois_from(boxes)
+    if ptype == "ROIPool":
+        ref = oracle.roi_pool(feat, rois, 1 / 8, 7)[0]
+    elif ptype == "ROILoopPool":
+        ref = oracle.roi_loop_pool(feat, rois, 1 / 8, 7)[0]
+    else:
+        ref = oracle.roi_align(feat, rois, 1 / 8, 7, 0, ptype == "ROIAlignV2")
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-6)
+    # objectness folded into the kernel == the reference's separate pass (roi_heads.py:733-739)
+    out2 = pooler([feat.to(DEV)], [Boxes(b.to(DEV)) for b in boxes], objectness_logits=[o.to(DEV) for o in obj])
+    scale = torch.cat(obj) + 1
+    if ptype == "ROILoopPool":
+        scale = torch.cat([scale, scale, scale])
+    torch.testing.assert_close(out2.cpu(), ref * scale.view(-1, 1, 1, 1), rtol=1e-6, atol=1e-7)
+
+
+def test_roi_pooler_multi_level_mrrp():
+    # MRRP: three dilation branches = three "levels" at the same scale, level ids given (roi_heads.py:727-731)
+    g = synth.gen(18)
+    feats = [synth.features(2, 4, 30, 40, g) for _ in range(3)]
+    boxes = [synth.proposals(90, 240, 320, g, stress=False) for _ in range(2)]
+    lv = [torch.randint(0, 3, (90,), generator=g) for _ in range(2)]
+    pooler = ROIPooler(7, (1 / 8, 1 / 8, 1 / 8), 0, "ROILoopPool")
+    out = pooler([f.to(DEV) for f in feats], [Boxes(b.to(DEV)) for b in boxes], level_ids=[l.to(DEV) for l in lv])
+    rois, _ = synth.rois_from(boxes)
+    M = rois.size(0)
+    ref = torch.zeros(3 * M, 4, 7, 7)
+    lvc = torch.cat(lv)
+    for level in range(3):
+        inds = torch.nonzero(lvc == level, as_tuple=True)[0]
+        r = oracle.roi_loop_pool(feats[level], rois[inds], 1 / 8, 7)[0]
+        ref[torch.cat([inds, inds + M, inds + 2 * M])] = r
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_classifier_and_inference_golden(golden):
+    c = golden("align")["small"]
+    K, D = c["text"].shape
+    m = OpenVocabularyClassifier(D, num_classes=K, weight_path="rand", weight_dim=D, precision=ops.ALIGN_FP32).to(DEV)
+    m.projection = torch.nn.Identity()
+    logits = m(c["x"].to(DEV), c["text"].to(DEV), append_background=True)
+    torch.testing.assert_close(logits.cpu(), c["logits"], rtol=0, atol=5e-5)
+    d = golden("detections")
+    shapes = d["image_shapes"]
+    inst, kept, all_s, all_b = fast_rcnn_inference([b.to(DEV) for b in d["boxes"]], [p.to(DEV) for p in d["probs"]],
+                                                   shapes, d["score_thresh"], d["nms_thresh"], d["topk"],
+                                                   iou_mode=ops.IOU_TV_CPU)
+    for n in range(len(shapes)):
+        assert torch.equal(inst[n].pred_boxes.tensor.cpu(), d["det_boxes"][n])
+        assert torch.equal(inst[n].scores.cpu(), d["det_scores"][n])
+        assert torch.equal(inst[n].pred_classes.cpu(), d["det_classes"][n])
+        assert torch.equal(inst[n].pred_inds.cpu(), d["det_rows"][n])
+        assert torch.equal(kept[n].cpu(), d["kept_indices"][n])      # index among finite rows (:178-182)
+
+
+def test_refinement_flow_golden(golden):
+    f = golden("refine")
+    K = f["num_classes"]
+    props = _proposals(f["boxes"], [(1, 1)] * len(f["boxes"]))
+    targets, seeds = get_pgt_top_k([b.to(DEV) for b in f["boxes"]], [s.to(DEV) for s in f["scores"]], props,
+                                   [g.to(DEV) for g in f["gt_classes_img"]], f["img_scores"].to(DEV), K)
+    labelled, _ = label_proposals_wsl(props, seeds, K, 0.5)
+    for n in range(len(props)):
+        assert torch.equal(targets[n].gt_boxes.tensor.cpu(), f["seed_boxes"][n])
+        assert torch.equal(targets[n].gt_classes.cpu(), f["seed_classes"][n])
+        assert torch.equal(targets[n].gt_weights.cpu(), f["seed_weights"][n])
+        assert torch.equal(labelled[n].gt_classes.cpu(), f["gt_classes"][n])
+        assert torch.equal(labelled[n].gt_boxes.tensor.cpu(), f["gt_boxes"][n])
+        assert torch.equal(labelled[n].gt_weights.cpu(), f["gt_weights"][n])
+
+
+def test_training_slice_matches_pytorch():
+    """MIL loss + one refinement stage (config 3's step without backbone/FCs): forward values and the
+    gradients w.r.t. the region features through OUR kernels vs a plain PyTorch restatement of
+    fast_rcnn_open_vocabulary.py:318-427,726-820 and roi_heads.py:756-819."""
+    g = synth.gen(23)
+    K, D, Fdim = 20, 64, 48
+    sizes = [300, 200]
+    shapes = [(240, 320), (200, 304)]
+    boxes = [synth.proposals(s, h, w, g) for s, (h, w) in zip(sizes, shapes)]
+    x = torch.randn(sum(sizes), Fdim, generator=g)
+    text = synth.text_embeddings(K, D, g)
+    gt = [torch.tensor([3, 7]), torch.tensor([11])]
+    torch.manual_seed(0)
+    miner = ObjectMiningOutputLayers(Fdim, K).to(DEV)
+    head = OpenVocabularyClassifier(Fdim, num_classes=K, weight_path="rand", weight_dim=D, precision=ops.ALIGN_FP32).to(DEV)
+    refinery = InstanceRefinementOutputLayers(Fdim, K, head).to(DEV)
+    props = _proposals(boxes, shapes)
+    _, gt_int, gt_oh = get_image_level_gt([Instances(s, gt_classes=c.to(DEV)) for s, c in zip(shapes, gt)], K)
+
+    def run(ours):
+        xg = x.to(DEV).requires_grad_(True)
+        if ours:
+            scores, _ = miner(xg, props)
+            img = miner.predict_probs_img((scores, None), props)
+        else:
+            C, Dl = miner.cls(xg), miner.det(xg)
+            scores = torch.cat([F.softmax(c, 1) * F.softmax(d, 0) for c, d in zip(C.split(sizes), Dl.split(sizes))])
+            img = torch.clamp(torch.stack([s.sum(0) for s in scores.split(sizes)]), 1e-6, 1 - 1e-6)
+        loss_mil = F.binary_cross_entropy(img, gt_oh, reduction="mean")
+        prev = torch.cat([scores.detach(), scores.new_zeros(scores.shape[0], 1)], 1)
+        if ours:
+            _, seeds = get_pgt_top_k([b.to(DEV) for b in boxes], prev, props, gt_int, img.detach(), K)
+            lab, _ = label_proposals_wsl(props, seeds, K, 0.5)
+            gcls, gw = torch.cat([p.gt_classes for p in lab]), torch.cat([p.gt_weights for p in lab])
+            logits, _ = refinery(xg, text.to(DEV), True)
+        else:
+            off = [0, sizes[0], sum(sizes)]
+            goff = [0, 2, 3]
+            sd = oracle.pgt_top1(prev.cpu(), torch.cat(boxes), off, torch.cat(gt), goff, img.detach().cpu())
+            a = oracle.refine_assign(torch.cat(boxes), off, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"],
+                                     sd["seed_weights"], goff, sd["seed_count"], K, 0.5)
+            gcls, gw = a["gt_classes"].to(DEV), a["gt_weights"].to(DEV)
+            xp = head.projection(xg)
+            w = F.normalize(text.to(DEV).t().contiguous(), p=2, dim=0)
+            w = torch.cat([w, w.new_zeros(D, 1)], 1)
+            logits = torch.mm(50.0 * F.normalize(xp, p=2, dim=1), w)
+        ce = F.cross_entropy(logits, gcls, reduction="none") * gw           # :813-820
+        loss_ref = ce.sum() / max(int((gw > 1e-12).sum()), 1)
+        (loss_mil + loss_ref).backward()
+        return loss_mil.item(), loss_ref.item(), xg.grad.clone(), gcls
+
+    lm1, lr1, g1, c1 = run(True)
+    for p in list(miner.parameters()) + list(refinery.parameters()):
+        p.grad = None
+    lm2, lr2, g2, c2 = run(False)
+    assert torch.equal(c1, c2) and (c1 < K).any()
+    assert abs(lm1 - lm2) <= 1e-5 * abs(lm2) + 1e-7
+    assert abs(lr1 - lr2) <= 1e-4 * abs(lr2) + 1e-6
+    torch.testing.assert_close(g1, g2, rtol=2e-3, atol=2e-6)
