@@ -327,3 +327,29 @@ def test_detections_vs_oracle(mode):
     o = oracle.detections(torch.cat(probs), torch.cat(boxes), off, shapes, 1e-5, 0.3, 100, mode)
     for k in o:
         assert torch.equal(r[k].cpu(), o[k]), k
+
+
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
+def test_detections_prefix_fallback_and_long_columns(mode):
+    """Columns longer than 2048 candidates take the histogram pre-selection; when the selected prefix
+    runs dry before `topk` boxes are kept (here: the 2000 best-scoring boxes are near-duplicates) the
+    kernel must fall back to the full column and still return the reference's detections."""
+    g = synth.gen(77)
+    K, R = 3, 6000
+    shapes = [(800, 1200)]
+    base = synth.proposals(R, 800, 1200, g, stress=False)
+    boxes = base.clone()
+    boxes[:2000] = torch.tensor([100., 100., 400., 500.]) + torch.rand(2000, 4, generator=g)   # one cluster
+    probs = torch.rand(R, K + 1, generator=g) * 0.2
+    probs[:2000, 0] = 0.7 + 0.3 * torch.rand(2000, generator=g)     # class 0: the cluster scores highest,
+    probs[2000:, 0] = 0.5 + 0.2 * torch.rand(R - 2000, generator=g)  # ... the distinct boxes come after it
+    probs[:, 1] = 0.4 * torch.rand(R, generator=g)                   # class 1: plain long column, lower scores
+    probs[:, 2] = 1e-6                                               # class 2: nothing passes the threshold
+    off = [0, R]
+    r = ops.detections(probs.to(DEV), boxes.to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(shapes, dtype=torch.float32, device=DEV), R, 1e-5, 0.3, 100, mode)
+    o = oracle.detections(probs, boxes, off, shapes, 1e-5, 0.3, 100, mode)
+    for k in o:
+        assert torch.equal(r[k].cpu(), o[k]), k
+    # survivors of class 0 beyond the cluster only exist if the full column was processed
+    assert int(o["det_count"][0]) == 100 and (o["det_classes"][0] == 0).sum() > 50

@@ -165,8 +165,13 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
   }
 }
 
-struct FirstSlots {     // per-warp "lowest alive candidate" of the current chunk, double buffered
-  int tid[2][kNmsWarps];
+constexpr int kSelectBins = 4096;     // histogram over the 12 leading key bits
+constexpr int kSelectCap = 2048;      // selected-prefix capacity (keys) == histogram storage (16 KB)
+constexpr int kSelectTarget = 1024;   // aim: at least this many best candidates in the prefix
+constexpr int kSelectMin = 2048;      // columns shorter than this are simply sorted
+
+struct FirstSlots {     // "lowest alive candidate" of the current chunk: block-wide atomicMin + per-warp box
+  int first[3];          // rotating: round t uses [t % 3] and re-arms [(t + 1) % 3]
   float4 box[2][kNmsWarps];
 };
 
@@ -184,15 +189,17 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ FirstSlots slots;
-  __shared__ int s_n, s_base;
+  __shared__ int s_n, s_base, s_sel, s_bstar, s_m;
+  __shared__ int s_wsum[kNmsWarps];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);                 // [npad_cap]
   float4* kbox = reinterpret_cast<float4*>(sm + (size_t)npad_cap * sizeof(unsigned long long));   // [limit]
   float* karea = reinterpret_cast<float*>(kbox + limit);                                 // [limit]
   unsigned long long* kkey = reinterpret_cast<unsigned long long*>(karea + ((limit + 1) & ~1));   // [limit]
+  unsigned long long* ssel = kkey + limit;                                               // [kSelectCap] / histogram
   const int k = blockIdx.x, n = blockIdx.y;
   const int64_t r0 = offsets[n], r1 = offsets[n + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_n = 0;
+  if (threadIdx.x == 0) { s_n = 0; slots.first[0] = slots.first[1] = slots.first[2] = 0x7fffffff; }
   __syncthreads();
   const int K1 = K + 1;
   for (int64_t r = r0 + threadIdx.x; r < r1; r += kNmsThreads) {
@@ -203,49 +210,115 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
   __syncthreads();
   const int nc = s_n;
   if (nc == 0) return;
-  int npad = 1;
-  while (npad < nc) npad <<= 1;
-  for (int i = nc + threadIdx.x; i < npad; i += kNmsThreads) skey[i] = kDead;
-  __syncthreads();
-  bitonic_sort_smem(skey, npad);
 
-  int kept = 0, buf = 0;
-  for (int base = 0; base < nc && kept < limit; base += kNmsThreads) {
-    const int i = base + threadIdx.x;
-    bool alive = i < nc;
-    unsigned long long key = 0;
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (alive) {
-      key = skey[i];
-      box = __ldg(cboxes + r0 + (uint32_t)key);
-      for (int j = 0; j < kept && alive; ++j)
-        if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
-    }
-    // rounds: the lowest alive thread of the chunk is the next kept box
-    while (kept < limit) {
-      const unsigned bal = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) slots.tid[buf][wid] = bal ? (wid * 32 + __ffs(bal) - 1) : 0x7fffffff;
-      if (bal && lane == __ffs(bal) - 1) slots.box[buf][wid] = box;
-      __syncthreads();
-      int first = 0x7fffffff, fw = 0;
+  // Candidate list for the greedy pass.  A class rarely needs more than its best ~1000 candidates to
+  // collect `limit` survivors, so for long columns the top of the list is selected exactly with a
+  // 4096-bin histogram over the 12 leading key bits (no sort of the tail); if that prefix runs out
+  // before `limit` boxes are kept, the whole column is sorted and the pass repeated (rare, exact).
+  unsigned long long* list = skey;
+  int ln = nc;
+  bool complete = true;
+  if (nc > kSelectMin) {
+    int* hist = reinterpret_cast<int*>(ssel);
+    for (int i = threadIdx.x; i < kSelectBins; i += kNmsThreads) hist[i] = 0;
+    if (threadIdx.x == 0) { s_sel = 0; s_m = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc; i += kNmsThreads) atomicAdd(&hist[(int)(skey[i] >> 52)], 1);
+    __syncthreads();
+    constexpr int PER = kSelectBins / kNmsThreads;      // bins per thread
+    int mine = 0;
 #pragma unroll
-      for (int w = 0; w < kNmsWarps; ++w) {
-        const int t = slots.tid[buf][w];
-        if (t < first) { first = t; fw = w; }
-      }
-      if (first == 0x7fffffff) { buf ^= 1; break; }
-      const float4 kb = slots.box[buf][fw];
-      const float ka = area_rn(kb);
-      buf ^= 1;
-      if ((int)threadIdx.x == first) {
-        kbox[kept] = kb; karea[kept] = ka; kkey[kept] = key;
-        alive = false;
-      } else if (alive && (int)threadIdx.x > first && suppresses<MODE>(kb, ka, box, thr)) {
-        alive = false;
-      }
-      ++kept;
+    for (int j = 0; j < PER; ++j) mine += hist[threadIdx.x * PER + j];
+    int inc = mine;                                      // inclusive scan over threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    int before = inc - mine;
+    for (int w2 = 0; w2 < wid; ++w2) before += s_wsum[w2];
+    if (before < kSelectTarget && before + mine >= kSelectTarget) {   // exactly one thread
+      int cum = before;
+      for (int j = 0; j < PER; ++j) {
+        cum += hist[threadIdx.x * PER + j];
+        if (cum >= kSelectTarget) { s_sel = cum; s_bstar = threadIdx.x * PER + j; break; }
+      }
+    }
+    __syncthreads();
+    const int selcount = s_sel, bstar = s_bstar;
+    if (selcount > 0 && selcount <= kSelectCap && selcount < nc) {
+      __syncthreads();                                   // everyone is done reading the histogram
+      for (int i = threadIdx.x; i < nc; i += kNmsThreads) {
+        const unsigned long long key = skey[i];
+        if ((int)(key >> 52) <= bstar) ssel[atomicAdd(&s_m, 1)] = key;
+      }
+      __syncthreads();
+      list = ssel;
+      ln = selcount;
+      complete = false;
+    }
+  }
+  int kept = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int npad = 2;
+    while (npad < ln) npad <<= 1;
+    for (int i = ln + threadIdx.x; i < npad; i += kNmsThreads) list[i] = kDead;
+    __syncthreads();
+    bitonic_sort_smem(list, npad);
+
+    kept = 0;
+    int buf = 0, rnd = 0;
+    for (int base = 0; base < ln && kept < limit; base += kNmsThreads) {
+      const int i = base + threadIdx.x;
+      bool alive = i < ln;
+      unsigned long long key = 0;
+      float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (alive) {
+        key = list[i];
+        box = __ldg(cboxes + r0 + (uint32_t)key);
+        for (int j = 0; j < kept && alive; ++j)
+          if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
+      }
+      // rounds: the lowest alive thread of the chunk is the next kept box
+      while (kept < limit) {
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if (bal) {
+          const int fl = __ffs(bal) - 1;
+          if (lane == fl) {
+            slots.box[buf][wid] = box;
+            atomicMin(&slots.first[rnd], wid * 32 + fl);
+          }
+        }
+        // re-arm the slot of the NEXT round: its last readers (round t-2) all passed barrier t-1 already
+        if (threadIdx.x == 0) slots.first[rnd == 2 ? 0 : rnd + 1] = 0x7fffffff;
+        __syncthreads();
+        const int first = slots.first[rnd];
+        rnd = rnd == 2 ? 0 : rnd + 1;
+        if (first == 0x7fffffff) { buf ^= 1; break; }
+        const float4 kb = slots.box[buf][first >> 5];
+        const float ka = area_rn(kb);
+        buf ^= 1;
+        if ((int)threadIdx.x == first) {
+          kbox[kept] = kb; karea[kept] = ka; kkey[kept] = key;
+          alive = false;
+        } else if (alive && (int)threadIdx.x > first && suppresses<MODE>(kb, ka, box, thr)) {
+          alive = false;
+        }
+        ++kept;
+      }
+      __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
+    }
+    if (complete || kept >= limit) break;
+    // the selected prefix ran dry: redo the pass on the full column (the round slots are all re-armed:
+    // every exit above leaves them at 0x7fffffff or about to be, so reset them explicitly)
+    __syncthreads();
+    if (threadIdx.x == 0) slots.first[0] = slots.first[1] = slots.first[2] = 0x7fffffff;
+    list = skey;
+    ln = nc;
+    complete = true;
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x == 0) s_base = atomicAdd(&img_cnt[n], kept);
@@ -576,7 +649,8 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   while (npad_cap < max_rows_per_image) npad_cap <<= 1;
   const int limit = (int)std::min<int64_t>(topk, std::max<int64_t>(max_rows_per_image, 1));
   const size_t smem = (size_t)npad_cap * sizeof(unsigned long long) +
-                      (size_t)limit * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(float) * (size_t)(limit + 2);
+                      (size_t)limit * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(float) * (size_t)(limit + 2) +
+                      sizeof(unsigned long long) * (size_t)kSelectCap;
   if (smem > (size_t)kMaxSmemOptin - 2048) return WSOVOD_B200_EUNSUPPORTED;   // > 16384 proposals per image
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
