@@ -49,6 +49,33 @@ def test_roi_pool_bit_exact(N, C, H, W, R):
     assert torch.equal(out2.cpu(), o_ref) and arg2.numel() == 0
 
 
+def test_roi_pool_tiny_and_coinciding_bins():
+    """proposals narrower/shorter than 7 cells (coinciding bins), 1-cell and sub-cell boxes, boxes on the
+    map border: exercises the neighbour-column exchange of the fast kernel"""
+    g = synth.gen(314)
+    N, C, H, W = 2, 8, 40, 48
+    feat = synth.features(N, C, H, W, g, relu=False)
+    R = 600
+    cx = torch.rand(R, generator=g) * W * 8
+    cy = torch.rand(R, generator=g) * H * 8
+    w = torch.rand(R, generator=g) ** 3 * 120 + 0.5           # many boxes of 0..4 cells
+    h = torch.rand(R, generator=g) ** 3 * 120 + 0.5
+    boxes = torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+    rois = torch.cat([torch.randint(0, N, (R, 1), generator=g).float(), boxes], 1)
+    for with_arg in (True, False):
+        out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=with_arg)
+        o_ref, a_ref = oracle.roi_pool(feat, rois, 1 / 8, 7)
+        assert torch.equal(out.cpu(), o_ref)
+        if with_arg:
+            assert torch.equal(arg.cpu(), a_ref)
+    # equal values everywhere: the first index in h-major order must win in every bin
+    flat = torch.ones(1, 4, 30, 40)
+    rois2, _ = synth.rois_from([synth.proposals(300, 240, 320, g)])
+    out, arg = ops.roi_pool(flat.to(DEV), rois2.to(DEV), 1 / 8, 7, with_argmax=True)
+    o_ref, a_ref = oracle.roi_pool(flat, rois2, 1 / 8, 7)
+    assert torch.equal(out.cpu(), o_ref) and torch.equal(arg.cpu(), a_ref)
+
+
 def test_roi_pool_vs_torchvision_cuda_and_golden(golden):
     import torchvision  # noqa: F401
     g = golden("pool")
