@@ -68,3 +68,16 @@ def test_custom_ops_registered_with_fake_impls():
         assert out.shape == (30, 8, 7, 7) and arg.dtype == torch.int32
         out3, _ = torch.ops.wsovod_b200.roi_loop_pool(x, r, 0.125, 7, 7, None, 0.0, True)
         assert out3.shape == (90, 8, 7, 7)
+
+
+def test_apply_deltas_matches_box2box_restatement():
+    """the PyTorch box decode kept outside the kernels == detectron2's Box2BoxTransform (oracle/d2_shim.py)"""
+    from oracle.d2_shim import Box2BoxTransform
+    from wsovod_b200.modeling.roi_heads import apply_deltas
+    g = torch.Generator().manual_seed(3)
+    boxes = torch.rand(200, 4, generator=g) * 300
+    boxes[:, 2:] += boxes[:, :2]
+    deltas = torch.randn(200, 4, generator=g)
+    deltas[:5, 2:] = 50.0                      # hits the log(1000/16) clamp
+    ref = Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).apply_deltas(deltas, boxes)
+    assert torch.equal(apply_deltas(deltas, boxes), ref)

@@ -125,7 +125,8 @@ def test_roi_pool_backward():
     torch.testing.assert_close(x.grad.cpu(), ref, rtol=1e-5, atol=1e-5)   # atomics: order differs
 
 
-@pytest.mark.parametrize("N,C,H,W,R", [(1, 4, 30, 40, 300), (2, 3, 23, 37, 200), (2, 1, 16, 16, 64)])
+@pytest.mark.parametrize("N,C,H,W,R", [(1, 4, 30, 40, 300), (2, 3, 23, 37, 200), (2, 1, 16, 16, 64), (1, 6, 100, 152, 300),
+                                         (2, 16, 60, 80, 500)])
 def test_roi_loop_pool_vs_oracle(N, C, H, W, R):
     feat, rois = _pool_case(N, C, H, W, R, seed=77 + C, relu=True, wild=False)
     out, arg = ops.roi_loop_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7)
@@ -133,6 +134,11 @@ def test_roi_loop_pool_vs_oracle(N, C, H, W, R):
     assert out.shape == (3 * rois.size(0), C, 7, 7)
     assert torch.equal(out.cpu(), o_ref)
     assert torch.equal(arg.cpu(), a_ref)
+    # value-only fast path (what a frozen backbone uses), with the objectness epilogue
+    obj = torch.rand(rois.size(0))
+    out2, arg2 = ops.roi_loop_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, obj.to(DEV), 1.0, with_argmax=False)
+    s3 = torch.cat([obj, obj, obj]) + 1
+    assert arg2.numel() == 0 and torch.equal(out2.cpu(), o_ref * s3.view(-1, 1, 1, 1))
 
 
 @pytest.mark.parametrize("sr,aligned", [(0, False), (0, True), (2, False), (2, True)])

@@ -181,6 +181,62 @@ __global__ void roi_bins7_kernel(const float* __restrict__ rois, int64_t R, int 
   }
 }
 
+// prologue of the ROILoopPool fast path: one thread per (proposal, bin).  bins[2*i] = bin of the ROI's own
+// grid, bins[2*i+1] = bin of the outer (x1.8) box's grid; rects[2*r] = inner (/1.8) box, rects[2*r+1] =
+// the ROI, both as (h_lo | h_hi << 16, w_lo | w_hi << 16) with int16 fields (exclusion tests are strict).
+// Geometry: ROILoopPool_cuda.cu:34-103,144-166, same expressions as roi_prepare_kernel<MODE_LOOP>.
+__global__ void roi_loopbins7_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W, float scale,
+                                     int32_t* __restrict__ bidx, int32_t* __restrict__ counts,
+                                     uint2* __restrict__ bins, uint2* __restrict__ rects) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 49) return;
+  const int64_t r = i / 49;
+  const int bin = (int)(i - r * 49);
+  const int ph = bin / 7, pw = bin - ph * 7;
+  const float* roi = rois + r * 5;
+  const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
+  const float ratio = 1.8f;
+  float rw_ = x2 - x1, rh_ = y2 - y1;
+  float iw = rw_ / ratio, ih = rh_ / ratio;
+  float ow = rw_ * ratio, oh = rh_ * ratio;
+  float irw = rw_ - iw, irh = rh_ - ih;
+  float orw = ow - rw_, orh = oh - rh_;
+  float x1i = x1 + irw / 2, y1i = y1 + irh / 2, x2i = x2 - irw / 2, y2i = y2 - irh / 2;
+  float x1o = x1 - orw / 2, y1o = y1 - orh / 2, x2o = x2 + orw / 2, y2o = y2 + orh / 2;
+  const float xmax = (float)(1.0 * W / scale), ymax = (float)(1.0 * H / scale);
+  x1i = fminf(fmaxf(x1i, 0.f), xmax); y1i = fminf(fmaxf(y1i, 0.f), ymax);
+  x2i = fminf(fmaxf(x2i, 0.f), xmax); y2i = fminf(fmaxf(y2i, 0.f), ymax);
+  x1o = fminf(fmaxf(x1o, 0.f), xmax); y1o = fminf(fmaxf(y1o, 0.f), ymax);
+  x2o = fminf(fmaxf(x2o, 0.f), xmax); y2o = fminf(fmaxf(y2o, 0.f), ymax);
+  auto one = [&](int rsh, int rsw, int reh, int rew) {
+    const float bh = __fdiv_rn((float)max(reh - rsh + 1, 1), 7.f);
+    const float bw = __fdiv_rn((float)max(rew - rsw + 1, 1), 7.f);
+    const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + rsh, 0), H);
+    const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + rsh, 0), H);
+    const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + rsw, 0), W);
+    const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + rsw, 0), W);
+    return make_uint2((uint32_t)hs | ((uint32_t)he << 16), (uint32_t)ws | ((uint32_t)we << 16));
+  };
+  const int rsw = round_i(x1 * scale), rsh = round_i(y1 * scale), rew = round_i(x2 * scale), reh = round_i(y2 * scale);
+  bins[2 * i] = one(rsh, rsw, reh, rew);
+  bins[2 * i + 1] = one(round_i(y1o * scale), round_i(x1o * scale), round_i(y2o * scale), round_i(x2o * scale));
+  if (bin == 0) {
+    auto sat = [](int v) { return (uint32_t)(uint16_t)(int16_t)min(max(v, -32768), 32767); };
+    rects[2 * r] = make_uint2(sat(round_i(y1i * scale)) | (sat(round_i(y2i * scale)) << 16),
+                              sat(round_i(x1i * scale)) | (sat(round_i(x2i * scale)) << 16));
+    rects[2 * r + 1] = make_uint2(sat(rsh) | (sat(reh) << 16), sat(rsw) | (sat(rew) << 16));
+    int b = (int)roi[0];
+    b = min(max(b, 0), N - 1);
+    bidx[r] = b;
+    atomicAdd(&counts[b], 1);
+    if (r > 0) {
+      int pb = (int)rois[(r - 1) * 5];
+      pb = min(max(pb, 0), N - 1);
+      if (pb > b) atomicOr(&counts[N], 1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // prologue 2: stable grouping of proposal ids by image (one CTA per image)
 // ------------------------------------------------------------------------------------------------
@@ -570,6 +626,124 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
   }
 }
 
+// ROILoopPool fast path (values only; argmax requests use the generic kernel): roi | frame | context.
+// Rows are cut into left / middle / right segments against the excluded rectangle, so there is no
+// per-cell predicate and the context scan never loads the excluded interior.  All maxima start at 0
+// ("assum all input is >=0", ROILoopPool_cuda.cu:107-113).
+template <int CB>
+__device__ __forceinline__ void scan_seg(float* acc, uint32_t row, int w0, int w1) {
+  constexpr uint32_t CS = 4u * CB;
+  uint32_t a = row + (uint32_t)w0 * CS;
+#pragma unroll 2
+  for (int w = w0; w < w1; ++w, a += CS) {
+    float f[CB];
+    lds_cell<CB>(a, f);
+#pragma unroll
+    for (int k = 0; k < CB; ++k) acc[k] = fmaxf(acc[k], f[k]);
+  }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, const uint2* __restrict__ bins,
+                                                             const uint2* __restrict__ rects) {
+  using V = typename Vec<CB>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int BINS = 49;
+  constexpr uint32_t CS = 4u * CB;
+  const int H = p.H, W = p.W, HW = H * W;
+  const int bid = blockIdx.x;
+  const int cg = bid % p.CG;
+  const int sidx = (bid / p.CG) % p.S;
+  const int n = bid / (p.CG * p.S);
+  const int c0 = cg * CB;
+  const int nc = min(CB, p.C - c0);
+  int start = 0;
+  for (int m = 0; m < n; ++m) start += __ldg(p.counts + m);
+  const int cnt = __ldg(p.counts + n);
+  const int per = (cnt + p.S - 1) / p.S;
+  const int pos0 = sidx * per;
+  const int nroi = min(cnt, pos0 + per) - pos0;
+  if (nroi <= 0) return;
+  {
+    const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+    V* sp = reinterpret_cast<V*>(smem_raw);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float f[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
+      sp[i] = pack<CB>(f);
+    }
+  }
+  __syncthreads();
+  uint32_t sbase;
+  {
+    unsigned long long s64;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
+    sbase = (uint32_t)s64;
+  }
+  const uint32_t pitch = (uint32_t)W * CS;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = nroi * BINS;
+  const int32_t* order = p.order + start + pos0;
+  const int64_t block_stride = p.R * (int64_t)p.C * BINS;
+  for (int flat = wid * 32 + lane; flat < total; flat += nw * 32) {
+    const int rpos = flat / BINS;
+    const int bin = flat - rpos * BINS;
+    const int r = __ldg(order + rpos);
+    const uint2 ea = __ldg(bins + 2 * ((int64_t)r * BINS + bin));
+    const uint2 eb = __ldg(bins + 2 * ((int64_t)r * BINS + bin) + 1);
+    const uint2 ri = __ldg(rects + 2 * (int64_t)r);
+    const uint2 rr = __ldg(rects + 2 * (int64_t)r + 1);
+    float scale = 1.f;
+    if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
+    float com[CB], mid[CB], ctx[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) { com[k] = 0.f; mid[k] = 0.f; ctx[k] = 0.f; }
+    {  // ROI grid: `com` = cells outside the inner box (the frame), `mid` = cells strictly inside it
+      const int hs = ea.x & 0xffff, he = ea.x >> 16, ws = ea.y & 0xffff, we = ea.y >> 16;
+      const int ish = (int16_t)(ri.x & 0xffff), ieh = (int16_t)(ri.x >> 16);
+      const int isw = (int16_t)(ri.y & 0xffff), iew = (int16_t)(ri.y >> 16);
+      const int l1 = min(we, max(ws, isw + 1));        // [ws, l1) left of / on the inner box's left edge
+      const int r0 = max(l1, min(we, iew));            // [r0, we) on / right of its right edge
+      uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+      for (int h = hs; h < he; ++h, row += pitch) {
+        if (h > ish && h < ieh) {
+          scan_seg<CB>(com, row, ws, l1);
+          scan_seg<CB>(mid, row, l1, r0);
+          scan_seg<CB>(com, row, r0, we);
+        } else {
+          scan_seg<CB>(com, row, ws, we);
+        }
+      }
+    }
+    {  // outer-box grid: cells strictly inside the ROI are excluded (and never loaded)
+      const int hs = eb.x & 0xffff, he = eb.x >> 16, ws = eb.y & 0xffff, we = eb.y >> 16;
+      const int ish = (int16_t)(rr.x & 0xffff), ieh = (int16_t)(rr.x >> 16);
+      const int isw = (int16_t)(rr.y & 0xffff), iew = (int16_t)(rr.y >> 16);
+      const int l1 = min(we, max(ws, isw + 1));
+      const int r0 = max(l1, min(we, iew));
+      uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+      for (int h = hs; h < he; ++h, row += pitch) {
+        if (h > ish && h < ieh) {
+          scan_seg<CB>(ctx, row, ws, l1);
+          scan_seg<CB>(ctx, row, r0, we);
+        } else {
+          scan_seg<CB>(ctx, row, ws, we);
+        }
+      }
+    }
+    const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin;
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+      if (k < nc) {
+        const float vr = fmaxf(com[k], mid[k]);
+        __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(vr, scale) : vr);
+        __stcs(p.output + o + k * BINS + block_stride, p.row_scale ? __fmul_rn(com[k], scale) : com[k]);
+        __stcs(p.output + o + k * BINS + 2 * block_stride, p.row_scale ? __fmul_rn(ctx[k], scale) : ctx[k]);
+      }
+  }
+}
+
 // backward: grad_input[b, c, argmax] += grad_output (ROILoopPool_cuda.cu:206-248)
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
                                     const int32_t* __restrict__ argmax, int64_t total, int64_t R, int N,
@@ -591,7 +765,7 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // host side
 // ------------------------------------------------------------------------------------------------
 struct PoolWs {
-  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; size_t bytes;
+  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; uint2* rects; size_t bytes;
 };
 
 static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
@@ -605,13 +779,17 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
   size_t ew = mode == MODE_LOOP ? 4 * (PH + PW) + 8 : 2 * (PH + PW);
   size_t o_edges = take(mode == MODE_ALIGN ? 0 : sizeof(int16_t) * ew * (size_t)R);
   size_t o_align = take(mode == MODE_ALIGN ? sizeof(float) * 8 * (size_t)R : 0);
-  size_t o_bins = take(mode == MODE_POOL && PH == 7 && PW == 7 ? sizeof(uint2) * 49 * (size_t)R : 0);
+  const bool seven = PH == 7 && PW == 7;
+  size_t o_bins = take(seven && mode == MODE_POOL ? sizeof(uint2) * 49 * (size_t)R
+                       : seven && mode == MODE_LOOP ? sizeof(uint2) * 98 * (size_t)R : 0);
+  size_t o_rects = take(seven && mode == MODE_LOOP ? sizeof(uint2) * 2 * (size_t)R : 0);
   w.counts = (int32_t*)(base + o_counts);
   w.bidx = (int32_t*)(base + o_bidx);
   w.order = (int32_t*)(base + o_order);
   w.edges = (int16_t*)(base + o_edges);
   w.alignp = (float*)(base + o_align);
   w.bins = (uint2*)(base + o_bins);
+  w.rects = (uint2*)(base + o_rects);
   w.bytes = off;
   return w;
 }
@@ -687,6 +865,28 @@ static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, c
   return after_launch();
 }
 
+template <int CB>
+static int launch_loop7(PoolParams& p, const uint2* bins, const uint2* rects, int64_t R, cudaStream_t st) {
+  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float);
+  p.CG = (int)ceil_div(p.C, CB);
+  int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
+  per_sm = std::max(per_sm, 1);
+  const int threads = per_sm == 1 ? 1024 : 512;
+  const int64_t slots = (int64_t)kNumSMs * per_sm;
+  int64_t S = ceil_div(4 * slots, (int64_t)p.N * p.CG);
+  const int64_t avg = std::max<int64_t>(R / std::max(p.N, 1), 1);
+  S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 96)));
+  p.S = (int)S;
+  if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
+  auto kern = roi_loop7_kernel<CB>;
+  if (smem > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(unsigned)((int64_t)p.N * p.S * p.CG), threads, smem, st>>>(p, bins, rects);
+  return after_launch();
+}
+
 static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
                        const float* rois, int64_t R, float scale, int PH, int PW, int sampling_ratio,
                        int aligned, const float* row_scale, float row_scale_bias, float* output,
@@ -709,8 +909,13 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   const size_t plane_bytes = (size_t)H * W * sizeof(float);
   const bool fast7 = mode == MODE_POOL && PH == 7 && PW == 7 && C >= 2 && 2 * plane_bytes <= (size_t)kMaxSmemOptin;
   const bool fast7_cb4 = fast7 && C >= 3 && 4 * plane_bytes <= (size_t)kMaxSmemOptin;
+  // 3-way fast path: values only (an argmax request -- trainable backbone -- takes the generic kernel)
+  const bool loop7 = mode == MODE_LOOP && PH == 7 && PW == 7 && !argmax && C >= 2 && 2 * plane_bytes <= (size_t)kMaxSmemOptin;
+  const bool loop7_cb4 = loop7 && C >= 3 && 4 * plane_bytes <= (size_t)kMaxSmemOptin;
   if (fast7)
     roi_bins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins);
+  else if (loop7)
+    roi_loopbins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins, w.rects);
   else if (mode == MODE_POOL)
     roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, fast7 ? w.bins : nullptr);
   else if (mode == MODE_LOOP)
@@ -729,6 +934,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
   p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+  if (loop7) return loop7_cb4 ? launch_loop7<4>(p, w.bins, w.rects, R, st) : launch_loop7<2>(p, w.bins, w.rects, R, st);
   if (fast7) return fast7_cb4 ? launch_pool7<4>(p, w.bins, R, argmax != nullptr, st)
                              : launch_pool7<2>(p, w.bins, R, argmax != nullptr, st);
   if (mode == MODE_POOL) return argmax ? dispatch_plane<MODE_POOL, true>(p, R, st) : dispatch_plane<MODE_POOL, false>(p, R, st);

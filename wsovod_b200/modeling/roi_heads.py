@@ -8,6 +8,7 @@ wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py (``ObjectMiningOutputLaye
 kernel call here.  The Linear layers (cls/det/bbox_pred, projection) stay PyTorch (out of scope).
 Proposals are duck-typed: anything with ``len()``, ``.proposal_boxes.tensor`` and ``.image_size``.
 """
+import math
 from typing import List, Tuple
 
 import torch
@@ -15,6 +16,27 @@ from torch import nn
 
 from .. import ops
 from ..structures import Boxes, Instances
+
+
+def apply_deltas(deltas, boxes, weights=(10.0, 10.0, 5.0, 5.0), scale_clamp=math.log(1000.0 / 16)):
+    """detectron2 Box2BoxTransform.apply_deltas (call sites fast_rcnn_open_vocabulary.py:987-1017); box
+    decoding is outside the accelerated path and stays plain PyTorch, op for op."""
+    deltas = deltas.float()
+    boxes = boxes.to(deltas.dtype)
+    widths = boxes[:, 2] - boxes[:, 0]
+    heights = boxes[:, 3] - boxes[:, 1]
+    ctr_x = boxes[:, 0] + 0.5 * widths
+    ctr_y = boxes[:, 1] + 0.5 * heights
+    wx, wy, ww, wh = weights
+    dx, dy = deltas[:, 0::4] / wx, deltas[:, 1::4] / wy
+    dw = torch.clamp(deltas[:, 2::4] / ww, max=scale_clamp)
+    dh = torch.clamp(deltas[:, 3::4] / wh, max=scale_clamp)
+    pcx = dx * widths[:, None] + ctr_x[:, None]
+    pcy = dy * heights[:, None] + ctr_y[:, None]
+    pw = torch.exp(dw) * widths[:, None]
+    ph = torch.exp(dh) * heights[:, None]
+    out = torch.stack((pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph), dim=-1)
+    return out.reshape(deltas.shape)
 
 
 def _offsets(proposals, device):
@@ -91,7 +113,8 @@ class InstanceRefinementOutputLayers(nn.Module):
     """Refinement head (fast_rcnn_open_vocabulary.py:621-1058): class_head logits (+ optional bbox_pred)."""
 
     def __init__(self, input_size, num_classes, class_head, test_score_thresh=0.0, test_nms_thresh=0.5,
-                 test_topk_per_image=100, refine_reg=False, box_dim=4, iou_mode=ops.IOU_TV_CUDA):
+                 test_topk_per_image=100, refine_reg=False, box_dim=4, iou_mode=ops.IOU_TV_CUDA,
+                 bbox_reg_weights=(10.0, 10.0, 5.0, 5.0)):
         super().__init__()
         self.num_classes = num_classes
         self.cls = class_head
@@ -103,6 +126,7 @@ class InstanceRefinementOutputLayers(nn.Module):
         self.test_score_thresh, self.test_nms_thresh = test_score_thresh, test_nms_thresh
         self.test_topk_per_image = test_topk_per_image
         self.iou_mode = iou_mode
+        self.bbox_reg_weights = bbox_reg_weights
 
     def forward(self, x, classifier=None, append_background=True):
         if x.dim() > 2:
@@ -123,15 +147,32 @@ class InstanceRefinementOutputLayers(nn.Module):
         return (probs / len(predictions)).split([len(p) for p in proposals], dim=0)       # :1052-1058
 
     def predict_boxes(self, predictions, proposals):
-        return [p.proposal_boxes.tensor for p in proposals]    # class-agnostic, deltas applied by the caller
+        """:964-985 -- class-agnostic boxes: apply_deltas(proposal_deltas, proposal_boxes)"""
+        if not len(proposals):
+            return []
+        _, deltas = predictions
+        boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        return apply_deltas(deltas, boxes, self.bbox_reg_weights).split([len(p) for p in proposals])
+
+    def predict_boxes_K(self, predictions, proposals):
+        """:987-1017 -- mean of the heads' deltas, then apply_deltas"""
+        if not len(proposals):
+            return []
+        deltas = torch.zeros_like(predictions[0][1])
+        for _, d in predictions:
+            deltas += d
+        deltas = deltas / len(predictions)
+        boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        return apply_deltas(deltas, boxes, self.bbox_reg_weights).split([len(p) for p in proposals])
 
     def inference(self, predictions, proposals):
         """:894-924 -- predictions: (scores, deltas) or a list of them (one per refinement head)"""
         if isinstance(predictions[0], tuple):
             scores = self.predict_probs_K(predictions, proposals)
+            boxes = self.predict_boxes_K(predictions, proposals)
         else:
             scores = self.predict_probs(predictions, proposals)
-        boxes = self.predict_boxes(predictions, proposals)
+            boxes = self.predict_boxes(predictions, proposals)
         shapes = [p.image_size for p in proposals]
         return fast_rcnn_inference(boxes, scores, shapes, self.test_score_thresh, self.test_nms_thresh,
                                    self.test_topk_per_image, iou_mode=self.iou_mode)
