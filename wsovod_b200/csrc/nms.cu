@@ -165,6 +165,7 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
   }
 }
 
+constexpr int kRunsPerThread = 4;      // top-k merge handles K <= 4 * kNmsThreads classes
 constexpr int kSelectBins = 4096;     // histogram over the 12 leading key bits
 constexpr int kSelectCap = 2048;      // selected-prefix capacity (keys) == histogram storage (16 KB)
 constexpr int kSelectTarget = 1024;   // aim: at least this many best candidates in the prefix
@@ -186,7 +187,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
     const float* __restrict__ probs, const int64_t* __restrict__ offsets, const uint8_t* __restrict__ valid,
     const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap,
-    int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride) {
+    int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
+    int2* __restrict__ runs) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ FirstSlots slots;
   __shared__ int s_n, s_base, s_sel, s_bstar, s_m;
@@ -209,7 +211,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
   }
   __syncthreads();
   const int nc = s_n;
-  if (nc == 0) return;
+  if (nc == 0) {
+    if (threadIdx.x == 0) runs[(int64_t)n * K + k] = make_int2(0, 0);
+    return;
+  }
 
   // Candidate list for the greedy pass.  A class rarely needs more than its best ~1000 candidates to
   // collect `limit` survivors, so for long columns the top of the list is selected exactly with a
@@ -321,7 +326,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
     __syncthreads();
   }
   __syncthreads();
-  if (threadIdx.x == 0) s_base = atomicAdd(&img_cnt[n], kept);
+  if (threadIdx.x == 0) {
+    s_base = atomicAdd(&img_cnt[n], kept);
+    runs[(int64_t)n * K + k] = make_int2(s_base, kept);      // this class's survivors: a score-descending run
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
     const unsigned long long key = kkey[i];
@@ -335,7 +343,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_class_kernel(
 __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
     const int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
     const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk, int sort_cap,
-    float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
+    const int2* __restrict__ runs, float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
     int64_t* __restrict__ det_rows, int64_t* __restrict__ det_count) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ ArgMinSlots slots;
@@ -344,7 +352,48 @@ __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
   const int cnt = img_cnt[n];
   unsigned long long* keys = img_kept + (int64_t)n * kept_stride;
   int got;
-  if (sort_cap > 0) {
+  if (runs != nullptr) {
+    // K-way merge: every class left a score-descending run; thread t owns runs t, t+T, ... and offers
+    // the best head among them, a block arg-min picks the winner, its owner advances that run.
+    const int2* rn = runs + (int64_t)n * K;
+    // the head of each owned run and its successor live in registers: only the winner touches memory,
+    // and it reloads two elements ahead, so no round waits on L2
+    int pos[kRunsPerThread], len[kRunsPerThread], off[kRunsPerThread];
+    unsigned long long head[kRunsPerThread], next[kRunsPerThread];
+#pragma unroll
+    for (int j = 0; j < kRunsPerThread; ++j) {
+      const int c = threadIdx.x + j * kNmsThreads;
+      const int2 v = c < K ? rn[c] : make_int2(0, 0);
+      off[j] = v.x; len[j] = v.y; pos[j] = 0;
+      head[j] = len[j] > 0 ? keys[off[j]] : kDead;
+      next[j] = len[j] > 1 ? keys[off[j] + 1] : kDead;
+    }
+    got = 0;
+    int buf = 0;
+    for (int i = 0; i < topk; ++i) {
+      unsigned long long best = kDead;
+      int bj = -1;
+#pragma unroll
+      for (int j = 0; j < kRunsPerThread; ++j)
+        if (head[j] < best) { best = head[j]; bj = j; }
+      unsigned long long wkey = best;
+      int wtid = bj >= 0 ? (int)threadIdx.x : -1;
+      block_argmin(wkey, wtid, slots, buf);
+      buf ^= 1;
+      if (wtid < 0) break;
+      if (wtid == (int)threadIdx.x) {
+#pragma unroll
+        for (int j = 0; j < kRunsPerThread; ++j)
+          if (j == bj) {
+            ++pos[j];
+            head[j] = next[j];
+            next[j] = pos[j] + 1 < len[j] ? keys[off[j] + pos[j] + 1] : kDead;
+          }
+        sel[i] = wkey;
+      }
+      ++got;
+    }
+  } else if (sort_cap > 0) {
     // the image's kept list fits shared memory: one bitonic sort, the first topk keys are the answer
     unsigned long long* sk = sel + topk;
     int npad = 2;
@@ -532,7 +581,7 @@ static NmsWs nms_plan(int64_t M, int64_t G) {
   return w;
 }
 
-struct DetWs { size_t valid, cboxes, img_cnt, img_kept, bytes; int64_t kept_stride; };
+struct DetWs { size_t valid, cboxes, img_cnt, img_kept, runs, bytes; int64_t kept_stride; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
   size_t o = 0;
@@ -542,6 +591,7 @@ static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   w.cboxes = take(sizeof(float4) * (size_t)M);
   w.img_cnt = take(sizeof(int32_t) * (size_t)(N + 1));
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
+  w.runs = take(sizeof(int2) * (size_t)(N * std::max<int64_t>(K, 1)));
   w.bytes = o;
   return w;
 }
@@ -658,6 +708,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   float4* cboxes = (float4*)(ws + w.cboxes);
   int32_t* img_cnt = (int32_t*)(ws + w.img_cnt);
   unsigned long long* img_kept = (unsigned long long*)(ws + w.img_kept);
+  int2* runs = (int2*)(ws + w.runs);
   cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;
   int rc;
@@ -671,7 +722,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     }
     dim3 grid((unsigned)K, (unsigned)N);
     kern<<<grid, kNmsThreads, smem, st>>>(probs, offsets, valid, cboxes, (int)K, score_thresh,
-                                         cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, img_cnt, img_kept, w.kept_stride);
+                                         cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, img_cnt, img_kept, w.kept_stride, runs);
     if ((rc = after_launch())) return rc;
   }
   // final ordering: sort the image's kept list in shared memory when it fits (K * topk <= 16384 keys)
@@ -684,7 +735,8 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     if (e != cudaSuccess) return (int)e;
   }
   det_topk_kernel<<<(unsigned)N, kNmsThreads, tsmem, st>>>(
-      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap, det_boxes,
-      det_scores, det_classes, det_rows, det_count);
+      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap,
+      (M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads) ? runs : nullptr, det_boxes, det_scores, det_classes,
+      det_rows, det_count);
   return after_launch();
 }
