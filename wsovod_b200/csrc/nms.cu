@@ -168,7 +168,7 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
 constexpr int kRunsPerThread = 4;      // top-k merge handles K <= 4 * kNmsThreads classes
 constexpr int kSelectBins = 4096;     // histogram over the 12 leading key bits
 constexpr int kSelectCap = 2048;      // selected-prefix capacity (keys) == histogram storage (16 KB)
-constexpr int kSelectTarget = 1024;   // aim: at least this many best candidates in the prefix
+constexpr int kSelectTarget = 512;    // aim: at least this many best candidates in the prefix
 constexpr int kSelectMin = 2048;      // columns shorter than this are simply sorted
 
 struct FirstSlots {     // "lowest alive candidate" of the current chunk: block-wide atomicMin + per-warp box
