@@ -38,9 +38,10 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+        hdrs.append(os.path.join(os.path.dirname(HERE), "include", "wsovod_b200.h"))
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "common.cuh")),
-                os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "wsovod_b200.h"))):
+                [os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
             continue
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -151,7 +151,6 @@ AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward
   w.what = take(sizeof(float) * (size_t)(w.Kp * w.Dp));            // normalised text matrix
   w.wt = take(backward ? sizeof(float) * (size_t)(K * D) : 0);     // its transpose (backward)
   w.dy = take(backward ? sizeof(float) * (size_t)(M * D) : 0);     // backward scratch
-  w.tmaps = take(512);                                             // two CUtensorMap (TF32 path)
   w.rowstat = take(precision == WSOVOD_B200_ALIGN_TF32 && K + 1 > 256 ? sizeof(float) * 2 * (size_t)M : 0);
   w.bytes = o;
   return w;

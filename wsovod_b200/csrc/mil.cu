@@ -215,9 +215,7 @@ WSOVOD_API int wsovod_b200_mil_fwd(const float* cls, const float* det, const int
   float2* stats = (float2*)(ws + pl.off_stats);
   float* sums = (float*)(ws + pl.off_sums);
   dim3 grid(pl.chunks, (unsigned)N);
-  const int KT = (int)std::min<int64_t>(K, kMilThreads);
   mil_colstats_kernel<<<grid, kMilThreads, sizeof(float2) * kMilThreads, st>>>(det, offsets, (int)K, pl.chunks, stats);
-  (void)KT;
   if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)K * (2 + kMilWarps);
   if (smem > 32 * 1024) {

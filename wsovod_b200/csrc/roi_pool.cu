@@ -835,7 +835,10 @@ static int dispatch_plane(PoolParams& p, int64_t R, cudaStream_t st) {
   p.S = (int)S;
   if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
   switch (cb) {
-    case 4: return launch_plane<4, MODE == MODE_LOOP ? MODE_POOL : MODE, true, ARG>(p, threads, smem, st);
+    case 4:
+      // never selected for MODE_LOOP (cb <= 2 there); instantiate the pooling flavour to keep ptxas quiet
+      if (MODE == MODE_LOOP) return WSOVOD_B200_EINVAL;
+      return launch_plane<4, MODE == MODE_LOOP ? MODE_POOL : MODE, true, ARG>(p, threads, smem, st);
     case 2: return launch_plane<2, MODE, true, ARG>(p, threads, smem, st);
     case 1: return launch_plane<1, MODE, true, ARG>(p, threads, smem, st);
     default: return launch_plane<1, MODE, false, ARG>(p, 512, 0, st);
