@@ -386,3 +386,72 @@ def test_detections_prefix_fallback_and_long_columns(mode):
         assert torch.equal(r[k].cpu(), o[k]), k
     # survivors of class 0 beyond the cluster only exist if the full column was processed
     assert int(o["det_count"][0]) == 100 and (o["det_classes"][0] == 0).sum() > 50
+
+
+# ------------------------------------------------------------------------------ (1) block-max fast path
+def _pool_scan(feat, rois, scale, **kw):
+    """the plain scan kernels (the block-max path switched off for one call)"""
+    import os
+    os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+    try:
+        return ops.roi_pool(feat, rois, scale, 7, with_argmax=False, **kw)[0]
+    finally:
+        del os.environ["WSOVOD_B200_POOL_SCAN"]
+
+
+@pytest.mark.parametrize("N,C,H,W,R,seed", [(2, 9, 60, 80, 900, 1), (1, 3, 86, 128, 1500, 2), (3, 6, 100, 152, 700, 3),
+                                             (1, 2, 150, 180, 400, 4), (2, 1, 7, 5, 300, 5), (1, 4, 1, 1, 50, 6),
+                                             (1, 5, 117, 120, 300, 7)])
+def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
+    """values-only 7x7 pooling through the block-max planes (roi_pool_pyr.cu): every (kh, kw) phase, the
+    direct-scan fallback phase (whole-map proposals on big maps), border-clipped bins, NaN / -inf cells,
+    proposals in arbitrary batch order -- bit-exact against the oracle and against the scan kernels."""
+    g = synth.gen(900 + seed)
+    feat = synth.features(N, C, H, W, g, relu=False)
+    flat = feat.view(-1)
+    idx = torch.randint(0, flat.numel(), (max(flat.numel() // 50, 1),), generator=g)
+    flat[idx[::2]] = float("nan")
+    flat[idx[1::2]] = float("-inf")
+    boxes = []
+    for _ in range(N):
+        b = synth.proposals(R, H * 8, W * 8, g)
+        k = R // 8
+        b[:k, :2] = torch.rand(k, 2, generator=g) * 40 - 20        # whole-map and beyond
+        b[:k, 2] = W * 8 - torch.rand(k, generator=g) * 40 + 20
+        b[:k, 3] = H * 8 - torch.rand(k, generator=g) * 40 + 20
+        b[k:2 * k] += torch.randn(k, 4, generator=g) * 150          # out-of-image, inverted
+        b[2 * k:3 * k] = (b[2 * k:3 * k] / 8).round() * 8           # integer cell grid
+        boxes.append(b)
+    rois, _ = synth.rois_from(boxes)
+    rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    obj = torch.rand(rois.size(0), generator=g)
+    ref, _ = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
+    assert arg.numel() == 0
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(_pool_scan(feat.to(DEV), rois.to(DEV), 1 / 8), out)
+    out_s, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
+                            with_argmax=False)
+    fin = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref))
+    sc = fin * (obj + 1).view(-1, 1, 1, 1)
+    got = out_s.cpu()
+    assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
+
+
+def test_roi_pool_blockmax_empty_images_and_single_class():
+    """images without proposals, one proposal only, all proposals in one (kh, kw) class"""
+    g = synth.gen(77)
+    feat = synth.features(4, 8, 40, 56, g, relu=False)
+    b = synth.proposals(200, 320, 448, g)
+    rois = torch.cat([torch.full((200, 1), 2.0), b], 1)             # images 0, 1, 3 stay empty
+    ref, _ = oracle.roi_pool(feat, rois, 1 / 8, 7)
+    out, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
+    assert torch.equal(out.cpu(), ref)
+    one = rois[:1].contiguous()
+    ref, _ = oracle.roi_pool(feat, one, 1 / 8, 7)
+    out, _ = ops.roi_pool(feat.to(DEV), one.to(DEV), 1 / 8, 7, with_argmax=False)
+    assert torch.equal(out.cpu(), ref)
+    same = torch.tensor([[1.0, 64.0, 64.0, 64.0 + 8 * 27, 64.0 + 8 * 20]]).repeat(300, 1)   # 28 x 21 cells
+    ref, _ = oracle.roi_pool(feat, same, 1 / 8, 7)
+    out, _ = ops.roi_pool(feat.to(DEV), same.to(DEV), 1 / 8, 7, with_argmax=False)
+    assert torch.equal(out.cpu(), ref)

@@ -1,0 +1,43 @@
+"""Pooling-only timing (values-only max-pool; block-max path vs the scan kernels).
+Usage: python tools/kbench_pool.py [c1 c2 c5 ...]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wsovod_b200 import ops, synth  # noqa: E402
+from tools.kbench import timeit  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def main():
+    names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["c2"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for name in names:
+        w = synth.workload(name)
+        N, C, H, W, R = (w[k] for k in "NCHWR")
+        feat, rois, obj = w["features"].to(DEV), w["rois"].to(DEV), w["objectness"].to(DEV)
+        out_bytes = N * R * C * 49 * 4
+        res = {"config": name}
+        for tag, env in (("blockmax", None), ("scan", "1")):
+            if env:
+                os.environ["WSOVOD_B200_POOL_SCAN"] = env
+            else:
+                os.environ.pop("WSOVOD_B200_POOL_SCAN", None)
+            ms = timeit(lambda: ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False), iters=15, flush=flush)
+            res[f"{tag}_ms"] = round(ms, 4)
+            res[f"{tag}_GBs"] = round((out_bytes + feat.numel() * 4) / ms / 1e6, 1)
+        os.environ.pop("WSOVOD_B200_POOL_SCAN", None)
+        a = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
+        os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+        b = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
+        os.environ.pop("WSOVOD_B200_POOL_SCAN", None)
+        res["equal"] = bool(torch.equal(a, b))
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,10 +15,18 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace wsovod {
 
 enum { MODE_POOL = 0, MODE_LOOP = 1, MODE_ALIGN = 2 };
+
+// roi_pool_pyr.cu: block-max fast path (7x7, values only)
+size_t pool7_pyr_workspace(int64_t N, int64_t R);
+int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R);
+int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, const float* rois, int64_t R,
+              float scale, const float* row_scale, float row_scale_bias, float* output, void* workspace,
+              cudaStream_t st);
 
 struct PoolParams {
   const float* input;
@@ -764,8 +772,15 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the plain scan kernels (read per call, no state kept)
+static bool pool_scan_forced() {
+  const char* v = getenv("WSOVOD_B200_POOL_SCAN");
+  return v && v[0] == '1';
+}
+
 struct PoolWs {
-  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; uint2* rects; size_t bytes;
+  int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; uint2* rects;
+  void* pyr; size_t bytes;
 };
 
 static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
@@ -783,6 +798,7 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
   size_t o_bins = take(seven && mode == MODE_POOL ? sizeof(uint2) * 49 * (size_t)R
                        : seven && mode == MODE_LOOP ? sizeof(uint2) * 98 * (size_t)R : 0);
   size_t o_rects = take(seven && mode == MODE_LOOP ? sizeof(uint2) * 2 * (size_t)R : 0);
+  size_t o_pyr = take(seven && mode == MODE_POOL ? pool7_pyr_workspace(N, R) : 0);
   w.counts = (int32_t*)(base + o_counts);
   w.bidx = (int32_t*)(base + o_bidx);
   w.order = (int32_t*)(base + o_order);
@@ -790,6 +806,7 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
   w.alignp = (float*)(base + o_align);
   w.bins = (uint2*)(base + o_bins);
   w.rects = (uint2*)(base + o_rects);
+  w.pyr = base + o_pyr;
   w.bytes = off;
   return w;
 }
@@ -904,6 +921,9 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   if (!workspace || ws_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
   w = carve(workspace, mode, N, R, PH, PW);
   cudaStream_t st = (cudaStream_t)stream;
+  // values-only 7x7 max-pool: block-max planes (roi_pool_pyr.cu) when the padded plane fits shared memory
+  if (mode == MODE_POOL && PH == 7 && PW == 7 && !argmax && !pool_scan_forced() && pool7_pyr_cb(C, H, W, R))
+    return pool7_pyr(input, N, C, H, W, rois, R, scale, row_scale, row_scale_bias, output, w.pyr, st);
   cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;
   const int pt = 128;
