@@ -44,7 +44,8 @@ int main(int argc, char** argv) {
     if (it % 11 == 0) src[(size_t)(U(rng) * H * W) % src.size()] = -INFINITY;
     Plane P;
     P.H = H; P.W = W; P.WP = W + kPad; P.ncell = (H + kPad) * P.WP;
-    P.d.assign((size_t)(H + kPad + kTailRows) * P.WP, -FLT_MAX);
+    P.d.assign((size_t)(H + kPad + kTailRows) * P.WP + 1, -FLT_MAX);
+    P.d[zero_cell(H, W)] = 0.f;   // empty bins point here
     const int R = 120;
     const float iw = W / scale, ih = H / scale;
     std::vector<float> rois((size_t)R * 4);
@@ -92,13 +93,15 @@ int main(int argc, char** argv) {
             if (phase == PH_FALLBACK) { ++fallback; continue; }
             const uint32_t d = bin_desc(x1, y1, x2, y2, scale, H, W, phase, ph, pw);
             float got;
-            if (d >> 31) got = 0.f;
-            else {
+            if (((d >> 24) & 63) != (uint32_t)(ph * 7 + pw)) { printf("bin bits broken\n"); return 1; }
+            {
               got = -FLT_MAX;
               const int cell = d & 0xffff, lh = (d >> 16) & 15, lw = (d >> 20) & 15;
               for (int i = 0; i < ch; ++i)
                 for (int j = 0; j < cw; ++j) {
                   const int ro = i * kh < lh ? i * kh : lh, co = j * kw < lw ? j * kw : lw;
+                  const bool need = (i == 0 || (i - 1) * kh < lh) && (j == 0 || (j - 1) * kw < lw);
+                  if (!need) continue;   // the kernel skips blocks that repeat the previous one
                   got = fmaxf(got, P.d[cell + ro * P.WP + co]);
                   ++loads;
                 }

@@ -126,32 +126,42 @@ WS_HD void bin_blocks(int s, int e, int k, int L, int& pos0, int& last) {
 }
 
 // per-proposal key (classification result)
-//   bits 0-3 phase | 4-5 ch-1 | 6-7 cw-1
+//   bits 0-3 phase | 4-5 ch-1 | 6-7 cw-1 | 8 lanes walk the bins column-major
+// Column-major lane order when the bins are wider than tall: the 8 lanes of a shared-memory phase then
+// differ in their row (3 bank groups apart per row with the odd pitch) instead of in a column stride
+// that is likely to repeat bank groups (simulated: 23.9 -> 21.9 wavefronts per 32 bins).
+constexpr uint32_t kKeyTransposed = 1u << 8;
 WS_HD uint32_t proposal_key(float x1, float y1, float x2, float y2, float scale, int H, int W) {
   const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);
   int kh, ch, kw, cw;
   axis_class(ah, H, kh, ch);
   axis_class(aw, W, kw, cw);
   if (ch > kMaxLoads || cw > kMaxLoads) return (uint32_t)PH_FALLBACK;
-  return (uint32_t)phase_of(kh, kw) | ((uint32_t)(ch - 1) << 4) | ((uint32_t)(cw - 1) << 6);
+  return (uint32_t)phase_of(kh, kw) | ((uint32_t)(ch - 1) << 4) | ((uint32_t)(cw - 1) << 6) |
+         (aw.bin > ah.bin ? kKeyTransposed : 0u);
 }
+// output bin served by lane slot q (0..48) of a proposal
+WS_HD int slot_bin(uint32_t key, int q) { return (key & kKeyTransposed) ? (q % 7) * 7 + q / 7 : q; }
 WS_HD int key_phase(uint32_t key) { return (int)(key & 15u); }
 WS_HD int key_bucket(uint32_t key) { return (int)((key & 15u) * 16u + ((key >> 4) & 15u)); }
 
 // 32-bit bin descriptor: bits 0-15 cell index of the first block in the padded plane,
-//   16-19 rows to the last block, 20-23 columns to the last block, 31 empty bin
+//   16-19 rows to the last block, 20-23 columns to the last block, 24-29 output bin, 31 empty bin.
+// An empty bin points at the all-zero cell behind the plane, so the kernel needs no special case.
 constexpr uint32_t kDescEmpty = 0x80000000u;
+WS_HD int zero_cell(int H, int W) { return (H + kPad + kTailRows) * (W + kPad); }
 WS_HD uint32_t bin_desc(float x1, float y1, float x2, float y2, float scale, int H, int W, int phase, int ph, int pw) {
   const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);
   int hs, he, ws, we;
   bin_edges(ah, ph, H, hs, he);
   bin_edges(aw, pw, W, ws, we);
-  if (he <= hs || we <= ws) return kDescEmpty;
+  const uint32_t binbits = (uint32_t)(ph * 7 + pw) << 24;
+  if (he <= hs || we <= ws) return kDescEmpty | binbits | (uint32_t)zero_cell(H, W);
   int p0h, lh, p0w, lw;
   bin_blocks(hs, he, phase_kh(phase), H, p0h, lh);
   bin_blocks(ws, we, phase_kw(phase), W, p0w, lw);
   const int cell = (p0h + kPad) * (W + kPad) + (p0w + kPad);
-  return (uint32_t)cell | ((uint32_t)lh << 16) | ((uint32_t)lw << 20);
+  return (uint32_t)cell | ((uint32_t)lh << 16) | ((uint32_t)lw << 20) | binbits;
 }
 
 }  // namespace pyr

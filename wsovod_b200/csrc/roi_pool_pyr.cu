@@ -20,12 +20,12 @@ using namespace pyr;
 struct PyrWs {
   int32_t* hist;        // [N, kBuckets]
   int32_t* img_start;   // [N + 1]   first sorted position of each image
-  int32_t* phase_off;   // [N, kPhases + 1] phase boundaries (positions relative to the image start)
+  int32_t* bucket_off;  // [N, kBuckets + 1] bucket boundaries (positions relative to the image start)
   int32_t* bidx;        // [R]
   uint32_t* pkey;       // [R]
   int32_t* order;       // [R]   proposal id at each sorted position
-  uint32_t* pinfo;      // [R]   proposal id | (ch-1) << 26 | (cw-1) << 28 at each sorted position
-  uint32_t* desc;       // [R, 49] bin descriptors in sorted position order
+  uint2* pinfo;         // [R]   (proposal id, bits of row_scale + bias) at each sorted position
+  uint32_t* desc;       // [R, 49] bin descriptors in sorted position / lane slot order
   size_t bytes;
 };
 
@@ -36,11 +36,11 @@ static PyrWs pyr_carve(void* ws, int64_t N, int64_t R) {
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return base + o; };
   w.hist = (int32_t*)take(sizeof(int32_t) * (size_t)N * kBuckets);
   w.img_start = (int32_t*)take(sizeof(int32_t) * (size_t)(N + 1));
-  w.phase_off = (int32_t*)take(sizeof(int32_t) * (size_t)N * (kPhases + 1));
+  w.bucket_off = (int32_t*)take(sizeof(int32_t) * (size_t)N * (kBuckets + 1));
   w.bidx = (int32_t*)take(sizeof(int32_t) * (size_t)R);
   w.pkey = (uint32_t*)take(sizeof(uint32_t) * (size_t)R);
   w.order = (int32_t*)take(sizeof(int32_t) * (size_t)R);
-  w.pinfo = (uint32_t*)take(sizeof(uint32_t) * (size_t)R);
+  w.pinfo = (uint2*)take(sizeof(uint2) * (size_t)R);
   w.desc = (uint32_t*)take(sizeof(uint32_t) * (size_t)R * 49);
   w.bytes = off;
   return w;
@@ -89,27 +89,25 @@ __global__ void pyr_scan_kernel(const int32_t* __restrict__ hist, int N, int32_t
   }
 }
 
-// one CTA per image: bucket offsets, phase boundaries, scatter of proposal ids.  The order inside a
-// bucket is whatever the shared-memory atomics give: every output element is written exactly once
-// from position-independent data, so the result does not depend on it.
+// one CTA per image: bucket offsets and scatter of proposal ids.  The order inside a bucket is whatever
+// the shared-memory atomics give: every output element is written exactly once from
+// position-independent data, so the result does not depend on it.
 __global__ void pyr_order_kernel(const int32_t* __restrict__ bidx, const uint32_t* __restrict__ pkey,
                                  const int32_t* __restrict__ hist, const int32_t* __restrict__ img_start,
-                                 int64_t R, int32_t* __restrict__ order, int32_t* __restrict__ phase_off) {
+                                 int64_t R, int32_t* __restrict__ order, int32_t* __restrict__ bucket_off) {
   __shared__ int s_cur[kBuckets];
   const int n = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
     int run = 0;
     for (int k = 0; k < kBuckets; ++k) {
-      if ((k & 15) == 0) phase_off[n * (kPhases + 1) + (k >> 4)] = run;
+      bucket_off[n * (kBuckets + 1) + k] = run;
       s_cur[k] = run;
       run += hist[(int64_t)n * kBuckets + k];
     }
-    phase_off[n * (kPhases + 1) + kPhases] = run;
+    bucket_off[n * (kBuckets + 1) + kBuckets] = run;
   }
   __syncthreads();
   const int base = img_start[n];
-  // rois usually arrive grouped by image: only scan the range that can hold this image's rows when the
-  // grouping is intact is not knowable here, so scan everything (R reads per image, trivial)
   for (int64_t r = tid; r < R; r += blockDim.x) {
     if (bidx[r] != n) continue;
     const int pos = atomicAdd(&s_cur[key_bucket(pkey[r])], 1);
@@ -117,20 +115,26 @@ __global__ void pyr_order_kernel(const int32_t* __restrict__ bidx, const uint32_
   }
 }
 
+// one thread per (sorted position, lane slot): the descriptor of the bin that slot serves
 __global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H, int W, float scale,
                                 const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
-                                uint32_t* __restrict__ pinfo, uint32_t* __restrict__ desc) {
+                                const float* __restrict__ row_scale, float row_scale_bias,
+                                uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 49) return;
   const int64_t gpos = i / 49;
-  const int bin = (int)(i - gpos * 49);
-  const int ph = bin / 7, pw = bin - ph * 7;
+  const int q = (int)(i - gpos * 49);
   const int r = order[gpos];
   const uint32_t key = pkey[r];
+  const int bin = slot_bin(key, q);
+  const int ph = bin / 7, pw = bin - ph * 7;
   const float* roi = rois + (int64_t)r * 5;
   const int phase = key_phase(key);
   desc[i] = phase == PH_FALLBACK ? 0u : bin_desc(roi[1], roi[2], roi[3], roi[4], scale, H, W, phase, ph, pw);
-  if (bin == 0) pinfo[gpos] = (uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28);
+  if (q == 0) {
+    const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
+    pinfo[gpos] = make_uint2((uint32_t)r, __float_as_uint(sc));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,21 +143,15 @@ __global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H
 struct PyrParams {
   const float* input;
   const float* rois;
-  const float* row_scale;
-  float row_scale_bias;
   float scale;
   float* output;
   const int32_t* img_start;
-  const int32_t* phase_off;
-  const uint32_t* pinfo;
+  const int32_t* bucket_off;
+  const uint2* pinfo;
   const uint32_t* desc;
   int32_t N, C, H, W;
   int32_t CG, S;
 };
-
-template <int CB> struct PVec;
-template <> struct PVec<4> { using T = float4; };
-template <> struct PVec<2> { using T = float2; };
 
 template <int CB> __device__ __forceinline__ void p_lds(uint32_t addr, float* f);
 template <> __device__ __forceinline__ void p_lds<4>(uint32_t addr, float* f) {
@@ -174,7 +172,7 @@ template <> __device__ __forceinline__ void p_sts<2>(uint32_t addr, const float*
 // (2: block 2x1), in the padded layout; pad cells and absent channels hold the identity -FLT_MAX.
 template <int CB>
 __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W,
-                                          int mode) {
+                                       int mode) {
   constexpr uint32_t CS = 4u * CB;
   const int WP = W + kPad, ncell = (H + kPad) * WP, HW = H * W;
   for (int idx = threadIdx.x; idx < ncell; idx += blockDim.x) {
@@ -234,6 +232,62 @@ __device__ __noinline__ void pyr_double(uint32_t sbase, int ncell, int stride) {
   __syncthreads();
 }
 
+// One bucket slice = `total` lane slots (49 per proposal) whose proposals all need CH x CW blocks per bin.
+// Per pass a lane reads one descriptor word (coalesced) and its proposal's (id, scale) pair, both
+// fetched one pass ahead, issues up to CH*CW LDS (a block is skipped where it would repeat the
+// previous one: the bin is not larger than the blocks before it) and stores CB scalars.
+template <int CB, int CH, int CW, bool FULL>
+__device__ __forceinline__ void pyr_run(uint32_t sbase, uint32_t pitch, uint32_t khp, uint32_t kwb,
+                                        const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
+                                        int total, float* __restrict__ outc, uint32_t c49, int nc, int flat0,
+                                        int stride) {
+  constexpr uint32_t CS = 4u * CB;
+  int f = flat0;
+  uint32_t d_n = 0;
+  uint2 pi_n = make_uint2(0u, 0u);
+  if (f < total) {
+    d_n = __ldg(dsc + f);
+    pi_n = __ldg(pin + (uint32_t)f / 49u);
+  }
+  while (f < total) {
+    const uint32_t d = d_n;
+    const uint2 pi = pi_n;
+    const int fn = f + stride;
+    if (fn < total) {
+      d_n = __ldg(dsc + fn);
+      pi_n = __ldg(pin + (uint32_t)fn / 49u);
+    }
+    const uint32_t a0 = sbase + (d & 0xffffu) * CS;
+    const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * CS;
+    // the plane holds no NaN / -inf (pyr_stage clamps at -FLT_MAX), so the first block seeds the maximum
+    float m[CB];
+    p_lds<CB>(a0, m);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
+      const bool ni = i == 0 || (uint32_t)(i - 1) * khp < lhp;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        if (i == 0 && j == 0) continue;
+        const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
+        const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
+        if (ni && nj) {
+          float v[CB];
+          p_lds<CB>(a0 + ro + co, v);
+#pragma unroll
+          for (int k = 0; k < CB; ++k) m[k] = fmaxf(m[k], v[k]);
+        }
+      }
+    }
+    const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
+    float* o = outc + (size_t)pi.x * c49 + ((d >> 24) & 63u);
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+      if (FULL || k < nc) __stcs(o + k * 49, __fmul_rn(m[k], sc));
+    f = fn;
+  }
+}
+
 template <int CB>
 __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -256,23 +310,31 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  {  // identity tail rows (never written again)
+  {  // identity tail rows and the all-zero cell empty bins point at (never written again)
     float id[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) id[k] = -FLT_MAX;
     for (int i = ncell + (int)threadIdx.x; i < ntot; i += blockDim.x) p_sts<CB>(sbase + (uint32_t)i * CS, id);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < CB; ++k) id[k] = 0.f;
+      p_sts<CB>(sbase + (uint32_t)ntot * CS, id);
+    }
   }
   const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+  float* outc = p.output + (size_t)c0 * BINS;
+  const uint32_t c49 = (uint32_t)p.C * BINS;
   const uint32_t pitch = (uint32_t)WP * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int stride = nw * 32;
-  const int32_t* poff = p.phase_off + n * (kPhases + 1);
+  const int flat0 = wid * 32 + lane;
+  const int32_t* boff = p.bucket_off + n * (kBuckets + 1);
 
   for (int phase = 0; phase < kPhases; ++phase) {
-    const int lo = __ldg(poff + phase), hi = __ldg(poff + phase + 1);
-    const int rem = __ldg(poff + chain_end(phase) + 1) - lo;   // proposals left in this chain
+    const int plo = __ldg(boff + phase * 16);
+    const int rem = __ldg(boff + (chain_end(phase) + 1) * 16) - plo;   // proposals left in this chain
     if (rem > 0 && phase != PH_FALLBACK) {
-      __syncthreads();                                         // everyone is done reading the old plane
+      __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
         case PH_11: pyr_stage<CB>(sbase, src, nc, H, W, 0); __syncthreads(); break;
         case PH_21: pyr_double<CB>(sbase, ncell, WP); break;
@@ -283,75 +345,51 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         case PH_14: pyr_double<CB>(sbase, ncell, 2); break;
         case PH_24: pyr_double<CB>(sbase, ncell, WP); break;
         default:    pyr_stage<CB>(sbase, src, nc, H, W, 2); __syncthreads();
-                    pyr_double<CB>(sbase, ncell, 2 * WP); break;   // PH_41
+                    pyr_double<CB>(sbase, ncell, 2 * WP); break;       // PH_41
       }
     }
-    if (hi <= lo) continue;
-    const int per = (hi - lo + p.S - 1) / p.S;
-    const int plo = lo + sidx * per;
-    const int phi = min(hi, plo + per);
-    if (phi <= plo) continue;
-    const int total = (phi - plo) * BINS;
-    const uint32_t* dsc = p.desc + (int64_t)(gstart + plo) * BINS;
-    const uint32_t* pin = p.pinfo + gstart + plo;
-
     if (phase != PH_FALLBACK) {
       const uint32_t khp = (uint32_t)phase_kh(phase) * pitch, kwb = (uint32_t)phase_kw(phase) * CS;
-      // software pipeline: descriptor / proposal word / scale of the NEXT pass are fetched during this one
-      int flat = wid * 32 + lane;
-      uint32_t d_n = 0, pi_n = 0;
-      int bin_n = 0;
-      float sc_n = 1.f;
-      auto fetch = [&](int f) {
-        if (f < total) {
-          const int rp = f / BINS;
-          bin_n = f - rp * BINS;
-          d_n = __ldg(dsc + f);
-          pi_n = __ldg(pin + rp);
-          if (p.row_scale) sc_n = __fadd_rn(__ldg(p.row_scale + (pi_n & 0x3ffffffu)), p.row_scale_bias);
+      for (int sub = 0; sub < 16; ++sub) {
+        const int lo = __ldg(boff + phase * 16 + sub), hi = __ldg(boff + phase * 16 + sub + 1);
+        if (hi <= lo) continue;
+        const int per = (hi - lo + p.S - 1) / p.S;
+        const int slo = lo + sidx * per;
+        const int shi = min(hi, slo + per);
+        if (shi <= slo) continue;
+        const int total = (shi - slo) * BINS;
+        const uint32_t* dsc = p.desc + (size_t)(gstart + slo) * BINS;
+        const uint2* pin = p.pinfo + gstart + slo;
+#define PYR_CASE(CH, CW) \
+  case ((CH - 1) + (CW - 1) * 4): \
+    if (nc == CB) pyr_run<CB, CH, CW, true>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    else pyr_run<CB, CH, CW, false>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    break;
+        switch (sub) {
+          PYR_CASE(1, 1) PYR_CASE(1, 2) PYR_CASE(1, 3) PYR_CASE(1, 4)
+          PYR_CASE(2, 1) PYR_CASE(2, 2) PYR_CASE(2, 3) PYR_CASE(2, 4)
+          PYR_CASE(3, 1) PYR_CASE(3, 2) PYR_CASE(3, 3) PYR_CASE(3, 4)
+          PYR_CASE(4, 1) PYR_CASE(4, 2) PYR_CASE(4, 3) PYR_CASE(4, 4)
         }
-      };
-      fetch(flat);
-      for (; flat < total; flat += stride) {
-        const uint32_t d = d_n, pi = pi_n;
-        const int bin = bin_n;
-        const float scale = sc_n;
-        fetch(flat + stride);
-        const uint32_t addr = sbase + (d & 0xffffu) * CS;
-        const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * CS;
-        const int ch = (int)((pi >> 26) & 3u) + 1, cw = (int)((pi >> 28) & 3u) + 1;
-        float m[CB];
-#pragma unroll
-        for (int k = 0; k < CB; ++k) m[k] = -FLT_MAX;
-        uint32_t ro = 0;
-        for (int i = 0; i < ch; ++i, ro += khp) {
-          const uint32_t ra = addr + min(ro, lhp);
-          uint32_t co = 0;
-          for (int j = 0; j < cw; ++j, co += kwb) {
-            float f[CB];
-            p_lds<CB>(ra + min(co, lwb), f);
-#pragma unroll
-            for (int k = 0; k < CB; ++k) m[k] = fmaxf(m[k], f[k]);
-          }
-        }
-        const bool empty = (d >> 31) != 0;
-        const int64_t o = ((int64_t)(pi & 0x3ffffffu) * p.C + c0) * BINS + bin;
-#pragma unroll
-        for (int k = 0; k < CB; ++k)
-          if (k < nc) {
-            const float v = empty ? 0.f : m[k];
-            __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(v, scale) : v);
-          }
+#undef PYR_CASE
       }
     } else {
-      // bins needing more than kMaxLoads blocks per axis (or maps beyond the descriptor range): direct
-      // scan of the (1,1) plane with edges recomputed from the roi
-      for (int flat = wid * 32 + lane; flat < total; flat += stride) {
+      // bins needing more than kMaxLoads blocks per axis: direct scan of the (1,1) plane with edges
+      // recomputed from the roi (lane slot = output bin)
+      const int lo = plo, hi = __ldg(boff + (phase + 1) * 16);
+      if (hi <= lo) continue;
+      const int per = (hi - lo + p.S - 1) / p.S;
+      const int slo = lo + sidx * per;
+      const int shi = min(hi, slo + per);
+      if (shi <= slo) continue;
+      const int total = (shi - slo) * BINS;
+      const uint2* pin = p.pinfo + gstart + slo;
+      for (int flat = flat0; flat < total; flat += stride) {
         const int rp = flat / BINS;
         const int bin = flat - rp * BINS;
         const int ph = bin / 7, pw = bin - ph * 7;
-        const int r = (int)(__ldg(pin + rp) & 0x3ffffffu);
-        const float* roi = p.rois + (int64_t)r * 5;
+        const uint2 pi = __ldg(pin + rp);
+        const float* roi = p.rois + (int64_t)pi.x * 5;
         const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
         int hs, he, ws, we;
         bin_edges(ah, ph, H, hs, he);
@@ -371,12 +409,10 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
             }
           }
         }
-        float scale = 1.f;
-        if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
-        const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin;
+        float* o = outc + (size_t)pi.x * c49 + bin;
 #pragma unroll
         for (int k = 0; k < CB; ++k)
-          if (k < nc) __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(m[k], scale) : m[k]);
+          if (k < nc) __stcs(o + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
       }
     }
   }
@@ -384,12 +420,12 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
 
 // shared memory of the padded plane (+ identity tail rows)
 static size_t pyr_smem(int64_t H, int64_t W, int cb) {
-  return (size_t)(H + kPad + kTailRows) * (size_t)(W + kPad) * 4u * (size_t)cb;
+  return ((size_t)(H + kPad + kTailRows) * (size_t)(W + kPad) + 1) * 4u * (size_t)cb;   // + the zero cell
 }
 
 // channels per CTA the pyramid path would use for this map (0: does not apply)
 int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R) {
-  if ((H + kPad) * (W + kPad) > 65535 || R >= (1 << 26)) return 0;
+  if ((H + kPad + kTailRows) * (W + kPad) >= 65535 || C * 49 >= (1LL << 32)) return 0;
   if (C >= 3 && pyr_smem(H, W, 4) <= (size_t)kMaxSmemOptin) return 4;
   if (pyr_smem(H, W, 2) <= (size_t)kMaxSmemOptin) return 2;
   return 0;
@@ -428,13 +464,14 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   if ((rc = after_launch())) return rc;
   pyr_scan_kernel<<<1, 1024, 0, st>>>(w.hist, (int)N, w.img_start);
   if ((rc = after_launch())) return rc;
-  pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.img_start, R, w.order, w.phase_off);
+  pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.img_start, R, w.order, w.bucket_off);
   if ((rc = after_launch())) return rc;
-  pyr_bins_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, w.pinfo, w.desc);
+  pyr_bins_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, row_scale,
+                                                                    row_scale_bias, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
-  p.input = input; p.rois = rois; p.row_scale = row_scale; p.row_scale_bias = row_scale_bias; p.scale = scale;
-  p.output = output; p.img_start = w.img_start; p.phase_off = w.phase_off; p.pinfo = w.pinfo; p.desc = w.desc;
+  p.input = input; p.rois = rois; p.scale = scale;
+  p.output = output; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
   return cb == 4 ? pyr_launch_main<4>(p, R, st) : pyr_launch_main<2>(p, R, st);
 }
