@@ -1,0 +1,127 @@
+// Micro-benchmark: how fast can the pooled tensor's write pattern go by itself?  (R,C,7,7) fp32, a CTA owns
+// (image, 4 channels) and writes 4 x 196-byte runs per proposal (stride C*196 B between proposals).
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o store_pattern store_pattern.cu && ./store_pattern
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+template <int POLICY>
+__device__ __forceinline__ void st(float* p, float v) {
+  if (POLICY == 0) __stcs(p, v);
+  else if (POLICY == 1) *p = v;
+  else if (POLICY == 2) __stwt(p, v);
+  else __stcg(p, v);
+}
+
+template <int POLICY>
+__global__ void __launch_bounds__(1024, 1) pattern(float* out, int C, int R, int CG, int skew) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = R * 49;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  // skew: CTAs start at different proposals (emulates drift between channel groups)
+  const int start = skew ? (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)R) : 0;
+  for (int f = wid * 32 + lane; f < total; f += nw * 32) {
+    int r = f / 49;
+    const int bin = f - r * 49;
+    r += start; if (r >= R) r -= R;
+    float* o = outc + (size_t)r * c49 + bin;
+    const float v = (float)f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st<POLICY>(o + k * 49, v + k);
+  }
+}
+
+// (1) 784-byte chunk per (proposal, channel group) written as 49 float4 (same bytes, same chunk addresses)
+__global__ void __launch_bounds__(1024, 1) chunk128(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int total = R * 49;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int f = threadIdx.x; f < total; f += blockDim.x) {
+    const int r = f / 49, v = f - r * 49;
+    __stcs(reinterpret_cast<float4*>(outc + (size_t)r * c49) + v, make_float4(1.f, 2.f, 3.f, (float)f));
+  }
+}
+// (3) the same chunk written as 196 consecutive scalars (lanes walk the run)
+__global__ void __launch_bounds__(1024, 1) chunk32(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int total = R * 196;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int f = threadIdx.x; f < total; f += blockDim.x) {
+    const int r = f / 196, v = f - r * 196;
+    __stcs(outc + (size_t)r * c49 + v, (float)f);
+  }
+}
+// (4) 784-byte chunks through shared memory and cp.async.bulk (TMA) stores: one warp stages 32 chunks
+__global__ void __launch_bounds__(1024, 1) chunk_tma(float* out, int C, int R, int CG) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  float* stage = reinterpret_cast<float*>(smem) + wid * 2 * 196;   // two chunks per warp (double buffer)
+  int buf = 0;
+  for (int r = wid; r < R; r += nw) {
+    float* sb = stage + buf * 196;
+    // wait until the bulk store that last read this buffer is done (<= 1 group may stay in flight)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    for (int v = lane; v < 196; v += 32) sb[v] = (float)(r + v);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(sb);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 784;" ::"l"(outc + (size_t)r * c49), "r"(sa) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    buf ^= 1;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void linear(float4* out, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    __stcs(out + i, make_float4(1.f, 2.f, 3.f, 4.f));
+}
+
+int main() {
+  const int N = 8, C = 512, R = 4000;
+  const size_t elems = (size_t)N * R * C * 49;
+  float* out;
+  cudaMalloc(&out, elems * 4);
+  char* flush;
+  cudaMalloc(&flush, 256 << 20);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  auto run = [&](const char* name, auto fn) {
+    float best = 1e9f;
+    for (int it = 0; it < 6; ++it) {
+      cudaMemsetAsync(flush, it, 256 << 20);
+      cudaEventRecord(a);
+      fn();
+      cudaEventRecord(b);
+      cudaEventSynchronize(b);
+      float ms; cudaEventElapsedTime(&ms, a, b);
+      if (it > 0 && ms < best) best = ms;
+    }
+    printf("%-28s %.3f ms  %.0f GB/s  (%s)\n", name, best, elems * 4 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+  };
+  run("linear float4 .cs", [&] { linear<<<148 * 8, 512>>>((float4*)out, elems / 4); });
+  run("pattern .cs", [&] { pattern<0><<<N * 128, 1024>>>(out, C, R, 128, 0); });
+  run("pattern default", [&] { pattern<1><<<N * 128, 1024>>>(out, C, R, 128, 0); });
+  run("pattern .wt", [&] { pattern<2><<<N * 128, 1024>>>(out, C, R, 128, 0); });
+  run("pattern .cg", [&] { pattern<3><<<N * 128, 1024>>>(out, C, R, 128, 0); });
+  run("pattern .cs skewed", [&] { pattern<0><<<N * 128, 1024>>>(out, C, R, 128, 1); });
+  run("pattern default skewed", [&] { pattern<1><<<N * 128, 1024>>>(out, C, R, 128, 1); });
+  run("chunk 784B as float4", [&] { chunk128<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("chunk 784B as float4 512thr", [&] { chunk128<<<N * 128, 512>>>(out, C, R, 128); });
+  run("chunk 784B as scalars", [&] { chunk32<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("chunk 784B TMA bulk", [&] { chunk_tma<<<N * 128, 1024, 32 * 2 * 784>>>(out, C, R, 128); });
+  cudaFuncSetAttribute(chunk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  run("chunk 784B TMA bulk +150KB smem", [&] { chunk_tma<<<N * 128, 1024, 200 * 1024>>>(out, C, R, 128); });
+  run("pattern .cs 512thr", [&] { pattern<0><<<N * 128, 512>>>(out, C, R, 128, 0); });
+  return 0;
+}

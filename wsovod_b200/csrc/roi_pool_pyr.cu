@@ -12,6 +12,7 @@
 #include "pool_pyr.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace wsovod {
 
@@ -24,7 +25,7 @@ struct PyrWs {
   int32_t* bidx;        // [R]
   uint32_t* pkey;       // [R]
   int32_t* order;       // [R]   proposal id at each sorted position
-  uint2* pinfo;         // [R]   (proposal id, bits of row_scale + bias) at each sorted position
+  uint2* pinfo;         // [R]   (proposal id | (ch-1) << 26 | (cw-1) << 28, bits of row_scale + bias) per sorted position
   uint32_t* desc;       // [R, 49] bin descriptors in sorted position / lane slot order
   size_t bytes;
 };
@@ -65,49 +66,59 @@ __global__ void pyr_classify_kernel(const float* __restrict__ rois, int64_t R, i
   atomicAdd(&hist[(int64_t)b * kBuckets + key_bucket(key)], 1);
 }
 
-// exclusive scan of the per-image totals (one CTA; thread t owns a contiguous run of images)
-__global__ void pyr_scan_kernel(const int32_t* __restrict__ hist, int N, int32_t* __restrict__ img_start) {
-  __shared__ int s_part[1024];
-  const int tid = threadIdx.x;
-  const int q = (N + blockDim.x - 1) / blockDim.x;
-  const int n0 = min(tid * q, N), n1 = min(n0 + q, N);
-  int sum = 0;
-  for (int n = n0; n < n1; ++n)
-    for (int k = 0; k < kBuckets; ++k) sum += hist[(int64_t)n * kBuckets + k];
-  s_part[tid] = sum;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int t = 0; t < (int)blockDim.x; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
-    img_start[N] = run;
-  }
-  __syncthreads();
-  int run = s_part[tid];
-  for (int n = n0; n < n1; ++n) {
-    img_start[n] = run;
-    for (int k = 0; k < kBuckets; ++k) run += hist[(int64_t)n * kBuckets + k];
-  }
-}
-
-// one CTA per image: bucket offsets and scatter of proposal ids.  The order inside a bucket is whatever
-// the shared-memory atomics give: every output element is written exactly once from
-// position-independent data, so the result does not depend on it.
-__global__ void pyr_order_kernel(const int32_t* __restrict__ bidx, const uint32_t* __restrict__ pkey,
-                                 const int32_t* __restrict__ hist, const int32_t* __restrict__ img_start,
-                                 int64_t R, int32_t* __restrict__ order, int32_t* __restrict__ bucket_off) {
+// one CTA per image: first sorted position of the image (sum of the histograms before it), bucket
+// offsets (block scan), scatter of proposal ids.  The order inside a bucket is whatever the
+// shared-memory atomics give: every output element is written exactly once from position-independent
+// data, so the result does not depend on it.
+__global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restrict__ bidx, const uint32_t* __restrict__ pkey,
+                                                        const int32_t* __restrict__ hist, int N, int64_t R,
+                                                        int32_t* __restrict__ order, int32_t* __restrict__ img_start,
+                                                        int32_t* __restrict__ bucket_off) {
   __shared__ int s_cur[kBuckets];
-  const int n = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_red[16];
+  __shared__ int s_base, s_total;
+  static_assert(kBuckets <= 512, "one bucket per thread");
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // (1) proposals of the images before this one
+  int sum = 0;
+  for (int64_t i = tid; i < (int64_t)n * kBuckets; i += blockDim.x) sum += hist[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_red[wid] = sum;
+  // (2) exclusive scan of this image's buckets (kBuckets <= 5 * 32: warps 0..4, one bucket per lane)
+  int mine = 0;
+  if (tid < kBuckets) mine = hist[(int64_t)n * kBuckets + tid];
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __shared__ int s_wtot[16];
+  if (lane == 31) s_wtot[wid] = incl;
+  __syncthreads();
   if (tid == 0) {
-    int run = 0;
-    for (int k = 0; k < kBuckets; ++k) {
-      bucket_off[n * (kBuckets + 1) + k] = run;
-      s_cur[k] = run;
-      run += hist[(int64_t)n * kBuckets + k];
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    s_base = t;
+  }
+  int wbase = 0;
+  for (int w = 0; w < wid; ++w) wbase += s_wtot[w];
+  if (tid < kBuckets) {
+    const int excl = wbase + incl - mine;
+    s_cur[tid] = excl;
+    bucket_off[n * (kBuckets + 1) + tid] = excl;
+    if (tid == kBuckets - 1) {
+      bucket_off[n * (kBuckets + 1) + kBuckets] = excl + mine;
+      s_total = excl + mine;
     }
-    bucket_off[n * (kBuckets + 1) + kBuckets] = run;
   }
   __syncthreads();
-  const int base = img_start[n];
+  const int base = s_base;
+  if (tid == 0) {
+    img_start[n] = base;
+    if (n == N - 1) img_start[N] = base + s_total;
+  }
   for (int64_t r = tid; r < R; r += blockDim.x) {
     if (bidx[r] != n) continue;
     const int pos = atomicAdd(&s_cur[key_bucket(pkey[r])], 1);
@@ -133,7 +144,7 @@ __global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H
   desc[i] = phase == PH_FALLBACK ? 0u : bin_desc(roi[1], roi[2], roi[3], roi[4], scale, H, W, phase, ph, pw);
   if (q == 0) {
     const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
-    pinfo[gpos] = make_uint2((uint32_t)r, __float_as_uint(sc));
+    pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
   }
 }
 
@@ -151,6 +162,7 @@ struct PyrParams {
   const uint32_t* desc;
   int32_t N, C, H, W;
   int32_t CG, S;
+  int32_t debug;   // experiments only (WSOVOD_B200_POOL_DEBUG): 1 no stores, 2 no descriptor loads, 4 no rebuilds
 };
 
 template <int CB> __device__ __forceinline__ void p_lds(uint32_t addr, float* f);
@@ -169,34 +181,42 @@ template <> __device__ __forceinline__ void p_sts<2>(uint32_t addr, const float*
 }
 
 // D <- plane of the map (mode 0), max with the right neighbour (1: block 1x2) or the lower neighbour
-// (2: block 2x1), in the padded layout; pad cells and absent channels hold the identity -FLT_MAX.
+// (2: block 2x1), in the padded layout; pad cells and absent channels hold the identity -FLT_MAX, and
+// NaN / -inf cells are clamped to it (they can never win a bin: `v > maxval` with maxval = -FLT_MAX).
+// Four cells per thread are in flight (the loop is L2-latency bound otherwise).
 template <int CB>
 __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W,
                                        int mode) {
   constexpr uint32_t CS = 4u * CB;
+  constexpr int U = 4;
   const int WP = W + kPad, ncell = (H + kPad) * WP, HW = H * W;
-  for (int idx = threadIdx.x; idx < ncell; idx += blockDim.x) {
-    const int hh = idx / WP, ww = idx - hh * WP;
-    const int h = hh - kPad, w = ww - kPad;
-    float f[CB];
+  const int dnb = mode == 1 ? 1 : W;   // neighbour offset in the unpadded plane
+  for (int base = threadIdx.x; base < ncell; base += U * (int)blockDim.x) {
+    float f[U][CB], g[U][CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) f[k] = -FLT_MAX;
-    if (h >= 0 && w >= 0) {
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * (int)blockDim.x;
+      const int hh = idx / WP, ww = idx - hh * WP;
+      const int h = hh - kPad, w = ww - kPad;
+      const bool in = idx < ncell && h >= 0 && w >= 0;
+      const bool in2 = idx < ncell && mode != 0 &&
+                       (mode == 1 ? (h >= 0 && w + 1 >= 0 && w + 1 < W) : (w >= 0 && h + 1 >= 0 && h + 1 < H));
+      const float* q = src + h * W + w;
 #pragma unroll
-      for (int k = 0; k < CB; ++k)
-        if (k < nc) f[k] = fmaxf(f[k], __ldg(src + (int64_t)k * HW + h * W + w));
+      for (int k = 0; k < CB; ++k) {
+        f[u][k] = (in && k < nc) ? __ldg(q + (int64_t)k * HW) : -FLT_MAX;
+        g[u][k] = (in2 && k < nc) ? __ldg(q + (int64_t)k * HW + dnb) : -FLT_MAX;
+      }
     }
-    if (mode == 1 && h >= 0 && w + 1 >= 0 && w + 1 < W) {
 #pragma unroll
-      for (int k = 0; k < CB; ++k)
-        if (k < nc) f[k] = fmaxf(f[k], __ldg(src + (int64_t)k * HW + h * W + w + 1));
-    }
-    if (mode == 2 && w >= 0 && h + 1 >= 0 && h + 1 < H) {
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * (int)blockDim.x;
+      if (idx < ncell) {
 #pragma unroll
-      for (int k = 0; k < CB; ++k)
-        if (k < nc) f[k] = fmaxf(f[k], __ldg(src + (int64_t)k * HW + (h + 1) * W + w));
+        for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
+        p_sts<CB>(sbase + (uint32_t)idx * CS, f[u]);
+      }
     }
-    p_sts<CB>(sbase + (uint32_t)idx * CS, f);
   }
 }
 
@@ -232,36 +252,34 @@ __device__ __noinline__ void pyr_double(uint32_t sbase, int ncell, int stride) {
   __syncthreads();
 }
 
+template <int CB> struct PV;
+template <> struct PV<4> { using T = float4; };
+template <> struct PV<2> { using T = float2; };
+__device__ __forceinline__ void pv_max(float* m, const float4& v) {
+  m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); m[2] = fmaxf(m[2], v.z); m[3] = fmaxf(m[3], v.w);
+}
+__device__ __forceinline__ void pv_max(float* m, const float2& v) { m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); }
+__device__ __forceinline__ void pv_set(float* m, const float4& v) { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+__device__ __forceinline__ void pv_set(float* m, const float2& v) { m[0] = v.x; m[1] = v.y; }
+
 // One bucket slice = `total` lane slots (49 per proposal) whose proposals all need CH x CW blocks per bin.
-// Per pass a lane reads one descriptor word (coalesced) and its proposal's (id, scale) pair, both
+// A lane handles TWO slots per pass (f and f + stride: independent LDS chains hide each other's
+// latency); per slot it reads one descriptor word (coalesced) and its proposal's (id, scale) pair, both
 // fetched one pass ahead, issues up to CH*CW LDS (a block is skipped where it would repeat the
 // previous one: the bin is not larger than the blocks before it) and stores CB scalars.
 template <int CB, int CH, int CW, bool FULL>
-__device__ __forceinline__ void pyr_run(uint32_t sbase, uint32_t pitch, uint32_t khp, uint32_t kwb,
+__device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pitch, uint32_t khp, uint32_t kwb,
                                         const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
                                         int total, float* __restrict__ outc, uint32_t c49, int nc, int flat0,
-                                        int stride) {
+                                        int stride, int debug) {
+  using V = typename PV<CB>::T;
   constexpr uint32_t CS = 4u * CB;
-  int f = flat0;
-  uint32_t d_n = 0;
-  uint2 pi_n = make_uint2(0u, 0u);
-  if (f < total) {
-    d_n = __ldg(dsc + f);
-    pi_n = __ldg(pin + (uint32_t)f / 49u);
-  }
-  while (f < total) {
-    const uint32_t d = d_n;
-    const uint2 pi = pi_n;
-    const int fn = f + stride;
-    if (fn < total) {
-      d_n = __ldg(dsc + fn);
-      pi_n = __ldg(pin + (uint32_t)fn / 49u);
-    }
-    const uint32_t a0 = sbase + (d & 0xffffu) * CS;
+  auto one = [&](const uint32_t d, const uint2 pi) {
+    const uint32_t a0 = (d & 0xffffu) * CS;
     const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * CS;
     // the plane holds no NaN / -inf (pyr_stage clamps at -FLT_MAX), so the first block seeds the maximum
     float m[CB];
-    p_lds<CB>(a0, m);
+    pv_set(m, *reinterpret_cast<const V*>(plane + a0));
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
@@ -271,20 +289,36 @@ __device__ __forceinline__ void pyr_run(uint32_t sbase, uint32_t pitch, uint32_t
         if (i == 0 && j == 0) continue;
         const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
         const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
-        if (ni && nj) {
-          float v[CB];
-          p_lds<CB>(a0 + ro + co, v);
-#pragma unroll
-          for (int k = 0; k < CB; ++k) m[k] = fmaxf(m[k], v[k]);
-        }
+        if (ni && nj) pv_max(m, *reinterpret_cast<const V*>(plane + a0 + ro + co));
       }
     }
     const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
-    float* o = outc + (size_t)pi.x * c49 + ((d >> 24) & 63u);
+    float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + ((d >> 24) & 63u);
 #pragma unroll
     for (int k = 0; k < CB; ++k)
-      if (FULL || k < nc) __stcs(o + k * 49, __fmul_rn(m[k], sc));
-    f = fn;
+      if ((FULL || k < nc) && (!(debug & 1) || m[k] == 12345.678f)) __stcs(o + k * 49, __fmul_rn(m[k], sc));
+  };
+  const int step = 2 * stride;
+  int f = flat0;
+  uint32_t d0 = 0, d1 = 0;
+  uint2 p0 = make_uint2(0u, 0u), p1 = p0;
+  if (f < total) { d0 = __ldg(dsc + f); p0 = __ldg(pin + (uint32_t)f / 49u); }
+  if (f + stride < total) { d1 = __ldg(dsc + f + stride); p1 = __ldg(pin + (uint32_t)(f + stride) / 49u); }
+  while (f < total) {
+    const uint32_t c0 = d0, c1 = d1;
+    const uint2 q0 = p0, q1 = p1;
+    const bool second = f + stride < total;
+    const int g = f + step;
+    if (debug & 2) {
+      d0 = (d0 + 7u) & 0x0fff1fffu; p0.x = (p0.x + 1u) & 0x3fffu;
+      d1 = (d1 + 9u) & 0x0fff1fffu; p1.x = (p1.x + 3u) & 0x3fffu;
+    } else {
+      if (g < total) { d0 = __ldg(dsc + g); p0 = __ldg(pin + (uint32_t)g / 49u); }
+      if (g + stride < total) { d1 = __ldg(dsc + g + stride); p1 = __ldg(pin + (uint32_t)(g + stride) / 49u); }
+    }
+    one(c0, q0);
+    if (second) one(c1, q1);
+    f = g;
   }
 }
 
@@ -328,12 +362,14 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int stride = nw * 32;
   const int flat0 = wid * 32 + lane;
-  const int32_t* boff = p.bucket_off + n * (kBuckets + 1);
+  __shared__ int boff[kBuckets + 1];   // this image's bucket boundaries
+  for (int i = threadIdx.x; i <= kBuckets; i += blockDim.x) boff[i] = __ldg(p.bucket_off + n * (kBuckets + 1) + i);
+  __syncthreads();
 
   for (int phase = 0; phase < kPhases; ++phase) {
-    const int plo = __ldg(boff + phase * 16);
-    const int rem = __ldg(boff + (chain_end(phase) + 1) * 16) - plo;   // proposals left in this chain
-    if (rem > 0 && phase != PH_FALLBACK) {
+    const int plo = boff[phase * 16];
+    const int rem = boff[(chain_end(phase) + 1) * 16] - plo;   // proposals left in this chain
+    if (rem > 0 && phase != PH_FALLBACK && !((p.debug & 4) && phase != PH_11)) {
       __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
         case PH_11: pyr_stage<CB>(sbase, src, nc, H, W, 0); __syncthreads(); break;
@@ -351,7 +387,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     if (phase != PH_FALLBACK) {
       const uint32_t khp = (uint32_t)phase_kh(phase) * pitch, kwb = (uint32_t)phase_kw(phase) * CS;
       for (int sub = 0; sub < 16; ++sub) {
-        const int lo = __ldg(boff + phase * 16 + sub), hi = __ldg(boff + phase * 16 + sub + 1);
+        const int lo = boff[phase * 16 + sub], hi = boff[phase * 16 + sub + 1];
         if (hi <= lo) continue;
         const int per = (hi - lo + p.S - 1) / p.S;
         const int slo = lo + sidx * per;
@@ -362,8 +398,8 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         const uint2* pin = p.pinfo + gstart + slo;
 #define PYR_CASE(CH, CW) \
   case ((CH - 1) + (CW - 1) * 4): \
-    if (nc == CB) pyr_run<CB, CH, CW, true>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
-    else pyr_run<CB, CH, CW, false>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    if (nc == CB) pyr_run<CB, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride, p.debug); \
+    else pyr_run<CB, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride, p.debug); \
     break;
         switch (sub) {
           PYR_CASE(1, 1) PYR_CASE(1, 2) PYR_CASE(1, 3) PYR_CASE(1, 4)
@@ -376,7 +412,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     } else {
       // bins needing more than kMaxLoads blocks per axis: direct scan of the (1,1) plane with edges
       // recomputed from the roi (lane slot = output bin)
-      const int lo = plo, hi = __ldg(boff + (phase + 1) * 16);
+      const int lo = plo, hi = boff[(phase + 1) * 16];
       if (hi <= lo) continue;
       const int per = (hi - lo + p.S - 1) / p.S;
       const int slo = lo + sidx * per;
@@ -389,7 +425,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         const int bin = flat - rp * BINS;
         const int ph = bin / 7, pw = bin - ph * 7;
         const uint2 pi = __ldg(pin + rp);
-        const float* roi = p.rois + (int64_t)pi.x * 5;
+        const float* roi = p.rois + (int64_t)(pi.x & 0x3ffffffu) * 5;
         const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
         int hs, he, ws, we;
         bin_edges(ah, ph, H, hs, he);
@@ -409,13 +445,215 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
             }
           }
         }
-        float* o = outc + (size_t)pi.x * c49 + bin;
+        float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + bin;
 #pragma unroll
         for (int k = 0; k < CB; ++k)
           if (k < nc) __stcs(o + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel, TMA-store flavour (CB = 4, C % 4 == 0)
+// ------------------------------------------------------------------------------------------------
+// The pooled tensor's natural write pattern -- four 128-byte warp stores 196 bytes apart per pass -- tops
+// out at 2.2 TB/s on a B200 however little else the kernel does (tools/ubench/store_pattern.cu), while
+// the 784-byte block out[r, c0:c0+4, :, :] written as one bulk copy reaches 5.6 TB/s.  So here a warp
+// owns a contiguous run of whole proposals, stages each proposal's 4 x 49 results in shared memory and
+// hands the finished block to the TMA (cp.async.bulk shared -> global, 16-byte aligned because C % 4
+// == 0); the LSU only sees conflict-free STS.  Two staging buffers per warp: the copy of proposal q-2 is
+// waited for (read side only) before proposal q overwrites its buffer.
+constexpr int kWThreads = 768;
+constexpr int kWWarps = kWThreads / 32;
+constexpr int kChunkBytes = 4 * 49 * 4;   // out[r, c0:c0+4] : 784 B
+constexpr int kStageBytes = kWWarps * 2 * kChunkBytes;
+
+template <int CH, int CW>
+__device__ __forceinline__ void pyr_bin4(const unsigned char* plane, uint32_t d, uint32_t pitch, uint32_t khp,
+                                         uint32_t kwb, float* m) {
+  const uint32_t a0 = (d & 0xffffu) * 16u;
+  const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * 16u;
+  pv_set(m, *reinterpret_cast<const float4*>(plane + a0));
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
+    const bool ni = i == 0 || (uint32_t)(i - 1) * khp < lhp;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+      if (i == 0 && j == 0) continue;
+      const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
+      const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
+      if (ni && nj) pv_max(m, *reinterpret_cast<const float4*>(plane + a0 + ro + co));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) roi_pool7_pyrw_kernel(const PyrParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int BINS = 49, CB = 4;
+  constexpr uint32_t CS = 16u;
+  const int H = p.H, W = p.W, HW = H * W;
+  const int WP = W + kPad, ncell = (H + kPad) * WP, ntot = (H + kPad + kTailRows) * WP;
+  const int bid = blockIdx.x;
+  const int cg = bid % p.CG;
+  const int sidx = (bid / p.CG) % p.S;
+  const int n = bid / (p.CG * p.S);
+  const int c0 = cg * CB;
+  const int gstart = __ldg(p.img_start + n);
+  const int cnt = __ldg(p.img_start + n + 1) - gstart;
+  if (cnt <= 0) return;
+  __shared__ int boff[kBuckets + 1];   // this image's bucket boundaries
+  for (int i = threadIdx.x; i <= kBuckets; i += blockDim.x) boff[i] = __ldg(p.bucket_off + n * (kBuckets + 1) + i);
+  uint32_t sbase;
+  {
+    unsigned long long s64;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
+    sbase = (uint32_t)s64;
+  }
+  {  // identity tail rows and the all-zero cell empty bins point at (never written again)
+    float id[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) id[k] = -FLT_MAX;
+    for (int i = ncell + (int)threadIdx.x; i < ntot; i += blockDim.x) p_sts<CB>(sbase + (uint32_t)i * CS, id);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < CB; ++k) id[k] = 0.f;
+      p_sts<CB>(sbase + (uint32_t)ntot * CS, id);
+    }
+  }
+  __syncthreads();
+  const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+  float* outc = p.output + (size_t)c0 * BINS;
+  const size_t c49 = (size_t)p.C * BINS;
+  const uint32_t pitch = (uint32_t)WP * CS;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // staging: two 784-byte blocks per warp behind the plane (16-byte aligned)
+  const uint32_t plane_bytes = ((uint32_t)(ntot + 1) * CS + 127u) & ~127u;
+  float* stage = reinterpret_cast<float*>(smem_raw + plane_bytes) + wid * (2 * kChunkBytes / 4);
+  const uint32_t stage_s = sbase + plane_bytes + (uint32_t)wid * (2u * kChunkBytes);
+
+  for (int phase = 0; phase < kPhases; ++phase) {
+    const int lo = boff[phase * 16], hi = boff[(phase + 1) * 16];
+    const int rem = boff[(chain_end(phase) + 1) * 16] - lo;   // proposals left in this chain
+    if (rem > 0 && phase != PH_FALLBACK && !((p.debug & 4) && phase != PH_11)) {
+      __syncthreads();                                         // everyone is done reading the old plane
+      switch (phase) {
+        case PH_11: pyr_stage<CB>(sbase, src, CB, H, W, 0); __syncthreads(); break;
+        case PH_21: pyr_double<CB>(sbase, ncell, WP); break;
+        case PH_22: pyr_double<CB>(sbase, ncell, 1); break;
+        case PH_42: pyr_double<CB>(sbase, ncell, 2 * WP); break;
+        case PH_44: pyr_double<CB>(sbase, ncell, 2); break;
+        case PH_12: pyr_stage<CB>(sbase, src, CB, H, W, 1); __syncthreads(); break;
+        case PH_14: pyr_double<CB>(sbase, ncell, 2); break;
+        case PH_24: pyr_double<CB>(sbase, ncell, WP); break;
+        default:    pyr_stage<CB>(sbase, src, CB, H, W, 2); __syncthreads();
+                    pyr_double<CB>(sbase, ncell, 2 * WP); break;   // PH_41
+      }
+    }
+    if (hi <= lo) continue;
+    // this CTA's slice of the phase, then this warp's contiguous run of whole proposals
+    const int per = (hi - lo + p.S - 1) / p.S;
+    const int slo = lo + sidx * per;
+    const int shi = min(hi, slo + per);
+    if (shi <= slo) continue;
+    const int np = shi - slo;
+    const int per_w = (np + kWWarps - 1) / kWWarps;
+    const int w0 = min(np, wid * per_w), w1 = min(np, w0 + per_w);
+    const int total = (w1 - w0) * BINS;
+    if (total <= 0) continue;
+    const uint32_t* dsc = p.desc + (size_t)(gstart + slo + w0) * BINS;
+    const uint2* pin = p.pinfo + gstart + slo + w0;
+    const uint32_t khp = (uint32_t)phase_kh(phase) * pitch, kwb = (uint32_t)phase_kw(phase) * CS;
+    const uint32_t dzero = kDescEmpty | (uint32_t)ntot;   // idle lanes read the zero cell
+    const bool fallback = phase == PH_FALLBACK;
+
+    // two passes of look-ahead (see pyr_run)
+    uint32_t d_a = dzero, d_b = dzero;
+    uint2 pi_a = make_uint2(0u, 0u), pi_b = pi_a;
+    if (lane < total) { d_a = __ldg(dsc + lane); pi_a = __ldg(pin + (uint32_t)lane / 49u); }
+    if (32 + lane < total) { d_b = __ldg(dsc + 32 + lane); pi_b = __ldg(pin + (uint32_t)(32 + lane) / 49u); }
+    for (int g0 = 0; g0 < total; g0 += 32) {
+      const int g = g0 + lane;
+      const bool act = g < total;
+      const uint32_t d = d_a;
+      const uint2 pi = pi_a;
+      d_a = d_b;
+      pi_a = pi_b;
+      d_b = dzero;
+      if (g + 64 < total) { d_b = __ldg(dsc + g + 64); pi_b = __ldg(pin + (uint32_t)(g + 64) / 49u); }
+      const int q = (int)((uint32_t)g / 49u);          // proposal within this warp's run
+      const int slot = g - q * BINS;
+      float m[CB];
+      int bin;
+      if (!fallback) {
+        // warp-uniform block counts: the largest of the (at most two) proposals in this pass; lanes
+        // whose proposal needs fewer skip the surplus blocks through the duplicate-block predicates
+        const int ch = act ? (int)((pi.x >> 26) & 3u) : 0, cw = act ? (int)((pi.x >> 28) & 3u) : 0;
+        const int chm = __reduce_max_sync(0xffffffffu, ch), cwm = __reduce_max_sync(0xffffffffu, cw);
+        bin = (int)((d >> 24) & 63u);
+#define PYRW_CASE(CH, CW) \
+  case ((CH - 1) * 4 + (CW - 1)): pyr_bin4<CH, CW>(smem_raw, d, pitch, khp, kwb, m); break;
+        switch (chm * 4 + cwm) {
+          PYRW_CASE(1, 1) PYRW_CASE(1, 2) PYRW_CASE(1, 3) PYRW_CASE(1, 4)
+          PYRW_CASE(2, 1) PYRW_CASE(2, 2) PYRW_CASE(2, 3) PYRW_CASE(2, 4)
+          PYRW_CASE(3, 1) PYRW_CASE(3, 2) PYRW_CASE(3, 3) PYRW_CASE(3, 4)
+          PYRW_CASE(4, 1) PYRW_CASE(4, 2) PYRW_CASE(4, 3) PYRW_CASE(4, 4)
+        }
+#undef PYRW_CASE
+      } else {
+        // bins needing more than kMaxLoads blocks per axis: direct scan of the (1,1) plane with edges
+        // recomputed from the roi (lane slot = output bin)
+        bin = slot;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) m[k] = 0.f;
+        if (act) {
+          const int ph = bin / 7, pw = bin - ph * 7;
+          const float* roi = p.rois + (int64_t)(pi.x & 0x3ffffffu) * 5;
+          const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
+          int hs, he, ws, we;
+          bin_edges(ah, ph, H, hs, he);
+          bin_edges(aw, pw, W, ws, we);
+          if (he > hs && we > ws) {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) m[k] = -FLT_MAX;
+            for (int h = hs; h < he; ++h) {
+              const unsigned char* a = smem_raw + (uint32_t)((h + kPad) * WP + ws + kPad) * CS;
+              for (int w = ws; w < we; ++w, a += CS) pv_max(m, *reinterpret_cast<const float4*>(a));
+            }
+          }
+        }
+      }
+      // a proposal starts in this pass -> its buffer must be free: the copy of the proposal two before it
+      // (committed at least a pass ago) has to be done READING shared memory
+      const unsigned starts = __ballot_sync(0xffffffffu, act && slot == 0);
+      if (starts) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+      if (act && !((p.debug & 1) && m[0] != 12345.678f)) {
+        const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
+        float* sb = stage + (q & 1) * (kChunkBytes / 4) + bin;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) sb[k * BINS] = __fmul_rn(m[k], sc);
+      }
+      // the proposal whose last slot (49 q + 48) lies in [g0, g0 + 32) is complete: bulk-copy it out
+      const int qc = (g0 + 31 - 48 >= 0) ? (g0 + 31 - 48) / BINS : -1;
+      const int last = qc * BINS + 48;
+      if (qc >= 0 && last >= g0 && last < total) {
+        const uint32_t rr = __shfl_sync(0xffffffffu, pi.x, last - g0) & 0x3ffffffu;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(outc + (size_t)rr * c49), "r"(stage_s + (uint32_t)(qc & 1) * kChunkBytes), "n"(kChunkBytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // shared memory of the padded plane (+ identity tail rows)
@@ -425,9 +663,9 @@ static size_t pyr_smem(int64_t H, int64_t W, int cb) {
 
 // channels per CTA the pyramid path would use for this map (0: does not apply)
 int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R) {
-  if ((H + kPad + kTailRows) * (W + kPad) >= 65535 || C * 49 >= (1LL << 32)) return 0;
-  if (C >= 3 && pyr_smem(H, W, 4) <= (size_t)kMaxSmemOptin) return 4;
-  if (pyr_smem(H, W, 2) <= (size_t)kMaxSmemOptin) return 2;
+  if ((H + kPad + kTailRows) * (W + kPad) >= 65535 || R >= (1 << 26) || C * 49 >= (1LL << 32)) return 0;
+  if (C >= 3 && pyr_smem(H, W, 4) + 1024 <= (size_t)kMaxSmemOptin) return 4;   // + static shared memory
+  if (pyr_smem(H, W, 2) + 1024 <= (size_t)kMaxSmemOptin) return 2;
   return 0;
 }
 
@@ -462,9 +700,7 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   int rc;
   pyr_classify_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.pkey, w.hist);
   if ((rc = after_launch())) return rc;
-  pyr_scan_kernel<<<1, 1024, 0, st>>>(w.hist, (int)N, w.img_start);
-  if ((rc = after_launch())) return rc;
-  pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.img_start, R, w.order, w.bucket_off);
+  pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
   pyr_bins_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, row_scale,
                                                                     row_scale_bias, w.pinfo, w.desc);
@@ -473,6 +709,22 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   p.input = input; p.rois = rois; p.scale = scale;
   p.output = output; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
+  { const char* dbg = getenv("WSOVOD_B200_POOL_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  const size_t smem_w = ((pyr_smem(H, W, 4) + 127) & ~(size_t)127) + kStageBytes;
+  const bool tma = cb == 4 && C % 4 == 0 && ((uintptr_t)output & 15) == 0 && smem_w + 1024 <= (size_t)kMaxSmemOptin &&
+                   !(p.debug & 16);
+  if (tma) {
+    p.CG = (int)(C / 4);
+    const int64_t units = N * p.CG;
+    int64_t S = units >= 2 * kNumSMs ? 1 : ceil_div(2 * kNumSMs, units);
+    S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(std::max<int64_t>(R / std::max<int64_t>(N, 1), 1), 512)));
+    p.S = (int)S;
+    if (units * S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
+    e = cudaFuncSetAttribute(roi_pool7_pyrw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+    if (e != cudaSuccess) return (int)e;
+    roi_pool7_pyrw_kernel<<<(unsigned)(units * S), kWThreads, smem_w, st>>>(p);
+    return after_launch();
+  }
   return cb == 4 ? pyr_launch_main<4>(p, R, st) : pyr_launch_main<2>(p, R, st);
 }
 
