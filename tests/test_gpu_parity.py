@@ -389,19 +389,33 @@ def test_detections_prefix_fallback_and_long_columns(mode):
 
 
 # ------------------------------------------------------------------------------ (1) block-max fast path
-def _pool_scan(feat, rois, scale, **kw):
-    """the plain scan kernels (the block-max path switched off for one call)"""
-    import os
-    os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+import contextlib  # noqa: E402
+import os  # noqa: E402
+
+
+@contextlib.contextmanager
+def _pool_variant(scan=None, tma=None):
+    """select the values-only pooling kernel for the calls inside: scan=True the plain scan kernels,
+    scan=False the block-max path wherever it applies (the library's own choice needs >= 3000 proposals
+    per image), tma=True its bulk-store flavour"""
+    old = {k: os.environ.get(k) for k in ("WSOVOD_B200_POOL_SCAN", "WSOVOD_B200_POOL_TMA")}
+    if scan is not None:
+        os.environ["WSOVOD_B200_POOL_SCAN"] = "1" if scan else "0"
+    if tma is not None:
+        os.environ["WSOVOD_B200_POOL_TMA"] = "1" if tma else "0"
     try:
-        return ops.roi_pool(feat, rois, scale, 7, with_argmax=False, **kw)[0]
+        yield
     finally:
-        del os.environ["WSOVOD_B200_POOL_SCAN"]
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 @pytest.mark.parametrize("N,C,H,W,R,seed", [(2, 9, 60, 80, 900, 1), (1, 3, 86, 128, 1500, 2), (3, 6, 100, 152, 700, 3),
                                              (1, 2, 150, 180, 400, 4), (2, 1, 7, 5, 300, 5), (1, 4, 1, 1, 50, 6),
-                                             (1, 5, 117, 120, 300, 7)])
+                                             (1, 5, 117, 120, 300, 7), (2, 8, 60, 80, 1200, 8), (1, 12, 86, 128, 2500, 9)])
 def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
     """values-only 7x7 pooling through the block-max planes (roi_pool_pyr.cu): every (kh, kw) phase, the
     direct-scan fallback phase (whole-map proposals on big maps), border-clipped bins, NaN / -inf cells,
@@ -426,16 +440,20 @@ def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
     rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
     obj = torch.rand(rois.size(0), generator=g)
     ref, _ = oracle.roi_pool(feat, rois, 1 / 8, 7)
-    out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
-    assert arg.numel() == 0
-    assert torch.equal(out.cpu(), ref)
-    assert torch.equal(_pool_scan(feat.to(DEV), rois.to(DEV), 1 / 8), out)
-    out_s, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
-                            with_argmax=False)
     fin = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref))
     sc = fin * (obj + 1).view(-1, 1, 1, 1)
-    got = out_s.cpu()
-    assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
+    with _pool_variant(scan=True):
+        scan = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)[0]
+    for tma in (False, True):     # plain stores / staged blocks leaving through cp.async.bulk (C % 4 == 0 only)
+        with _pool_variant(scan=False, tma=tma):
+            out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
+            out_s, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
+                                    with_argmax=False)
+        assert arg.numel() == 0
+        assert torch.equal(out.cpu(), ref)
+        assert torch.equal(scan, out)
+        got = out_s.cpu()
+        assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
 
 
 def test_roi_pool_blockmax_empty_images_and_single_class():
@@ -444,14 +462,10 @@ def test_roi_pool_blockmax_empty_images_and_single_class():
     feat = synth.features(4, 8, 40, 56, g, relu=False)
     b = synth.proposals(200, 320, 448, g)
     rois = torch.cat([torch.full((200, 1), 2.0), b], 1)             # images 0, 1, 3 stay empty
-    ref, _ = oracle.roi_pool(feat, rois, 1 / 8, 7)
-    out, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
-    assert torch.equal(out.cpu(), ref)
-    one = rois[:1].contiguous()
-    ref, _ = oracle.roi_pool(feat, one, 1 / 8, 7)
-    out, _ = ops.roi_pool(feat.to(DEV), one.to(DEV), 1 / 8, 7, with_argmax=False)
-    assert torch.equal(out.cpu(), ref)
     same = torch.tensor([[1.0, 64.0, 64.0, 64.0 + 8 * 27, 64.0 + 8 * 20]]).repeat(300, 1)   # 28 x 21 cells
-    ref, _ = oracle.roi_pool(feat, same, 1 / 8, 7)
-    out, _ = ops.roi_pool(feat.to(DEV), same.to(DEV), 1 / 8, 7, with_argmax=False)
-    assert torch.equal(out.cpu(), ref)
+    for tma in (False, True):
+        with _pool_variant(scan=False, tma=tma):
+            for r in (rois, rois[:1].contiguous(), same):
+                ref, _ = oracle.roi_pool(feat, r, 1 / 8, 7)
+                out, _ = ops.roi_pool(feat.to(DEV), r.to(DEV), 1 / 8, 7, with_argmax=False)
+                assert torch.equal(out.cpu(), ref)

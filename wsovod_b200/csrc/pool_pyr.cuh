@@ -137,6 +137,10 @@ WS_HD uint32_t proposal_key(float x1, float y1, float x2, float y2, float scale,
   axis_class(ah, H, kh, ch);
   axis_class(aw, W, kw, cw);
   if (ch > kMaxLoads || cw > kMaxLoads) return (uint32_t)PH_FALLBACK;
+  // block counts are rounded up to {2, 4}: four buckets per phase keep the per-bucket lane runs long;
+  // a bin that needs fewer blocks skips the surplus ones (duplicate-block predicates in the kernels)
+  ch = ch <= 2 ? 2 : 4;
+  cw = cw <= 2 ? 2 : 4;
   return (uint32_t)phase_of(kh, kw) | ((uint32_t)(ch - 1) << 4) | ((uint32_t)(cw - 1) << 6) |
          (aw.bin > ah.bin ? kKeyTransposed : 0u);
 }

@@ -772,10 +772,15 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the plain scan kernels (read per call, no state kept)
-static bool pool_scan_forced() {
+// Which values-only 7x7 kernel?  The block-max path pays ~10 plane rebuilds per (image, channel group),
+// so it needs enough proposals per image to win (B200: 1.45 vs 2.51 ms at 4000 proposals/image, 0.21 vs
+// 0.17 ms at 2000).  Test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the scan kernels, =0 the block-max
+// path wherever it applies (read per call, no state kept).
+static bool pool_use_blockmax(int64_t N, int64_t R) {
   const char* v = getenv("WSOVOD_B200_POOL_SCAN");
-  return v && v[0] == '1';
+  if (v && v[0] == '1') return false;
+  if (v && v[0] == '0') return true;
+  return R >= 3000 * N;
 }
 
 struct PoolWs {
@@ -922,7 +927,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   w = carve(workspace, mode, N, R, PH, PW);
   cudaStream_t st = (cudaStream_t)stream;
   // values-only 7x7 max-pool: block-max planes (roi_pool_pyr.cu) when the padded plane fits shared memory
-  if (mode == MODE_POOL && PH == 7 && PW == 7 && !argmax && !pool_scan_forced() && pool7_pyr_cb(C, H, W, R))
+  if (mode == MODE_POOL && PH == 7 && PW == 7 && !argmax && pool_use_blockmax(N, R) && pool7_pyr_cb(C, H, W, R))
     return pool7_pyr(input, N, C, H, W, rois, R, scale, row_scale, row_scale_bias, output, w.pyr, st);
   cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;

@@ -469,12 +469,14 @@ constexpr int kWWarps = kWThreads / 32;
 constexpr int kChunkBytes = 4 * 49 * 4;   // out[r, c0:c0+4] : 784 B
 constexpr int kStageBytes = kWWarps * 2 * kChunkBytes;
 
+__device__ __forceinline__ void lds4(uint32_t addr, float* f) {   // not volatile: free to be scheduled early
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr));
+}
 template <int CH, int CW>
-__device__ __forceinline__ void pyr_bin4(const unsigned char* plane, uint32_t d, uint32_t pitch, uint32_t khp,
-                                         uint32_t kwb, float* m) {
-  const uint32_t a0 = (d & 0xffffu) * 16u;
+__device__ __forceinline__ void pyr_bin4(uint32_t sbase, uint32_t d, uint32_t pitch, uint32_t khp, uint32_t kwb, float* m) {
+  const uint32_t a0 = sbase + (d & 0xffffu) * 16u;
   const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * 16u;
-  pv_set(m, *reinterpret_cast<const float4*>(plane + a0));
+  lds4(a0, m);
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
@@ -484,8 +486,72 @@ __device__ __forceinline__ void pyr_bin4(const unsigned char* plane, uint32_t d,
       if (i == 0 && j == 0) continue;
       const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
       const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
-      if (ni && nj) pv_max(m, *reinterpret_cast<const float4*>(plane + a0 + ro + co));
+      if (ni && nj) {
+        float v[4];
+        lds4(a0 + ro + co, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], v[k]);
+      }
     }
+  }
+}
+
+// One warp, one bucket segment of its run: `total` lane slots (49 per proposal), all proposals needing at
+// most CH x CW blocks per bin.  Pass = 32 consecutive slots.  s0 = slot of lane 0 inside proposal q0:
+// the pass finishes proposal q0 iff s0 >= 17 and starts a new one iff s0 == 0 or s0 >= 18 -- all
+// warp-uniform.  Results go to the warp's two staging blocks (proposal parity), finished blocks leave
+// through cp.async.bulk.
+template <int CH, int CW>
+__device__ __forceinline__ void pyrw_segment(uint32_t sbase, uint32_t pitch, uint32_t khp, uint32_t kwb,
+                                             const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
+                                             int total, float* __restrict__ outc, size_t c49, uint32_t stage_s,
+                                             uint32_t dzero, int lane, int debug) {
+  // the previous segment's last block may still be in flight from this warp's buffers
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  // two passes of look-ahead (see pyr_run)
+  uint32_t d_a = dzero, d_b = dzero;
+  uint2 pi_a = make_uint2(0u, 0u), pi_b = pi_a;
+  if (lane < total) { d_a = __ldg(dsc + lane); pi_a = __ldg(pin + (uint32_t)lane / 49u); }
+  if (32 + lane < total) { d_b = __ldg(dsc + 32 + lane); pi_b = __ldg(pin + (uint32_t)(32 + lane) / 49u); }
+  int s0 = 0, q0 = 0;
+  for (int g0 = 0; g0 < total; g0 += 32) {
+    const uint32_t d = d_a;
+    const uint2 pi = pi_a;
+    d_a = d_b;
+    pi_a = pi_b;
+    d_b = dzero;
+    const int gn = g0 + 64 + lane;
+    if (gn < total) { d_b = __ldg(dsc + gn); pi_b = __ldg(pin + (uint32_t)gn / 49u); }
+    float m[4];
+    pyr_bin4<CH, CW>(sbase, d, pitch, khp, kwb, m);
+    if (s0 == 0 || s0 >= 18) {   // a proposal starts: its buffer (used two proposals ago) must be drained
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (g0 + lane < total && !((debug & 1) && m[0] != 12345.678f)) {
+      const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
+      const int par = (q0 + (s0 + lane >= 49 ? 1 : 0)) & 1;
+      const uint32_t sa = stage_s + (uint32_t)par * kChunkBytes + ((d >> 24) & 63u) * 4u;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(__fmul_rn(m[0], sc)) : "memory");
+      asm volatile("st.shared.f32 [%0+196], %1;" ::"r"(sa), "f"(__fmul_rn(m[1], sc)) : "memory");
+      asm volatile("st.shared.f32 [%0+392], %1;" ::"r"(sa), "f"(__fmul_rn(m[2], sc)) : "memory");
+      asm volatile("st.shared.f32 [%0+588], %1;" ::"r"(sa), "f"(__fmul_rn(m[3], sc)) : "memory");
+    }
+    if (s0 >= 17) {   // proposal q0 is complete (its last slot is lane 48 - s0 of this pass)
+      const uint32_t rr = __shfl_sync(0xffffffffu, pi.x, 48 - s0) & 0x3ffffffu;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(outc + (size_t)rr * c49), "r"(stage_s + (uint32_t)(q0 & 1) * kChunkBytes), "n"(kChunkBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      s0 -= 49;
+      ++q0;
+    }
+    s0 += 32;
   }
 }
 
@@ -530,7 +596,6 @@ __global__ void __launch_bounds__(kWThreads, 1) roi_pool7_pyrw_kernel(const PyrP
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // staging: two 784-byte blocks per warp behind the plane (16-byte aligned)
   const uint32_t plane_bytes = ((uint32_t)(ntot + 1) * CS + 127u) & ~127u;
-  float* stage = reinterpret_cast<float*>(smem_raw + plane_bytes) + wid * (2 * kChunkBytes / 4);
   const uint32_t stage_s = sbase + plane_bytes + (uint32_t)wid * (2u * kChunkBytes);
 
   for (int phase = 0; phase < kPhases; ++phase) {
@@ -560,97 +625,57 @@ __global__ void __launch_bounds__(kWThreads, 1) roi_pool7_pyrw_kernel(const PyrP
     const int np = shi - slo;
     const int per_w = (np + kWWarps - 1) / kWWarps;
     const int w0 = min(np, wid * per_w), w1 = min(np, w0 + per_w);
-    const int total = (w1 - w0) * BINS;
-    if (total <= 0) continue;
-    const uint32_t* dsc = p.desc + (size_t)(gstart + slo + w0) * BINS;
-    const uint2* pin = p.pinfo + gstart + slo + w0;
+    if (w1 <= w0) continue;
     const uint32_t khp = (uint32_t)phase_kh(phase) * pitch, kwb = (uint32_t)phase_kw(phase) * CS;
     const uint32_t dzero = kDescEmpty | (uint32_t)ntot;   // idle lanes read the zero cell
     const bool fallback = phase == PH_FALLBACK;
 
-    // two passes of look-ahead (see pyr_run)
-    uint32_t d_a = dzero, d_b = dzero;
-    uint2 pi_a = make_uint2(0u, 0u), pi_b = pi_a;
-    if (lane < total) { d_a = __ldg(dsc + lane); pi_a = __ldg(pin + (uint32_t)lane / 49u); }
-    if (32 + lane < total) { d_b = __ldg(dsc + 32 + lane); pi_b = __ldg(pin + (uint32_t)(32 + lane) / 49u); }
-    for (int g0 = 0; g0 < total; g0 += 32) {
-      const int g = g0 + lane;
-      const bool act = g < total;
-      const uint32_t d = d_a;
-      const uint2 pi = pi_a;
-      d_a = d_b;
-      pi_a = pi_b;
-      d_b = dzero;
-      if (g + 64 < total) { d_b = __ldg(dsc + g + 64); pi_b = __ldg(pin + (uint32_t)(g + 64) / 49u); }
-      const int q = (int)((uint32_t)g / 49u);          // proposal within this warp's run
-      const int slot = g - q * BINS;
+    if (!fallback) {
+      // the run is sorted by bucket: walk its (at most four) bucket segments with the unrolled loop of
+      // each bucket's block counts
+      for (int sub = 5; sub < 16; sub += (sub == 7 ? 6 : 2)) {   // (ch-1) + 4 (cw-1) in {5, 7, 13, 15}
+        const int b0 = max(boff[phase * 16 + sub], slo + w0), b1 = min(boff[phase * 16 + sub + 1], slo + w1);
+        if (b1 <= b0) continue;
+        const uint32_t* dsc = p.desc + (size_t)(gstart + b0) * BINS;
+        const uint2* pin = p.pinfo + gstart + b0;
+        const int total = (b1 - b0) * BINS;
+        switch (sub) {
+          case 5:  pyrw_segment<2, 2>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane, p.debug); break;
+          case 7:  pyrw_segment<4, 2>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane, p.debug); break;
+          case 13: pyrw_segment<2, 4>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane, p.debug); break;
+          default: pyrw_segment<4, 4>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane, p.debug); break;
+        }
+      }
+      continue;
+    }
+    // fallback phase: bins needing more than kMaxLoads blocks per axis -- direct scan of the (1,1) plane
+    // with edges recomputed from the roi (lane slot = output bin), plain stores
+    const uint2* pin = p.pinfo + gstart + slo + w0;
+    const int total = (w1 - w0) * BINS;
+    for (int g = lane; g < total; g += 32) {
+      const int q = (int)((uint32_t)g / 49u);
+      const int bin = g - q * BINS;
+      const int ph = bin / 7, pw = bin - ph * 7;
+      const uint2 pi = __ldg(pin + q);
+      const float* roi = p.rois + (int64_t)(pi.x & 0x3ffffffu) * 5;
+      const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
+      int hs, he, ws, we;
+      bin_edges(ah, ph, H, hs, he);
+      bin_edges(aw, pw, W, ws, we);
       float m[CB];
-      int bin;
-      if (!fallback) {
-        // warp-uniform block counts: the largest of the (at most two) proposals in this pass; lanes
-        // whose proposal needs fewer skip the surplus blocks through the duplicate-block predicates
-        const int ch = act ? (int)((pi.x >> 26) & 3u) : 0, cw = act ? (int)((pi.x >> 28) & 3u) : 0;
-        const int chm = __reduce_max_sync(0xffffffffu, ch), cwm = __reduce_max_sync(0xffffffffu, cw);
-        bin = (int)((d >> 24) & 63u);
-#define PYRW_CASE(CH, CW) \
-  case ((CH - 1) * 4 + (CW - 1)): pyr_bin4<CH, CW>(smem_raw, d, pitch, khp, kwb, m); break;
-        switch (chm * 4 + cwm) {
-          PYRW_CASE(1, 1) PYRW_CASE(1, 2) PYRW_CASE(1, 3) PYRW_CASE(1, 4)
-          PYRW_CASE(2, 1) PYRW_CASE(2, 2) PYRW_CASE(2, 3) PYRW_CASE(2, 4)
-          PYRW_CASE(3, 1) PYRW_CASE(3, 2) PYRW_CASE(3, 3) PYRW_CASE(3, 4)
-          PYRW_CASE(4, 1) PYRW_CASE(4, 2) PYRW_CASE(4, 3) PYRW_CASE(4, 4)
-        }
-#undef PYRW_CASE
-      } else {
-        // bins needing more than kMaxLoads blocks per axis: direct scan of the (1,1) plane with edges
-        // recomputed from the roi (lane slot = output bin)
-        bin = slot;
 #pragma unroll
-        for (int k = 0; k < CB; ++k) m[k] = 0.f;
-        if (act) {
-          const int ph = bin / 7, pw = bin - ph * 7;
-          const float* roi = p.rois + (int64_t)(pi.x & 0x3ffffffu) * 5;
-          const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
-          int hs, he, ws, we;
-          bin_edges(ah, ph, H, hs, he);
-          bin_edges(aw, pw, W, ws, we);
-          if (he > hs && we > ws) {
+      for (int k = 0; k < CB; ++k) m[k] = 0.f;
+      if (he > hs && we > ws) {
 #pragma unroll
-            for (int k = 0; k < CB; ++k) m[k] = -FLT_MAX;
-            for (int h = hs; h < he; ++h) {
-              const unsigned char* a = smem_raw + (uint32_t)((h + kPad) * WP + ws + kPad) * CS;
-              for (int w = ws; w < we; ++w, a += CS) pv_max(m, *reinterpret_cast<const float4*>(a));
-            }
-          }
+        for (int k = 0; k < CB; ++k) m[k] = -FLT_MAX;
+        for (int h = hs; h < he; ++h) {
+          const unsigned char* a = smem_raw + (uint32_t)((h + kPad) * WP + ws + kPad) * CS;
+          for (int w = ws; w < we; ++w, a += CS) pv_max(m, *reinterpret_cast<const float4*>(a));
         }
       }
-      // a proposal starts in this pass -> its buffer must be free: the copy of the proposal two before it
-      // (committed at least a pass ago) has to be done READING shared memory
-      const unsigned starts = __ballot_sync(0xffffffffu, act && slot == 0);
-      if (starts) {
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-      }
-      if (act && !((p.debug & 1) && m[0] != 12345.678f)) {
-        const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
-        float* sb = stage + (q & 1) * (kChunkBytes / 4) + bin;
+      float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + bin;
 #pragma unroll
-        for (int k = 0; k < CB; ++k) sb[k * BINS] = __fmul_rn(m[k], sc);
-      }
-      // the proposal whose last slot (49 q + 48) lies in [g0, g0 + 32) is complete: bulk-copy it out
-      const int qc = (g0 + 31 - 48 >= 0) ? (g0 + 31 - 48) / BINS : -1;
-      const int last = qc * BINS + 48;
-      if (qc >= 0 && last >= g0 && last < total) {
-        const uint32_t rr = __shfl_sync(0xffffffffu, pi.x, last - g0) & 0x3ffffffu;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                       ::"l"(outc + (size_t)rr * c49), "r"(stage_s + (uint32_t)(qc & 1) * kChunkBytes), "n"(kChunkBytes)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
+      for (int k = 0; k < CB; ++k) __stcs(o + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
     }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -711,8 +736,10 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
   { const char* dbg = getenv("WSOVOD_B200_POOL_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   const size_t smem_w = ((pyr_smem(H, W, 4) + 127) & ~(size_t)127) + kStageBytes;
-  const bool tma = cb == 4 && C % 4 == 0 && ((uintptr_t)output & 15) == 0 && smem_w + 1024 <= (size_t)kMaxSmemOptin &&
-                   !(p.debug & 16);
+  // experimental (WSOVOD_B200_POOL_TMA=1): correct, but not yet faster than the plain stores at c2 (1.55 vs 1.45 ms)
+  const char* want_tma = getenv("WSOVOD_B200_POOL_TMA");
+  const bool tma = want_tma && want_tma[0] == '1' && cb == 4 && C % 4 == 0 && ((uintptr_t)output & 15) == 0 &&
+                   smem_w + 1024 <= (size_t)kMaxSmemOptin;
   if (tma) {
     p.CG = (int)(C / 4);
     const int64_t units = N * p.CG;
