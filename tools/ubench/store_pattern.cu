@@ -33,6 +33,49 @@ __global__ void __launch_bounds__(1024, 1) pattern(float* out, int C, int R, int
   }
 }
 
+// (V1) warp-owned proposals: 49 bins as 32 + 17 lanes, the 8 stores of a proposal back to back
+__global__ void __launch_bounds__(1024, 1) pattern_warp(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int r = wid; r < R; r += nw) {
+    float* o = outc + (size_t)r * c49;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __stcs(o + k * 49 + lane, (float)r);
+      if (lane < 17) __stcs(o + k * 49 + 32 + lane, (float)r);
+    }
+  }
+}
+// (V2) same shape of accesses on a fake layout with 48 floats per (proposal, channel): every warp store is
+// 64-byte aligned, i.e. only whole 32-byte sectors are written
+__global__ void __launch_bounds__(1024, 1) pattern48(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = R * 48;
+  const size_t c48 = (size_t)C * 48;
+  float* outc = out + (size_t)cg * 4 * 48 + (size_t)n * R * c48;
+  for (int f = wid * 32 + lane; f < total; f += nw * 32) {
+    const int r = f / 48, bin = f - r * 48;
+    float* o = outc + (size_t)r * c48 + bin;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(o + k * 48, (float)f);
+  }
+}
+// (V3) real layout, each lane stores its 4 channels for bin AND the warp only ever writes whole proposals:
+// lanes walk 196 consecutive floats of the chunk but in (bin-major) order: lane l, step t -> run index
+__global__ void __launch_bounds__(1024, 1) pattern_shuffled(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int r = wid; r < R; r += nw) {
+    float* o = outc + (size_t)r * c49;
+    for (int v = lane; v < 196; v += 32) __stcs(o + v, (float)r);
+  }
+}
+
 // (1) 784-byte chunk per (proposal, channel group) written as 49 float4 (same bytes, same chunk addresses)
 __global__ void __launch_bounds__(1024, 1) chunk128(float* out, int C, int R, int CG) {
   const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
@@ -116,6 +159,9 @@ int main() {
   run("pattern .cg", [&] { pattern<3><<<N * 128, 1024>>>(out, C, R, 128, 0); });
   run("pattern .cs skewed", [&] { pattern<0><<<N * 128, 1024>>>(out, C, R, 128, 1); });
   run("pattern default skewed", [&] { pattern<1><<<N * 128, 1024>>>(out, C, R, 128, 1); });
+  run("V1 warp-owned 32+17 lanes", [&] { pattern_warp<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V2 fake 48-float runs (whole sectors)", [&] { pattern48<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V3 warp-owned chunk, consecutive", [&] { pattern_shuffled<<<N * 128, 1024>>>(out, C, R, 128); });
   run("chunk 784B as float4", [&] { chunk128<<<N * 128, 1024>>>(out, C, R, 128); });
   run("chunk 784B as float4 512thr", [&] { chunk128<<<N * 128, 512>>>(out, C, R, 128); });
   run("chunk 784B as scalars", [&] { chunk32<<<N * 128, 1024>>>(out, C, R, 128); });
