@@ -313,7 +313,7 @@ def main():
                        "global_proposals_per_step": world * M, "pool_argmax": with_arg,
                        "l2": "inputs+outputs per step (3.5 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "roofline": {"bound": "hbm", "kernel": "roi_pool7_kernel (ROI pool)", "achieved": pool_gbs,
+            "roofline": {"bound": "hbm", "kernel": "roi_pool7_pyr_kernel (ROI max-pool, block-max planes)", "achieved": pool_gbs,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
                          "peak_source": peaks["source"], "traffic": load_traffic(with_arg),
                          "share_of_step": t_pool / (ms_total / args.steps)},

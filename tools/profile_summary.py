@@ -49,8 +49,10 @@ def main():
                 v, u = float(r[idx[m]]), units[idx[m]].lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
             tot = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            if k.startswith("roi_pool7_pyr_kernel<4>") or k.startswith("roi_pool7_pyr_kernel<(int)4>"):
+                traffic["roi_pool"] = tot          # values-only pooling of bench.py: the block-max kernel
             if k.startswith("roi_pool7_kernel<4, 0>") or k.startswith("roi_pool7_kernel<(int)4, (bool)0>"):
-                traffic["roi_pool"] = tot
+                traffic.setdefault("roi_pool_scan", tot)
             if k.startswith("roi_pool7_kernel<4, 1>") or k.startswith("roi_pool7_kernel<(int)4, (bool)1>"):
                 traffic["roi_pool+argmax"] = tot
     traffic["source"] = f"ncu --set full, {os.path.basename(rep)}, config c2, dram__bytes_read.sum + dram__bytes_write.sum per launch"

@@ -18,7 +18,10 @@ sizes = w["image_sizes"].to(DEV)
 boxes = rois[:, 1:].contiguous()
 for _ in range(reps):
     out, arg = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
-    out2, _ = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)
+    out2, _ = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)          # block-max kernel (>= 3000 proposals/image)
+    os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+    out3, _ = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)          # the scan kernel it replaced
+    del os.environ["WSOVOD_B200_POOL_SCAN"]
     _, probs = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)
     det = ops.detections(probs, boxes, off, sizes, w["R"], 1e-5, 0.3, 100, ops.IOU_TV_CUDA)
 torch.cuda.synchronize()

@@ -694,22 +694,26 @@ int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R) {
   return 0;
 }
 
+static int64_t pyr_split(int64_t units, int64_t proposals_per_image) {
+  if (units >= 100) return 1;
+  const int64_t fill = ceil_div(kNumSMs, std::max<int64_t>(units, 1));
+  return std::max<int64_t>(1, std::min<int64_t>(fill, proposals_per_image / 1500));
+}
+
 template <int CB>
 static int pyr_launch_main(PyrParams& p, int64_t R, cudaStream_t st) {
   const size_t smem = pyr_smem(p.H, p.W, CB);
   p.CG = (int)ceil_div(p.C, CB);
-  // every CTA of an image rebuilds all planes, so proposals are only split when (image, channel group)
-  // units alone cannot fill the machine twice over
+  // every CTA of an image rebuilds all planes, so an image's proposals are only split over several CTAs
+  // when the (image, channel group) units cannot even fill most of one wave (one image of C = 512 gives
+  // 128 units: 0.21 ms unsplit against 0.54 ms split three ways on a B200)
   const int64_t units = (int64_t)p.N * p.CG;
-  int64_t S = units >= 2 * kNumSMs ? 1 : ceil_div(2 * kNumSMs, units);
-  const int64_t avg = std::max<int64_t>(R / std::max(p.N, 1), 1);
-  S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 512)));
-  p.S = (int)S;
-  if (units * S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
+  p.S = (int)pyr_split(units, R / std::max<int64_t>(p.N, 1));
+  if (units * p.S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
   auto kern = roi_pool7_pyr_kernel<CB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<(unsigned)(units * S), 1024, smem, st>>>(p);
+  kern<<<(unsigned)(units * p.S), 1024, smem, st>>>(p);
   return after_launch();
 }
 
@@ -743,8 +747,7 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   if (tma) {
     p.CG = (int)(C / 4);
     const int64_t units = N * p.CG;
-    int64_t S = units >= 2 * kNumSMs ? 1 : ceil_div(2 * kNumSMs, units);
-    S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(std::max<int64_t>(R / std::max<int64_t>(N, 1), 1), 512)));
+    const int64_t S = pyr_split(units, R / std::max<int64_t>(N, 1));
     p.S = (int)S;
     if (units * S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
     e = cudaFuncSetAttribute(roi_pool7_pyrw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
