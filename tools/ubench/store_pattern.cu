@@ -48,6 +48,64 @@ __global__ void __launch_bounds__(1024, 1) pattern_warp(float* out, int C, int R
     }
   }
 }
+// (V1b) as V1 but channel-major inside each half: k0 A, k1 A, k2 A, k3 A, k0 B, ... (adjacent pieces 4 stores apart)
+__global__ void __launch_bounds__(1024, 1) pattern_warp_b(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int r = wid; r < R; r += nw) {
+    float* o = outc + (size_t)r * c49;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(o + k * 49 + lane, (float)r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (lane < 17) __stcs(o + k * 49 + 32 + lane, (float)r);
+  }
+}
+// (V4) every warp walks a contiguous run of slots, 64 per pass (slot f and f + 32 per lane, any alignment
+// against the 49-slot proposals); ORDER 0: k-major per half (k0 A..k3 A, k0 B..k3 B), 1: halves adjacent
+template <int ORDER>
+__global__ void __launch_bounds__(1024, 1) pattern_contig(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  const int per_w = (R + nw - 1) / nw;
+  const int r0 = min(R, wid * per_w), r1 = min(R, r0 + per_w);
+  const int total = (r1 - r0) * 49;
+  for (int g = lane; g < total; g += 64) {
+    const int ra = g / 49, ba = g - ra * 49;
+    const int g2 = g + 32, rb = g2 / 49, bb = g2 - rb * 49;
+    float* oa = outc + (size_t)(r0 + ra) * c49 + ba;
+    float* ob = outc + (size_t)(r0 + rb) * c49 + bb;
+    const bool hb = g2 < total;
+    if (ORDER == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) __stcs(oa + k * 49, (float)g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (hb) __stcs(ob + k * 49, (float)g);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { __stcs(oa + k * 49, (float)g); if (hb) __stcs(ob + k * 49, (float)g); }
+    }
+  }
+}
+// (V5) contiguous run, ONE slot per lane per pass (32 slots per pass)
+__global__ void __launch_bounds__(1024, 1) pattern_contig32(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  const int per_w = (R + nw - 1) / nw;
+  const int r0 = min(R, wid * per_w), r1 = min(R, r0 + per_w);
+  const int total = (r1 - r0) * 49;
+  for (int g = lane; g < total; g += 32) {
+    const int ra = g / 49, ba = g - ra * 49;
+    float* oa = outc + (size_t)(r0 + ra) * c49 + ba;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(oa + k * 49, (float)g);
+  }
+}
 // (V2) same shape of accesses on a fake layout with 48 floats per (proposal, channel): every warp store is
 // 64-byte aligned, i.e. only whole 32-byte sectors are written
 __global__ void __launch_bounds__(1024, 1) pattern48(float* out, int C, int R, int CG) {
@@ -160,6 +218,10 @@ int main() {
   run("pattern .cs skewed", [&] { pattern<0><<<N * 128, 1024>>>(out, C, R, 128, 1); });
   run("pattern default skewed", [&] { pattern<1><<<N * 128, 1024>>>(out, C, R, 128, 1); });
   run("V1 warp-owned 32+17 lanes", [&] { pattern_warp<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V1b warp-owned, k-major halves", [&] { pattern_warp_b<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V4 contiguous 64/pass k-major", [&] { pattern_contig<0><<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V4 contiguous 64/pass halves adjacent", [&] { pattern_contig<1><<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V5 contiguous 32/pass", [&] { pattern_contig32<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V2 fake 48-float runs (whole sectors)", [&] { pattern48<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V3 warp-owned chunk, consecutive", [&] { pattern_shuffled<<<N * 128, 1024>>>(out, C, R, 128); });
   run("chunk 784B as float4", [&] { chunk128<<<N * 128, 1024>>>(out, C, R, 128); });

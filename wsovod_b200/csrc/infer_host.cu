@@ -113,33 +113,53 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
   const size_t plane = sizeof(float) * (size_t)(C * H * W);
   const int64_t out_row = C * (int64_t)pooled * pooled;
   const size_t ws_pool_bytes = a.ws_align - a.ws_pool, ws_align_bytes = a.ws_det - a.ws_align;
-  // per image: copy (features, embeddings) -> pool -> align; image n+1's copies overlap image n's kernels
+  // Copies: all feature planes first, then the region embeddings.  Pooling of image n starts when its plane
+  // has landed (the big kernels overlap the rest of the copies); alignment only needs the embeddings, so
+  // what is left after the LAST byte arrives is one alignment launch + the detections, not a pooling.
+  std::vector<cudaEvent_t> ev_emb((size_t)N, nullptr);
+  auto cleanup2 = [&]() { for (auto x : ev_emb) if (x) cudaEventDestroy(x); };
+#define CK2(call) do { e = (call); if (e != cudaSuccess) { cleanup2(); cleanup(); return (int)e; } } while (0)
+#define RC2(call) do { rc = (call); if (rc) { cleanup2(); cleanup(); return rc; } } while (0)
+  for (int64_t n = 0; n < N; ++n) {
+    CK2(h2d(a.feat + plane * (size_t)n, h_features + (size_t)n * (size_t)(C * H * W), plane));
+    if (piped) {
+      CK2(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
+      CK2(cudaEventRecord(ev[n], cs));
+    }
+  }
   for (int64_t n = 0; n < N; ++n) {
     const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
-    CK(h2d(a.feat + plane * (size_t)n, h_features + (size_t)n * (size_t)(C * H * W), plane));
-    CK(h2d(a.emb + sizeof(float) * (size_t)(r0 * D), h_region_emb + r0 * D, sizeof(float) * (size_t)(rn * D)));
+    CK2(h2d(a.emb + sizeof(float) * (size_t)(r0 * D), h_region_emb + r0 * D, sizeof(float) * (size_t)(rn * D)));
     if (piped) {
-      CK(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
-      CK(cudaEventRecord(ev[n], cs));
+      CK2(cudaEventCreateWithFlags(&ev_emb[n], cudaEventDisableTiming));
+      CK2(cudaEventRecord(ev_emb[n], cs));
     }
   }
   // One pooling launch per image (N = 1, that image's plane and rois) so it can start as soon as the
   // image has landed.  The rois keep their global batch index; with N = 1 the kernel clamps it to 0.
   for (int64_t n = 0; n < N; ++n) {
     const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
-    if (piped) CK(cudaStreamWaitEvent(st, ev[n], 0));
+    if (piped) CK2(cudaStreamWaitEvent(st, ev[n], 0));
     if (rn == 0) continue;
-    RC(wsovod_b200_roi_pool_fwd((const float*)(d + a.feat + plane * (size_t)n), 1, C, H, W,
-                                (const float*)(d + a.rois) + 5 * r0, rn,
-                                spatial_scale, pooled, pooled,
-                                h_objectness ? (const float*)(d + a.obj) + r0 : nullptr, 1.0f,
-                                (float*)(d + a.pooled) + r0 * out_row,
-                                with_argmax ? (int32_t*)(d + a.argmax) + r0 * out_row : nullptr,
-                                d + a.ws_pool, ws_pool_bytes, st));
-    RC(wsovod_b200_align_fwd((const float*)(d + a.emb) + r0 * D, (const float*)(d + a.text), rn, D, K, temperature,
-                             1, 1, nullptr, precision, nullptr, (float*)(d + a.probs) + r0 * (K + 1),
-                             d + a.ws_align, ws_align_bytes, st));
+    RC2(wsovod_b200_roi_pool_fwd((const float*)(d + a.feat + plane * (size_t)n), 1, C, H, W,
+                                 (const float*)(d + a.rois) + 5 * r0, rn,
+                                 spatial_scale, pooled, pooled,
+                                 h_objectness ? (const float*)(d + a.obj) + r0 : nullptr, 1.0f,
+                                 (float*)(d + a.pooled) + r0 * out_row,
+                                 with_argmax ? (int32_t*)(d + a.argmax) + r0 * out_row : nullptr,
+                                 d + a.ws_pool, ws_pool_bytes, st));
   }
+  for (int64_t n = 0; n < N; ++n) {
+    const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
+    if (piped) CK2(cudaStreamWaitEvent(st, ev_emb[n], 0));
+    if (rn == 0) continue;
+    RC2(wsovod_b200_align_fwd((const float*)(d + a.emb) + r0 * D, (const float*)(d + a.text), rn, D, K, temperature,
+                              1, 1, nullptr, precision, nullptr, (float*)(d + a.probs) + r0 * (K + 1),
+                              d + a.ws_align, ws_align_bytes, st));
+  }
+  cleanup2();
+#undef CK2
+#undef RC2
   // class-agnostic boxes = the proposal boxes (columns 1..4 of rois) -> packed [R,4] copy (rois rows are
   // 20 B apart) into the embedding buffer, which align_fwd has finished reading on this stream
   float* dboxes = (float*)(d + a.emb);
