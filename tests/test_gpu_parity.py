@@ -396,7 +396,7 @@ import os  # noqa: E402
 @contextlib.contextmanager
 def _pool_variant(scan=None, tma=None):
     """select the values-only pooling kernel for the calls inside: scan=True the plain scan kernels,
-    scan=False the block-max path wherever it applies (the library's own choice needs >= 3000 proposals
+    scan=False the block-max path wherever it applies (the library's own choice needs >= 1200 proposals
     per image), tma=True its bulk-store flavour"""
     old = {k: os.environ.get(k) for k in ("WSOVOD_B200_POOL_SCAN", "WSOVOD_B200_POOL_TMA")}
     if scan is not None:

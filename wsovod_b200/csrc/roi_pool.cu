@@ -773,14 +773,15 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // host side
 // ------------------------------------------------------------------------------------------------
 // Which values-only 7x7 kernel?  The block-max path pays ~10 plane rebuilds per (image, channel group),
-// so it needs enough proposals per image to win (B200: 1.45 vs 2.51 ms at 4000 proposals/image, 0.21 vs
-// 0.17 ms at 2000).  Test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the scan kernels, =0 the block-max
+// so it needs enough proposals per image to win: on a B200 the two cross at 1000-1200 proposals per
+// image for every map / batch shape tried (tools/kbench_pool_sweep.py: 8 x 4000 proposals 1.45 vs 2.51 ms,
+// 1 x 2000 on a 60x80 map 0.135 vs 0.166 ms, 8 x 500 0.63 vs 0.40 ms).  Test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the scan kernels, =0 the block-max
 // path wherever it applies (read per call, no state kept).
 static bool pool_use_blockmax(int64_t N, int64_t R) {
   const char* v = getenv("WSOVOD_B200_POOL_SCAN");
   if (v && v[0] == '1') return false;
   if (v && v[0] == '0') return true;
-  return R >= 3000 * N;
+  return R >= 1200 * N;
 }
 
 struct PoolWs {
