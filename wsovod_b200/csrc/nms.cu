@@ -174,29 +174,24 @@ constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == hist
 // waves of 4 x 148 = 592
 constexpr int kDcThreads = 384;
 constexpr int kSelectTarget = 512;    // aim: at least this many best candidates in the prefix
-constexpr int kSelectMin = 2048;      // columns shorter than this are simply sorted
-
-struct FirstSlots {     // "lowest alive candidate" of the current chunk: block-wide atomicMin + per-warp box
-  int first[3];          // rotating: round t uses [t % 3] and re-arms [(t + 1) % 3]
-  float4 box[2][kNmsWarps];
-};
+constexpr int kSelectMin = 512;       // columns shorter than this are simply sorted
 
 // one CTA per (class, image):
 //   1. gather the column's candidates (score > thr, finite row) as 64-bit keys in shared memory
 //   2. bitonic-sort them once (score descending, row ascending)
 //   3. greedy NMS over the sorted list in chunks of one candidate per thread: a chunk is first tested
-//      against the boxes kept so far, then resolved with "lowest alive thread is kept, suppresses the
-//      rest" rounds (one barrier per kept box); stops at `limit` kept boxes
+//      against the boxes kept so far, then resolved warp by warp (shuffle broadcast + ballot inside the
+//      warp, one barrier per warp); stops at `limit` kept boxes
 //   4. append (score, row*K+class) keys to the image's kept list
 template <int MODE>
-__global__ void __launch_bounds__(kDcThreads) det_class_kernel(
+__global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     const float* __restrict__ probs, const int64_t* __restrict__ offsets, const uint8_t* __restrict__ valid,
     const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap,
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
     int2* __restrict__ runs) {
   extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ FirstSlots slots;
   __shared__ int s_n, s_base, s_sel, s_bstar, s_m;
+  __shared__ int s_new[2];
   __shared__ int s_wsum[kNmsWarps];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);                 // [npad_cap]
   float4* kbox = reinterpret_cast<float4*>(sm + (size_t)npad_cap * sizeof(unsigned long long));   // [limit]
@@ -206,7 +201,7 @@ __global__ void __launch_bounds__(kDcThreads) det_class_kernel(
   const int k = blockIdx.x, n = blockIdx.y;
   const int64_t r0 = offsets[n], r1 = offsets[n + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_n = 0; slots.first[0] = slots.first[1] = slots.first[2] = 0x7fffffff; }
+  if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const int K1 = K + 1;
   for (int64_t r = r0 + threadIdx.x; r < r1; r += kDcThreads) {
@@ -221,15 +216,19 @@ __global__ void __launch_bounds__(kDcThreads) det_class_kernel(
     return;
   }
 
-  // Candidate list for the greedy pass.  A class rarely needs more than its best ~1000 candidates to
-  // collect `limit` survivors, so for long columns the top of the list is selected exactly with a
-  // 4096-bin histogram over the 12 leading key bits (no sort of the tail); if that prefix runs out
-  // before `limit` boxes are kept, the whole column is sorted and the pass repeated (rare, exact).
+  // Candidate list for the greedy pass.  A class rarely needs more than its best few hundred candidates
+  // to collect `limit` survivors (c2: ~120 for 100), so the top of the column is selected exactly with a
+  // 2048-bin histogram over the 11 leading key bits (no sort of the tail) -- first a short prefix
+  // (>= 2 * limit keys), then a longer one (>= kSelectTarget), then the whole column: a pass whose prefix
+  // runs dry before `limit` boxes are kept is repeated on the next level (exact).
   unsigned long long* list = skey;
   int ln = nc;
   bool complete = true;
-  if (nc > kSelectMin) {
+  // CTA-uniform: selects the smallest histogram prefix holding >= target keys into ssel; false if it does
+  // not fit (or is the whole column anyway)
+  auto select_prefix = [&](int target) -> bool {
     int* hist = reinterpret_cast<int*>(ssel);
+    __syncthreads();                                     // ssel / s_* free to be rewritten
     for (int i = threadIdx.x; i < kSelectBins; i += kDcThreads) hist[i] = 0;
     if (threadIdx.x == 0) { s_sel = 0; s_m = 0; }
     __syncthreads();
@@ -250,29 +249,34 @@ __global__ void __launch_bounds__(kDcThreads) det_class_kernel(
     __syncthreads();
     int before = inc - mine;
     for (int w2 = 0; w2 < wid; ++w2) before += s_wsum[w2];
-    if (before < kSelectTarget && before + mine >= kSelectTarget) {   // exactly one thread
+    if (before < target && before + mine >= target) {    // exactly one thread
       int cum = before;
       for (int j = 0; j < PER && threadIdx.x * PER + j < kSelectBins; ++j) {
         cum += hist[threadIdx.x * PER + j];
-        if (cum >= kSelectTarget) { s_sel = cum; s_bstar = threadIdx.x * PER + j; break; }
+        if (cum >= target) { s_sel = cum; s_bstar = threadIdx.x * PER + j; break; }
       }
     }
     __syncthreads();
     const int selcount = s_sel, bstar = s_bstar;
-    if (selcount > 0 && selcount <= kSelectCap && selcount < nc) {
-      __syncthreads();                                   // everyone is done reading the histogram
-      for (int i = threadIdx.x; i < nc; i += kDcThreads) {
-        const unsigned long long key = skey[i];
-        if ((int)(key >> kSelectShift) <= bstar) ssel[atomicAdd(&s_m, 1)] = key;
-      }
-      __syncthreads();
-      list = ssel;
-      ln = selcount;
-      complete = false;
+    if (!(selcount > 0 && selcount <= kSelectCap && selcount < nc)) return false;
+    __syncthreads();                                     // everyone is done reading the histogram
+    for (int i = threadIdx.x; i < nc; i += kDcThreads) {
+      const unsigned long long key = skey[i];
+      if ((int)(key >> kSelectShift) <= bstar) ssel[atomicAdd(&s_m, 1)] = key;
     }
-  }
+    __syncthreads();
+    list = ssel;
+    ln = selcount;
+    complete = false;
+    return true;
+  };
   int kept = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    list = skey; ln = nc; complete = true;
+    if (attempt < 2 && nc > kSelectMin) {
+      const int target = attempt == 0 ? max(2 * limit, 128) : kSelectTarget;
+      if ((attempt == 1 && target <= max(2 * limit, 128)) || !select_prefix(target)) continue;   // next level
+    }
     int npad = 2;
     while (npad < ln) npad <<= 1;
     for (int i = ln + threadIdx.x; i < npad; i += kDcThreads) list[i] = kDead;
@@ -280,7 +284,6 @@ __global__ void __launch_bounds__(kDcThreads) det_class_kernel(
     bitonic_sort_smem(list, npad);
 
     kept = 0;
-    int buf = 0, rnd = 0;
     for (int base = 0; base < ln && kept < limit; base += kDcThreads) {
       const int i = base + threadIdx.x;
       bool alive = i < ln;
@@ -292,43 +295,43 @@ __global__ void __launch_bounds__(kDcThreads) det_class_kernel(
         for (int j = 0; j < kept && alive; ++j)
           if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
       }
-      // rounds: the lowest alive thread of the chunk is the next kept box
-      while (kept < limit) {
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if (bal) {
-          const int fl = __ffs(bal) - 1;
-          if (lane == fl) {
-            slots.box[buf][wid] = box;
-            atomicMin(&slots.first[rnd], wid * 32 + fl);
+      // The chunk is resolved warp by warp in list order.  The warp whose turn it is settles its 32
+      // candidates among themselves -- every still-alive lane, in order, is kept, its box is broadcast
+      // with shuffles and the ballot of the lanes it suppresses clears them -- and appends the kept
+      // boxes to the shared list; after one barrier the later warps test their alive lanes against just
+      // those new boxes.  Barriers per chunk: one per warp that still had work (typically ~5 until
+      // `limit` boxes are kept), not one per kept box.
+      const float my_area = area_rn(box);
+      for (int w = 0; w < kDcThreads / 32 && kept < limit; ++w) {
+        if (wid == w) {
+          unsigned am = __ballot_sync(0xffffffffu, alive);
+          int nnew = 0;
+          while (am && kept + nnew < limit) {
+            const int sl = __ffs(am) - 1;                      // next kept lane
+            const float4 kb = make_float4(__shfl_sync(0xffffffffu, box.x, sl), __shfl_sync(0xffffffffu, box.y, sl),
+                                          __shfl_sync(0xffffffffu, box.z, sl), __shfl_sync(0xffffffffu, box.w, sl));
+            const float ka = __shfl_sync(0xffffffffu, my_area, sl);
+            if (lane == sl) { kbox[kept + nnew] = kb; karea[kept + nnew] = ka; kkey[kept + nnew] = key; }
+            const bool sup = lane > sl && ((am >> lane) & 1u) && suppresses<MODE>(kb, ka, box, thr);
+            am &= ~__ballot_sync(0xffffffffu, sup);
+            am &= ~(1u << sl);
+            ++nnew;
           }
+          alive = false;                                       // kept or suppressed, or past the limit: done either way
+          if (lane == 0) s_new[w & 1] = nnew;
         }
-        // re-arm the slot of the NEXT round: its last readers (round t-2) all passed barrier t-1 already
-        if (threadIdx.x == 0) slots.first[rnd == 2 ? 0 : rnd + 1] = 0x7fffffff;
         __syncthreads();
-        const int first = slots.first[rnd];
-        rnd = rnd == 2 ? 0 : rnd + 1;
-        if (first == 0x7fffffff) { buf ^= 1; break; }
-        const float4 kb = slots.box[buf][first >> 5];
-        const float ka = area_rn(kb);
-        buf ^= 1;
-        if ((int)threadIdx.x == first) {
-          kbox[kept] = kb; karea[kept] = ka; kkey[kept] = key;
-          alive = false;
-        } else if (alive && (int)threadIdx.x > first && suppresses<MODE>(kb, ka, box, thr)) {
-          alive = false;
+        const int nnew = s_new[w & 1];      // the next writer of this slot (step w+2) is two barriers away
+        if (wid > w && alive) {
+          for (int j = kept; j < kept + nnew && alive; ++j)
+            if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
         }
-        ++kept;
+        kept += nnew;
       }
       __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
     }
     if (complete || kept >= limit) break;
-    // the selected prefix ran dry: redo the pass on the full column (the round slots are all re-armed:
-    // every exit above leaves them at 0x7fffffff or about to be, so reset them explicitly)
-    __syncthreads();
-    if (threadIdx.x == 0) slots.first[0] = slots.first[1] = slots.first[2] = 0x7fffffff;
-    list = skey;
-    ln = nc;
-    complete = true;
+    // the selected prefix ran dry: redo the pass on the next level
     __syncthreads();
   }
   __syncthreads();
