@@ -394,15 +394,13 @@ import os  # noqa: E402
 
 
 @contextlib.contextmanager
-def _pool_variant(scan=None, tma=None):
+def _pool_variant(scan=None):
     """select the values-only pooling kernel for the calls inside: scan=True the plain scan kernels,
     scan=False the block-max path wherever it applies (the library's own choice needs >= 1200 proposals
-    per image), tma=True its bulk-store flavour"""
-    old = {k: os.environ.get(k) for k in ("WSOVOD_B200_POOL_SCAN", "WSOVOD_B200_POOL_TMA")}
+    per image)"""
+    old = {k: os.environ.get(k) for k in ("WSOVOD_B200_POOL_SCAN",)}
     if scan is not None:
         os.environ["WSOVOD_B200_POOL_SCAN"] = "1" if scan else "0"
-    if tma is not None:
-        os.environ["WSOVOD_B200_POOL_TMA"] = "1" if tma else "0"
     try:
         yield
     finally:
@@ -444,16 +442,15 @@ def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
     sc = fin * (obj + 1).view(-1, 1, 1, 1)
     with _pool_variant(scan=True):
         scan = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)[0]
-    for tma in (False, True):     # plain stores / staged blocks leaving through cp.async.bulk (C % 4 == 0 only)
-        with _pool_variant(scan=False, tma=tma):
-            out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
-            out_s, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
-                                    with_argmax=False)
-        assert arg.numel() == 0
-        assert torch.equal(out.cpu(), ref)
-        assert torch.equal(scan, out)
-        got = out_s.cpu()
-        assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
+    with _pool_variant(scan=False):
+        out, arg = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=False)
+        out_s, _ = ops.roi_pool(feat.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
+                                with_argmax=False)
+    assert arg.numel() == 0
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(scan, out)
+    got = out_s.cpu()
+    assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
 
 
 def test_roi_pool_blockmax_empty_images_and_single_class():
@@ -463,9 +460,8 @@ def test_roi_pool_blockmax_empty_images_and_single_class():
     b = synth.proposals(200, 320, 448, g)
     rois = torch.cat([torch.full((200, 1), 2.0), b], 1)             # images 0, 1, 3 stay empty
     same = torch.tensor([[1.0, 64.0, 64.0, 64.0 + 8 * 27, 64.0 + 8 * 20]]).repeat(300, 1)   # 28 x 21 cells
-    for tma in (False, True):
-        with _pool_variant(scan=False, tma=tma):
-            for r in (rois, rois[:1].contiguous(), same):
-                ref, _ = oracle.roi_pool(feat, r, 1 / 8, 7)
-                out, _ = ops.roi_pool(feat.to(DEV), r.to(DEV), 1 / 8, 7, with_argmax=False)
-                assert torch.equal(out.cpu(), ref)
+    with _pool_variant(scan=False):
+        for r in (rois, rois[:1].contiguous(), same):
+            ref, _ = oracle.roi_pool(feat, r, 1 / 8, 7)
+            out, _ = ops.roi_pool(feat.to(DEV), r.to(DEV), 1 / 8, 7, with_argmax=False)
+            assert torch.equal(out.cpu(), ref)

@@ -106,6 +106,38 @@ __global__ void __launch_bounds__(1024, 1) pattern_contig32(float* out, int C, i
     for (int k = 0; k < 4; ++k) __stcs(oa + k * 49, (float)g);
   }
 }
+// (V6) strided passes over a slot stream padded to 64 slots per proposal (49 real + 15 idle): every warp
+// store stays inside one proposal (bins 0..31 or 32..48), the two halves come from different warps
+__global__ void __launch_bounds__(1024, 1) pattern_pad64(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = R * 64;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int f = wid * 32 + lane; f < total; f += nw * 32) {
+    const int r = f >> 6, bin = f & 63;
+    if (bin >= 49) continue;
+    float* o = outc + (size_t)r * c49 + bin;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(o + k * 49, (float)f);
+  }
+}
+// (V7) as V6 but a lane handles slot f and f + 32 of the SAME proposal (one warp = one proposal per pass)
+__global__ void __launch_bounds__(1024, 1) pattern_pad64_pair(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int r = wid; r < R; r += nw) {
+    float* o = outc + (size_t)r * c49 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(o + k * 49, (float)r);
+    if (lane < 17) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) __stcs(o + 32 + k * 49, (float)r);
+    }
+  }
+}
 // (V2) same shape of accesses on a fake layout with 48 floats per (proposal, channel): every warp store is
 // 64-byte aligned, i.e. only whole 32-byte sectors are written
 __global__ void __launch_bounds__(1024, 1) pattern48(float* out, int C, int R, int CG) {
@@ -222,6 +254,8 @@ int main() {
   run("V4 contiguous 64/pass k-major", [&] { pattern_contig<0><<<N * 128, 1024>>>(out, C, R, 128); });
   run("V4 contiguous 64/pass halves adjacent", [&] { pattern_contig<1><<<N * 128, 1024>>>(out, C, R, 128); });
   run("V5 contiguous 32/pass", [&] { pattern_contig32<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V6 padded 64 slots, strided passes", [&] { pattern_pad64<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V7 padded, one proposal per warp pass", [&] { pattern_pad64_pair<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V2 fake 48-float runs (whole sectors)", [&] { pattern48<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V3 warp-owned chunk, consecutive", [&] { pattern_shuffled<<<N * 128, 1024>>>(out, C, R, 128); });
   run("chunk 784B as float4", [&] { chunk128<<<N * 128, 1024>>>(out, C, R, 128); });

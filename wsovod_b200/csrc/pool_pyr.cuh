@@ -150,9 +150,11 @@ WS_HD int key_phase(uint32_t key) { return (int)(key & 15u); }
 WS_HD int key_bucket(uint32_t key) { return (int)((key & 15u) * 16u + ((key >> 4) & 15u)); }
 
 // 32-bit bin descriptor: bits 0-15 cell index of the first block in the padded plane,
-//   16-19 rows to the last block, 20-23 columns to the last block, 24-29 output bin, 31 empty bin.
+//   16-19 rows to the last block, 20-23 columns to the last block, 24-29 output bin, 30 idle slot, 31 empty bin.
 // An empty bin points at the all-zero cell behind the plane, so the kernel needs no special case.
 constexpr uint32_t kDescEmpty = 0x80000000u;
+constexpr uint32_t kDescIdle = 0x40000000u;   // lane slot without a bin (slots 49..63 of a proposal)
+constexpr int kSlots = 64;                    // lane slots per proposal in the descriptor stream
 WS_HD int zero_cell(int H, int W) { return (H + kPad + kTailRows) * (W + kPad); }
 WS_HD uint32_t bin_desc(float x1, float y1, float x2, float y2, float scale, int H, int W, int phase, int ph, int pw) {
   const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);

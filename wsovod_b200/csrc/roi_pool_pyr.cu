@@ -26,7 +26,7 @@ struct PyrWs {
   uint32_t* pkey;       // [R]
   int32_t* order;       // [R]   proposal id at each sorted position
   uint2* pinfo;         // [R]   (proposal id | (ch-1) << 26 | (cw-1) << 28, bits of row_scale + bias) per sorted position
-  uint32_t* desc;       // [R, 49] bin descriptors in sorted position / lane slot order
+  uint32_t* desc;       // [R, 64] bin descriptors in sorted position / lane slot order (slots 49..63 idle)
   size_t bytes;
 };
 
@@ -42,7 +42,7 @@ static PyrWs pyr_carve(void* ws, int64_t N, int64_t R) {
   w.pkey = (uint32_t*)take(sizeof(uint32_t) * (size_t)R);
   w.order = (int32_t*)take(sizeof(int32_t) * (size_t)R);
   w.pinfo = (uint2*)take(sizeof(uint2) * (size_t)R);
-  w.desc = (uint32_t*)take(sizeof(uint32_t) * (size_t)R * 49);
+  w.desc = (uint32_t*)take(sizeof(uint32_t) * (size_t)R * kSlots);
   w.bytes = off;
   return w;
 }
@@ -126,15 +126,22 @@ __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restric
   }
 }
 
-// one thread per (sorted position, lane slot): the descriptor of the bin that slot serves
+// one thread per (sorted position, lane slot): the descriptor of the bin that slot serves.  With four
+// channels per CTA a proposal takes kSlots = 64 slots, 49 bins + 15 idle ones: every 32-lane pass of the
+// main kernel then stays inside ONE proposal, which is what the pooled tensor's write path needs -- warp
+// stores that straddle two proposals (two pieces 100 KB apart, four partial 32-byte sectors) cost the
+// whole c2 kernel 1.41 ms in stores alone, proposal-aligned passes 0.88 ms
+// (tools/ubench/store_pattern.cu, "pattern" vs "V6").  The two-channel flavour (larger maps, fewer
+// bytes per pass) is not store-bound and keeps the dense 49-slot stream.
 __global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H, int W, float scale,
                                 const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
-                                const float* __restrict__ row_scale, float row_scale_bias,
+                                const float* __restrict__ row_scale, float row_scale_bias, int slots,
                                 uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * 49) return;
-  const int64_t gpos = i / 49;
-  const int q = (int)(i - gpos * 49);
+  if (i >= R * slots) return;
+  const int64_t gpos = i / slots;
+  const int q = (int)(i - gpos * slots);
+  if (q >= 49) { desc[i] = kDescIdle; return; }
   const int r = order[gpos];
   const uint32_t key = pkey[r];
   const int bin = slot_bin(key, q);
@@ -265,12 +272,13 @@ __device__ __forceinline__ void pv_max(float* m, const float2& v) { m[0] = fmaxf
 __device__ __forceinline__ void pv_set(float* m, const float4& v) { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
 __device__ __forceinline__ void pv_set(float* m, const float2& v) { m[0] = v.x; m[1] = v.y; }
 
-// One bucket slice = `total` lane slots (49 per proposal) whose proposals all need CH x CW blocks per bin.
-// A lane handles TWO slots per pass (f and f + stride: independent LDS chains hide each other's
-// latency); per slot it reads one descriptor word (coalesced) and its proposal's (id, scale) pair, both
-// fetched one pass ahead, issues up to CH*CW LDS (a block is skipped where it would repeat the
-// previous one: the bin is not larger than the blocks before it) and stores CB scalars.
-template <int CB, int CH, int CW, bool FULL>
+// One bucket slice = `total` lane slots (kSlots = 64 per proposal, 15 of them idle) whose proposals all need
+// at most CH x CW blocks per bin.  A lane handles TWO slots per pass (f and f + stride: independent LDS
+// chains hide each other's latency); per slot it reads one descriptor word (coalesced) and its
+// proposal's (id, scale) pair, both fetched one pass ahead, issues up to CH*CW LDS (a block is skipped
+// where it would repeat the previous one: the bin is not larger than the blocks before it) and stores
+// CB scalars.  Passes are aligned to proposals (f is a multiple of 32, a proposal of 64 slots).
+template <int CB, int SLOTS, int CH, int CW, bool FULL>
 __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pitch, uint32_t khp, uint32_t kwb,
                                         const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
                                         int total, float* __restrict__ outc, uint32_t c49, int nc, int flat0,
@@ -278,6 +286,7 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
   using V = typename PV<CB>::T;
   constexpr uint32_t CS = 4u * CB;
   auto one = [&](const uint32_t d, const uint2 pi) {
+    if (d & kDescIdle) return;                 // slots 49..63 of a proposal
     const uint32_t a0 = (d & 0xffffu) * CS;
     const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * CS;
     // the plane holds no NaN / -inf (pyr_stage clamps at -FLT_MAX), so the first block seeds the maximum
@@ -303,19 +312,20 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
   };
   const int step = 2 * stride;
   int f = flat0;
-  uint32_t d0 = 0, d1 = 0;
+  uint32_t d0 = kDescIdle, d1 = kDescIdle;
   uint2 p0 = make_uint2(0u, 0u), p1 = p0;
-  if (f < total) { d0 = __ldg(dsc + f); p0 = __ldg(pin + (uint32_t)f / 49u); }
-  if (f + stride < total) { d1 = __ldg(dsc + f + stride); p1 = __ldg(pin + (uint32_t)(f + stride) / 49u); }
+  if (f < total) { d0 = __ldg(dsc + f); p0 = __ldg(pin + (uint32_t)f / (uint32_t)SLOTS); }
+  if (f + stride < total) { d1 = __ldg(dsc + f + stride); p1 = __ldg(pin + (uint32_t)(f + stride) / (uint32_t)SLOTS); }
   while (f < total) {
     const uint32_t c0 = d0, c1 = d1;
     const uint2 q0 = p0, q1 = p1;
-    const bool second = f + stride < total;
     const int g = f + step;
-    if (g < total) { d0 = __ldg(dsc + g); p0 = __ldg(pin + (uint32_t)g / 49u); }
-    if (g + stride < total) { d1 = __ldg(dsc + g + stride); p1 = __ldg(pin + (uint32_t)(g + stride) / 49u); }
+    d0 = kDescIdle;
+    d1 = kDescIdle;
+    if (g < total) { d0 = __ldg(dsc + g); p0 = __ldg(pin + (uint32_t)g / (uint32_t)SLOTS); }
+    if (g + stride < total) { d1 = __ldg(dsc + g + stride); p1 = __ldg(pin + (uint32_t)(g + stride) / (uint32_t)SLOTS); }
     one(c0, q0);
-    if (second) one(c1, q1);
+    one(c1, q1);
     f = g;
   }
 }
@@ -324,6 +334,7 @@ template <int CB>
 __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int BINS = 49;
+  constexpr int SLOTS = CB == 4 ? kSlots : 49;   // lane slots per proposal in the descriptor stream
   constexpr uint32_t CS = 4u * CB;
   const int H = p.H, W = p.W, HW = H * W;
   const int WP = W + kPad, ncell = (H + kPad) * WP, ntot = (H + kPad + kTailRows) * WP;
@@ -391,13 +402,13 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         const int slo = lo + sidx * per;
         const int shi = min(hi, slo + per);
         if (shi <= slo) continue;
-        const int total = (shi - slo) * BINS;
-        const uint32_t* dsc = p.desc + (size_t)(gstart + slo) * BINS;
+        const int total = (shi - slo) * SLOTS;
+        const uint32_t* dsc = p.desc + (size_t)(gstart + slo) * SLOTS;
         const uint2* pin = p.pinfo + gstart + slo;
 #define PYR_CASE(CH, CW) \
   case ((CH - 1) + (CW - 1) * 4): \
-    if (nc == CB) pyr_run<CB, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
-    else pyr_run<CB, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    if (nc == CB) pyr_run<CB, SLOTS, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    else pyr_run<CB, SLOTS, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
     break;
         switch (sub) {
           PYR_CASE(2, 2) PYR_CASE(4, 2) PYR_CASE(2, 4) PYR_CASE(4, 4)
@@ -447,233 +458,6 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
       }
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// main kernel, TMA-store flavour (CB = 4, C % 4 == 0)
-// ------------------------------------------------------------------------------------------------
-// The pooled tensor's natural write pattern -- four 128-byte warp stores 196 bytes apart per pass -- tops
-// out at 2.2 TB/s on a B200 however little else the kernel does (tools/ubench/store_pattern.cu), while
-// the 784-byte block out[r, c0:c0+4, :, :] written as one bulk copy reaches 5.6 TB/s.  So here a warp
-// owns a contiguous run of whole proposals, stages each proposal's 4 x 49 results in shared memory and
-// hands the finished block to the TMA (cp.async.bulk shared -> global, 16-byte aligned because C % 4
-// == 0); the LSU only sees conflict-free STS.  Two staging buffers per warp: the copy of proposal q-2 is
-// waited for (read side only) before proposal q overwrites its buffer.
-constexpr int kWThreads = 768;
-constexpr int kWWarps = kWThreads / 32;
-constexpr int kChunkBytes = 4 * 49 * 4;   // out[r, c0:c0+4] : 784 B
-constexpr int kStageBytes = kWWarps * 2 * kChunkBytes;
-
-__device__ __forceinline__ void lds4(uint32_t addr, float* f) {   // not volatile: free to be scheduled early
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr));
-}
-template <int CH, int CW>
-__device__ __forceinline__ void pyr_bin4(uint32_t sbase, uint32_t d, uint32_t pitch, uint32_t khp, uint32_t kwb, float* m) {
-  const uint32_t a0 = sbase + (d & 0xffffu) * 16u;
-  const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * 16u;
-  lds4(a0, m);
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
-    const bool ni = i == 0 || (uint32_t)(i - 1) * khp < lhp;
-#pragma unroll
-    for (int j = 0; j < CW; ++j) {
-      if (i == 0 && j == 0) continue;
-      const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
-      const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
-      if (ni && nj) {
-        float v[4];
-        lds4(a0 + ro + co, v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], v[k]);
-      }
-    }
-  }
-}
-
-// One warp, one bucket segment of its run: `total` lane slots (49 per proposal), all proposals needing at
-// most CH x CW blocks per bin.  Pass = 32 consecutive slots.  s0 = slot of lane 0 inside proposal q0:
-// the pass finishes proposal q0 iff s0 >= 17 and starts a new one iff s0 == 0 or s0 >= 18 -- all
-// warp-uniform.  Results go to the warp's two staging blocks (proposal parity), finished blocks leave
-// through cp.async.bulk.
-template <int CH, int CW>
-__device__ __forceinline__ void pyrw_segment(uint32_t sbase, uint32_t pitch, uint32_t khp, uint32_t kwb,
-                                             const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
-                                             int total, float* __restrict__ outc, size_t c49, uint32_t stage_s,
-                                             uint32_t dzero, int lane) {
-  // the previous segment's last block may still be in flight from this warp's buffers
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  __syncwarp();
-  // two passes of look-ahead (see pyr_run)
-  uint32_t d_a = dzero, d_b = dzero;
-  uint2 pi_a = make_uint2(0u, 0u), pi_b = pi_a;
-  if (lane < total) { d_a = __ldg(dsc + lane); pi_a = __ldg(pin + (uint32_t)lane / 49u); }
-  if (32 + lane < total) { d_b = __ldg(dsc + 32 + lane); pi_b = __ldg(pin + (uint32_t)(32 + lane) / 49u); }
-  int s0 = 0, q0 = 0;
-  for (int g0 = 0; g0 < total; g0 += 32) {
-    const uint32_t d = d_a;
-    const uint2 pi = pi_a;
-    d_a = d_b;
-    pi_a = pi_b;
-    d_b = dzero;
-    const int gn = g0 + 64 + lane;
-    if (gn < total) { d_b = __ldg(dsc + gn); pi_b = __ldg(pin + (uint32_t)gn / 49u); }
-    float m[4];
-    pyr_bin4<CH, CW>(sbase, d, pitch, khp, kwb, m);
-    if (s0 == 0 || s0 >= 18) {   // a proposal starts: its buffer (used two proposals ago) must be drained
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-    }
-    if (g0 + lane < total) {
-      const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
-      const int par = (q0 + (s0 + lane >= 49 ? 1 : 0)) & 1;
-      const uint32_t sa = stage_s + (uint32_t)par * kChunkBytes + ((d >> 24) & 63u) * 4u;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(__fmul_rn(m[0], sc)) : "memory");
-      asm volatile("st.shared.f32 [%0+196], %1;" ::"r"(sa), "f"(__fmul_rn(m[1], sc)) : "memory");
-      asm volatile("st.shared.f32 [%0+392], %1;" ::"r"(sa), "f"(__fmul_rn(m[2], sc)) : "memory");
-      asm volatile("st.shared.f32 [%0+588], %1;" ::"r"(sa), "f"(__fmul_rn(m[3], sc)) : "memory");
-    }
-    if (s0 >= 17) {   // proposal q0 is complete (its last slot is lane 48 - s0 of this pass)
-      const uint32_t rr = __shfl_sync(0xffffffffu, pi.x, 48 - s0) & 0x3ffffffu;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(outc + (size_t)rr * c49), "r"(stage_s + (uint32_t)(q0 & 1) * kChunkBytes), "n"(kChunkBytes)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      s0 -= 49;
-      ++q0;
-    }
-    s0 += 32;
-  }
-}
-
-__global__ void __launch_bounds__(kWThreads, 1) roi_pool7_pyrw_kernel(const PyrParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int BINS = 49, CB = 4;
-  constexpr uint32_t CS = 16u;
-  const int H = p.H, W = p.W, HW = H * W;
-  const int WP = W + kPad, ncell = (H + kPad) * WP, ntot = (H + kPad + kTailRows) * WP;
-  const int bid = blockIdx.x;
-  const int cg = bid % p.CG;
-  const int sidx = (bid / p.CG) % p.S;
-  const int n = bid / (p.CG * p.S);
-  const int c0 = cg * CB;
-  const int gstart = __ldg(p.img_start + n);
-  const int cnt = __ldg(p.img_start + n + 1) - gstart;
-  if (cnt <= 0) return;
-  __shared__ int boff[kBuckets + 1];   // this image's bucket boundaries
-  for (int i = threadIdx.x; i <= kBuckets; i += blockDim.x) boff[i] = __ldg(p.bucket_off + n * (kBuckets + 1) + i);
-  uint32_t sbase;
-  {
-    unsigned long long s64;
-    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
-    sbase = (uint32_t)s64;
-  }
-  {  // identity tail rows and the all-zero cell empty bins point at (never written again)
-    float id[CB];
-#pragma unroll
-    for (int k = 0; k < CB; ++k) id[k] = -FLT_MAX;
-    for (int i = ncell + (int)threadIdx.x; i < ntot; i += blockDim.x) p_sts<CB>(sbase + (uint32_t)i * CS, id);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < CB; ++k) id[k] = 0.f;
-      p_sts<CB>(sbase + (uint32_t)ntot * CS, id);
-    }
-  }
-  __syncthreads();
-  const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
-  float* outc = p.output + (size_t)c0 * BINS;
-  const size_t c49 = (size_t)p.C * BINS;
-  const uint32_t pitch = (uint32_t)WP * CS;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // staging: two 784-byte blocks per warp behind the plane (16-byte aligned)
-  const uint32_t plane_bytes = ((uint32_t)(ntot + 1) * CS + 127u) & ~127u;
-  const uint32_t stage_s = sbase + plane_bytes + (uint32_t)wid * (2u * kChunkBytes);
-
-  for (int phase = 0; phase < kPhases; ++phase) {
-    const int lo = boff[phase * 16], hi = boff[(phase + 1) * 16];
-    const int rem = boff[(chain_end(phase) + 1) * 16] - lo;   // proposals left in this chain
-    if (rem > 0 && phase != PH_FALLBACK) {
-      __syncthreads();                                         // everyone is done reading the old plane
-      switch (phase) {
-        case PH_11: pyr_stage<CB>(sbase, src, CB, H, W, 0); __syncthreads(); break;
-        case PH_21: pyr_double<CB>(sbase, ncell, WP); break;
-        case PH_22: pyr_double<CB>(sbase, ncell, 1); break;
-        case PH_42: pyr_double<CB>(sbase, ncell, 2 * WP); break;
-        case PH_44: pyr_double<CB>(sbase, ncell, 2); break;
-        case PH_12: pyr_stage<CB>(sbase, src, CB, H, W, 1); __syncthreads(); break;
-        case PH_14: pyr_double<CB>(sbase, ncell, 2); break;
-        case PH_24: pyr_double<CB>(sbase, ncell, WP); break;
-        default:    pyr_stage<CB>(sbase, src, CB, H, W, 2); __syncthreads();
-                    pyr_double<CB>(sbase, ncell, 2 * WP); break;   // PH_41
-      }
-    }
-    if (hi <= lo) continue;
-    // this CTA's slice of the phase, then this warp's contiguous run of whole proposals
-    const int per = (hi - lo + p.S - 1) / p.S;
-    const int slo = lo + sidx * per;
-    const int shi = min(hi, slo + per);
-    if (shi <= slo) continue;
-    const int np = shi - slo;
-    const int per_w = (np + kWWarps - 1) / kWWarps;
-    const int w0 = min(np, wid * per_w), w1 = min(np, w0 + per_w);
-    if (w1 <= w0) continue;
-    const uint32_t khp = (uint32_t)phase_kh(phase) * pitch, kwb = (uint32_t)phase_kw(phase) * CS;
-    const uint32_t dzero = kDescEmpty | (uint32_t)ntot;   // idle lanes read the zero cell
-    const bool fallback = phase == PH_FALLBACK;
-
-    if (!fallback) {
-      // the run is sorted by bucket: walk its (at most four) bucket segments with the unrolled loop of
-      // each bucket's block counts
-      for (int sub = 5; sub < 16; sub += (sub == 7 ? 6 : 2)) {   // (ch-1) + 4 (cw-1) in {5, 7, 13, 15}
-        const int b0 = max(boff[phase * 16 + sub], slo + w0), b1 = min(boff[phase * 16 + sub + 1], slo + w1);
-        if (b1 <= b0) continue;
-        const uint32_t* dsc = p.desc + (size_t)(gstart + b0) * BINS;
-        const uint2* pin = p.pinfo + gstart + b0;
-        const int total = (b1 - b0) * BINS;
-        switch (sub) {
-          case 5:  pyrw_segment<2, 2>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane); break;
-          case 7:  pyrw_segment<4, 2>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane); break;
-          case 13: pyrw_segment<2, 4>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane); break;
-          default: pyrw_segment<4, 4>(sbase, pitch, khp, kwb, dsc, pin, total, outc, c49, stage_s, dzero, lane); break;
-        }
-      }
-      continue;
-    }
-    // fallback phase: bins needing more than kMaxLoads blocks per axis -- direct scan of the (1,1) plane
-    // with edges recomputed from the roi (lane slot = output bin), plain stores
-    const uint2* pin = p.pinfo + gstart + slo + w0;
-    const int total = (w1 - w0) * BINS;
-    for (int g = lane; g < total; g += 32) {
-      const int q = (int)((uint32_t)g / 49u);
-      const int bin = g - q * BINS;
-      const int ph = bin / 7, pw = bin - ph * 7;
-      const uint2 pi = __ldg(pin + q);
-      const float* roi = p.rois + (int64_t)(pi.x & 0x3ffffffu) * 5;
-      const Axis ah = axis_of(roi[2], roi[4], p.scale), aw = axis_of(roi[1], roi[3], p.scale);
-      int hs, he, ws, we;
-      bin_edges(ah, ph, H, hs, he);
-      bin_edges(aw, pw, W, ws, we);
-      float m[CB];
-#pragma unroll
-      for (int k = 0; k < CB; ++k) m[k] = 0.f;
-      if (he > hs && we > ws) {
-#pragma unroll
-        for (int k = 0; k < CB; ++k) m[k] = -FLT_MAX;
-        for (int h = hs; h < he; ++h) {
-          const unsigned char* a = smem_raw + (uint32_t)((h + kPad) * WP + ws + kPad) * CS;
-          for (int w = ws; w < we; ++w, a += CS) pv_max(m, *reinterpret_cast<const float4*>(a));
-        }
-      }
-      float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + bin;
-#pragma unroll
-      for (int k = 0; k < CB; ++k) __stcs(o + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
-    }
-  }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // shared memory of the padded plane (+ identity tail rows)
@@ -726,29 +510,14 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   if ((rc = after_launch())) return rc;
   pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
-  pyr_bins_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, row_scale,
-                                                                    row_scale_bias, w.pinfo, w.desc);
+  const int slots = cb == 4 ? kSlots : 49;
+  pyr_bins_kernel<<<(unsigned)ceil_div(R * slots, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, row_scale,
+                                                                     row_scale_bias, slots, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
   p.input = input; p.rois = rois; p.scale = scale;
   p.output = output; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
-  const size_t smem_w = ((pyr_smem(H, W, 4) + 127) & ~(size_t)127) + kStageBytes;
-  // experimental (WSOVOD_B200_POOL_TMA=1): correct, but not yet faster than the plain stores at c2 (1.55 vs 1.45 ms)
-  const char* want_tma = getenv("WSOVOD_B200_POOL_TMA");
-  const bool tma = want_tma && want_tma[0] == '1' && cb == 4 && C % 4 == 0 && ((uintptr_t)output & 15) == 0 &&
-                   smem_w + 1024 <= (size_t)kMaxSmemOptin;
-  if (tma) {
-    p.CG = (int)(C / 4);
-    const int64_t units = N * p.CG;
-    const int64_t S = pyr_split(units, R / std::max<int64_t>(N, 1));
-    p.S = (int)S;
-    if (units * S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
-    e = cudaFuncSetAttribute(roi_pool7_pyrw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-    if (e != cudaSuccess) return (int)e;
-    roi_pool7_pyrw_kernel<<<(unsigned)(units * S), kWThreads, smem_w, st>>>(p);
-    return after_launch();
-  }
   return cb == 4 ? pyr_launch_main<4>(p, R, st) : pyr_launch_main<2>(p, R, st);
 }
 
