@@ -138,6 +138,36 @@ __global__ void __launch_bounds__(1024, 1) pattern_pad64_pair(float* out, int C,
     }
   }
 }
+// (V8) three proposals per 160 slots (147 bins + 13 idle): passes 2 and 4 of every five hold two proposals.
+// SPLIT=0: one store instruction per channel (straddles), SPLIT=1: two, one per proposal
+template <int SPLIT>
+__global__ void __launch_bounds__(1024, 1) pattern_3in5(float* out, int C, int R, int CG) {
+  const int cg = blockIdx.x % CG, n = blockIdx.x / CG;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int groups = R / 3;
+  const int total = groups * 160;
+  const size_t c49 = (size_t)C * 49;
+  float* outc = out + (size_t)cg * 4 * 49 + (size_t)n * R * c49;
+  for (int f = wid * 32 + lane; f < total; f += nw * 32) {
+    const int grp = f / 160, s = f - grp * 160;
+    if (s >= 147) continue;
+    const int which = s >= 98 ? 2 : (s >= 49 ? 1 : 0);
+    const int bin = s - which * 49;
+    const int first = (f - lane) - grp * 160;                  // slot of lane 0
+    const int wfirst = first >= 98 ? 2 : (first >= 49 ? 1 : 0);
+    float* o = outc + (size_t)(grp * 3 + which) * c49 + bin;
+    const bool a = which == wfirst;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (SPLIT) {
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.global.cs.f32 [%0], %1; }" ::"l"(o + k * 49), "f"((float)f), "r"((unsigned)a) : "memory");
+        asm volatile("{ .reg .pred p; setp.eq.u32 p, %2, 0; @p st.global.cs.f32 [%0], %1; }" ::"l"(o + k * 49), "f"((float)f), "r"((unsigned)a) : "memory");
+      } else {
+        __stcs(o + k * 49, (float)f);
+      }
+    }
+  }
+}
 // (V2) same shape of accesses on a fake layout with 48 floats per (proposal, channel): every warp store is
 // 64-byte aligned, i.e. only whole 32-byte sectors are written
 __global__ void __launch_bounds__(1024, 1) pattern48(float* out, int C, int R, int CG) {
@@ -256,6 +286,8 @@ int main() {
   run("V5 contiguous 32/pass", [&] { pattern_contig32<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V6 padded 64 slots, strided passes", [&] { pattern_pad64<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V7 padded, one proposal per warp pass", [&] { pattern_pad64_pair<<<N * 128, 1024>>>(out, C, R, 128); });
+  run("V8 3 proposals / 5 passes, straddling", [&] { pattern_3in5<0><<<N * 128, 1024>>>(out, C, R - R % 3, 128); });
+  run("V8 3 proposals / 5 passes, split stores", [&] { pattern_3in5<1><<<N * 128, 1024>>>(out, C, R - R % 3, 128); });
   run("V2 fake 48-float runs (whole sectors)", [&] { pattern48<<<N * 128, 1024>>>(out, C, R, 128); });
   run("V3 warp-owned chunk, consecutive", [&] { pattern_shuffled<<<N * 128, 1024>>>(out, C, R, 128); });
   run("chunk 784B as float4", [&] { chunk128<<<N * 128, 1024>>>(out, C, R, 128); });

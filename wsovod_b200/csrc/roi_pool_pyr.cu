@@ -186,47 +186,47 @@ template <> __device__ __forceinline__ void p_sts<2>(uint32_t addr, const float*
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(f[0]), "f"(f[1]) : "memory");
 }
 
-// D <- plane of the map (mode 0), max with the right neighbour (1: block 1x2) or the lower neighbour
+// D <- plane of the map (MODE 0), max with the right neighbour (1: block 1x2) or the lower neighbour
 // (2: block 2x1), in the padded layout; pad cells and absent channels hold the identity -FLT_MAX, and
 // NaN / -inf cells are clamped to it (they can never win a bin: `v > maxval` with maxval = -FLT_MAX).
-// Four cells per thread are in flight (the loop is L2-latency bound otherwise).
-template <int CB>
-__device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W,
-                                       int mode) {
+// A warp takes whole rows of the padded plane (row hh = warp, warp + #warps, ...), lanes walk the columns
+// 32 at a time: addresses are (row pointer of the channel) + column, the only predicates are the row /
+// column borders, and up to 8 x CB loads per lane are in flight.
+template <int CB, int MODE>
+__device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W) {
   constexpr uint32_t CS = 4u * CB;
-  constexpr int U = 4;
-  const int WP = W + kPad, ncell = (H + kPad) * WP, HW = H * W;
-  const int dnb = mode == 1 ? 1 : W;   // neighbour offset in the unpadded plane
-  const int T = (int)blockDim.x, dh = T / WP, dw = T - dh * WP;   // one step of T cells = dh rows + dw columns
-  int idx = threadIdx.x;
-  int hh = idx / WP, ww = idx - hh * WP;
-  for (; idx < ncell; idx += U * T) {
-    float f[U][CB], g[U][CB];
-    int h2 = hh, w2 = ww;
+  const int WP = W + kPad, HP = H + kPad, HW = H * W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int hh = wid; hh < HP; hh += nw) {
+    const int h = hh - kPad;
+    const uint32_t srow = sbase + (uint32_t)(hh * WP) * CS;
+    const bool hin = h >= 0;                                   // a real map row
+    const bool h2 = MODE == 2 && h + 1 >= 0 && h + 1 < H;      // its lower neighbour exists
+    const float* rowp = src + (int64_t)(hin ? h : 0) * W;
+    const float* rowq = src + (int64_t)(h2 ? h + 1 : 0) * W;
+    for (int ww0 = 0; ww0 < WP; ww0 += 64) {
+      float f[2][CB], g[2][CB];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int h = h2 - kPad, w = w2 - kPad;
-      const bool live = idx + u * T < ncell;
-      const bool in = live && h >= 0 && w >= 0;
-      const bool in2 = live && mode != 0 && (mode == 1 ? (h >= 0 && w + 1 >= 0 && w + 1 < W) : (w >= 0 && h + 1 >= 0 && h + 1 < H));
-      const int e = h * W + w;
+      for (int u = 0; u < 2; ++u) {
+        const int ww = ww0 + u * 32 + lane, w = ww - kPad;
+        const bool in = hin && ww < WP && w >= 0;
+        const bool in2 = ww < WP && (MODE == 1 ? (hin && w + 1 >= 0 && w + 1 < W) : (MODE == 2 && h2 && w >= 0));
 #pragma unroll
-      for (int k = 0; k < CB; ++k) {
-        f[u][k] = (in && k < nc) ? __ldg(src + (e + k * HW)) : -FLT_MAX;
-        g[u][k] = (in2 && k < nc) ? __ldg(src + (e + k * HW + dnb)) : -FLT_MAX;
+        for (int k = 0; k < CB; ++k) {
+          f[u][k] = (in && k < nc) ? __ldg(rowp + (int64_t)k * HW + w) : -FLT_MAX;
+          g[u][k] = (in2 && k < nc) ? __ldg((MODE == 1 ? rowp + 1 : rowq) + (int64_t)k * HW + w) : -FLT_MAX;
+        }
       }
-      h2 += dh; w2 += dw;
-      if (w2 >= WP) { w2 -= WP; ++h2; }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (idx + u * T < ncell) {
+      for (int u = 0; u < 2; ++u) {
+        const int ww = ww0 + u * 32 + lane;
+        if (ww < WP) {
 #pragma unroll
-        for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
-        p_sts<CB>(sbase + (uint32_t)(idx + u * T) * CS, f[u]);
+          for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
+          p_sts<CB>(srow + (uint32_t)ww * CS, f[u]);
+        }
       }
     }
-    hh = h2; ww = w2;
   }
 }
 
@@ -381,15 +381,15 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     if (rem > 0 && phase != PH_FALLBACK) {
       __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
-        case PH_11: pyr_stage<CB>(sbase, src, nc, H, W, 0); __syncthreads(); break;
+        case PH_11: pyr_stage<CB, 0>(sbase, src, nc, H, W); __syncthreads(); break;
         case PH_21: pyr_double<CB>(sbase, ncell, WP); break;
         case PH_22: pyr_double<CB>(sbase, ncell, 1); break;
         case PH_42: pyr_double<CB>(sbase, ncell, 2 * WP); break;
         case PH_44: pyr_double<CB>(sbase, ncell, 2); break;
-        case PH_12: pyr_stage<CB>(sbase, src, nc, H, W, 1); __syncthreads(); break;
+        case PH_12: pyr_stage<CB, 1>(sbase, src, nc, H, W); __syncthreads(); break;
         case PH_14: pyr_double<CB>(sbase, ncell, 2); break;
         case PH_24: pyr_double<CB>(sbase, ncell, WP); break;
-        default:    pyr_stage<CB>(sbase, src, nc, H, W, 2); __syncthreads();
+        default:    pyr_stage<CB, 2>(sbase, src, nc, H, W); __syncthreads();
                     pyr_double<CB>(sbase, ncell, 2 * WP); break;       // PH_41
       }
     }
