@@ -348,6 +348,49 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   }
 }
 
+// single-warp K-way merge of score-descending runs (keys ascending): lane l owns runs l, l + 32, ... (RW of
+// them); writes the first `topk` keys of the merged order to sel[], returns how many there were
+template <int RW>
+__device__ __forceinline__ int warp_merge_runs(const int2* __restrict__ rn, const unsigned long long* __restrict__ keys,
+                                               int K, int topk, unsigned long long* sel) {
+  const int lane = threadIdx.x & 31;
+  int pos[RW], len[RW], off[RW];
+  unsigned long long head[RW], next[RW];
+#pragma unroll
+  for (int j = 0; j < RW; ++j) {
+    const int c = lane + j * 32;
+    const int2 v = c < K ? rn[c] : make_int2(0, 0);
+    off[j] = v.x; len[j] = v.y; pos[j] = 0;
+    head[j] = len[j] > 0 ? keys[off[j]] : kDead;
+    next[j] = len[j] > 1 ? keys[off[j] + 1] : kDead;
+  }
+  int g = 0;
+  for (int i = 0; i < topk; ++i) {
+    unsigned long long best = head[0];
+    int bj = 0;
+#pragma unroll
+    for (int j = 1; j < RW; ++j)
+      if (head[j] < best) { best = head[j]; bj = j; }
+    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
+    const uint32_t hmin = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
+    if (hmin == 0xffffffffu && lmin == 0xffffffffu) break;          // every run is exhausted (kDead)
+    // keys are unique (row * K + class in the low word): exactly one lane holds (hmin, lmin)
+    if (hi == hmin && lo == lmin) {
+#pragma unroll
+      for (int j = 0; j < RW; ++j)
+        if (j == bj) {
+          ++pos[j];
+          head[j] = next[j];
+          next[j] = pos[j] + 1 < len[j] ? keys[off[j] + pos[j] + 1] : kDead;
+        }
+      sel[i] = best;
+    }
+    ++g;
+  }
+  return g;
+}
+
 // one CTA per image: the topk best kept candidates, in order (:207-208), and the output gather
 __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
     const int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
@@ -362,52 +405,14 @@ __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
   unsigned long long* keys = img_kept + (int64_t)n * kept_stride;
   int got;
   __shared__ int s_got;
-  constexpr int kWarpRuns = 8;       // single-warp merge: lane l owns runs l, l+32, ... (K <= 256 classes)
-  if (runs != nullptr && K <= 32 * kWarpRuns) {
-    // K-way merge by ONE warp: no barrier per pick, the heads (and their successors) live in registers,
-    // a pick is a 5-step shuffle arg-min (c2: 100 picks in ~3 us instead of 100 block-wide rounds)
+  if (runs != nullptr && K <= 32 * 8) {
+    // K-way merge by ONE warp (no barrier per pick): lane l owns runs l, l+32, ...; heads and their
+    // successors live in registers; a pick is two warp REDUX (minimum of the score words, then of the
+    // id words among the lanes that tie) and a ballot
     if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
       const int2* rn = runs + (int64_t)n * K;
-      int pos[kWarpRuns], len[kWarpRuns], off[kWarpRuns];
-      unsigned long long head[kWarpRuns], next[kWarpRuns];
-#pragma unroll
-      for (int j = 0; j < kWarpRuns; ++j) {
-        const int c = lane + j * 32;
-        const int2 v = c < K ? rn[c] : make_int2(0, 0);
-        off[j] = v.x; len[j] = v.y; pos[j] = 0;
-        head[j] = len[j] > 0 ? keys[off[j]] : kDead;
-        next[j] = len[j] > 1 ? keys[off[j] + 1] : kDead;
-      }
-      int g = 0;
-      for (int i = 0; i < topk; ++i) {
-        unsigned long long best = kDead;
-        int bj = -1;
-#pragma unroll
-        for (int j = 0; j < kWarpRuns; ++j)
-          if (head[j] < best) { best = head[j]; bj = j; }
-        unsigned long long wkey = best;
-        int wl = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long ok = __shfl_xor_sync(0xffffffffu, wkey, o);
-          const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-          if (ok < wkey || (ok == wkey && ol < wl)) { wkey = ok; wl = ol; }
-        }
-        if (wkey == kDead) break;       // keys are unique (row * K + class in the low word): one winner
-        if (wl == lane) {
-#pragma unroll
-          for (int j = 0; j < kWarpRuns; ++j)
-            if (j == bj) {
-              ++pos[j];
-              head[j] = next[j];
-              next[j] = pos[j] + 1 < len[j] ? keys[off[j] + pos[j] + 1] : kDead;
-            }
-          sel[i] = wkey;
-        }
-        ++g;
-      }
-      if (lane == 0) s_got = g;
+      const int g = K <= 96 ? warp_merge_runs<3>(rn, keys, K, topk, sel) : warp_merge_runs<8>(rn, keys, K, topk, sel);
+      if (threadIdx.x == 0) s_got = g;
     }
     __syncthreads();
     got = s_got;
