@@ -413,7 +413,8 @@ def _pool_variant(scan=None):
 
 @pytest.mark.parametrize("N,C,H,W,R,seed", [(2, 9, 60, 80, 900, 1), (1, 3, 86, 128, 1500, 2), (3, 6, 100, 152, 700, 3),
                                              (1, 2, 150, 180, 400, 4), (2, 1, 7, 5, 300, 5), (1, 4, 1, 1, 50, 6),
-                                             (1, 5, 117, 120, 300, 7), (2, 8, 60, 80, 1200, 8), (1, 12, 86, 128, 2500, 9)])
+                                             (1, 5, 117, 120, 300, 7), (2, 8, 60, 80, 1200, 8), (1, 12, 86, 128, 2500, 9),
+                                             (1, 8, 40, 56, 3300, 10)])   # last: few channel groups -> proposals split over CTAs
 def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
     """values-only 7x7 pooling through the block-max planes (roi_pool_pyr.cu): every (kh, kw) phase, the
     direct-scan fallback phase (whole-map proposals on big maps), border-clipped bins, NaN / -inf cells,
