@@ -1,0 +1,46 @@
+"""Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_case.py
+The block-max pooling path is forced (WSOVOD_B200_POOL_SCAN=0) and checked against the scan kernels."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wsovod_b200 import ops, synth  # noqa: E402
+
+DEV = "cuda:0"
+g = synth.gen(3)
+N, C, H, W, R, K, D = 2, 8, 24, 30, 160, 12, 64
+feat = synth.features(N, C, H, W, g, relu=False).to(DEV)
+boxes = [synth.proposals(R, H * 8, W * 8, g) for _ in range(N)]
+boxes[0][:20, 2:] = torch.tensor([W * 8.0, H * 8.0])      # whole-map proposals: big blocks, clipped bins
+rois, off = synth.rois_from(boxes)
+rois = rois.to(DEV)
+obj = synth.objectness(N * R, g).to(DEV)
+os.environ["WSOVOD_B200_POOL_SCAN"] = "0"
+a = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
+os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+b = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
+del os.environ["WSOVOD_B200_POOL_SCAN"]
+assert torch.equal(a, b)
+ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
+ops.roi_loop_pool(feat, rois, 1 / 8, 7, with_argmax=False)
+x, t = synth.region_embeddings(N * R, D, g).to(DEV), synth.text_embeddings(K, D, g).to(DEV)
+_, probs = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)
+ops.align(x, t, 50.0, True, True, None, ops.ALIGN_FP32, True, True)
+offd = torch.tensor(off, device=DEV)
+sizes = torch.tensor([[H * 8.0, W * 8.0]] * N, device=DEV)
+bx = rois[:, 1:].contiguous()
+det = ops.detections(probs, bx, offd, sizes, R, 1e-5, 0.3, 20, ops.IOU_TV_CUDA)
+Cl, Dl = synth.mil_logits(N * R, K, g)
+s, img = ops.mil(Cl.to(DEV), Dl.to(DEV), offd)
+gts = synth.image_labels(N, K, g)
+goff = [0]
+for gt in gts:
+    goff.append(goff[-1] + len(gt))
+sd = ops.pgt_top1(s, bx, offd, torch.cat(gts).to(DEV), torch.tensor(goff, device=DEV), img)
+ops.refine_assign(bx, offd, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"], sd["seed_weights"],
+                  torch.tensor(goff, device=DEV), sd["seed_count"], K, 0.5)
+torch.cuda.synchronize()
+print("sanitize case ok", int(det["det_count"].sum()))

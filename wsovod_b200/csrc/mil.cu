@@ -3,9 +3,10 @@
 //   scores[r,k] = softmax_k(cls[r,:])[k] * softmax_{r in image}(det[:,k])[r]
 //   img[n,k]    = clamp(sum_r scores[r,k], 1e-6, 1-1e-6)
 // (roi_heads/fast_rcnn_open_vocabulary.py:338-357,604-618: there a Python loop over images issuing ~6
-// tiny kernels each.)  Here: three launches for the whole batch, all HBM-streaming:
+// tiny kernels each.)  Here: four launches for the whole batch, all HBM-streaming:
 //   1. mil_colstats : per (image, row-chunk) online (max, sum exp) of every det column   -> partials
-//   2. mil_scores   : merges the partials (L2-resident, a few KB), one warp per proposal row computes
+//   1b. mil_colmerge: merges the partials once per image                                  -> (max, 1/sum)
+//   2. mil_scores   : one warp per proposal row computes
 //                     the row softmax with shuffle reductions, multiplies, stores, and accumulates the
 //                     per-column score sums in a fixed order                              -> partials
 //   3. mil_finalize : img = clamp(sum of partials)
@@ -24,18 +25,22 @@ struct MilPlan {
   size_t off_stats;  // float2 [N, chunks, K]
   size_t off_sums;   // float  [N, chunks, K]
   size_t off_asum;   // float  [N, chunks, K] (backward)
+  size_t off_cstat;  // float2 [N, K] merged column statistics (max, 1 / sum exp)
   size_t bytes;
 };
 
 static MilPlan mil_plan(int64_t M, int64_t N, int64_t K) {
   MilPlan p;
   int64_t avg = N > 0 ? ceil_div(M, N) : 1;
-  // enough chunks to spread one image over many SMs, each chunk at least 64 rows
-  p.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, ceil_div(avg, 64)));
+  // enough chunks to spread one image over the whole GPU (c3: one image of 5024 rows -> 157 CTAs), each
+  // chunk at least 32 rows; the per-column partials are merged ONCE per image (mil_colmerge_kernel), not
+  // by every CTA of the scores pass
+  p.chunks = (int)std::max<int64_t>(1, std::min<int64_t>(160, ceil_div(avg, 32)));
   size_t o = 0;
   p.off_stats = o; o += align_up(sizeof(float2) * (size_t)(N * p.chunks * K), 256);
   p.off_sums = o;  o += align_up(sizeof(float) * (size_t)(N * p.chunks * K), 256);
   p.off_asum = o;  o += align_up(sizeof(float) * (size_t)(N * p.chunks * K), 256);
+  p.off_cstat = o; o += align_up(sizeof(float2) * (size_t)(N * K), 256);
   p.bytes = o;
   return p;
 }
@@ -90,6 +95,26 @@ __global__ void __launch_bounds__(kMilThreads) mil_colstats_kernel(
   }
 }
 
+// 1b. merge the row-chunk partials of every det column: cstat[n, k] = (max, 1 / sum exp).  One warp per
+//     column: lanes take the chunks 32 apart, then a shuffle tree (fixed order: deterministic)
+__global__ void mil_colmerge_kernel(const float2* __restrict__ stats, int K, int chunks, float2* __restrict__ cstat) {
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  float m = 0.f, s = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const float2 t = stats[((int64_t)n * chunks + c) * K + k];
+    merge_ms(m, s, t.x, t.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    merge_ms(m, s, m2, s2);
+  }
+  if (lane == 0) cstat[(int64_t)n * K + k] = make_float2(m, s > 0.f ? 1.f / s : 0.f);
+}
+
 // 2. scores.  smem: colm[K], cinv[K] (merged det column stats), wsum[kMilWarps][K] (per-warp sums)
 template <bool BWD>
 __global__ void __launch_bounds__(kMilThreads) mil_scores_kernel(
@@ -107,13 +132,9 @@ __global__ void __launch_bounds__(kMilThreads) mil_scores_kernel(
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < K; k += kMilThreads) {
-    float m = 0.f, s = 0.f;
-    for (int c = 0; c < chunks; ++c) {
-      const float2 t = stats[((int64_t)n * chunks + c) * K + k];
-      merge_ms(m, s, t.x, t.y);
-    }
-    colm[k] = m;
-    cinv[k] = s > 0.f ? 1.f / s : 0.f;
+    const float2 t = stats[(int64_t)n * K + k];     // merged by mil_colmerge_kernel
+    colm[k] = t.x;
+    cinv[k] = t.y;
   }
   for (int i = threadIdx.x; i < kMilWarps * K; i += kMilThreads) wsum[i] = 0.f;
   __syncthreads();
@@ -175,15 +196,18 @@ __global__ void __launch_bounds__(kMilThreads) mil_scores_kernel(
     }
 }
 
-// 3. finalize: out[n,k] = (clamp) sum over chunks
+// 3. finalize: out[n,k] = (clamp) sum over chunks.  One warp per (n, k): lanes add the chunks 32 apart, then a
+//    shuffle tree -- a fixed summation order, so the result is deterministic
 __global__ void mil_finalize_kernel(const float* __restrict__ sums, int64_t NK, int K, int chunks,
                                     int do_clamp, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= NK) return;
   const int64_t n = i / K, k = i - n * K;
   float t = 0.f;
-  for (int c = 0; c < chunks; ++c) t += sums[(n * chunks + c) * K + k];
-  out[i] = do_clamp ? fminf(fmaxf(t, 1e-6f), 1.0f - 1e-6f) : t;
+  for (int c = lane; c < chunks; c += 32) t += sums[(n * chunks + c) * K + k];
+  t = warp_sum(t);
+  if (lane == 0) out[i] = do_clamp ? fminf(fmaxf(t, 1e-6f), 1.0f - 1e-6f) : t;
 }
 
 }  // namespace wsovod
@@ -215,19 +239,22 @@ WSOVOD_API int wsovod_b200_mil_fwd(const float* cls, const float* det, const int
   float2* stats = (float2*)(ws + pl.off_stats);
   float* sums = (float*)(ws + pl.off_sums);
   dim3 grid(pl.chunks, (unsigned)N);
+  float2* cstat = (float2*)(ws + pl.off_cstat);
   mil_colstats_kernel<<<grid, kMilThreads, sizeof(float2) * kMilThreads, st>>>(det, offsets, (int)K, pl.chunks, stats);
+  if ((rc = after_launch())) return rc;
+  mil_colmerge_kernel<<<dim3((unsigned)ceil_div(K, 8), (unsigned)N), 256, 0, st>>>(stats, (int)K, pl.chunks, cstat);
   if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)K * (2 + kMilWarps);
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mil_scores_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  mil_scores_kernel<false><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, stats, scores, sums,
+  mil_scores_kernel<false><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, cstat, scores, sums,
                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   if ((rc = after_launch())) return rc;
   if (img_scores) {
     const int64_t NK = N * K;
-    mil_finalize_kernel<<<(unsigned)ceil_div(NK, 256), 256, 0, st>>>(sums, NK, (int)K, pl.chunks, 1, img_scores);
+    mil_finalize_kernel<<<(unsigned)ceil_div(NK, 8), 256, 0, st>>>(sums, NK, (int)K, pl.chunks, 1, img_scores);
     if ((rc = after_launch())) return rc;
   }
   return 0;
@@ -249,20 +276,23 @@ WSOVOD_API int wsovod_b200_mil_bwd(const float* grad_scores, const float* grad_i
   float* asum = (float*)(ws + pl.off_asum);
   float* atot = (float*)(ws + pl.bytes);
   dim3 grid(pl.chunks, (unsigned)N);
+  float2* cstat = (float2*)(ws + pl.off_cstat);
   mil_colstats_kernel<<<grid, kMilThreads, sizeof(float2) * kMilThreads, st>>>(det, offsets, (int)K, pl.chunks, stats);
+  if ((rc = after_launch())) return rc;
+  mil_colmerge_kernel<<<dim3((unsigned)ceil_div(K, 8), (unsigned)N), 256, 0, st>>>(stats, (int)K, pl.chunks, cstat);
   if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)K * (2 + kMilWarps);
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mil_scores_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  mil_scores_kernel<true><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, stats, nullptr, asum,
+  mil_scores_kernel<true><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, cstat, nullptr, asum,
                                                         grad_scores, grad_img, nullptr, nullptr, nullptr, 0);
   if ((rc = after_launch())) return rc;
   const int64_t NK = N * K;
-  mil_finalize_kernel<<<(unsigned)ceil_div(NK, 256), 256, 0, st>>>(asum, NK, (int)K, pl.chunks, 0, atot);
+  mil_finalize_kernel<<<(unsigned)ceil_div(NK, 8), 256, 0, st>>>(asum, NK, (int)K, pl.chunks, 0, atot);
   if ((rc = after_launch())) return rc;
-  mil_scores_kernel<true><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, stats, nullptr, asum,
+  mil_scores_kernel<true><<<grid, kMilThreads, smem, st>>>(cls, det, offsets, (int)K, pl.chunks, cstat, nullptr, asum,
                                                         grad_scores, grad_img, atot, grad_cls, grad_det, 1);
   return after_launch();
 }
