@@ -156,18 +156,26 @@ constexpr uint32_t kDescEmpty = 0x80000000u;
 constexpr uint32_t kDescIdle = 0x40000000u;   // lane slot without a bin (slots 49..63 of a proposal)
 constexpr int kSlots = 64;                    // lane slots per proposal in the descriptor stream
 WS_HD int zero_cell(int H, int W) { return (H + kPad + kTailRows) * (W + kPad); }
+// One axis of a descriptor, computed once per (proposal, bin row / bin column): bits 0-15 the first block's
+// offset in the padded plane (rows: (p0 + kPad) * (W + kPad) cells, columns: p0 + kPad), 16-19 distance
+// to the last block, 31 empty.  A bin descriptor is the sum of its row and column entries.
+WS_HD uint32_t axis_entry(const Axis& a, int p, int L, int k, int cell_stride) {
+  int s, e;
+  bin_edges(a, p, L, s, e);
+  if (e <= s) return kDescEmpty;
+  int p0, last;
+  bin_blocks(s, e, k, L, p0, last);
+  return (uint32_t)((p0 + kPad) * cell_stride) | ((uint32_t)last << 16);
+}
+WS_HD uint32_t combine_desc(uint32_t row_entry, uint32_t col_entry, int bin, int H, int W) {
+  const uint32_t binbits = (uint32_t)bin << 24;
+  if ((row_entry | col_entry) & kDescEmpty) return kDescEmpty | binbits | (uint32_t)zero_cell(H, W);
+  return ((row_entry & 0xffffu) + (col_entry & 0xffffu)) | (row_entry & 0xf0000u) | ((col_entry & 0xf0000u) << 4) | binbits;
+}
 WS_HD uint32_t bin_desc(float x1, float y1, float x2, float y2, float scale, int H, int W, int phase, int ph, int pw) {
   const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);
-  int hs, he, ws, we;
-  bin_edges(ah, ph, H, hs, he);
-  bin_edges(aw, pw, W, ws, we);
-  const uint32_t binbits = (uint32_t)(ph * 7 + pw) << 24;
-  if (he <= hs || we <= ws) return kDescEmpty | binbits | (uint32_t)zero_cell(H, W);
-  int p0h, lh, p0w, lw;
-  bin_blocks(hs, he, phase_kh(phase), H, p0h, lh);
-  bin_blocks(ws, we, phase_kw(phase), W, p0w, lw);
-  const int cell = (p0h + kPad) * (W + kPad) + (p0w + kPad);
-  return (uint32_t)cell | ((uint32_t)lh << 16) | ((uint32_t)lw << 20) | binbits;
+  return combine_desc(axis_entry(ah, ph, H, phase_kh(phase), W + kPad), axis_entry(aw, pw, W, phase_kw(phase), 1),
+                      ph * 7 + pw, H, W);
 }
 
 }  // namespace pyr

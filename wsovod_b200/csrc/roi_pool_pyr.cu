@@ -19,7 +19,9 @@ namespace wsovod {
 using namespace pyr;
 
 struct PyrWs {
-  int32_t* hist;        // [N, kBuckets]
+  int32_t* hist;        // [N, kBuckets] followed by cursor [N, kBuckets] (zeroed together)
+  int32_t* cursor;      // [N, kBuckets] scatter cursors of pyr_order_kernel
+  uint32_t* axtab;      // [R, 14] per-proposal row / column descriptor entries (pool_pyr.cuh: axis_entry)
   int32_t* img_start;   // [N + 1]   first sorted position of each image
   int32_t* bucket_off;  // [N, kBuckets + 1] bucket boundaries (positions relative to the image start)
   int32_t* bidx;        // [R]
@@ -35,7 +37,9 @@ static PyrWs pyr_carve(void* ws, int64_t N, int64_t R) {
   size_t off = 0;
   char* base = (char*)ws;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return base + o; };
-  w.hist = (int32_t*)take(sizeof(int32_t) * (size_t)N * kBuckets);
+  w.hist = (int32_t*)take(sizeof(int32_t) * (size_t)N * kBuckets * 2);
+  w.cursor = w.hist + (size_t)N * kBuckets;
+  w.axtab = (uint32_t*)take(sizeof(uint32_t) * (size_t)R * 14);
   w.img_start = (int32_t*)take(sizeof(int32_t) * (size_t)(N + 1));
   w.bucket_off = (int32_t*)take(sizeof(int32_t) * (size_t)N * (kBuckets + 1));
   w.bidx = (int32_t*)take(sizeof(int32_t) * (size_t)R);
@@ -54,26 +58,38 @@ size_t pool7_pyr_workspace(int64_t N, int64_t R) { return pyr_carve(nullptr, N, 
 // ------------------------------------------------------------------------------------------------
 __global__ void pyr_classify_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W, float scale,
                                     int32_t* __restrict__ bidx, uint32_t* __restrict__ pkey,
-                                    int32_t* __restrict__ hist) {
+                                    int32_t* __restrict__ hist, uint32_t* __restrict__ axtab) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float* roi = rois + r * 5;
   int b = (int)roi[0];
   b = min(max(b, 0), N - 1);
-  const uint32_t key = proposal_key(roi[1], roi[2], roi[3], roi[4], scale, H, W);
+  const float x1 = roi[1], y1 = roi[2], x2 = roi[3], y2 = roi[4];
+  const uint32_t key = proposal_key(x1, y1, x2, y2, scale, H, W);
   bidx[r] = b;
   pkey[r] = key;
   atomicAdd(&hist[(int64_t)b * kBuckets + key_bucket(key)], 1);
+  const int phase = key_phase(key);
+  if (phase != PH_FALLBACK) {     // the 7 row and 7 column entries every bin descriptor of this proposal is made of
+    const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);
+    const int kh = phase_kh(phase), kw = phase_kw(phase);
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      axtab[r * 14 + p] = axis_entry(ah, p, H, kh, W + kPad);
+      axtab[r * 14 + 7 + p] = axis_entry(aw, p, W, kw, 1);
+    }
+  }
 }
 
-// one CTA per image: first sorted position of the image (sum of the histograms before it), bucket
-// offsets (block scan), scatter of proposal ids.  The order inside a bucket is whatever the
-// shared-memory atomics give: every output element is written exactly once from position-independent
-// data, so the result does not depend on it.
+// grid (image, part): every CTA derives the first sorted position of its image (sum of the histograms before
+// it) and the bucket offsets (block scan); part p scatters the proposal ids of its slice of the roi list
+// through global per-bucket cursors.  The order inside a bucket is whatever the atomics give: every
+// output element is written exactly once from position-independent data, so the result does not
+// depend on it.
 __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restrict__ bidx, const uint32_t* __restrict__ pkey,
-                                                        const int32_t* __restrict__ hist, int N, int64_t R,
-                                                        int32_t* __restrict__ order, int32_t* __restrict__ img_start,
-                                                        int32_t* __restrict__ bucket_off) {
+                                                        const int32_t* __restrict__ hist, int32_t* __restrict__ cursor,
+                                                        int N, int64_t R, int32_t* __restrict__ order,
+                                                        int32_t* __restrict__ img_start, int32_t* __restrict__ bucket_off) {
   __shared__ int s_cur[kBuckets];
   __shared__ int s_red[16];
   __shared__ int s_base, s_total;
@@ -107,21 +123,24 @@ __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restric
   if (tid < kBuckets) {
     const int excl = wbase + incl - mine;
     s_cur[tid] = excl;
-    bucket_off[n * (kBuckets + 1) + tid] = excl;
-    if (tid == kBuckets - 1) {
-      bucket_off[n * (kBuckets + 1) + kBuckets] = excl + mine;
-      s_total = excl + mine;
+    if (blockIdx.y == 0) {
+      bucket_off[n * (kBuckets + 1) + tid] = excl;
+      if (tid == kBuckets - 1) bucket_off[n * (kBuckets + 1) + kBuckets] = excl + mine;
     }
+    if (tid == kBuckets - 1) s_total = excl + mine;
   }
   __syncthreads();
   const int base = s_base;
-  if (tid == 0) {
+  if (tid == 0 && blockIdx.y == 0) {
     img_start[n] = base;
     if (n == N - 1) img_start[N] = base + s_total;
   }
-  for (int64_t r = tid; r < R; r += blockDim.x) {
+  const int64_t per = (R + gridDim.y - 1) / gridDim.y;
+  const int64_t r_lo = (int64_t)blockIdx.y * per, r_hi = min(R, r_lo + per);
+  for (int64_t r = r_lo + tid; r < r_hi; r += blockDim.x) {
     if (bidx[r] != n) continue;
-    const int pos = atomicAdd(&s_cur[key_bucket(pkey[r])], 1);
+    const int bucket = key_bucket(pkey[r]);
+    const int pos = s_cur[bucket] + atomicAdd(&cursor[(int64_t)n * kBuckets + bucket], 1);
     order[base + pos] = (int32_t)r;
   }
 }
@@ -133,10 +152,9 @@ __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restric
 // whole c2 kernel 1.41 ms in stores alone, proposal-aligned passes 0.88 ms
 // (tools/ubench/store_pattern.cu, "pattern" vs "V6").  The two-channel flavour (larger maps, fewer
 // bytes per pass) is not store-bound and keeps the dense 49-slot stream.
-__global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H, int W, float scale,
-                                const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
-                                const float* __restrict__ row_scale, float row_scale_bias, int slots,
-                                uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
+__global__ void pyr_bins_kernel(int64_t R, int H, int W, const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
+                                const uint32_t* __restrict__ axtab, const float* __restrict__ row_scale,
+                                float row_scale_bias, int slots, uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * slots) return;
   const int64_t gpos = i / slots;
@@ -146,9 +164,9 @@ __global__ void pyr_bins_kernel(const float* __restrict__ rois, int64_t R, int H
   const uint32_t key = pkey[r];
   const int bin = slot_bin(key, q);
   const int ph = bin / 7, pw = bin - ph * 7;
-  const float* roi = rois + (int64_t)r * 5;
-  const int phase = key_phase(key);
-  desc[i] = phase == PH_FALLBACK ? 0u : bin_desc(roi[1], roi[2], roi[3], roi[4], scale, H, W, phase, ph, pw);
+  desc[i] = key_phase(key) == PH_FALLBACK
+                ? 0u
+                : combine_desc(__ldg(axtab + (int64_t)r * 14 + ph), __ldg(axtab + (int64_t)r * 14 + 7 + pw), bin, H, W);
   if (q == 0) {
     const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
     pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
@@ -503,15 +521,16 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   const int cb = pool7_pyr_cb(C, H, W, R);
   if (!cb) return WSOVOD_B200_EINVAL;
   PyrWs w = pyr_carve(workspace, N, R);
-  cudaError_t e = cudaMemsetAsync(w.hist, 0, sizeof(int32_t) * (size_t)N * kBuckets, st);
+  cudaError_t e = cudaMemsetAsync(w.hist, 0, sizeof(int32_t) * (size_t)N * kBuckets * 2, st);   // histogram + cursors
   if (e != cudaSuccess) return (int)e;
   int rc;
-  pyr_classify_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.pkey, w.hist);
+  pyr_classify_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.pkey, w.hist, w.axtab);
   if ((rc = after_launch())) return rc;
-  pyr_order_kernel<<<(unsigned)N, 512, 0, st>>>(w.bidx, w.pkey, w.hist, (int)N, R, w.order, w.img_start, w.bucket_off);
+  const unsigned parts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(R, 2048)));
+  pyr_order_kernel<<<dim3((unsigned)N, parts), 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.cursor, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
   const int slots = cb == 4 ? kSlots : 49;
-  pyr_bins_kernel<<<(unsigned)ceil_div(R * slots, 256), 256, 0, st>>>(rois, R, (int)H, (int)W, scale, w.order, w.pkey, row_scale,
+  pyr_bins_kernel<<<(unsigned)ceil_div(R * slots, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
                                                                      row_scale_bias, slots, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
