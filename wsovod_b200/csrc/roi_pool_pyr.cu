@@ -8,6 +8,12 @@
 // with doubling steps D[i] = max(D[i], D[i + stride]).  Values are exact copies of input cells, so the
 // result is bit-identical to the scan of ROILoopPool_cpu.cpp:52-79 (max is order independent; NaN and
 // -inf never win against the -FLT_MAX start exactly as `v > maxval` never lets them).
+//
+// Launch sequence on the caller's stream: memset (histogram + cursors) -> pyr_classify (per proposal: class
+// key, 7 + 7 descriptor entries) -> pyr_order (per image: bucket offsets, scatter) -> pyr_bins (per lane
+// slot: 32-bit descriptor) -> roi_pool7_pyr_kernel (1024 threads, one CTA per SM, grid = images x channel
+// groups [x proposal splits]).  With four channels per CTA the lane-slot stream is padded to 64 slots
+// per proposal so that no warp store straddles two proposals (Kernel 1b).
 #include "common.cuh"
 #include "pool_pyr.cuh"
 
