@@ -123,7 +123,8 @@ def cpu_reference_leg(w, budget_s=20.0):
 def run_reference(args, w, rank):
     if rank != 0:
         return
-    cpu_path, cores, images, props = cpu_reference_leg(w)
+    # the whole --steps K run has to end within a few minutes: ~150 s of CPU work in total
+    cpu_path, cores, images, props = cpu_reference_leg(w, budget_s=max(2.0, min(20.0, 150.0 / max(args.steps, 1))))
     for _ in range(args.warmup):
         cpu_path.run_slice(w, images=1, proposals=min(props, 200))
     t, n = 0.0, 0
