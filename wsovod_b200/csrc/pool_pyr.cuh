@@ -127,9 +127,11 @@ WS_HD void bin_blocks(int s, int e, int k, int L, int& pos0, int& last) {
 
 // per-proposal key (classification result)
 //   bits 0-3 phase | 4-5 ch-1 | 6-7 cw-1 | 8 lanes walk the bins column-major
-// Column-major lane order when the bins are wider than tall: the 8 lanes of a shared-memory phase then
-// differ in their row (3 bank groups apart per row with the odd pitch) instead of in a column stride
-// that is likely to repeat bank groups (simulated: 23.9 -> 21.9 wavefronts per 32 bins).
+// Bit 8 (column-major lane order: the 8 lanes of a shared-memory phase then differ in their row instead of in
+// a column stride that repeats bank groups; simulated 23.9 -> 21.9 LDS wavefronts per 32 bins) is
+// supported by the descriptor stream but no longer set: lanes that walk a run with stride 7 scatter every
+// warp store over the whole 196-byte run, and on the B200 the extra partial-sector writes cost more than
+// the bank conflicts saved (c2: 1.314 ms with the heuristic, 1.303 ms without).
 constexpr uint32_t kKeyTransposed = 1u << 8;
 WS_HD uint32_t proposal_key(float x1, float y1, float x2, float y2, float scale, int H, int W) {
   const Axis ah = axis_of(y1, y2, scale), aw = axis_of(x1, x2, scale);
@@ -141,8 +143,7 @@ WS_HD uint32_t proposal_key(float x1, float y1, float x2, float y2, float scale,
   // a bin that needs fewer blocks skips the surplus ones (duplicate-block predicates in the kernels)
   ch = ch <= 2 ? 2 : 4;
   cw = cw <= 2 ? 2 : 4;
-  return (uint32_t)phase_of(kh, kw) | ((uint32_t)(ch - 1) << 4) | ((uint32_t)(cw - 1) << 6) |
-         (aw.bin > ah.bin ? kKeyTransposed : 0u);
+  return (uint32_t)phase_of(kh, kw) | ((uint32_t)(ch - 1) << 4) | ((uint32_t)(cw - 1) << 6);
 }
 // output bin served by lane slot q (0..48) of a proposal
 WS_HD int slot_bin(uint32_t key, int q) { return (key & kKeyTransposed) ? (q % 7) * 7 + q / 7 : q; }
