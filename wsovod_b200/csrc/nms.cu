@@ -48,6 +48,8 @@ __device__ __forceinline__ bool suppresses(const float4 bi, const float ai, cons
   w = fmaxf(w, 0.f);
   h = fmaxf(h, 0.f);
   const float inter = __fmul_rn(w, h);
+  // disjoint boxes (the common case): 0 / den is +-0 or NaN, never > thr for thr >= 0 -- skip the division
+  if (inter == 0.f && thr >= 0.f) return false;
   float den;
   if (MODE == 0) {
     const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
@@ -148,6 +150,31 @@ __global__ void det_rows_kernel(const float* __restrict__ probs, const float* __
   }
 }
 
+// scoresT[k][r] = probs[r][k] for finite rows, -inf otherwise: det_class then reads its column as one
+// contiguous run instead of one 4-byte word out of every 32-byte sector of a row-major matrix that all K
+// class CTAs of the image walk at the same time (c2: 82 MB of sector traffic for 10 MB of scores)
+__global__ void __launch_bounds__(256) det_transpose_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ valid,
+                                                            int64_t M, int K, float* __restrict__ scoresT) {
+  __shared__ float tile[32][33];
+  const int64_t rb = (int64_t)blockIdx.x * 32;
+  const int kb = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int K1 = K + 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = rb + ty + i * 8;
+    const int k = kb + tx;
+    tile[ty + i * 8][tx] = (r < M && k < K && valid[r]) ? __ldg(probs + r * K1 + k) : -INFINITY;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = kb + ty + i * 8;
+    const int64_t r = rb + tx;
+    if (k < K && r < M) scoresT[(int64_t)k * M + r] = tile[tx][ty + i * 8];
+  }
+}
+
 // in-place bitonic sort (ascending) of npad = 2^k keys in shared memory by the whole CTA
 __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
@@ -173,6 +200,7 @@ constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == hist
 // so the 80 x 8 = 640 (class, image) CTAs of c2 are resident at once (740 slots) instead of taking two
 // waves of 4 x 148 = 592
 constexpr int kDcThreads = 384;
+constexpr int kDcWindow = 2;          // warps ahead of the resolving one that keep up with the kept list
 constexpr int kSelectTarget = 512;    // aim: at least this many best candidates in the prefix
 constexpr int kSelectMin = 512;       // columns shorter than this are simply sorted
 
@@ -185,8 +213,8 @@ constexpr int kSelectMin = 512;       // columns shorter than this are simply so
 //   4. append (score, row*K+class) keys to the image's kept list
 template <int MODE>
 __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
-    const float* __restrict__ probs, const int64_t* __restrict__ offsets, const uint8_t* __restrict__ valid,
-    const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap,
+    const float* __restrict__ scoresT, int64_t M, const int64_t* __restrict__ offsets,
+    const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap, bool fixed_runs,
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
     int2* __restrict__ runs) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -203,11 +231,16 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const int K1 = K + 1;
-  for (int64_t r = r0 + threadIdx.x; r < r1; r += kDcThreads) {
-    if (!valid[r]) continue;
-    const float s = __ldg(probs + r * K1 + k);
-    if (s > score_thr) skey[atomicAdd(&s_n, 1)] = make_key(s, (uint32_t)(r - r0));   // :194
+  // the column is one contiguous run of scoresT (rows that failed the finite filter hold -inf)
+  const float* col = scoresT + (int64_t)k * M + r0;
+  const int nrows = (int)(r1 - r0);
+  for (int rb = threadIdx.x; rb < nrows; rb += 4 * kDcThreads) {
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = rb + u * kDcThreads < nrows ? __ldg(col + rb + u * kDcThreads) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (s[u] > score_thr) skey[atomicAdd(&s_n, 1)] = make_key(s[u], (uint32_t)(rb + u * kDcThreads));   // :194
   }
   __syncthreads();
   const int nc = s_n;
@@ -289,44 +322,66 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
       bool alive = i < ln;
       unsigned long long key = 0;
       float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+      int tested = 0;       // kept boxes this candidate has been tested against
+      // candidate against kept boxes [from, to): four independent tests per trip
+      auto catch_up = [&](int from, int to) {
+        int j = from;
+        for (; j + 4 <= to && alive; j += 4) {
+          const bool s0 = suppresses<MODE>(kbox[j], karea[j], box, thr);
+          const bool s1 = suppresses<MODE>(kbox[j + 1], karea[j + 1], box, thr);
+          const bool s2 = suppresses<MODE>(kbox[j + 2], karea[j + 2], box, thr);
+          const bool s3 = suppresses<MODE>(kbox[j + 3], karea[j + 3], box, thr);
+          alive = !(s0 | s1 | s2 | s3);
+        }
+        for (; j < to && alive; ++j)
+          if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
+      };
       if (alive) {
         key = list[i];
         box = __ldg(cboxes + r0 + (uint32_t)key);
-        for (int j = 0; j < kept && alive; ++j)
-          if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
+        if (wid < kDcWindow) { catch_up(0, kept); tested = kept; }
       }
       // The chunk is resolved warp by warp in list order.  The warp whose turn it is settles its 32
       // candidates among themselves -- every still-alive lane, in order, is kept, its box is broadcast
       // with shuffles and the ballot of the lanes it suppresses clears them -- and appends the kept
-      // boxes to the shared list; after one barrier the later warps test their alive lanes against just
-      // those new boxes.  Barriers per chunk: one per warp that still had work (typically ~5 until
+      // boxes to the shared list; after one barrier the next kDcWindow warps test their alive lanes against
+      // the kept boxes they have not seen yet.  Barriers per chunk: one per warp that still had work (typically ~5 until
       // `limit` boxes are kept), not one per kept box.
       const float my_area = area_rn(box);
       for (int w = 0; w < kDcThreads / 32 && kept < limit; ++w) {
         if (wid == w) {
           unsigned am = __ballot_sync(0xffffffffu, alive);
+          // all pairs first (independent tests, pipelined): bit j of supby = alive lane j < me covers me
+          unsigned supby = 0;
+#pragma unroll 4
+          for (int j = 0; j < 31; ++j) {
+            const float4 kb = make_float4(__shfl_sync(0xffffffffu, box.x, j), __shfl_sync(0xffffffffu, box.y, j),
+                                          __shfl_sync(0xffffffffu, box.z, j), __shfl_sync(0xffffffffu, box.w, j));
+            const float ka = __shfl_sync(0xffffffffu, my_area, j);
+            if (((am >> j) & 1u) && lane > j && alive && suppresses<MODE>(kb, ka, box, thr)) supby |= 1u << j;
+          }
+          // then the serial part is a ballot per kept box
           int nnew = 0;
+          unsigned keepm = 0;
           while (am && kept + nnew < limit) {
             const int sl = __ffs(am) - 1;                      // next kept lane
-            const float4 kb = make_float4(__shfl_sync(0xffffffffu, box.x, sl), __shfl_sync(0xffffffffu, box.y, sl),
-                                          __shfl_sync(0xffffffffu, box.z, sl), __shfl_sync(0xffffffffu, box.w, sl));
-            const float ka = __shfl_sync(0xffffffffu, my_area, sl);
-            if (lane == sl) { kbox[kept + nnew] = kb; karea[kept + nnew] = ka; kkey[kept + nnew] = key; }
-            const bool sup = lane > sl && ((am >> lane) & 1u) && suppresses<MODE>(kb, ka, box, thr);
-            am &= ~__ballot_sync(0xffffffffu, sup);
+            keepm |= 1u << sl;
+            am &= ~__ballot_sync(0xffffffffu, (supby >> sl) & 1u);
             am &= ~(1u << sl);
             ++nnew;
+          }
+          if ((keepm >> lane) & 1u) {
+            const int o = kept + __popc(keepm & ((1u << lane) - 1u));
+            kbox[o] = box; karea[o] = my_area; kkey[o] = key;
           }
           alive = false;                                       // kept or suppressed, or past the limit: done either way
           if (lane == 0) s_new[w & 1] = nnew;
         }
         __syncthreads();
-        const int nnew = s_new[w & 1];      // the next writer of this slot (step w+2) is two barriers away
-        if (wid > w && alive) {
-          for (int j = kept; j < kept + nnew && alive; ++j)
-            if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
-        }
-        kept += nnew;
+        kept += s_new[w & 1];               // the next writer of this slot (step w+2) is two barriers away
+        // Only the warps about to take their turn catch up with the kept list: most chunks end after a few
+        // steps (`limit` boxes kept), and the warps behind the window never need to test anything.
+        if (wid > w && wid <= w + kDcWindow && alive) { catch_up(tested, kept); tested = kept; }
       }
       __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
     }
@@ -336,7 +391,8 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    s_base = atomicAdd(&img_cnt[n], kept);
+    // with the run merge downstream every class owns a fixed slot of the image's list (no atomic round trip)
+    s_base = fixed_runs ? k * limit : atomicAdd(&img_cnt[n], kept);
     runs[(int64_t)n * K + k] = make_int2(s_base, kept);      // this class's survivors: a score-descending run
   }
   __syncthreads();
@@ -645,7 +701,7 @@ static NmsWs nms_plan(int64_t M, int64_t G) {
   return w;
 }
 
-struct DetWs { size_t valid, cboxes, img_cnt, img_kept, runs, bytes; int64_t kept_stride; };
+struct DetWs { size_t valid, cboxes, img_cnt, img_kept, runs, scoresT, bytes; int64_t kept_stride; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
   size_t o = 0;
@@ -656,6 +712,7 @@ static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   w.img_cnt = take(sizeof(int32_t) * (size_t)(N + 1));
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
   w.runs = take(sizeof(int2) * (size_t)(N * std::max<int64_t>(K, 1)));
+  w.scoresT = take(sizeof(float) * (size_t)(M * K));
   w.bytes = o;
   return w;
 }
@@ -776,6 +833,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;
   int rc;
+  const bool use_runs = M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads;
   if (M > 0 && K > 0) {
     det_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, valid, cboxes);
     if ((rc = after_launch())) return rc;
@@ -784,9 +842,12 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
+    float* scoresT = (float*)(ws + w.scoresT);
+    det_transpose_kernel<<<dim3((unsigned)ceil_div(M, 32), (unsigned)ceil_div(K, 32)), 256, 0, st>>>(probs, valid, M, (int)K, scoresT);
+    if ((rc = after_launch())) return rc;
     dim3 grid((unsigned)K, (unsigned)N);
-    kern<<<grid, kDcThreads, smem, st>>>(probs, offsets, valid, cboxes, (int)K, score_thresh,
-                                         cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, img_cnt, img_kept, w.kept_stride, runs);
+    kern<<<grid, kDcThreads, smem, st>>>(scoresT, M, offsets, cboxes, (int)K, score_thresh,
+                                         cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, use_runs, img_cnt, img_kept, w.kept_stride, runs);
     if ((rc = after_launch())) return rc;
   }
   // final ordering: sort the image's kept list in shared memory when it fits (K * topk <= 16384 keys)
@@ -800,7 +861,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   }
   det_topk_kernel<<<(unsigned)N, kNmsThreads, tsmem, st>>>(
       img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap,
-      (M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads) ? runs : nullptr, det_boxes, det_scores, det_classes,
+      use_runs ? runs : nullptr, det_boxes, det_scores, det_classes,
       det_rows, det_count);
   return after_launch();
 }
