@@ -362,6 +362,31 @@ def test_detections_vs_oracle(mode):
         assert torch.equal(r[k].cpu(), o[k]), k
 
 
+@pytest.mark.parametrize("thr", [0.5, 0.25, 1.0 / 3.0, 0.2])
+@pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
+def test_detections_threshold_ties(mode, thr):
+    """Boxes snapped to a coarse grid: many pairs overlap by exactly 1/2, 1/3, 1/4, 1/5 ... -- quotients that
+    sit on (or one rounding away from) the threshold, where the kernel's approximate-quotient screening must
+    hand over to the exact IEEE division."""
+    g = synth.gen(43)
+    K, sizes = 6, [1800, 900]
+    shapes = [(480, 640), (320, 480)]
+    boxes = []
+    for s, (h, w) in zip(sizes, shapes):
+        x1 = torch.randint(0, w // 32 - 2, (s,), generator=g).float() * 32
+        y1 = torch.randint(0, h // 32 - 2, (s,), generator=g).float() * 32
+        bw = torch.randint(1, 5, (s,), generator=g).float() * 32
+        bh = torch.randint(1, 5, (s,), generator=g).float() * 32
+        boxes.append(torch.stack([x1, y1, x1 + bw, y1 + bh], 1))
+    probs = [torch.softmax(torch.randn(s, K + 1, generator=g) * 2.0, -1) for s in sizes]
+    off = _offs(sizes)
+    r = ops.detections(torch.cat(probs).to(DEV), torch.cat(boxes).to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(shapes, dtype=torch.float32, device=DEV), max(sizes), 1e-5, thr, 100, mode)
+    o = oracle.detections(torch.cat(probs), torch.cat(boxes), off, shapes, 1e-5, thr, 100, mode)
+    for k in o:
+        assert torch.equal(r[k].cpu(), o[k]), k
+
+
 @pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
 def test_detections_prefix_fallback_and_long_columns(mode):
     """Columns longer than 2048 candidates take the histogram pre-selection; when the selected prefix

@@ -59,6 +59,34 @@ __device__ __forceinline__ bool suppresses(const float4 bi, const float ai, cons
   }
   return __fdiv_rn(inter, den) > thr;
 }
+// Branch-free screening of the same test: 0 = no, 1 = yes, 2 = too close to call (run suppresses()).
+// The quotient comes from the approximate divide (MUFU.RCP * inter, <= 2 ulp off the real quotient, and the
+// IEEE quotient is within 0.5 ulp of it), so whenever |q - thr| > 1e-5 * thr -- 80 ulp -- the approximate and
+// the IEEE quotient lie on the same side of thr.  Operands outside [2^-20, 2^100] (denormal / overflowing
+// quotients, NaN) and negative thresholds are never screened.  Disjoint boxes (inter == 0) give +-0 or NaN,
+// which no thr >= 0 is below.
+template <int MODE>
+__device__ __forceinline__ int suppresses_fast(const float4 bi, const float ai, const float4 bj, const float thr) {
+  float w = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+  float h = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+  w = fmaxf(w, 0.f);
+  h = fmaxf(h, 0.f);
+  const float inter = __fmul_rn(w, h);
+  float den;
+  if (MODE == 0) {
+    const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+    den = __fsub_rn(__fadd_rn(ai, aj), inter);
+  } else {
+    den = __fsub_rn(__fmaf_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y), ai), inter);
+  }
+  constexpr float kLo = 9.5367431640625e-07f, kHi = 1.2676506002282294e30f;   // 2^-20, 2^100
+  const float q = __fdividef(inter, den);
+  const bool zero = inter == 0.f;
+  const bool ranged = inter >= kLo && inter <= kHi && den >= kLo && den <= kHi;
+  const bool clear = fabsf(__fsub_rn(q, thr)) > __fmul_rn(1e-5f, thr);
+  const bool sure = thr >= 0.f && (zero || (ranged && clear));
+  return sure ? ((!zero && q > thr) ? 1 : 0) : 2;
+}
 __device__ __forceinline__ float area_rn(const float4 b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }
@@ -327,11 +355,15 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
       auto catch_up = [&](int from, int to) {
         int j = from;
         for (; j + 4 <= to && alive; j += 4) {
-          const bool s0 = suppresses<MODE>(kbox[j], karea[j], box, thr);
-          const bool s1 = suppresses<MODE>(kbox[j + 1], karea[j + 1], box, thr);
-          const bool s2 = suppresses<MODE>(kbox[j + 2], karea[j + 2], box, thr);
-          const bool s3 = suppresses<MODE>(kbox[j + 3], karea[j + 3], box, thr);
-          alive = !(s0 | s1 | s2 | s3);
+          int d[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u] = suppresses_fast<MODE>(kbox[j + u], karea[j + u], box, thr);
+          if ((d[0] | d[1] | d[2] | d[3]) & 2) {             // rare: a quotient within 1e-5 of the threshold
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (d[u] == 2) d[u] = suppresses<MODE>(kbox[j + u], karea[j + u], box, thr) ? 1 : 0;
+          }
+          alive = (d[0] | d[1] | d[2] | d[3]) == 0;
         }
         for (; j < to && alive; ++j)
           if (suppresses<MODE>(kbox[j], karea[j], box, thr)) alive = false;
@@ -352,13 +384,26 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
         if (wid == w) {
           unsigned am = __ballot_sync(0xffffffffu, alive);
           // all pairs first (independent tests, pipelined): bit j of supby = alive lane j < me covers me
-          unsigned supby = 0;
+          unsigned supby = 0, unsure = 0;
+          const unsigned pairs = alive ? (am & ((1u << lane) - 1u)) : 0u;     // alive lanes ahead of an alive me
 #pragma unroll 4
           for (int j = 0; j < 31; ++j) {
             const float4 kb = make_float4(__shfl_sync(0xffffffffu, box.x, j), __shfl_sync(0xffffffffu, box.y, j),
                                           __shfl_sync(0xffffffffu, box.z, j), __shfl_sync(0xffffffffu, box.w, j));
             const float ka = __shfl_sync(0xffffffffu, my_area, j);
-            if (((am >> j) & 1u) && lane > j && alive && suppresses<MODE>(kb, ka, box, thr)) supby |= 1u << j;
+            const int d = suppresses_fast<MODE>(kb, ka, box, thr);
+            supby |= (unsigned)(d == 1) << j;
+            unsure |= (unsigned)(d == 2) << j;
+          }
+          supby &= pairs;
+          unsure &= pairs;
+          // rare: quotients within 1e-5 of the threshold are settled by the exact test
+          for (unsigned u = __reduce_or_sync(0xffffffffu, unsure); u; u &= u - 1) {
+            const int j = __ffs(u) - 1;
+            const float4 kb = make_float4(__shfl_sync(0xffffffffu, box.x, j), __shfl_sync(0xffffffffu, box.y, j),
+                                          __shfl_sync(0xffffffffu, box.z, j), __shfl_sync(0xffffffffu, box.w, j));
+            const float ka = __shfl_sync(0xffffffffu, my_area, j);
+            if (((unsure >> j) & 1u) && suppresses<MODE>(kb, ka, box, thr)) supby |= 1u << j;
           }
           // then the serial part is a ballot per kept box
           int nnew = 0;
@@ -381,7 +426,7 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
         kept += s_new[w & 1];               // the next writer of this slot (step w+2) is two barriers away
         // Only the warps about to take their turn catch up with the kept list: most chunks end after a few
         // steps (`limit` boxes kept), and the warps behind the window never need to test anything.
-        if (wid > w && wid <= w + kDcWindow && alive) { catch_up(tested, kept); tested = kept; }
+        if (kept < limit && wid > w && wid <= w + kDcWindow && alive) { catch_up(tested, kept); tested = kept; }
       }
       __syncthreads();      // kbox/karea of this chunk visible before the next chunk's pre-test
     }
