@@ -220,6 +220,31 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
   }
 }
 
+// the same sort for npad <= blockDim.x keys held one per thread: compare-exchange distances below 32 are
+// shuffles, only the larger ones go through shared memory (npad = 256: 12 barriers instead of 36)
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long* keys, int npad) {
+  const int t = threadIdx.x;
+  unsigned long long v = t < npad ? keys[t] : kDead;
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long o;
+      if (j >= 32) {
+        __syncthreads();                         // the previous exchange has been read
+        if (t < npad) keys[t] = v;
+        __syncthreads();
+        o = t < npad ? keys[t ^ j] : kDead;
+      } else {
+        o = __shfl_xor_sync(0xffffffffu, v, j);
+      }
+      const bool take_min = ((t & j) == 0) == ((t & k) == 0);
+      v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+    }
+  }
+  __syncthreads();
+  if (t < npad) keys[t] = v;
+  __syncthreads();
+}
+
 constexpr int kRunsPerThread = 4;      // top-k merge handles K <= 4 * kNmsThreads classes
 constexpr int kSelectBins = 2048;     // histogram over the 11 leading key bits (quarter octaves of the score)
 constexpr int kSelectShift = 53;
@@ -228,6 +253,7 @@ constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == hist
 // so the 80 x 8 = 640 (class, image) CTAs of c2 are resident at once (740 slots) instead of taking two
 // waves of 4 x 148 = 592
 constexpr int kDcThreads = 384;
+constexpr int kDcHead = 128;          // candidates settled by the all-pairs head stage
 constexpr int kDcWindow = 2;          // warps ahead of the resolving one that keep up with the kept list
 constexpr int kSelectTarget = 512;    // aim: at least this many best candidates in the prefix
 constexpr int kSelectMin = 512;       // columns shorter than this are simply sorted
@@ -248,12 +274,14 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ int s_n, s_base, s_sel, s_bstar, s_m;
   __shared__ int s_new[2];
+  __shared__ int s_head;
   __shared__ int s_wsum[kNmsWarps];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);                 // [npad_cap]
   float4* kbox = reinterpret_cast<float4*>(sm + (size_t)npad_cap * sizeof(unsigned long long));   // [limit]
   float* karea = reinterpret_cast<float*>(kbox + limit);                                 // [limit]
   unsigned long long* kkey = reinterpret_cast<unsigned long long*>(karea + ((limit + 1) & ~1));   // [limit]
-  unsigned long long* ssel = kkey + limit;                                               // [kSelectCap] / histogram
+  unsigned long long* ssel = reinterpret_cast<unsigned long long*>(                      // [kSelectCap] / histogram, 16-byte aligned
+      (reinterpret_cast<uintptr_t>(kkey + limit) + 15) & ~(uintptr_t)15);
   const int k = blockIdx.x, n = blockIdx.y;
   const int64_t r0 = offsets[n], r1 = offsets[n + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -262,13 +290,20 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   // the column is one contiguous run of scoresT (rows that failed the finite filter hold -inf)
   const float* col = scoresT + (int64_t)k * M + r0;
   const int nrows = (int)(r1 - r0);
-  for (int rb = threadIdx.x; rb < nrows; rb += 4 * kDcThreads) {
+  for (int rb = threadIdx.x; rb - lane < nrows; rb += 4 * kDcThreads) {      // warp-uniform trip count
     float s[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) s[u] = rb + u * kDcThreads < nrows ? __ldg(col + rb + u * kDcThreads) : -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (s[u] > score_thr) skey[atomicAdd(&s_n, 1)] = make_key(s[u], (uint32_t)(rb + u * kDcThreads));   // :194
+    for (int u = 0; u < 4; ++u) {
+      const bool pass = s[u] > score_thr;                                     // :194
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m == 0) continue;
+      int at = 0;
+      if (lane == 0) at = atomicAdd(&s_n, __popc(m));                         // one append per warp, not per key
+      at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+      if (pass) skey[at] = make_key(s[u], (uint32_t)(rb + u * kDcThreads));
+    }
   }
   __syncthreads();
   const int nc = s_n;
@@ -342,10 +377,88 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     while (npad < ln) npad <<= 1;
     for (int i = ln + threadIdx.x; i < npad; i += kDcThreads) list[i] = kDead;
     __syncthreads();
-    bitonic_sort_smem(list, npad);
+    if (npad <= 256) bitonic_sort_regs(list, npad);
+    else bitonic_sort_smem(list, npad);
 
     kept = 0;
-    for (int base = 0; base < ln && kept < limit; base += kDcThreads) {
+    int base0 = 0;
+    // Head of the list (first 128 candidates -- enough for `limit` = 100 survivors on most columns): all
+    // pair tests at once, spread over ten warps (warp <-> 32 candidates x 32 candidates ahead of them, the
+    // lower triangle of a 4 x 4 block matrix), then ONE warp settles the four groups in order with ballots.
+    // Needs 4 KB of spare shared memory behind the list.
+    unsigned char* spare = nullptr;
+    if (list != ssel) spare = reinterpret_cast<unsigned char*>(ssel);
+    else if (npad <= kSelectCap - 512) spare = reinterpret_cast<unsigned char*>(ssel + npad);
+    if (spare != nullptr) {
+      const int P = min(ln, kDcHead);
+      float4* stage = reinterpret_cast<float4*>(spare);                     // [kDcHead] candidate boxes
+      unsigned* supby = reinterpret_cast<unsigned*>(spare + kDcHead * sizeof(float4));   // [kDcHead][4]
+      if (threadIdx.x < P) stage[threadIdx.x] = __ldg(cboxes + r0 + (uint32_t)list[threadIdx.x]);
+      __syncthreads();
+      if (wid < 10) {
+        const int g = wid < 1 ? 0 : wid < 3 ? 1 : wid < 6 ? 2 : 3;          // my candidates: group g
+        const int p = wid - (g * (g + 1)) / 2;                              // tested against group p <= g
+        const int i = 32 * g + lane;
+        if (32 * g < P) {
+          const float4 bi = stage[min(i, P - 1)];
+          const int jend = min(32, P - 32 * p);
+          unsigned sup = 0, uns = 0;
+#pragma unroll 4
+          for (int jj = 0; jj < jend; ++jj) {
+            const float4 kb = stage[32 * p + jj];
+            const int d = suppresses_fast<MODE>(kb, area_rn(kb), bi, thr);
+            sup |= (unsigned)(d == 1) << jj;
+            uns |= (unsigned)(d == 2) << jj;
+          }
+          const unsigned ahead = p < g ? 0xffffffffu : ((1u << lane) - 1u);
+          sup &= ahead;
+          for (uns &= ahead; uns; uns &= uns - 1) {                         // rare: settle near-threshold pairs exactly
+            const int jj = __ffs(uns) - 1;
+            const float4 kb = stage[32 * p + jj];
+            if (suppresses<MODE>(kb, area_rn(kb), bi, thr)) sup |= 1u << jj;
+          }
+          if (i < P) supby[i * 4 + p] = sup;
+        }
+      }
+      __syncthreads();
+      if (wid == 0) {
+        unsigned km[4] = {0u, 0u, 0u, 0u};
+        int total = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (32 * g < P && total < limit) {
+            const int i = 32 * g + lane;
+            bool alive = i < P;
+#pragma unroll
+            for (int p = 0; p < g; ++p)
+              if (alive && (supby[i * 4 + p] & km[p])) alive = false;
+            const unsigned diag = alive ? supby[i * 4 + g] : 0u;
+            // kept = alive and not covered by a kept lane ahead: iterate the ballot to its fixed point (lane l
+            // is final after l + 1 rounds at the latest; chains are short, so it takes two or three)
+            unsigned kmg = __ballot_sync(0xffffffffu, alive);
+            for (;;) {
+              const unsigned nk = __ballot_sync(0xffffffffu, alive && !(diag & kmg));
+              if (nk == kmg) break;
+              kmg = nk;
+            }
+            const int rank = __popc(kmg & ((1u << lane) - 1u));
+            const bool keep = ((kmg >> lane) & 1u) && total + rank < limit;
+            kmg = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              const float4 kb = stage[i];
+              kbox[total + rank] = kb; karea[total + rank] = area_rn(kb); kkey[total + rank] = list[i];
+            }
+            total += __popc(kmg);
+            km[g] = kmg;
+          }
+        }
+        if (lane == 0) s_head = total;
+      }
+      __syncthreads();
+      kept = s_head;
+      base0 = P;
+    }
+    for (int base = base0; base < ln && kept < limit; base += kDcThreads) {
       const int i = base + threadIdx.x;
       bool alive = i < ln;
       unsigned long long key = 0;
@@ -866,7 +979,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   const int limit = (int)std::min<int64_t>(topk, std::max<int64_t>(max_rows_per_image, 1));
   const size_t smem = (size_t)npad_cap * sizeof(unsigned long long) +
                       (size_t)limit * (sizeof(float4) + sizeof(unsigned long long)) + sizeof(float) * (size_t)(limit + 2) +
-                      sizeof(unsigned long long) * (size_t)kSelectCap;
+                      sizeof(unsigned long long) * (size_t)kSelectCap + 16;
   if (smem > (size_t)kMaxSmemOptin - 2048) return WSOVOD_B200_EUNSUPPORTED;   // > 16384 proposals per image
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
