@@ -362,7 +362,7 @@ def test_detections_vs_oracle(mode):
         assert torch.equal(r[k].cpu(), o[k]), k
 
 
-@pytest.mark.parametrize("thr", [0.5, 0.25, 1.0 / 3.0, 0.2])
+@pytest.mark.parametrize("thr", [0.5, 0.25, 1.0 / 3.0, 0.2, 0.0, 1.0, 1e-7])
 @pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
 def test_detections_threshold_ties(mode, thr):
     """Boxes snapped to a coarse grid: many pairs overlap by exactly 1/2, 1/3, 1/4, 1/5 ... -- quotients that

@@ -59,12 +59,13 @@ __device__ __forceinline__ bool suppresses(const float4 bi, const float ai, cons
   }
   return __fdiv_rn(inter, den) > thr;
 }
-// Branch-free screening of the same test: 0 = no, 1 = yes, 2 = too close to call (run suppresses()).
-// The quotient comes from the approximate divide (MUFU.RCP * inter, <= 2 ulp off the real quotient, and the
-// IEEE quotient is within 0.5 ulp of it), so whenever |q - thr| > 1e-5 * thr -- 80 ulp -- the approximate and
-// the IEEE quotient lie on the same side of thr.  Operands outside [2^-20, 2^100] (denormal / overflowing
-// quotients, NaN) and negative thresholds are never screened.  Disjoint boxes (inter == 0) give +-0 or NaN,
-// which no thr >= 0 is below.
+// Branch-free screening of the same test without the division: 0 = no, 1 = yes, 2 = too close to call
+// (run suppresses()).  With t = fl(thr * den) and e = fl(inter - t), |e| > 2^-18 * t implies that the real
+// quotient Q = inter / den is more than 3.7e-6 * thr away from thr, on the side sign(e) says (the two
+// roundings in e move it by at most 2^-23 * t), and the IEEE quotient is within 2^-24 * Q of Q -- so it
+// compares with thr the same way.  Needs a normal, positive den (zero / negative / NaN denominators of
+// degenerate boxes go to the exact test; an infinite one makes t infinite and fails |e| > inf) and a
+// threshold in [1e-6, 1e6] (anything else is never screened).  Disjoint boxes have e = -t: a sure "no".
 template <int MODE>
 __device__ __forceinline__ int suppresses_fast(const float4 bi, const float ai, const float4 bj, const float thr) {
   float w = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
@@ -79,13 +80,11 @@ __device__ __forceinline__ int suppresses_fast(const float4 bi, const float ai, 
   } else {
     den = __fsub_rn(__fmaf_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y), ai), inter);
   }
-  constexpr float kLo = 9.5367431640625e-07f, kHi = 1.2676506002282294e30f;   // 2^-20, 2^100
-  const float q = __fdividef(inter, den);
-  const bool zero = inter == 0.f;
-  const bool ranged = inter >= kLo && inter <= kHi && den >= kLo && den <= kHi;
-  const bool clear = fabsf(__fsub_rn(q, thr)) > __fmul_rn(1e-5f, thr);
-  const bool sure = thr >= 0.f && (zero || (ranged && clear));
-  return sure ? ((!zero && q > thr) ? 1 : 0) : 2;
+  const float t = __fmul_rn(thr, den);
+  const float e = __fsub_rn(inter, t);
+  const bool sure = thr >= 1e-6f && thr <= 1e6f && den >= 8.6736173798840355e-19f /* 2^-60 */ &&
+                    fabsf(e) > __fmul_rn(t, 3.814697265625e-06f /* 2^-18 */);
+  return sure ? (e > 0.f ? 1 : 0) : 2;
 }
 __device__ __forceinline__ float area_rn(const float4 b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -392,8 +391,13 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     if (spare != nullptr) {
       const int P = min(ln, kDcHead);
       float4* stage = reinterpret_cast<float4*>(spare);                     // [kDcHead] candidate boxes
-      unsigned* supby = reinterpret_cast<unsigned*>(spare + kDcHead * sizeof(float4));   // [kDcHead][4]
-      if (threadIdx.x < P) stage[threadIdx.x] = __ldg(cboxes + r0 + (uint32_t)list[threadIdx.x]);
+      float* sarea = reinterpret_cast<float*>(spare + kDcHead * sizeof(float4));             // [kDcHead] their areas
+      unsigned* supby = reinterpret_cast<unsigned*>(sarea + kDcHead);       // [10 tiles][32]: who ahead of me covers me
+      if (threadIdx.x < P) {
+        const float4 b = __ldg(cboxes + r0 + (uint32_t)list[threadIdx.x]);
+        stage[threadIdx.x] = b;
+        sarea[threadIdx.x] = area_rn(b);
+      }
       __syncthreads();
       if (wid < 10) {
         const int g = wid < 1 ? 0 : wid < 3 ? 1 : wid < 6 ? 2 : 3;          // my candidates: group g
@@ -403,21 +407,25 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
           const float4 bi = stage[min(i, P - 1)];
           const int jend = min(32, P - 32 * p);
           unsigned sup = 0, uns = 0;
-#pragma unroll 4
-          for (int jj = 0; jj < jend; ++jj) {
-            const float4 kb = stage[32 * p + jj];
-            const int d = suppresses_fast<MODE>(kb, area_rn(kb), bi, thr);
-            sup |= (unsigned)(d == 1) << jj;
-            uns |= (unsigned)(d == 2) << jj;
+          for (int jj = 0; jj < jend; jj += 4) {                            // the tail repeats the block's last box
+            unsigned s4 = 0, u4 = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = min(32 * p + jj + u, P - 1);
+              const int d = suppresses_fast<MODE>(stage[j], sarea[j], bi, thr);
+              if (d == 1) s4 |= 1u << u;
+              if (d == 2) u4 |= 1u << u;
+            }
+            sup |= s4 << jj;
+            uns |= u4 << jj;
           }
-          const unsigned ahead = p < g ? 0xffffffffu : ((1u << lane) - 1u);
+          const unsigned ahead = (p < g ? 0xffffffffu : ((1u << lane) - 1u)) & (jend < 32 ? (1u << jend) - 1u : 0xffffffffu);
           sup &= ahead;
           for (uns &= ahead; uns; uns &= uns - 1) {                         // rare: settle near-threshold pairs exactly
             const int jj = __ffs(uns) - 1;
-            const float4 kb = stage[32 * p + jj];
-            if (suppresses<MODE>(kb, area_rn(kb), bi, thr)) sup |= 1u << jj;
+            if (suppresses<MODE>(stage[32 * p + jj], sarea[32 * p + jj], bi, thr)) sup |= 1u << jj;
           }
-          if (i < P) supby[i * 4 + p] = sup;
+          if (i < P) supby[wid * 32 + lane] = sup;                           // tile (g, p) = g (g + 1) / 2 + p = wid
         }
       }
       __syncthreads();
@@ -431,8 +439,8 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
             bool alive = i < P;
 #pragma unroll
             for (int p = 0; p < g; ++p)
-              if (alive && (supby[i * 4 + p] & km[p])) alive = false;
-            const unsigned diag = alive ? supby[i * 4 + g] : 0u;
+              if (alive && (supby[((g * (g + 1)) / 2 + p) * 32 + lane] & km[p])) alive = false;
+            const unsigned diag = alive ? supby[((g * (g + 1)) / 2 + g) * 32 + lane] : 0u;
             // kept = alive and not covered by a kept lane ahead: iterate the ballot to its fixed point (lane l
             // is final after l + 1 rounds at the latest; chains are short, so it takes two or three)
             unsigned kmg = __ballot_sync(0xffffffffu, alive);
