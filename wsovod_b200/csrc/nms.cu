@@ -155,50 +155,58 @@ __device__ int select_greedy(unsigned long long* keys, const float4* boxes, int 
 // ------------------------------------------------------------------------------------------------
 // fused inference tail (fast_rcnn_inference_single_image, fast_rcnn_open_vocabulary.py:149-217)
 // ------------------------------------------------------------------------------------------------
-// rows: finite filter (:178-182) + Boxes.clip (:187-188)
-__global__ void det_rows_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
-                                const int64_t* __restrict__ offsets, const float* __restrict__ image_sizes,
-                                int64_t M, int N, int K1, uint8_t* __restrict__ valid,
-                                float4* __restrict__ cboxes) {
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per row
-  const int lane = threadIdx.x & 31;
-  if (r >= M) return;
-  const float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + r);
-  bool ok = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w);
-  for (int k = lane; k < K1; k += 32) ok &= isfinite(__ldg(probs + r * K1 + k));
-  ok = __all_sync(0xffffffffu, ok);
-  if (lane == 0) {
-    int lo = 0, hi = N - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= r) lo = mid; else hi = mid - 1; }
-    const float ih = image_sizes[2 * lo], iw = image_sizes[2 * lo + 1];
-    valid[r] = ok ? 1 : 0;
-    cboxes[r] = make_float4(fminf(fmaxf(b.x, 0.f), iw), fminf(fmaxf(b.y, 0.f), ih),
-                            fminf(fmaxf(b.z, 0.f), iw), fminf(fmaxf(b.w, 0.f), ih));
-  }
-}
-
-// scoresT[k][r] = probs[r][k] for finite rows, -inf otherwise: det_class then reads its column as one
+// rows: finite filter (:178-182) + Boxes.clip (:187-188), and the class-major copy of the scores:
+// scoresT[k][r] = probs[r][k] for finite rows, -inf otherwise.  det_class then reads its column as one
 // contiguous run instead of one 4-byte word out of every 32-byte sector of a row-major matrix that all K
-// class CTAs of the image walk at the same time (c2: 82 MB of sector traffic for 10 MB of scores)
-__global__ void __launch_bounds__(256) det_transpose_kernel(const float* __restrict__ probs, const uint8_t* __restrict__ valid,
-                                                            int64_t M, int K, float* __restrict__ scoresT) {
-  __shared__ float tile[32][33];
-  const int64_t rb = (int64_t)blockIdx.x * 32;
-  const int kb = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  const int K1 = K + 1;
+// class CTAs of the image walk at the same time (c2: 82 MB of sector traffic for 10 MB of scores).
+// One CTA owns 32 rows: a pass over the full rows settles which are finite, then the rows (L1-resident
+// by now) go through a 32 x 128 shared-memory tile per block of classes.
+constexpr int kRtRows = 32, kRtCols = 128;
+__global__ void __launch_bounds__(256) det_rows_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                       const int64_t* __restrict__ offsets, const float* __restrict__ image_sizes,
+                                                       int64_t M, int N, int K1, float4* __restrict__ cboxes,
+                                                       float* __restrict__ scoresT) {
+  __shared__ float tile[kRtRows][kRtCols + 1];
+  __shared__ uint8_t s_ok[kRtRows];
+  const int64_t rb = (int64_t)blockIdx.x * kRtRows;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;      // 8 warps, 4 rows each
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t r = rb + ty + i * 8;
-    const int k = kb + tx;
-    tile[ty + i * 8][tx] = (r < M && k < K && valid[r]) ? __ldg(probs + r * K1 + k) : -INFINITY;
+  for (int q = 0; q < 4; ++q) {
+    const int rl = wid * 4 + q;
+    const int64_t r = rb + rl;
+    bool ok = false;
+    if (r < M) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(boxes) + r);
+      ok = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w);
+      for (int k = lane; k < K1; k += 32) ok &= isfinite(__ldg(probs + r * K1 + k));
+      ok = __all_sync(0xffffffffu, ok);
+      if (lane == 0) {
+        int lo = 0, hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= r) lo = mid; else hi = mid - 1; }
+        const float ih = image_sizes[2 * lo], iw = image_sizes[2 * lo + 1];
+        cboxes[r] = make_float4(fminf(fmaxf(b.x, 0.f), iw), fminf(fmaxf(b.y, 0.f), ih),
+                                fminf(fmaxf(b.z, 0.f), iw), fminf(fmaxf(b.w, 0.f), ih));
+      }
+    }
+    if (lane == 0) s_ok[rl] = ok ? 1 : 0;
   }
   __syncthreads();
+  const int K = K1 - 1;
+  for (int kb = 0; kb < K; kb += kRtCols) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = kb + ty + i * 8;
-    const int64_t r = rb + tx;
-    if (k < K && r < M) scoresT[(int64_t)k * M + r] = tile[tx][ty + i * 8];
+    for (int q = 0; q < 4; ++q) {
+      const int rl = wid * 4 + q;
+      const int64_t r = rb + rl;
+      const bool row_ok = r < M && s_ok[rl];
+#pragma unroll
+      for (int c = lane; c < kRtCols; c += 32)
+        tile[rl][c] = (row_ok && kb + c < K) ? __ldg(probs + r * K1 + kb + c) : -INFINITY;
+    }
+    __syncthreads();
+    const int64_t r = rb + lane;
+    if (r < M)
+      for (int c = wid; c < kRtCols && kb + c < K; c += 8) scoresT[(int64_t)(kb + c) * M + r] = tile[lane][c];
+    __syncthreads();
   }
 }
 
@@ -867,13 +875,12 @@ static NmsWs nms_plan(int64_t M, int64_t G) {
   return w;
 }
 
-struct DetWs { size_t valid, cboxes, img_cnt, img_kept, runs, scoresT, bytes; int64_t kept_stride; };
+struct DetWs { size_t cboxes, img_cnt, img_kept, runs, scoresT, bytes; int64_t kept_stride; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
   size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
   w.kept_stride = K * std::max<int64_t>(topk, 0);
-  w.valid = take((size_t)M);
   w.cboxes = take(sizeof(float4) * (size_t)M);
   w.img_cnt = take(sizeof(int32_t) * (size_t)(N + 1));
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
@@ -991,7 +998,6 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   if (smem > (size_t)kMaxSmemOptin - 2048) return WSOVOD_B200_EUNSUPPORTED;   // > 16384 proposals per image
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  uint8_t* valid = (uint8_t*)(ws + w.valid);
   float4* cboxes = (float4*)(ws + w.cboxes);
   int32_t* img_cnt = (int32_t*)(ws + w.img_cnt);
   unsigned long long* img_kept = (unsigned long long*)(ws + w.img_kept);
@@ -1001,16 +1007,14 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   int rc;
   const bool use_runs = M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads;
   if (M > 0 && K > 0) {
-    det_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, valid, cboxes);
+    float* scoresT = (float*)(ws + w.scoresT);
+    det_rows_kernel<<<(unsigned)ceil_div(M, kRtRows), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes, scoresT);
     if ((rc = after_launch())) return rc;
     auto kern = iou_mode == 0 ? det_class_kernel<0> : det_class_kernel<1>;
     if (smem > 32 * 1024) {   // static slots + dynamic may cross the 48 KB default limit
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    float* scoresT = (float*)(ws + w.scoresT);
-    det_transpose_kernel<<<dim3((unsigned)ceil_div(M, 32), (unsigned)ceil_div(K, 32)), 256, 0, st>>>(probs, valid, M, (int)K, scoresT);
-    if ((rc = after_launch())) return rc;
     dim3 grid((unsigned)K, (unsigned)N);
     kern<<<grid, kDcThreads, smem, st>>>(scoresT, M, offsets, cboxes, (int)K, score_thresh,
                                          cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, use_runs, img_cnt, img_kept, w.kept_stride, runs);
