@@ -578,117 +578,105 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   }
 }
 
-// single-warp K-way merge of score-descending runs (keys ascending): lane l owns runs l, l + 32, ... (RW of
-// them); writes the first `topk` keys of the merged order to sel[], returns how many there were
-template <int RW>
-__device__ __forceinline__ int warp_merge_runs(const int2* __restrict__ rn, const unsigned long long* __restrict__ keys,
-                                               int K, int topk, unsigned long long* sel) {
-  const int lane = threadIdx.x & 31;
-  int pos[RW], len[RW], off[RW];
-  unsigned long long head[RW], next[RW];
-#pragma unroll
-  for (int j = 0; j < RW; ++j) {
-    const int c = lane + j * 32;
-    const int2 v = c < K ? rn[c] : make_int2(0, 0);
-    off[j] = v.x; len[j] = v.y; pos[j] = 0;
-    head[j] = len[j] > 0 ? keys[off[j]] : kDead;
-    next[j] = len[j] > 1 ? keys[off[j] + 1] : kDead;
-  }
-  int g = 0;
-  for (int i = 0; i < topk; ++i) {
-    unsigned long long best = head[0];
-    int bj = 0;
-#pragma unroll
-    for (int j = 1; j < RW; ++j)
-      if (head[j] < best) { best = head[j]; bj = j; }
-    const uint32_t hi = (uint32_t)(best >> 32), lo = (uint32_t)best;
-    const uint32_t hmin = __reduce_min_sync(0xffffffffu, hi);
-    const uint32_t lmin = __reduce_min_sync(0xffffffffu, hi == hmin ? lo : 0xffffffffu);
-    if (hmin == 0xffffffffu && lmin == 0xffffffffu) break;          // every run is exhausted (kDead)
-    // keys are unique (row * K + class in the low word): exactly one lane holds (hmin, lmin)
-    if (hi == hmin && lo == lmin) {
-#pragma unroll
-      for (int j = 0; j < RW; ++j)
-        if (j == bj) {
-          ++pos[j];
-          head[j] = next[j];
-          next[j] = pos[j] + 1 < len[j] ? keys[off[j] + pos[j] + 1] : kDead;
+// Pairwise merge of nl score-descending lists of <= L unique keys each (list t at src[t * L], length ls[t]) down
+// to one list of the L best, all pairs of a round at once: an element's place in the merged list is its
+// own index plus its lower bound in the partner list, found by a binary search in shared memory.
+// ceil(log2 nl) rounds of independent work.  On return the result is src[0 .. ls[0]).
+__device__ __forceinline__ void merge_lists(unsigned long long*& src, unsigned long long*& dst, int*& ls, int*& ld,
+                                            int nl, int L) {
+  while (nl > 1) {
+    const int pairs = nl >> 1;
+    for (int e = threadIdx.x; e < pairs * 2 * L; e += blockDim.x) {
+      const int p = e / (2 * L), rem = e - p * 2 * L;
+      const int side = rem >= L ? 1 : 0, i = rem - side * L;
+      const int a = 2 * p + side, b = 2 * p + 1 - side;
+      if (i < ls[a]) {
+        const unsigned long long x = src[(size_t)a * L + i];
+        const unsigned long long* B = src + (size_t)b * L;
+        int lo = 0, hi = min(ls[b], L - i);                       // places >= L are dropped anyway
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (B[mid] < x) lo = mid + 1; else hi = mid;
         }
-      sel[i] = best;
+        if (i + lo < L) dst[(size_t)p * L + i + lo] = x;
+      }
     }
-    ++g;
+    for (int p = threadIdx.x; p < pairs; p += blockDim.x) ld[p] = min(L, ls[2 * p] + ls[2 * p + 1]);
+    if (nl & 1) {                                                 // the odd list moves on unchanged
+      for (int i = threadIdx.x; i < ls[nl - 1]; i += blockDim.x) dst[(size_t)pairs * L + i] = src[(size_t)(nl - 1) * L + i];
+      if (threadIdx.x == 0) ld[pairs] = ls[nl - 1];
+    }
+    __syncthreads();
+    unsigned long long* t = src; src = dst; dst = t;
+    int* tl = ls; ls = ld; ld = tl;
+    nl = pairs + (nl & 1);
   }
-  return g;
 }
 
-// one CTA per image: the topk best kept candidates, in order (:207-208), and the output gather
+// The topk best kept candidates of an image, in order (:207-208), and the output gather.
+//   G > 0: every class left a score-descending run (det_class).  CTA (n, g) merges the runs of its share of
+//          the classes to one list of the topk best; the last of an image's G CTAs to finish (ticket counter)
+//          merges the G lists and writes the detections.
+//   G = 0 (more classes than the run table holds): one CTA per image sorts / selects from the packed list.
 __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
     const int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
-    const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk, int sort_cap,
-    const int2* __restrict__ runs, float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
+    const int64_t* __restrict__ offsets, const float4* __restrict__ cboxes, int K, int topk, int sort_cap, int G,
+    const int2* __restrict__ runs, unsigned long long* __restrict__ part, int* __restrict__ part_len, int* __restrict__ done,
+    float* __restrict__ det_boxes, float* __restrict__ det_scores, int64_t* __restrict__ det_classes,
     int64_t* __restrict__ det_rows, int64_t* __restrict__ det_count) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ ArgMinSlots slots;
+  __shared__ int s_ticket;
   unsigned long long* sel = reinterpret_cast<unsigned long long*>(sm);   // [topk]
   const int n = blockIdx.x;
-  const int cnt = img_cnt[n];
   unsigned long long* keys = img_kept + (int64_t)n * kept_stride;
   int got;
-  __shared__ int s_got;
-  if (runs != nullptr && K <= 32 * 8) {
-    // K-way merge by ONE warp (no barrier per pick): lane l owns runs l, l+32, ...; heads and their
-    // successors live in registers; a pick is two warp REDUX (minimum of the score words, then of the
-    // id words among the lanes that tie) and a ballot
-    if (threadIdx.x < 32) {
-      const int2* rn = runs + (int64_t)n * K;
-      const int g = K <= 96 ? warp_merge_runs<3>(rn, keys, K, topk, sel) : warp_merge_runs<8>(rn, keys, K, topk, sel);
-      if (threadIdx.x == 0) s_got = g;
+  if (G > 0) {
+    const int L = topk, g = blockIdx.y;
+    const int rpc = (K + G - 1) / G, cap = max(rpc, G);
+    unsigned long long* src = sel + topk;                         // [cap][L]
+    unsigned long long* dst = src + (size_t)cap * L;              // [ceil(cap / 2)][L]
+    int* ls = reinterpret_cast<int*>(dst + (size_t)((cap + 1) / 2) * L);   // [cap] list lengths
+    int* ld = ls + cap;                                           // [cap]
+    const int c0 = min(g * rpc, K), nl = min(K, c0 + rpc) - c0;
+    const int2* rn = runs + (int64_t)n * K + c0;
+    for (int e = threadIdx.x; e < nl * L; e += kNmsThreads) {
+      const int c = e / L, q = e - c * L;
+      const int2 r = rn[c];
+      if (q < r.y) src[e] = keys[r.x + q];
     }
+    for (int c = threadIdx.x; c < nl; c += kNmsThreads) ls[c] = min(rn[c].y, L);
+    if (nl == 0 && threadIdx.x == 0) ls[0] = 0;
     __syncthreads();
-    got = s_got;
-  } else if (runs != nullptr) {
-    // K-way merge: every class left a score-descending run; thread t owns runs t, t+T, ... and offers
-    // the best head among them, a block arg-min picks the winner, its owner advances that run.
-    const int2* rn = runs + (int64_t)n * K;
-    // the head of each owned run and its successor live in registers: only the winner touches memory,
-    // and it reloads two elements ahead, so no round waits on L2
-    int pos[kRunsPerThread], len[kRunsPerThread], off[kRunsPerThread];
-    unsigned long long head[kRunsPerThread], next[kRunsPerThread];
-#pragma unroll
-    for (int j = 0; j < kRunsPerThread; ++j) {
-      const int c = threadIdx.x + j * kNmsThreads;
-      const int2 v = c < K ? rn[c] : make_int2(0, 0);
-      off[j] = v.x; len[j] = v.y; pos[j] = 0;
-      head[j] = len[j] > 0 ? keys[off[j]] : kDead;
-      next[j] = len[j] > 1 ? keys[off[j] + 1] : kDead;
-    }
-    got = 0;
-    int buf = 0;
-    for (int i = 0; i < topk; ++i) {
-      unsigned long long best = kDead;
-      int bj = -1;
-#pragma unroll
-      for (int j = 0; j < kRunsPerThread; ++j)
-        if (head[j] < best) { best = head[j]; bj = j; }
-      unsigned long long wkey = best;
-      int wtid = bj >= 0 ? (int)threadIdx.x : -1;
-      block_argmin(wkey, wtid, slots, buf);
-      buf ^= 1;
-      if (wtid < 0) break;
-      if (wtid == (int)threadIdx.x) {
-#pragma unroll
-        for (int j = 0; j < kRunsPerThread; ++j)
-          if (j == bj) {
-            ++pos[j];
-            head[j] = next[j];
-            next[j] = pos[j] + 1 < len[j] ? keys[off[j] + pos[j] + 1] : kDead;
-          }
-        sel[i] = wkey;
+    merge_lists(src, dst, ls, ld, nl, L);
+    if (G > 1) {
+      unsigned long long* mine = part + ((int64_t)n * G + g) * L;
+      const int len = ls[0];
+      for (int i = threadIdx.x; i < len; i += kNmsThreads) mine[i] = src[i];
+      if (threadIdx.x == 0) part_len[n * G + g] = len;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_ticket = atomicAdd(&done[n], 1);
+      __syncthreads();
+      if (s_ticket != G - 1) return;                              // someone else finishes the image
+      __threadfence();
+      src = sel + topk; dst = src + (size_t)cap * L;
+      ls = reinterpret_cast<int*>(dst + (size_t)((cap + 1) / 2) * L); ld = ls + cap;
+      __syncthreads();
+      for (int t = threadIdx.x; t < G; t += kNmsThreads) ls[t] = __ldcg(part_len + n * G + t);
+      __syncthreads();
+      for (int e = threadIdx.x; e < G * L; e += kNmsThreads) {
+        const int t = e / L, q = e - t * L;
+        if (q < ls[t]) src[e] = __ldcg(part + ((int64_t)n * G + t) * L + q);
       }
-      ++got;
+      __syncthreads();
+      merge_lists(src, dst, ls, ld, G, L);
     }
+    got = ls[0];
+    for (int i = threadIdx.x; i < got; i += kNmsThreads) sel[i] = src[i];
   } else if (sort_cap > 0) {
     // the image's kept list fits shared memory: one bitonic sort, the first topk keys are the answer
+    const int cnt = img_cnt[n];
     unsigned long long* sk = sel + topk;
     int npad = 2;
     while (npad < cnt) npad <<= 1;
@@ -698,7 +686,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_topk_kernel(
     got = min(cnt, topk);
     for (int i = threadIdx.x; i < got; i += kNmsThreads) sel[i] = sk[i];
   } else {
-    got = select_greedy<0, false>(keys, nullptr, cnt, 0.f, topk, sel, slots);
+    got = select_greedy<0, false>(keys, nullptr, img_cnt[n], 0.f, topk, sel, slots);
   }
   __syncthreads();
   const int64_t r0 = offsets[n];
@@ -875,17 +863,21 @@ static NmsWs nms_plan(int64_t M, int64_t G) {
   return w;
 }
 
-struct DetWs { size_t cboxes, img_cnt, img_kept, runs, scoresT, bytes; int64_t kept_stride; };
+struct DetWs { size_t cboxes, img_cnt, img_kept, runs, scoresT, part, part_len, bytes; int64_t kept_stride; int G; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
   size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
   w.kept_stride = K * std::max<int64_t>(topk, 0);
+  // top-k stage: G CTAs per image, about eight class runs each (0: no run table, K too large)
+  w.G = (M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads) ? (int)std::min<int64_t>(32, ceil_div(K, 8)) : 0;
   w.cboxes = take(sizeof(float4) * (size_t)M);
-  w.img_cnt = take(sizeof(int32_t) * (size_t)(N + 1));
+  w.img_cnt = take(sizeof(int32_t) * (size_t)(2 * N + 1));      // per-image kept counters, then the top-k tickets
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
   w.runs = take(sizeof(int2) * (size_t)(N * std::max<int64_t>(K, 1)));
   w.scoresT = take(sizeof(float) * (size_t)(M * K));
+  w.part = take(sizeof(unsigned long long) * (size_t)(N * std::max(w.G, 1) * std::max<int64_t>(topk, 0)));
+  w.part_len = take(sizeof(int) * (size_t)(N * std::max(w.G, 1)));
   w.bytes = o;
   return w;
 }
@@ -1002,7 +994,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   int32_t* img_cnt = (int32_t*)(ws + w.img_cnt);
   unsigned long long* img_kept = (unsigned long long*)(ws + w.img_kept);
   int2* runs = (int2*)(ws + w.runs);
-  cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(N + 1), st);
+  cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(2 * N + 1), st);
   if (e != cudaSuccess) return (int)e;
   int rc;
   const bool use_runs = M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads;
@@ -1024,14 +1016,18 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   int sort_cap = 2;
   while (sort_cap < w.kept_stride) sort_cap <<= 1;
   if (w.kept_stride > 16384) sort_cap = 0;
-  const size_t tsmem = sizeof(unsigned long long) * ((size_t)topk + (size_t)sort_cap);
+  // run merge: sel[topk] + cap lists + ceil(cap / 2) merged lists + two length arrays, cap = max(runs per CTA, G)
+  const int G = w.G;
+  const int64_t cap = G > 0 ? std::max<int64_t>(ceil_div(K, G), G) : 0;
+  const size_t tsmem = G > 0 ? sizeof(unsigned long long) * ((size_t)topk + (size_t)(cap + (cap + 1) / 2) * (size_t)topk + (size_t)cap)
+                             : sizeof(unsigned long long) * ((size_t)topk + (size_t)sort_cap);
   if (tsmem > 32 * 1024) {
     e = cudaFuncSetAttribute(det_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
     if (e != cudaSuccess) return (int)e;
   }
-  det_topk_kernel<<<(unsigned)N, kNmsThreads, tsmem, st>>>(
-      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap,
-      use_runs ? runs : nullptr, det_boxes, det_scores, det_classes,
+  det_topk_kernel<<<dim3((unsigned)N, (unsigned)std::max(G, 1)), kNmsThreads, tsmem, st>>>(
+      img_cnt, img_kept, w.kept_stride, offsets, cboxes, (int)std::max<int64_t>(K, 1), (int)topk, sort_cap, G,
+      runs, (unsigned long long*)(ws + w.part), (int*)(ws + w.part_len), img_cnt + N + 1, det_boxes, det_scores, det_classes,
       det_rows, det_count);
   return after_launch();
 }
