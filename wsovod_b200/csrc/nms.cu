@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
     int2* __restrict__ runs) {
   extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ int s_n, s_base, s_sel, s_bstar, s_m;
+  __shared__ int s_n, s_base, s_sel, s_bstar, s_m, s_fitsel, s_fitb;
   __shared__ int s_new[2];
   __shared__ int s_head;
   __shared__ int s_wsum[kNmsWarps];
@@ -329,11 +329,13 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   bool complete = true;
   // CTA-uniform: selects the smallest histogram prefix holding >= target keys into ssel; false if it does
   // not fit (or is the whole column anyway)
-  auto select_prefix = [&](int target) -> bool {
+  // `fit` > 0: a prefix of at most `fit` keys (one key per thread of the register sort) is preferred to the
+  // smallest one reaching `target` as long as it still holds 3/4 of the target
+  auto select_prefix = [&](int target, int fit) -> bool {
     int* hist = reinterpret_cast<int*>(ssel);
     __syncthreads();                                     // ssel / s_* free to be rewritten
     for (int i = threadIdx.x; i < kSelectBins; i += kDcThreads) hist[i] = 0;
-    if (threadIdx.x == 0) { s_sel = 0; s_m = 0; }
+    if (threadIdx.x == 0) { s_sel = 0; s_m = 0; s_fitsel = 0; }
     __syncthreads();
     for (int i = threadIdx.x; i < nc; i += kDcThreads) atomicAdd(&hist[(int)(skey[i] >> kSelectShift)], 1);
     __syncthreads();
@@ -359,8 +361,18 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
         if (cum >= target) { s_sel = cum; s_bstar = threadIdx.x * PER + j; break; }
       }
     }
+    if (fit > 0 && before <= fit && before + mine > fit) {   // exactly one thread: the last bin with cum <= fit
+      int cum = before, b = threadIdx.x * PER - 1;
+      for (int j = 0; j < PER && threadIdx.x * PER + j < kSelectBins; ++j) {
+        if (cum + hist[threadIdx.x * PER + j] > fit) break;
+        cum += hist[threadIdx.x * PER + j];
+        b = threadIdx.x * PER + j;
+      }
+      s_fitsel = cum; s_fitb = b;
+    }
     __syncthreads();
-    const int selcount = s_sel, bstar = s_bstar;
+    const bool use_fit = fit > 0 && s_fitsel * 4 >= target * 3;
+    const int selcount = use_fit ? s_fitsel : s_sel, bstar = use_fit ? s_fitb : s_bstar;
     if (!(selcount > 0 && selcount <= kSelectCap && selcount < nc)) return false;
     __syncthreads();                                     // everyone is done reading the histogram
     for (int i = threadIdx.x; i < nc; i += kDcThreads) {
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     list = skey; ln = nc; complete = true;
     if (attempt < 2 && nc > kSelectMin) {
       const int target = attempt == 0 ? max(2 * limit, 128) : kSelectTarget;
-      if ((attempt == 1 && target <= max(2 * limit, 128)) || !select_prefix(target)) continue;   // next level
+      if ((attempt == 1 && target <= max(2 * limit, 128)) || !select_prefix(target, attempt == 0 ? 256 : 0)) continue;   // next level
     }
     int npad = 2;
     while (npad < ln) npad <<= 1;
