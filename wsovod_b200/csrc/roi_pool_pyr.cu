@@ -158,24 +158,34 @@ __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restric
 // whole c2 kernel 1.41 ms in stores alone, proposal-aligned passes 0.88 ms
 // (tools/ubench/store_pattern.cu, "pattern" vs "V6").  The two-channel flavour (larger maps, fewer
 // bytes per pass) is not store-bound and keeps the dense 49-slot stream.
+template <int SLOTS>
 __global__ void pyr_bins_kernel(int64_t R, int H, int W, const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
                                 const uint32_t* __restrict__ axtab, const float* __restrict__ row_scale,
-                                float row_scale_bias, int slots, uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
+                                float row_scale_bias, uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
+  // eight threads per proposal: thread t < 7 writes lane slots 7t .. 7t+6, thread 7 the idle tail and the
+  // proposal record (one wave of threads and one chain of dependent loads instead of a thread per slot)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * slots) return;
-  const int64_t gpos = i / slots;
-  const int q = (int)(i - gpos * slots);
-  if (q >= 49) { desc[i] = kDescIdle; return; }
+  const int64_t gpos = i >> 3;
+  const int t = (int)(i & 7);
+  if (gpos >= R) return;
   const int r = order[gpos];
   const uint32_t key = pkey[r];
-  const int bin = slot_bin(key, q);
-  const int ph = bin / 7, pw = bin - ph * 7;
-  desc[i] = key_phase(key) == PH_FALLBACK
-                ? 0u
-                : combine_desc(__ldg(axtab + (int64_t)r * 14 + ph), __ldg(axtab + (int64_t)r * 14 + 7 + pw), bin, H, W);
-  if (q == 0) {
+  uint32_t* d = desc + gpos * SLOTS;
+  if (t == 7) {
+#pragma unroll
+    for (int q = 49; q < SLOTS; ++q) d[q] = kDescIdle;
     const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
     pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
+    return;
+  }
+  const bool fallback = key_phase(key) == PH_FALLBACK;
+  const uint32_t* ax = axtab + (int64_t)r * 14;
+#pragma unroll
+  for (int u = 0; u < 7; ++u) {
+    const int q = t * 7 + u;
+    const int bin = slot_bin(key, q);
+    const int ph = bin / 7, pw = bin - ph * 7;
+    d[q] = fallback ? 0u : combine_desc(__ldg(ax + ph), __ldg(ax + 7 + pw), bin, H, W);
   }
 }
 
@@ -536,8 +546,12 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   pyr_order_kernel<<<dim3((unsigned)N, parts), 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.cursor, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
   const int slots = cb == 4 ? kSlots : 49;
-  pyr_bins_kernel<<<(unsigned)ceil_div(R * slots, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
-                                                                     row_scale_bias, slots, w.pinfo, w.desc);
+  if (cb == 4)
+    pyr_bins_kernel<kSlots><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
+                                                                               row_scale_bias, w.pinfo, w.desc);
+  else
+    pyr_bins_kernel<49><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
+                                                                           row_scale_bias, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
   p.input = input; p.rois = rois; p.scale = scale;
