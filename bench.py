@@ -147,6 +147,9 @@ def run_reference(args, w, rank):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
