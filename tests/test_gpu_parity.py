@@ -387,6 +387,24 @@ def test_detections_threshold_ties(mode, thr):
         assert torch.equal(r[k].cpu(), o[k]), k
 
 
+@pytest.mark.parametrize("K,topk,sizes", [(300, 7, [500, 0, 40]), (9, 100, [700, 300]), (1, 5, [64]), (33, 250, [900]),
+                                          (257, 100, [300, 10])])
+def test_detections_topk_merge_shapes(K, topk, sizes):
+    """The top-k stage splits an image's class runs over G = ceil(K / 8) <= 32 CTAs and the last one merges
+    their lists: class counts that leave the last CTAs without runs (K = 257, 300), one class, fewer
+    candidates than topk, an image without proposals, topk above the per-class run length."""
+    g = synth.gen(100 + K)
+    shapes = [(480, 640)] * len(sizes)
+    boxes = [synth.proposals(s, 480, 640, g) if s else torch.zeros(0, 4) for s in sizes]
+    probs = [torch.softmax(torch.randn(s, K + 1, generator=g) * 3.0, -1) for s in sizes]
+    off = _offs(sizes)
+    r = ops.detections(torch.cat(probs).to(DEV), torch.cat(boxes).to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(shapes, dtype=torch.float32, device=DEV), max(sizes), 1e-4, 0.4, topk, ops.IOU_TV_CUDA)
+    o = oracle.detections(torch.cat(probs), torch.cat(boxes), off, shapes, 1e-4, 0.4, topk, ops.IOU_TV_CUDA)
+    for k in o:
+        assert torch.equal(r[k].cpu(), o[k]), k
+
+
 @pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
 def test_detections_prefix_fallback_and_long_columns(mode):
     """Columns longer than 2048 candidates take the histogram pre-selection; when the selected prefix

@@ -33,6 +33,12 @@ offd = torch.tensor(off, device=DEV)
 sizes = torch.tensor([[H * 8.0, W * 8.0]] * N, device=DEV)
 bx = rois[:, 1:].contiguous()
 det = ops.detections(probs, bx, offd, sizes, R, 1e-5, 0.3, 20, ops.IOU_TV_CUDA)
+# a long column (histogram pre-selection, register sort, head stage + chunked continuation, two-level top-k merge)
+R2, K2 = 900, 19
+bx2 = synth.proposals(R2, 480, 640, g).to(DEV)
+pr2 = torch.softmax(torch.randn(R2, K2 + 1, generator=g) * 2.0, -1).to(DEV)
+det2 = ops.detections(pr2, bx2, torch.tensor([0, R2], device=DEV), torch.tensor([[480.0, 640.0]], device=DEV), R2, 1e-5,
+                      0.3, 100, ops.IOU_TV_CPU)
 Cl, Dl = synth.mil_logits(N * R, K, g)
 s, img = ops.mil(Cl.to(DEV), Dl.to(DEV), offd)
 gts = synth.image_labels(N, K, g)
@@ -43,4 +49,4 @@ sd = ops.pgt_top1(s, bx, offd, torch.cat(gts).to(DEV), torch.tensor(goff, device
 ops.refine_assign(bx, offd, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"], sd["seed_weights"],
                   torch.tensor(goff, device=DEV), sd["seed_count"], K, 0.5)
 torch.cuda.synchronize()
-print("sanitize case ok", int(det["det_count"].sum()))
+print("sanitize case ok", int(det["det_count"].sum()), int(det2["det_count"].sum()))
