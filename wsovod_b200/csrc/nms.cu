@@ -231,20 +231,23 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
 // shuffles, only the larger ones go through shared memory (npad = 256: 12 barriers instead of 36)
 __device__ __forceinline__ void bitonic_sort_regs(unsigned long long* keys, int npad) {
   const int t = threadIdx.x;
+  const bool busy = (t & ~31) < npad;            // warps past the keys only keep the barriers company
   unsigned long long v = t < npad ? keys[t] : kDead;
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      unsigned long long o;
+      unsigned long long o = kDead;
       if (j >= 32) {
         __syncthreads();                         // the previous exchange has been read
         if (t < npad) keys[t] = v;
         __syncthreads();
-        o = t < npad ? keys[t ^ j] : kDead;
-      } else {
+        if (t < npad) o = keys[t ^ j];
+      } else if (busy) {
         o = __shfl_xor_sync(0xffffffffu, v, j);
       }
-      const bool take_min = ((t & j) == 0) == ((t & k) == 0);
-      v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+      if (busy) {
+        const bool take_min = ((t & j) == 0) == ((t & k) == 0);
+        v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+      }
     }
   }
   __syncthreads();
