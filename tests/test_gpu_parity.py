@@ -388,11 +388,12 @@ def test_detections_threshold_ties(mode, thr):
 
 
 @pytest.mark.parametrize("K,topk,sizes", [(300, 7, [500, 0, 40]), (9, 100, [700, 300]), (1, 5, [64]), (33, 250, [900]),
-                                          (257, 100, [300, 10])])
+                                          (257, 100, [300, 10]), (20, 1000, [1500]), (6, 3000, [3500]), (5, 3000, [3500, 200])])
 def test_detections_topk_merge_shapes(K, topk, sizes):
     """The top-k stage splits an image's class runs over G = ceil(K / 8) <= 32 CTAs and the last one merges
     their lists: class counts that leave the last CTAs without runs (K = 257, 300), one class, fewer
-    candidates than topk, an image without proposals, topk above the per-class run length."""
+    candidates than topk, an image without proposals, topk above the per-class run length, and topk so large
+    that the run merge does not fit shared memory (packed list + selection / one sort instead)."""
     g = synth.gen(100 + K)
     shapes = [(480, 640)] * len(sizes)
     boxes = [synth.proposals(s, 480, 640, g) if s else torch.zeros(0, 4) for s in sizes]

@@ -878,6 +878,13 @@ static NmsWs nms_plan(int64_t M, int64_t G) {
   return w;
 }
 
+// shared memory of the run-merge flavour of det_topk: sel[topk] + cap lists + ceil(cap / 2) merged lists + two
+// length arrays, cap = max(runs per CTA, G)
+static size_t det_topk_smem(int64_t K, int G, int64_t topk) {
+  const int64_t cap = std::max<int64_t>(ceil_div(K, G), G);
+  return sizeof(unsigned long long) * ((size_t)topk + (size_t)(cap + (cap + 1) / 2) * (size_t)topk + (size_t)cap);
+}
+
 struct DetWs { size_t cboxes, img_cnt, img_kept, runs, scoresT, part, part_len, bytes; int64_t kept_stride; int G; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
@@ -886,6 +893,7 @@ static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   w.kept_stride = K * std::max<int64_t>(topk, 0);
   // top-k stage: G CTAs per image, about eight class runs each (0: no run table, K too large)
   w.G = (M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads) ? (int)std::min<int64_t>(32, ceil_div(K, 8)) : 0;
+  if (w.G > 0 && det_topk_smem(K, w.G, topk) > 200 * 1024) w.G = 0;     // very large topk: packed list + sort / selection
   w.cboxes = take(sizeof(float4) * (size_t)M);
   w.img_cnt = take(sizeof(int32_t) * (size_t)(2 * N + 1));      // per-image kept counters, then the top-k tickets
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
@@ -1012,7 +1020,7 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   cudaError_t e = cudaMemsetAsync(img_cnt, 0, sizeof(int32_t) * (size_t)(2 * N + 1), st);
   if (e != cudaSuccess) return (int)e;
   int rc;
-  const bool use_runs = M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads;
+  const bool use_runs = w.G > 0;
   if (M > 0 && K > 0) {
     float* scoresT = (float*)(ws + w.scoresT);
     det_rows_kernel<<<(unsigned)ceil_div(M, kRtRows), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes, scoresT);
@@ -1031,11 +1039,8 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
   int sort_cap = 2;
   while (sort_cap < w.kept_stride) sort_cap <<= 1;
   if (w.kept_stride > 16384) sort_cap = 0;
-  // run merge: sel[topk] + cap lists + ceil(cap / 2) merged lists + two length arrays, cap = max(runs per CTA, G)
   const int G = w.G;
-  const int64_t cap = G > 0 ? std::max<int64_t>(ceil_div(K, G), G) : 0;
-  const size_t tsmem = G > 0 ? sizeof(unsigned long long) * ((size_t)topk + (size_t)(cap + (cap + 1) / 2) * (size_t)topk + (size_t)cap)
-                             : sizeof(unsigned long long) * ((size_t)topk + (size_t)sort_cap);
+  const size_t tsmem = G > 0 ? det_topk_smem(K, G, topk) : sizeof(unsigned long long) * ((size_t)topk + (size_t)sort_cap);
   if (tsmem > 32 * 1024) {
     e = cudaFuncSetAttribute(det_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
     if (e != cudaSuccess) return (int)e;
