@@ -2,16 +2,21 @@
 //
 // Greedy NMS keeps a box iff no higher-scoring KEPT box of its class overlaps it by more than thr, so
 // only (candidates x kept) IoUs matter, not the (candidates^2)/2 bitmask torchvision's kernel fills.
-// One CTA owns one (image, class) segment, holds its candidates (key, box) in shared memory and
-// iterates:  [suppress everything the last kept box covers  +  block arg-max of what is still alive]
-// in ONE pass over shared memory per kept box, with one __syncthreads per pass.  No sort is needed:
-// the arg-max sequence IS the score-descending kept list.  The inference tail needs only the
-// DETECTIONS_PER_IMAGE best survivors of an image, and no class can contribute more than that many,
-// so every segment stops after `topk` kept boxes (exact, see DESIGN.md "Kernel 4").
+//
+//   detections (the inference tail): det_rows (finite filter, clip, class-major score copy) ->
+//     det_class (one CTA per (class, image): gather, exact pre-selection of the best candidates, sort,
+//     all-pairs head stage over the first 128, warp-by-warp chunks for the rest; stops at topk kept boxes)
+//     -> det_topk (pairwise parallel merge of the class runs, G CTAs per image).  The inference tail needs
+//     only the DETECTIONS_PER_IMAGE best survivors of an image and no class can contribute more than that
+//     many, so every class stops after `topk` kept boxes (exact, see DESIGN.md "Kernel 4").
+//   batched_nms (generic, any number of survivors): segments by group, one CTA per group iterating
+//     [suppress what the last kept box covers + block arg-max of what is still alive] in one pass over
+//     shared memory per kept box; the arg-max sequence IS the score-descending kept list.
 //
 // Keys: 64 bit = (order-inverted score bits << 32) | candidate id, so "smaller key" == "higher score,
 // then lower id" -- torchvision's stable descending sort.  IoU arithmetic is bit-exact to either
-// torchvision kernel (WSOVOD_B200_IOU_TV_CPU / _TV_CUDA), see suppresses().
+// torchvision kernel (WSOVOD_B200_IOU_TV_CPU / _TV_CUDA), see suppresses() and its division-free
+// screen suppresses_fast().
 #include "common.cuh"
 
 #include <math.h>
@@ -255,7 +260,7 @@ __device__ __forceinline__ void bitonic_sort_regs(unsigned long long* keys, int 
   __syncthreads();
 }
 
-constexpr int kRunsPerThread = 4;      // top-k merge handles K <= 4 * kNmsThreads classes
+constexpr int kMaxRunClasses = 2048;    // the run table / run merge of det_topk handles up to this many classes
 constexpr int kSelectBins = 2048;     // histogram over the 11 leading key bits (quarter octaves of the score)
 constexpr int kSelectShift = 53;
 constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == histogram storage (8 KB)
@@ -892,7 +897,7 @@ static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   auto take = [&](size_t b) { size_t r = o; o += align_up(b, 256); return r; };
   w.kept_stride = K * std::max<int64_t>(topk, 0);
   // top-k stage: G CTAs per image, about eight class runs each (0: no run table, K too large)
-  w.G = (M > 0 && K > 0 && K <= (int64_t)kRunsPerThread * kNmsThreads) ? (int)std::min<int64_t>(32, ceil_div(K, 8)) : 0;
+  w.G = (M > 0 && K > 0 && K <= kMaxRunClasses) ? (int)std::min<int64_t>(32, ceil_div(K, 8)) : 0;
   if (w.G > 0 && det_topk_smem(K, w.G, topk) > 200 * 1024) w.G = 0;     // very large topk: packed list + sort / selection
   w.cboxes = take(sizeof(float4) * (size_t)M);
   w.img_cnt = take(sizeof(int32_t) * (size_t)(2 * N + 1));      // per-image kept counters, then the top-k tickets
