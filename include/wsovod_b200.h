@@ -173,6 +173,32 @@ int wsovod_b200_refine_assign(const float* boxes, const int64_t* offsets,
                               int64_t* gt_classes, float* gt_boxes, float* gt_scores,
                               float* gt_weights, void* stream);
 
+/* SURVEY 8f-2 -- replaces InstanceRefinementOutputLayers.losses with cross_entropy_weighted and
+ * BBOX_REG_LOSS_TYPE "smooth_l1_weighted" (fast_rcnn_open_vocabulary.py:754-892), the consumer of
+ * refine_assign's gt_classes / gt_boxes / gt_weights:
+ *   w_i = gt_classes_i == -1 ? 0 : gt_weights_i;  valid = #(w_i > 1e-12)
+ *   out[0] = sum_i w_i * CE(logits[i, :K1], gt_classes_i, ignore_index = -1) / valid          (:811-819)
+ *   out[1] = sum_{0 <= gt_i < num_classes} w_i * sum_j smooth_l1(deltas_ij - target_ij, beta) / max(M, 1),
+ *            target = Box2BoxTransform(wx, wy, ww, wh).get_deltas(proposal_boxes_i, gt_boxes_i);
+ *            0 if any target is NaN (:871-874)                                                 (:865-892)
+ *   out[2] = valid, out[3] = 1 if a target was NaN;  lse[i] = logsumexp(logits[i]) (kept for backward).
+ * deltas: [M, dcols], dcols = 4 (class-agnostic), 4 * num_classes (class-specific) or 0 (no box loss:
+ * refine_reg false, boxes and deltas may be NULL).  Deterministic: per-CTA partial sums added in a fixed
+ * order in double precision.  Workspace: wsovod_b200_refine_loss_workspace(M) bytes. */
+size_t wsovod_b200_refine_loss_workspace(int64_t M);
+int wsovod_b200_refine_loss_fwd(const float* logits, int64_t K1, const int64_t* gt_classes,
+                                const float* gt_weights, const float* proposal_boxes, const float* gt_boxes,
+                                const float* deltas, int64_t dcols, int64_t M, int64_t num_classes,
+                                float wx, float wy, float ww, float wh, float beta, float* out,
+                                float* lse, void* workspace, size_t workspace_bytes, void* stream);
+/* backward: grad_out [2] (device: d/d out[0], d/d out[1]), fwd_out = the forward's out[4];
+ * grad_logits [M, K1] and grad_deltas [M, dcols] (either may be NULL). */
+int wsovod_b200_refine_loss_bwd(const float* grad_out, const float* fwd_out, const float* logits, int64_t K1,
+                                const float* lse, const int64_t* gt_classes, const float* gt_weights,
+                                const float* proposal_boxes, const float* gt_boxes, const float* deltas,
+                                int64_t dcols, int64_t M, int64_t num_classes, float wx, float wy, float ww,
+                                float wh, float beta, float* grad_logits, float* grad_deltas, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (4) per-class NMS.
  * ---------------------------------------------------------------------------------------------- */

@@ -183,6 +183,41 @@ def refine_assign(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_we
                 gt_boxes=gbox, gt_scores=gsc, gt_weights=gw)
 
 
+def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, num_classes,
+                  box_weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    """InstanceRefinementOutputLayers.losses, weighted flavours (fast_rcnn_open_vocabulary.py:754-892),
+    restated with differentiable torch CPU ops (a floating-point path: torch fp32 is the reference
+    arithmetic; pinned against the reference's own function in tests/golden/refine_loss.pt).
+    Returns (loss_cls, loss_box_reg); deltas=None is refine_reg off."""
+    import torch.nn.functional as F
+    w = gt_weights.clone()
+    w[gt_classes == -1] = 0.0                                                    # :786-788
+    valid = (w > 1e-12).to(w.dtype).sum()                                        # :790-791
+    ce = F.cross_entropy(logits, gt_classes, reduction="none", ignore_index=-1)  # :815
+    loss_cls = (ce * w).sum() / valid                                            # :816-819
+    if deltas is None:
+        return loss_cls, torch.zeros(())
+    fg = torch.nonzero((gt_classes >= 0) & (gt_classes < num_classes))[:, 0]     # :832
+    if deltas.shape[1] == 4:
+        fd = deltas[fg]                                                          # :833-834
+    else:
+        fd = deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]                 # :836-838
+    src, tgt = proposal_boxes[fg], gt_boxes[fg]
+    sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]                         # d2 Box2BoxTransform.get_deltas
+    scx, scy = src[:, 0] + 0.5 * sw, src[:, 1] + 0.5 * sh
+    tw, th = tgt[:, 2] - tgt[:, 0], tgt[:, 3] - tgt[:, 1]
+    tcx, tcy = tgt[:, 0] + 0.5 * tw, tgt[:, 1] + 0.5 * th
+    wx, wy, ww, wh = box_weights
+    target = torch.stack((wx * (tcx - scx) / sw, wy * (tcy - scy) / sh, ww * torch.log(tw / sw),
+                          wh * torch.log(th / sh)), dim=1)
+    if torch.isnan(target).any():                                                # :871-874
+        return loss_cls, torch.zeros(())
+    n = torch.abs(fd - target)                                                   # fvcore smooth_l1_loss
+    l = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+    loss_box = (l * w[fg, None]).sum()                                           # :879-880
+    return loss_cls, loss_box / max(gt_classes.numel(), 1.0)                     # :892
+
+
 IOU_TV_CPU = 0
 IOU_TV_CUDA = 1
 

@@ -242,6 +242,26 @@ class Box2BoxTransform:
     def __init__(self, weights, scale_clamp=math.log(1000.0 / 16)):
         self.weights, self.scale_clamp = weights, scale_clamp
 
+    def get_deltas(self, src_boxes, target_boxes):
+        """detectron2 Box2BoxTransform.get_deltas (box_regression.py, restated): (dx, dy, dw, dh) that
+        apply_deltas would need to move src onto target"""
+        src_widths = src_boxes[:, 2] - src_boxes[:, 0]
+        src_heights = src_boxes[:, 3] - src_boxes[:, 1]
+        src_ctr_x = src_boxes[:, 0] + 0.5 * src_widths
+        src_ctr_y = src_boxes[:, 1] + 0.5 * src_heights
+        target_widths = target_boxes[:, 2] - target_boxes[:, 0]
+        target_heights = target_boxes[:, 3] - target_boxes[:, 1]
+        target_ctr_x = target_boxes[:, 0] + 0.5 * target_widths
+        target_ctr_y = target_boxes[:, 1] + 0.5 * target_heights
+        wx, wy, ww, wh = self.weights
+        dx = wx * (target_ctr_x - src_ctr_x) / src_widths
+        dy = wy * (target_ctr_y - src_ctr_y) / src_heights
+        dw = ww * torch.log(target_widths / src_widths)
+        dh = wh * torch.log(target_heights / src_heights)
+        deltas = torch.stack((dx, dy, dw, dh), dim=1)
+        assert (src_widths > 0).all().item(), "Input boxes to Box2BoxTransform are not valid!"
+        return deltas
+
     def apply_deltas(self, deltas, boxes):
         deltas = deltas.float()
         boxes = boxes.to(deltas.dtype)

@@ -12,6 +12,8 @@ What runs verbatim from /root/reference (through oracle/d2_shim.py):
     fast_rcnn_inference
   * wsovod/modeling/roi_heads/roi_heads.py  WSOVODROIHeads.get_pgt_top_k,
     label_and_sample_proposals_wsl, _sample_proposals_wsl, get_image_level_gt
+  * wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py  InstanceRefinementOutputLayers.losses /
+    softmax_cross_entropy_loss / box_reg_loss (weighted flavours) with autograd for the gradients
 and from the installed torchvision 0.26 (the reference's un-vendored dependency):
   * torch.ops.torchvision.roi_pool / roi_align (CPU), torchvision.ops.boxes._batched_nms_vanilla
 The reference's ROILoopPool has no CPU path (ROILoopPool.h:62); its 3-way golden comes from the
@@ -176,6 +178,40 @@ def main():
         gt_classes=[p.gt_classes for p in labelled], gt_boxes=[p.gt_boxes.tensor for p in labelled],
         gt_scores=[p.gt_scores for p in labelled], gt_weights=[p.gt_weights for p in labelled],
     ), os.path.join(GOLD, "refine.pt"))
+
+    # ---- (3b) weighted refinement losses: InstanceRefinementOutputLayers.losses verbatim ---
+    cases = {}
+    for name, (dcols_per, beta, reg) in dict(agnostic=(1, 0.0, True), specific=(K, 0.5, True), noreg=(1, 0.0, False)).items():
+        head = types.SimpleNamespace(
+            cross_entropy_weighted=True, box_reg_loss_type="smooth_l1_weighted", refine_k=0, refine_reg=[reg],
+            loss_weight={}, box2box_transform=Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), smooth_l1_beta=beta,
+            num_classes=K)
+        head.softmax_cross_entropy_loss = types.MethodType(fr.InstanceRefinementOutputLayers.softmax_cross_entropy_loss, head)
+        head.box_reg_loss = types.MethodType(fr.InstanceRefinementOutputLayers.box_reg_loss, head)
+        props = []
+        for p in labelled:
+            q = Instances(p.image_size)
+            q.proposal_boxes = p.proposal_boxes
+            q.gt_boxes = p.gt_boxes
+            gc = p.gt_classes.clone()
+            gc[::11] = -1                                        # ignored rows (subsampling leaves -1)
+            q.gt_classes = gc
+            q.gt_weights = p.gt_weights.clone()
+            props.append(q)
+        M = sum(len(p) for p in props)
+        logits = (torch.randn(M, K + 1, generator=g) * 3).requires_grad_()
+        deltas = (torch.randn(M, 4 * dcols_per, generator=g) * 0.5).requires_grad_()
+        out = fr.InstanceRefinementOutputLayers.losses(head, (logits, deltas), props)
+        total = sum(out.values())
+        total.backward()
+        cases[name] = dict(
+            logits=logits.detach(), deltas=deltas.detach(), gt_classes=torch.cat([p.gt_classes for p in props]),
+            gt_weights=torch.cat([p.gt_weights for p in labelled]),
+            proposal_boxes=torch.cat([p.proposal_boxes.tensor for p in props]),
+            gt_boxes=torch.cat([p.gt_boxes.tensor for p in props]), num_classes=K, beta=beta, reg=reg,
+            loss_cls=out["loss_cls_r0"].detach(), loss_box=out.get("loss_box_reg_r0", torch.zeros(())).detach(),
+            grad_logits=logits.grad.clone(), grad_deltas=(deltas.grad.clone() if deltas.grad is not None else torch.zeros_like(deltas)))
+    torch.save(cases, os.path.join(GOLD, "refine_loss.pt"))
 
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

@@ -295,6 +295,85 @@ def test_refine_vs_oracle_full_size():
     assert (ao["gt_classes"] < K).sum() > 20           # the test actually has foreground
 
 
+# ------------------------------------------------------------------------------------------ (3b) losses
+def _loss_case(M, K, dcols, seed, fg_frac=0.3):
+    g = synth.gen(seed)
+    logits = torch.randn(M, K + 1, generator=g) * 3
+    deltas = torch.randn(M, dcols, generator=g) * 0.5
+    gt = torch.randint(0, K, (M,), generator=g)
+    gt[torch.rand(M, generator=g) > fg_frac] = K                 # background
+    gt[torch.rand(M, generator=g) < 0.1] = -1                    # ignored by the subsampling
+    w = torch.rand(M, generator=g)
+    w[torch.rand(M, generator=g) < 0.05] = 0.0                   # zero-weight rows do not count as valid
+    pb = synth.proposals(M, 480, 640, g, stress=False)
+    gb = synth.proposals(M, 480, 640, g, stress=False)
+    return logits, deltas, gt, w, pb, gb
+
+
+def _loss_run(logits, deltas, gt, w, pb, gb, K, beta, dev):
+    lg = logits.clone().to(dev).requires_grad_()
+    dl = None if deltas is None else deltas.clone().to(dev).requires_grad_()
+    args = (lg, dl, gt.to(dev), w.to(dev), pb.to(dev), gb.to(dev), K)
+    lc, lb = (ops.refine_losses(*args, smooth_l1_beta=beta) if dev != "cpu" else oracle.refine_losses(*args, beta=beta))
+    (lc * 1.7 + lb * 0.6).backward()
+    gd = None if dl is None else (torch.zeros_like(deltas) if dl.grad is None else dl.grad.cpu())
+    return lc.detach().cpu(), lb.detach().cpu(), lg.grad.cpu(), gd
+
+
+@pytest.mark.parametrize("M,K,specific,beta", [(5000, 80, False, 0.0), (3000, 20, True, 0.5), (777, 1203, False, 0.11),
+                                                (64, 5, True, 0.0), (1, 3, False, 0.0)])
+def test_refine_losses_vs_oracle(M, K, specific, beta):
+    """fused weighted CE + weighted smooth-L1 (forward and backward) against the torch restatement of the
+    reference; sums are accumulated in double on the GPU and pairwise in fp32 by torch: 1e-5 relative"""
+    case = _loss_case(M, K, 4 * K if specific else 4, 1000 + M)
+    a = _loss_run(*case, K, beta, DEV)
+    b = _loss_run(*case, K, beta, "cpu")
+    torch.testing.assert_close(a[0], b[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(a[1], b[1], rtol=1e-5, atol=1e-7)
+    # d/d logits = g (softmax - onehot): the subtraction cancels where the target class dominates, so the error
+    # is a few 1e-7 of the row's gradient scale (expf, fp32), not of the element
+    torch.testing.assert_close(a[2], b[2], rtol=2e-5, atol=3e-7 * float(b[2].abs().max()) + 1e-12)
+    torch.testing.assert_close(a[3], b[3], rtol=2e-5, atol=3e-7 * float(b[3].abs().max()) + 1e-12)
+
+
+def test_refine_losses_golden(golden):
+    """against the reference's own InstanceRefinementOutputLayers.losses (values and autograd gradients)"""
+    for name, c in golden("refine_loss").items():
+        lg = c["logits"].to(DEV).requires_grad_()
+        dl = c["deltas"].to(DEV).requires_grad_() if c["reg"] else None
+        lc, lb = ops.refine_losses(lg, dl, c["gt_classes"].to(DEV), c["gt_weights"].to(DEV), c["proposal_boxes"].to(DEV),
+                                   c["gt_boxes"].to(DEV), c["num_classes"], smooth_l1_beta=c["beta"])
+        torch.testing.assert_close(lc.detach().cpu(), c["loss_cls"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(lb.detach().cpu(), c["loss_box"], rtol=1e-5, atol=1e-8)
+        (lc + lb).backward()
+        torch.testing.assert_close(lg.grad.cpu(), c["grad_logits"], rtol=2e-5, atol=3e-7 * float(c["grad_logits"].abs().max()))
+        if dl is not None:
+            torch.testing.assert_close(dl.grad.cpu(), c["grad_deltas"], rtol=2e-5, atol=3e-7 * float(c["grad_deltas"].abs().max()))
+
+
+def test_refine_losses_edge_cases():
+    logits, deltas, gt, w, pb, gb = _loss_case(200, 7, 4, 5)
+    # a NaN regression target (inverted gt box on a foreground row): the reference returns zeros(1) (:871-874)
+    gt[3] = 2
+    gb[3] = torch.tensor([50.0, 10.0, 20.0, 40.0])
+    a = _loss_run(logits, deltas, gt, w, pb, gb, 7, 0.0, DEV)
+    b = _loss_run(logits, deltas, gt, w, pb, gb, 7, 0.0, "cpu")
+    assert float(a[1]) == 0.0 and float(b[1]) == 0.0 and float(a[3].abs().sum()) == 0.0
+    torch.testing.assert_close(a[0], b[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(a[2], b[2], rtol=2e-5, atol=3e-7 * float(b[2].abs().max()))
+    # every row ignored: 0 / 0 like the reference
+    lc, lb = ops.refine_losses(logits.to(DEV), deltas.to(DEV), torch.full((200,), -1, device=DEV), w.to(DEV), pb.to(DEV),
+                               gb.to(DEV), 7)
+    assert torch.isnan(lc) and float(lb) == 0.0
+    # no box regression (refine_reg off) and an empty batch
+    lc, lb = ops.refine_losses(logits.to(DEV), None, gt.to(DEV), w.to(DEV))
+    torch.testing.assert_close(lc.cpu(), b[0], rtol=1e-5, atol=1e-6)
+    assert float(lb) == 0.0
+    lc, lb = ops.refine_losses(torch.zeros(0, 8, device=DEV), torch.zeros(0, 4, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV),
+                               torch.zeros(0, device=DEV), torch.zeros(0, 4, device=DEV), torch.zeros(0, 4, device=DEV), 7)
+    assert torch.isnan(lc) and float(lb) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ (4)
 def _nms_case(M, ngroups, seed, grid=None):
     g = synth.gen(seed)

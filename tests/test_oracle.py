@@ -149,3 +149,19 @@ def test_cpu_path_matches_oracle():
     r = oracle.detections(probs, rois[:, 1:], [0, 300], [(480, 640)], 1e-5, 0.3, 100, oracle.IOU_TV_CPU)
     c = int(r["det_count"][0])
     assert torch.equal(r["det_rows"][0, :c], dets[0][3]) and torch.equal(r["det_classes"][0, :c], dets[0][2])
+
+
+def test_refine_losses_oracle_matches_reference_golden(golden):
+    """the torch restatement of InstanceRefinementOutputLayers.losses against the reference's own function
+    (values and autograd gradients), tests/golden/refine_loss.pt"""
+    for name, c in golden("refine_loss").items():
+        logits = c["logits"].clone().requires_grad_()
+        deltas = c["deltas"].clone().requires_grad_() if c["reg"] else None
+        lc, lb = oracle.refine_losses(logits, deltas, c["gt_classes"], c["gt_weights"], c["proposal_boxes"], c["gt_boxes"],
+                                      c["num_classes"], beta=c["beta"])
+        torch.testing.assert_close(lc.detach(), c["loss_cls"], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(lb.detach(), c["loss_box"], rtol=1e-6, atol=1e-8)
+        (lc + lb).backward()
+        torch.testing.assert_close(logits.grad, c["grad_logits"], rtol=1e-6, atol=1e-9)
+        if deltas is not None:
+            torch.testing.assert_close(deltas.grad, c["grad_deltas"], rtol=1e-6, atol=1e-9)

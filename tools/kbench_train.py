@@ -65,6 +65,36 @@ def main():
             return ops.refine_assign(boxes, off, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"],
                                      sd["seed_weights"], goffd, sd["seed_count"], K, 0.5)
         res["seeds_assign_ms"] = round(timeit(refine, flush=flush), 4)
+
+        # weighted refinement losses on the labels just made (fused op) and the same in plain torch ops
+        lab = refine()
+        logits = (torch.randn(M, K + 1, generator=g) * 3).to(DEV).requires_grad_(True)
+        deltas = (torch.randn(M, 4, generator=g) * 0.5).to(DEV).requires_grad_(True)
+
+        def losses_fb():
+            lc, lb = ops.refine_losses(logits, deltas, lab["gt_classes"], lab["gt_weights"], boxes, lab["gt_boxes"], K)
+            (lc + lb).backward()
+            logits.grad = None
+            deltas.grad = None
+        res["refine_losses_fwd_bwd_ms"] = round(timeit(losses_fb, flush=flush), 4)
+
+        def losses_torch():
+            import torch.nn.functional as F
+            gc, w = lab["gt_classes"], lab["gt_weights"].clone()
+            w[gc == -1] = 0.0
+            lc = (F.cross_entropy(logits, gc, reduction="none", ignore_index=-1) * w).sum() / (w > 1e-12).float().sum()
+            fg = torch.nonzero((gc >= 0) & (gc < K))[:, 0]
+            src, tgt = boxes[fg], lab["gt_boxes"][fg]
+            sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]
+            tw, th = tgt[:, 2] - tgt[:, 0], tgt[:, 3] - tgt[:, 1]
+            tdel = torch.stack((10 * (tgt[:, 0] + 0.5 * tw - src[:, 0] - 0.5 * sw) / sw,
+                                10 * (tgt[:, 1] + 0.5 * th - src[:, 1] - 0.5 * sh) / sh,
+                                5 * torch.log(tw / sw), 5 * torch.log(th / sh)), 1)
+            lb = ((deltas[fg] - tdel).abs() * w[fg, None]).sum() / max(M, 1)
+            (lc + lb).backward()
+            logits.grad = None
+            deltas.grad = None
+        res["refine_losses_torch_fwd_bwd_ms"] = round(timeit(losses_torch, flush=flush), 4)
         print(json.dumps(res), flush=True)
 
 

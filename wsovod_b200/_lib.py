@@ -50,6 +50,11 @@ SIGNATURES = {
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "wsovod_b200_refine_assign": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64,
                                           c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "wsovod_b200_refine_loss_workspace": (c_sz, [c_i64]),
+    "wsovod_b200_refine_loss_fwd": (c_int, [c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_f, c_f,
+                                            c_f, c_f, c_f, c_p, c_p, c_p, c_sz, c_p]),
+    "wsovod_b200_refine_loss_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64,
+                                            c_i64, c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p]),
     "wsovod_b200_batched_nms_workspace": (c_sz, [c_i64, c_i64]),
     "wsovod_b200_batched_nms": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_d, c_int, c_p, c_p, c_p, c_sz,
                                         c_p]),

@@ -165,6 +165,27 @@ class InstanceRefinementOutputLayers(nn.Module):
         boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
         return apply_deltas(deltas, boxes, self.bbox_reg_weights).split([len(p) for p in proposals])
 
+    def losses(self, predictions, proposals, num_classes=None, refine_k=0, smooth_l1_beta=0.0, loss_weight=None):
+        """:754-810 with cross_entropy_weighted and BBOX_REG_LOSS_TYPE "smooth_l1_weighted" (the shipped
+        configs): {"loss_cls_r<k>", "loss_box_reg_r<k>"} from one fused kernel (ops.refine_losses);
+        proposals carry proposal_boxes, gt_classes, gt_weights and (for the box term) gt_boxes"""
+        scores, deltas = predictions
+        gt_classes = torch.cat([p.gt_classes for p in proposals], dim=0)
+        gt_weights = torch.cat([p.gt_weights for p in proposals], dim=0)
+        out = {}
+        if self.refine_reg:
+            pboxes = torch.cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+            gboxes = torch.cat([(p.gt_boxes if p.has("gt_boxes") else p.proposal_boxes).tensor for p in proposals], dim=0)
+            lc, lb = ops.refine_losses(scores, deltas, gt_classes, gt_weights, pboxes, gboxes,
+                                       self.num_classes if num_classes is None else num_classes, self.bbox_reg_weights,
+                                       smooth_l1_beta)
+            out["loss_box_reg_r" + str(refine_k)] = lb
+        else:
+            lc, _ = ops.refine_losses(scores, None, gt_classes, gt_weights)
+        out["loss_cls_r" + str(refine_k)] = lc
+        lw = loss_weight or {}
+        return {k: v * lw.get(k, 1.0) for k, v in out.items()}
+
     def inference(self, predictions, proposals):
         """:894-924 -- predictions: (scores, deltas) or a list of them (one per refinement head)"""
         if isinstance(predictions[0], tuple):

@@ -493,6 +493,110 @@ def refine_assign(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_we
 
 
 # ------------------------------------------------------------------------------------------------
+# (3b) weighted refinement losses
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("wsovod_b200::refine_losses", mutates_args=())
+def _refine_losses(logits: torch.Tensor, deltas: Optional[torch.Tensor], gt_classes: torch.Tensor,
+                   gt_weights: torch.Tensor, proposal_boxes: Optional[torch.Tensor], gt_boxes: Optional[torch.Tensor],
+                   num_classes: int, wx: float, wy: float, ww: float, wh: float,
+                   beta: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes)
+    logits, gt_weights = _f32c(logits), _f32c(gt_weights)
+    gt_classes = gt_classes.to(torch.int64).contiguous()
+    if logits.dim() != 2 or gt_classes.numel() != logits.size(0) or gt_weights.numel() != logits.size(0):
+        raise RuntimeError("wsovod_b200::refine_losses expects logits (M,K+1), gt_classes (M), gt_weights (M)")
+    M, K1 = logits.shape
+    dcols = 0
+    if deltas is not None:
+        deltas, proposal_boxes, gt_boxes = _f32c(deltas), _f32c(proposal_boxes), _f32c(gt_boxes)
+        dcols = deltas.size(1) if deltas.dim() == 2 else -1
+        if deltas.size(0) != M or proposal_boxes.shape != (M, 4) or gt_boxes.shape != (M, 4):
+            raise RuntimeError("wsovod_b200::refine_losses expects deltas (M,4|4K) and boxes (M,4)")
+    dev = logits.device
+    with torch.cuda.device(dev):
+        out = torch.empty((4,), dtype=torch.float32, device=dev)
+        lse = torch.empty((M,), dtype=torch.float32, device=dev)
+        L = _lib.lib()
+        ws = _workspace(L.wsovod_b200_refine_loss_workspace(M), dev)
+        rc = L.wsovod_b200_refine_loss_fwd(_ptr(logits), K1, _ptr(gt_classes), _ptr(gt_weights), _ptr(proposal_boxes),
+                                           _ptr(gt_boxes), _ptr(deltas), dcols, M, num_classes, wx, wy, ww, wh, beta,
+                                           _ptr(out), _ptr(lse), _ptr(ws), ws.numel(), _stream(logits))
+    _lib.check(rc, "refine_loss_fwd")
+    return out, lse
+
+
+@_refine_losses.register_fake
+def _(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, num_classes, wx, wy, ww, wh, beta):
+    return logits.new_empty((4,)), logits.new_empty((logits.size(0),))
+
+
+@torch.library.custom_op("wsovod_b200::refine_losses_backward", mutates_args=())
+def _refine_losses_backward(grad_out: torch.Tensor, fwd_out: torch.Tensor, lse: torch.Tensor, logits: torch.Tensor,
+                            deltas: Optional[torch.Tensor], gt_classes: torch.Tensor, gt_weights: torch.Tensor,
+                            proposal_boxes: Optional[torch.Tensor], gt_boxes: Optional[torch.Tensor],
+                            num_classes: int, wx: float, wy: float, ww: float, wh: float,
+                            beta: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda(grad_out, fwd_out, lse, logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes)
+    logits, gt_weights, grad_out = _f32c(logits), _f32c(gt_weights), _f32c(grad_out)
+    gt_classes = gt_classes.to(torch.int64).contiguous()
+    M, K1 = logits.shape
+    dcols = 0
+    if deltas is not None:
+        deltas, proposal_boxes, gt_boxes = _f32c(deltas), _f32c(proposal_boxes), _f32c(gt_boxes)
+        dcols = deltas.size(1)
+    dev = logits.device
+    with torch.cuda.device(dev):
+        gl = torch.empty_like(logits)
+        gd = torch.empty_like(deltas) if deltas is not None else logits.new_empty((0,))
+        L = _lib.lib()
+        rc = L.wsovod_b200_refine_loss_bwd(_ptr(grad_out), _ptr(fwd_out), _ptr(logits), K1, _ptr(lse), _ptr(gt_classes),
+                                           _ptr(gt_weights), _ptr(proposal_boxes), _ptr(gt_boxes), _ptr(deltas), dcols,
+                                           M, num_classes, wx, wy, ww, wh, beta, _ptr(gl),
+                                           _ptr(gd) if deltas is not None else None, _stream(logits))
+    _lib.check(rc, "refine_loss_bwd")
+    return gl, gd
+
+
+@_refine_losses_backward.register_fake
+def _(grad_out, fwd_out, lse, logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, num_classes, wx, wy,
+      ww, wh, beta):
+    return torch.empty_like(logits), (torch.empty_like(deltas) if deltas is not None else logits.new_empty((0,)))
+
+
+def _refine_losses_setup(ctx, inputs, output):
+    logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, num_classes, wx, wy, ww, wh, beta = inputs
+    ctx.has_deltas = deltas is not None
+    ctx.consts = (num_classes, wx, wy, ww, wh, beta)
+    saved = [output[0], output[1], logits, gt_classes, gt_weights]
+    if ctx.has_deltas:
+        saved += [deltas, proposal_boxes, gt_boxes]
+    ctx.save_for_backward(*saved)
+
+
+def _refine_losses_bwd(ctx, g_out, g_lse):
+    out, lse, logits, gt_classes, gt_weights = ctx.saved_tensors[:5]
+    deltas, pb, gb = ctx.saved_tensors[5:] if ctx.has_deltas else (None, None, None)
+    gl, gd = torch.ops.wsovod_b200.refine_losses_backward(g_out[:2].contiguous(), out, lse, logits, deltas, gt_classes,
+                                                          gt_weights, pb, gb, *ctx.consts)
+    return (gl, gd if ctx.has_deltas else None) + (None,) * 10
+
+
+_refine_losses.register_autograd(_refine_losses_bwd, setup_context=_refine_losses_setup)
+
+
+def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes=None, gt_boxes=None, num_classes=None,
+                  box_weights=(10.0, 10.0, 5.0, 5.0), smooth_l1_beta=0.0):
+    """InstanceRefinementOutputLayers.losses with cross_entropy_weighted + "smooth_l1_weighted"
+    (fast_rcnn_open_vocabulary.py:754-892): returns (loss_cls, loss_box_reg) as 0-d tensors with autograd
+    to `logits` and `deltas`; `deltas=None` (refine_reg off) gives loss_box_reg = 0."""
+    K = int(num_classes) if num_classes is not None else logits.size(1) - 1
+    wx, wy, ww, wh = (float(v) for v in box_weights)
+    out, _ = torch.ops.wsovod_b200.refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, K,
+                                                 wx, wy, ww, wh, float(smooth_l1_beta))
+    return out[0], out[1]
+
+
+# ------------------------------------------------------------------------------------------------
 # (4) NMS
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("wsovod_b200::batched_nms", mutates_args=())
