@@ -177,10 +177,10 @@ int wsovod_b200_refine_assign(const float* boxes, const int64_t* offsets,
  * BBOX_REG_LOSS_TYPE "smooth_l1_weighted" (fast_rcnn_open_vocabulary.py:754-892), the consumer of
  * refine_assign's gt_classes / gt_boxes / gt_weights:
  *   w_i = gt_classes_i == -1 ? 0 : gt_weights_i;  valid = #(w_i > 1e-12)
- *   out[0] = sum_i w_i * CE(logits[i, :K1], gt_classes_i, ignore_index = -1) / valid          (:811-819)
+ *   out[0] = sum_i w_i * CE(logits[i, :K1], gt_classes_i, ignore_index = -1) / valid          (:813-820)
  *   out[1] = sum_{0 <= gt_i < num_classes} w_i * sum_j smooth_l1(deltas_ij - target_ij, beta) / max(M, 1),
  *            target = Box2BoxTransform(wx, wy, ww, wh).get_deltas(proposal_boxes_i, gt_boxes_i);
- *            0 if any target is NaN (:871-874)                                                 (:865-892)
+ *            0 if any target is NaN (:869-872)                                                 (:864-892)
  *   out[2] = valid, out[3] = 1 if a target was NaN;  lse[i] = logsumexp(logits[i]) (kept for backward).
  * deltas: [M, dcols], dcols = 4 (class-agnostic), 4 * num_classes (class-specific) or 0 (no box loss:
  * refine_reg false, boxes and deltas may be NULL).  Deterministic: per-CTA partial sums added in a fixed

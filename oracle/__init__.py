@@ -191,17 +191,17 @@ def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_box
     Returns (loss_cls, loss_box_reg); deltas=None is refine_reg off."""
     import torch.nn.functional as F
     w = gt_weights.clone()
-    w[gt_classes == -1] = 0.0                                                    # :786-788
-    valid = (w > 1e-12).to(w.dtype).sum()                                        # :790-791
-    ce = F.cross_entropy(logits, gt_classes, reduction="none", ignore_index=-1)  # :815
-    loss_cls = (ce * w).sum() / valid                                            # :816-819
+    w[gt_classes == -1] = 0.0                                                    # :791-792
+    valid = (w > 1e-12).to(w.dtype).sum()                                        # :794-795
+    ce = F.cross_entropy(logits, gt_classes, reduction="none", ignore_index=-1)  # :817
+    loss_cls = (ce * w).sum() / valid                                            # :818-820
     if deltas is None:
         return loss_cls, torch.zeros(())
-    fg = torch.nonzero((gt_classes >= 0) & (gt_classes < num_classes))[:, 0]     # :832
+    fg = torch.nonzero((gt_classes >= 0) & (gt_classes < num_classes))[:, 0]     # :833
     if deltas.shape[1] == 4:
-        fd = deltas[fg]                                                          # :833-834
+        fd = deltas[fg]                                                          # :834-835
     else:
-        fd = deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]                 # :836-838
+        fd = deltas.view(-1, num_classes, 4)[fg, gt_classes[fg]]                 # :836-839
     src, tgt = proposal_boxes[fg], gt_boxes[fg]
     sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]                         # d2 Box2BoxTransform.get_deltas
     scx, scy = src[:, 0] + 0.5 * sw, src[:, 1] + 0.5 * sh
@@ -210,11 +210,11 @@ def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_box
     wx, wy, ww, wh = box_weights
     target = torch.stack((wx * (tcx - scx) / sw, wy * (tcy - scy) / sh, ww * torch.log(tw / sw),
                           wh * torch.log(th / sh)), dim=1)
-    if torch.isnan(target).any():                                                # :871-874
+    if torch.isnan(target).any():                                                # :869-872
         return loss_cls, torch.zeros(())
     n = torch.abs(fd - target)                                                   # fvcore smooth_l1_loss
     l = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
-    loss_box = (l * w[fg, None]).sum()                                           # :879-880
+    loss_box = (l * w[fg, None]).sum()                                           # :874-878
     return loss_cls, loss_box / max(gt_classes.numel(), 1.0)                     # :892
 
 

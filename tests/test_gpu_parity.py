@@ -353,7 +353,7 @@ def test_refine_losses_golden(golden):
 
 def test_refine_losses_edge_cases():
     logits, deltas, gt, w, pb, gb = _loss_case(200, 7, 4, 5)
-    # a NaN regression target (inverted gt box on a foreground row): the reference returns zeros(1) (:871-874)
+    # a NaN regression target (inverted gt box on a foreground row): the reference returns zeros(1) (:869-872)
     gt[3] = 2
     gb[3] = torch.tensor([50.0, 10.0, 20.0, 40.0])
     a = _loss_run(logits, deltas, gt, w, pb, gb, 7, 0.0, DEV)

@@ -2,13 +2,13 @@
 // InstanceRefinementOutputLayers.losses with cross_entropy_weighted and "smooth_l1_weighted"
 // (fast_rcnn_open_vocabulary.py:754-892), forward and backward, one pass over the logits each.
 //
-//   w_i      = gt_classes_i == -1 ? 0 : gt_weights_i                                   (:786-788)
-//   valid    = #(w_i > 1e-12)                                                          (:790-791)
-//   loss_cls = sum_i w_i * CE(logits_i, gt_i; ignore_index = -1) / valid               (:811-819)
-//   loss_box = sum_{i fg} w_i * sum_j smooth_l1(delta_ij - target_ij; beta) / max(M, 1) (:865-892)
+//   w_i      = gt_classes_i == -1 ? 0 : gt_weights_i                                   (:790-792)
+//   valid    = #(w_i > 1e-12)                                                          (:794-795)
+//   loss_cls = sum_i w_i * CE(logits_i, gt_i; ignore_index = -1) / valid               (:813-820)
+//   loss_box = sum_{i fg} w_i * sum_j smooth_l1(delta_ij - target_ij; beta) / max(M, 1) (:864-892)
 //              fg: 0 <= gt_i < num_classes; target = Box2BoxTransform.get_deltas(proposal, gt box)
 //              (detectron2 box_regression.py: dx = wx (gcx - pcx) / pw, dw = ww log(gw / pw));
-//              a NaN target anywhere makes the reference return zeros(1) (:871-874): loss 0, no gradient.
+//              a NaN target anywhere makes the reference return zeros(1) (:869-872): loss 0, no gradient.
 //
 // The reference runs ~25 element-wise / indexing launches for this; here one warp owns a row (max,
 // sum-exp, the CE term, the four box terms), CTAs write partial sums, and a second tiny launch adds them
