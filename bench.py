@@ -147,9 +147,6 @@ def run_reference(args, w, rank):
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -175,7 +172,19 @@ def main():
         raise RuntimeError("bench.py (impl ours) needs a CUDA device: wsovod_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    rank, local_rank, world = shard.init("nccl")
+    # stdout carries exactly one JSON line: NCCL writes its "NCCL version ..." banner to fd 1 when the first
+    # communicator is created, so the init and the first collective run with fd 1 pointed at stderr
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local_rank, world = shard.init("nccl")
+        shard.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     N, C, H, W, R, K, D = (w[k] for k in "NCHWRKD")
     M = N * R
     feat, rois, obj = w["features"].to(dev), w["rois"].to(dev), w["objectness"].to(dev)
