@@ -14,6 +14,8 @@ What runs verbatim from /root/reference (through oracle/d2_shim.py):
     label_and_sample_proposals_wsl, _sample_proposals_wsl, get_image_level_gt
   * wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py  InstanceRefinementOutputLayers.losses /
     softmax_cross_entropy_loss / box_reg_loss (weighted flavours) with autograd for the gradients
+  * wsovod/data/detection_utils.py  unique_boxes, transform_proposals (the two functions are compiled from
+    the file's AST: importing the module would pull detectron2.data / PIL machinery they do not use)
 and from the installed torchvision 0.26 (the reference's un-vendored dependency):
   * torch.ops.torchvision.roi_pool / roi_align (CPU), torchvision.ops.boxes._batched_nms_vanilla
 The reference's ROILoopPool has no CPU path (ROILoopPool.h:62); its 3-way golden comes from the
@@ -212,6 +214,34 @@ def main():
             loss_cls=out["loss_cls_r0"].detach(), loss_box=out.get("loss_box_reg_r0", torch.zeros(())).detach(),
             grad_logits=logits.grad.clone(), grad_deltas=(deltas.grad.clone() if deltas.grad is not None else torch.zeros_like(deltas)))
     torch.save(cases, os.path.join(GOLD, "refine_loss.pt"))
+
+    # ---- (0) proposal ingest: unique_boxes / transform_proposals / the per-image sort --------
+    import ast
+    import numpy as np
+    src = open(os.path.join(REF, "wsovod", "data", "detection_utils.py")).read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("unique_boxes", "transform_proposals")]
+    ns = dict(np=np, torch=torch, Boxes=Boxes, Instances=Instances,
+              BoxMode=types.SimpleNamespace(XYXY_ABS=0, convert=lambda b, frm, to: b))
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "detection_utils.py", "exec"), ns)
+    rng = np.random.RandomState(7)
+    cases = {}
+    for name, (n, ih, iw, topk, msz) in dict(plain=(600, 480, 640, 400, 0), tiny=(300, 120, 160, 4000, 2), few=(5, 50, 60, 3, 0)).items():
+        bx = make_rois(n, 1, ih, iw, g)[:, 1:].numpy().astype(np.float64)
+        bx[: n // 4] = np.round(bx[: n // 4])                       # integer boxes: hash collisions after clip
+        bx[n // 4: n // 3] += rng.uniform(-0.4, 0.4, (n // 3 - n // 4, 4))   # near-duplicates that round together
+        bx[-n // 10:, 2:] += 300.0                                   # partly outside the image
+        lg = rng.rand(n)
+        lg[: n // 5] = np.round(lg[: n // 5], 1)                     # tied scores
+        inds = lg.argsort()[::-1]                                    # build.py:166-168
+        sb, sl = bx[inds], lg[inds]
+        dd = dict(proposal_boxes=sb.copy(), proposal_objectness_logits=sl.copy(), proposal_bbox_mode=0)
+        tf = types.SimpleNamespace(apply_box=lambda b: b)
+        ns["transform_proposals"](dd, (ih, iw), tf, proposal_topk=topk, min_box_size=msz)
+        cases[name] = dict(boxes=bx, logits=lg, image_shape=(ih, iw), topk=topk, min_box_size=msz,
+                           sorted_boxes=sb, sorted_logits=sl,
+                           unique=ns["unique_boxes"](Boxes(torch.as_tensor(sb).float())),
+                           out_boxes=dd["proposals"].proposal_boxes.tensor, out_logits=dd["proposals"].objectness_logits)
+    torch.save(cases, os.path.join(GOLD, "ingest.pt"))
 
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
