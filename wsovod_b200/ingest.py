@@ -12,6 +12,10 @@ Mirrors, with the same numpy calls where their tie behaviour matters:
   * `transform_proposals` (:220-266): [transform] -> clip to the image -> unique -> drop boxes with a side
     <= min_box_size -> the first `proposal_topk`.
 
+  * the concept (text) embedding file (open_vocabulary_classifier.py:51-57, rcnn_wsovod.py:299-305): whatever
+    `np.load(path, encoding="bytes", allow_pickle=True)` reads -- a .npy array or a pickled (K, D) tensor --
+    as a contiguous fp32 (K, D) matrix, the `classifier` argument of the alignment op.
+
 `batch()` turns the prepared images into the (M, 5) roi tensor / offsets / objectness vector the pooling op
 takes (poolers.py:81-108).
 """
@@ -78,6 +82,16 @@ def transform_proposals(boxes, objectness_logits, image_shape, *, proposal_topk,
     keep = ((b[:, 2] - b[:, 0]) > min_box_size) & ((b[:, 3] - b[:, 1]) > min_box_size)       # Boxes.nonempty
     b, logits = b[keep], logits[keep]
     return b[:proposal_topk], logits[:proposal_topk]
+
+
+def load_text_embeddings(path):
+    """(K, D) fp32 concept embeddings, one row per class (rcnn_wsovod.py:301-303; the train-time buffer is the
+    transpose, open_vocabulary_classifier.py:53-56)"""
+    w = np.load(path, encoding="bytes", allow_pickle=True)
+    w = (w.detach() if isinstance(w, torch.Tensor) else torch.as_tensor(np.asarray(w))).to(torch.float32).contiguous()
+    if w.dim() != 2:
+        raise ValueError("concept embedding file must hold a (K, D) matrix, got shape %s" % (tuple(w.shape),))
+    return w
 
 
 def batch(prepared):
