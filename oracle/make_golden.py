@@ -16,6 +16,7 @@ What runs verbatim from /root/reference (through oracle/d2_shim.py):
     softmax_cross_entropy_loss / box_reg_loss (weighted flavours) with autograd for the gradients
   * wsovod/data/detection_utils.py  unique_boxes, transform_proposals (the two functions are compiled from
     the file's AST: importing the module would pull detectron2.data / PIL machinery they do not use)
+  * wsovod/modeling/proposal_generator/proposal_utils.py  find_top_rpn_proposals (from the AST as well)
 and from the installed torchvision 0.26 (the reference's un-vendored dependency):
   * torch.ops.torchvision.roi_pool / roi_align (CPU), torchvision.ops.boxes._batched_nms_vanilla
 The reference's ROILoopPool has no CPU path (ROILoopPool.h:62); its 3-way golden comes from the
@@ -242,6 +243,27 @@ def main():
                            unique=ns["unique_boxes"](Boxes(torch.as_tensor(sb).float())),
                            out_boxes=dd["proposals"].proposal_boxes.tensor, out_logits=dd["proposals"].objectness_logits)
     torch.save(cases, os.path.join(GOLD, "ingest.pt"))
+
+    # ---- (4b) RPN proposal selection: find_top_rpn_proposals verbatim ------------------------
+    src = open(os.path.join(REF, "wsovod", "modeling", "proposal_generator", "proposal_utils.py")).read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("find_top_rpn_proposals", "_is_tracing")]
+    from typing import List as _List, Tuple as _Tuple
+    ns = dict(torch=torch, List=_List, Tuple=_Tuple, Boxes=Boxes, Instances=Instances, cat=d2_shim.cat,
+              batched_nms=d2_shim.batched_nms, move_device_like=lambda src_, dst_: src_)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "proposal_utils.py", "exec"), ns)
+    cases = {}
+    for name, (Nimg, lvls, pre, post, msz) in dict(single=(2, (3000,), 2000, 1000, 0.0), fpn=(3, (2500, 700, 200, 40), 1000, 600, 4.0)).items():
+        sizes = [(480, 640), (400, 600), (300, 512)][:Nimg]
+        props = [torch.stack([make_rois(n, 1, 480, 640, g)[:, 1:] for _ in range(Nimg)]) for n in lvls]
+        for p in props:
+            p[:, ::13] += torch.randn(Nimg, p[:, ::13].shape[1], 4, generator=g) * 200       # out of the image / inverted
+        logits = [torch.randn(Nimg, n, generator=g) for n in lvls]
+        logits[0][0, 5] = float("nan")
+        props[0][1, 9, 2] = float("inf")
+        res = ns["find_top_rpn_proposals"]([p.clone() for p in props], [l.clone() for l in logits], sizes, 0.7, pre, post, msz, False)
+        cases[name] = dict(proposals=props, logits=logits, image_sizes=sizes, nms_thresh=0.7, pre=pre, post=post, min_box_size=msz,
+                           boxes=[r.proposal_boxes.tensor for r in res], scores=[r.objectness_logits for r in res])
+    torch.save(cases, os.path.join(GOLD, "rpn_select.pt"))
 
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
