@@ -34,6 +34,11 @@ int wsovod_b200_abi_version(void);
 const char* wsovod_b200_strerror(int code);
 /* number of kernel launches issued by this library since load (bench.py's `gpu_launches`) */
 uint64_t wsovod_b200_launch_count(void);
+/* Process-wide tuning / test switches: which of several bit-identical kernels runs.  Not part of the
+ * reference's interface; results never depend on them.  Returns the previous value (or EINVAL). */
+#define WSOVOD_B200_TUNE_POOL_PATH 0  /* 0 library's choice (default), 1 scan kernels, 2 block-max planes */
+#define WSOVOD_B200_TUNE_POOL_GROUP 1 /* 1 bank-conflict-aware lane order of the block-max path (default), 0 row-major */
+int wsovod_b200_tune(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * (1) ROI pooling.  rois: [R,5] = (batch_index, x1, y1, x2, y2) in image pixels, fp32.

@@ -521,17 +521,12 @@ def _pool_variant(scan=None):
     """select the values-only pooling kernel for the calls inside: scan=True the plain scan kernels,
     scan=False the block-max path wherever it applies (the library's own choice needs >= 1200 proposals
     per image)"""
-    old = {k: os.environ.get(k) for k in ("WSOVOD_B200_POOL_SCAN",)}
-    if scan is not None:
-        os.environ["WSOVOD_B200_POOL_SCAN"] = "1" if scan else "0"
+    from wsovod_b200 import _lib
+    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO if scan is None else _lib.POOL_SCAN if scan else _lib.POOL_BLOCKMAX)
     try:
         yield
     finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+        _lib.tune(_lib.TUNE_POOL_PATH, old)
 
 
 @pytest.mark.parametrize("N,C,H,W,R,seed", [(2, 9, 60, 80, 900, 1), (1, 3, 86, 128, 1500, 2), (3, 6, 100, 152, 700, 3),

@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from wsovod_b200 import ops, synth  # noqa: E402
+from wsovod_b200 import _lib, ops, synth  # noqa: E402
 from tools.kbench import timeit  # noqa: E402
 
 DEV = "cuda:0"
@@ -22,16 +22,16 @@ def main():
         feat, rois, obj = w["features"].to(DEV), w["rois"].to(DEV), w["objectness"].to(DEV)
         out_bytes = N * R * C * 49 * 4
         res = {"config": name}
-        for tag, env in (("blockmax", "0"), ("scan", "1")):
-            os.environ["WSOVOD_B200_POOL_SCAN"] = env
+        for tag, env in (("blockmax", _lib.POOL_BLOCKMAX), ("scan", _lib.POOL_SCAN)):
+            _lib.tune(_lib.TUNE_POOL_PATH, env)
             ms = timeit(lambda: ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False), iters=15, flush=flush)
             res[f"{tag}_ms"] = round(ms, 4)
             res[f"{tag}_GBs"] = round((out_bytes + feat.numel() * 4) / ms / 1e6, 1)
-        os.environ["WSOVOD_B200_POOL_SCAN"] = "0"
+        _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
         a = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
-        os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+        _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
         b = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
-        os.environ.pop("WSOVOD_B200_POOL_SCAN", None)
+        _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
         res["equal"] = bool(torch.equal(a, b))
         ms = timeit(lambda: ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False), iters=15, flush=flush)
         res["default_ms"] = round(ms, 4)   # the library's own choice

@@ -2,7 +2,7 @@
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from wsovod_b200 import ops, synth  # noqa: E402
+from wsovod_b200 import _lib, ops, synth  # noqa: E402
 from tools.kbench import timeit  # noqa: E402
 DEV = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
@@ -13,7 +13,7 @@ for (N, C, H, W) in [(1, 512, 60, 80), (8, 512, 86, 128), (1, 512, 86, 128), (2,
         rois, _ = synth.rois_from([synth.proposals(R, H * 8, W * 8, g) for _ in range(N)])
         rois = rois.to(DEV)
         res = {"N": N, "C": C, "HW": [H, W], "R": R}
-        for tag, env in (("blockmax", "0"), ("scan", "1")):
-            os.environ["WSOVOD_B200_POOL_SCAN"] = env
+        for tag, env in (("blockmax", _lib.POOL_BLOCKMAX), ("scan", _lib.POOL_SCAN)):
+            _lib.tune(_lib.TUNE_POOL_PATH, env)
             res[tag + "_ms"] = round(timeit(lambda: ops.roi_pool(feat, rois, 1 / 8, 7, None, 0.0, False), iters=10, flush=flush), 4)
         print(json.dumps(res), flush=True)

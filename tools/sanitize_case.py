@@ -1,13 +1,13 @@
 """Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool racecheck python tools/sanitize_case.py
-The block-max pooling path is forced (WSOVOD_B200_POOL_SCAN=0) and checked against the scan kernels."""
+The block-max pooling path is forced (TUNE_POOL_PATH = block-max) and checked against the scan kernels."""
 import os
 import sys
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from wsovod_b200 import ops, synth  # noqa: E402
+from wsovod_b200 import _lib, ops, synth  # noqa: E402
 
 DEV = "cuda:0"
 g = synth.gen(3)
@@ -18,11 +18,11 @@ boxes[0][:20, 2:] = torch.tensor([W * 8.0, H * 8.0])      # whole-map proposals:
 rois, off = synth.rois_from(boxes)
 rois = rois.to(DEV)
 obj = synth.objectness(N * R, g).to(DEV)
-os.environ["WSOVOD_B200_POOL_SCAN"] = "0"
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
 a = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
-os.environ["WSOVOD_B200_POOL_SCAN"] = "1"
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
 b = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
-del os.environ["WSOVOD_B200_POOL_SCAN"]
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
 assert torch.equal(a, b)
 ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
 ops.roi_loop_pool(feat, rois, 1 / 8, 7, with_argmax=False)

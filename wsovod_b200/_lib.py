@@ -23,6 +23,7 @@ SIGNATURES = {
     "wsovod_b200_abi_version": (c_int, []),
     "wsovod_b200_strerror": (ctypes.c_char_p, [c_int]),
     "wsovod_b200_launch_count": (ctypes.c_uint64, []),
+    "wsovod_b200_tune": (c_int, [c_int, c_int]),
     "wsovod_b200_roi_pool_workspace": (c_sz, [c_i64, c_i64, c_int, c_int]),
     "wsovod_b200_roi_pool_fwd": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_f, c_int, c_int,
                                          c_p, c_f, c_p, c_p, c_p, c_sz, c_p]),
@@ -97,3 +98,12 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().wsovod_b200_launch_count())
+
+
+TUNE_POOL_PATH, TUNE_POOL_GROUP = 0, 1
+POOL_AUTO, POOL_SCAN, POOL_BLOCKMAX = 0, 1, 2
+
+
+def tune(key, value):
+    """wsovod_b200_tune: process-wide switch between bit-identical kernels (tests / benches); returns the old value"""
+    return int(lib().wsovod_b200_tune(int(key), int(value)))

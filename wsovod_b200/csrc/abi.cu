@@ -3,6 +3,12 @@
 
 namespace wsovod {
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_tune[TUNE_COUNT] = {{0}, {1}};
+}
+
+WSOVOD_API int wsovod_b200_tune(int key, int value) {
+  if (key < 0 || key >= wsovod::TUNE_COUNT) return WSOVOD_B200_EINVAL;
+  return wsovod::g_tune[key].exchange(value, std::memory_order_relaxed);
 }
 
 WSOVOD_API int wsovod_b200_abi_version(void) { return WSOVOD_B200_ABI_VERSION; }

@@ -21,6 +21,13 @@ constexpr int kMaxSmemOptin = 232448;    // 227 KB dynamic shared memory per CTA
 
 extern std::atomic<uint64_t> g_launches; // kernels launched by this library (bench `gpu_launches`)
 
+// process-wide tuning / test switches (wsovod_b200_tune): never change results, only which kernel runs
+enum { TUNE_POOL_PATH = 0,    // 0 = library's choice, 1 = scan kernels, 2 = block-max planes wherever they apply
+       TUNE_POOL_GROUP = 1,   // 1 = deal a pass's bins into bank-conflict-free quarter-warps (default), 0 = row-major lanes
+       TUNE_COUNT = 16 };
+extern std::atomic<int> g_tune[TUNE_COUNT];
+inline int tune(int key) { return g_tune[key].load(std::memory_order_relaxed); }
+
 inline int after_launch() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

@@ -775,12 +775,12 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
 // Which values-only 7x7 kernel?  The block-max path pays ~10 plane rebuilds per (image, channel group),
 // so it needs enough proposals per image to win: on a B200 the two cross at 1000-1200 proposals per
 // image for every map / batch shape tried (tools/kbench_pool_sweep.py: 8 x 4000 proposals 1.45 vs 2.51 ms,
-// 1 x 2000 on a 60x80 map 0.135 vs 0.166 ms, 8 x 500 0.63 vs 0.40 ms).  Test / bench hook: WSOVOD_B200_POOL_SCAN=1 forces the scan kernels, =0 the block-max
-// path wherever it applies (read per call, no state kept).
+// 1 x 2000 on a 60x80 map 0.135 vs 0.166 ms, 8 x 500 0.63 vs 0.40 ms).  Test / bench hook:
+// wsovod_b200_tune(WSOVOD_B200_TUNE_POOL_PATH, 1) forces the scan kernels, 2 the block-max path wherever it applies.
 static bool pool_use_blockmax(int64_t N, int64_t R) {
-  const char* v = getenv("WSOVOD_B200_POOL_SCAN");
-  if (v && v[0] == '1') return false;
-  if (v && v[0] == '0') return true;
+  const int v = tune(TUNE_POOL_PATH);
+  if (v == 1) return false;
+  if (v == 2) return true;
   return R >= 1200 * N;
 }
 

@@ -151,41 +151,110 @@ __global__ void __launch_bounds__(512) pyr_order_kernel(const int32_t* __restric
   }
 }
 
-// one thread per (sorted position, lane slot): the descriptor of the bin that slot serves.  With four
-// channels per CTA a proposal takes kSlots = 64 slots, 49 bins + 15 idle ones: every 32-lane pass of the
-// main kernel then stays inside ONE proposal, which is what the pooled tensor's write path needs -- warp
-// stores that straddle two proposals (two pieces 100 KB apart, four partial 32-byte sectors) cost the
-// whole c2 kernel 1.41 ms in stores alone, proposal-aligned passes 0.88 ms
-// (tools/ubench/store_pattern.cu, "pattern" vs "V6").  The two-channel flavour (larger maps, fewer
-// bytes per pass) is not store-bound and keeps the dense 49-slot stream.
-template <int SLOTS>
-__global__ void pyr_bins_kernel(int64_t R, int H, int W, const int32_t* __restrict__ order, const uint32_t* __restrict__ pkey,
-                                const uint32_t* __restrict__ axtab, const float* __restrict__ row_scale,
-                                float row_scale_bias, uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
-  // eight threads per proposal: thread t < 7 writes lane slots 7t .. 7t+6, thread 7 the idle tail and the
-  // proposal record (one wave of threads and one chain of dependent loads instead of a thread per slot)
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gpos = i >> 3;
-  const int t = (int)(i & 7);
-  if (gpos >= R) return;
-  const int r = order[gpos];
-  const uint32_t key = pkey[r];
-  uint32_t* d = desc + gpos * SLOTS;
-  if (t == 7) {
+// Descriptors of the lane slots of every sorted position.  With four channels per CTA a proposal takes
+// kSlots = 64 slots = two 32-lane passes of the main kernel: bins 0..31 in the first, bins 32..48 in the
+// second (15 idle slots), so that every warp store stays inside ONE proposal -- warp stores that straddle
+// two proposals (two pieces 100 KB apart, four partial 32-byte sectors) cost the whole c2 kernel 1.41 ms
+// in stores alone, proposal-aligned passes 0.88 ms (tools/ubench/store_pattern.cu, "pattern" vs "V6").
+// The two-channel flavour (larger maps, fewer bytes per pass) is not store-bound and keeps the dense
+// 49-slot stream.
+//
+// WHICH lane of a pass serves which of the pass's bins is free: the set of addresses a warp store covers
+// does not depend on it.  The hot loop's LDS.128 are issued per quarter-warp (8 lanes, 128 bytes), and a
+// quarter is conflict-free when its 8 cells fall into 8 different 16-byte bank groups (cell index mod 8).
+// Consecutive bins of a proposal step by a near-constant number of cells, so row-major lanes collide
+// whenever that step is even (simulated on c2: 1.73 wavefronts per ideal wavefront, ncu: 1.66).  GROUP
+// therefore deals the bins of a pass into quarters by first fit: a bin goes to the quarter where the
+// fewest of its (up to four) first block loads meet a bank group some lane of the quarter already uses
+// (ties: the fuller quarter).  tools/bank_sim.py replays it: 1.70 -> 1.44 wavefronts per ideal wavefront;
+// ncu on c2: 72.8 M -> 40.3 M conflict wavefronts of the main kernel.
+template <int SLOTS, bool GROUP>
+__global__ void __launch_bounds__(256) pyr_bins_kernel(int64_t R, int H, int W, const int32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ pkey, const uint32_t* __restrict__ axtab,
+                                                       const float* __restrict__ row_scale, float row_scale_bias,
+                                                       uint2* __restrict__ pinfo, uint32_t* __restrict__ desc) {
+  if constexpr (!GROUP) {
+    // eight threads per proposal: thread t < 7 writes lane slots 7t .. 7t+6, thread 7 the idle tail and the
+    // proposal record (one wave of threads and one chain of dependent loads instead of a thread per slot)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gpos = i >> 3;
+    const int t = (int)(i & 7);
+    if (gpos >= R) return;
+    const int r = order[gpos];
+    const uint32_t key = pkey[r];
+    uint32_t* d = desc + gpos * SLOTS;
+    if (t == 7) {
 #pragma unroll
-    for (int q = 49; q < SLOTS; ++q) d[q] = kDescIdle;
-    const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
-    pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
-    return;
-  }
-  const bool fallback = key_phase(key) == PH_FALLBACK;
-  const uint32_t* ax = axtab + (int64_t)r * 14;
+      for (int q = 49; q < SLOTS; ++q) d[q] = kDescIdle;
+      const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
+      pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
+      return;
+    }
+    const bool fallback = key_phase(key) == PH_FALLBACK;
+    const uint32_t* ax = axtab + (int64_t)r * 14;
 #pragma unroll
-  for (int u = 0; u < 7; ++u) {
-    const int q = t * 7 + u;
-    const int bin = slot_bin(key, q);
-    const int ph = bin / 7, pw = bin - ph * 7;
-    d[q] = fallback ? 0u : combine_desc(__ldg(ax + ph), __ldg(ax + 7 + pw), bin, H, W);
+    for (int u = 0; u < 7; ++u) {
+      const int q = t * 7 + u;
+      const int bin = slot_bin(key, q);
+      const int ph = bin / 7, pw = bin - ph * 7;
+      d[q] = fallback ? 0u : combine_desc(__ldg(ax + ph), __ldg(ax + 7 + pw), bin, H, W);
+    }
+  } else {
+    static_assert(!GROUP || SLOTS == kSlots, "grouping needs the proposal-aligned 64-slot stream");
+    // two threads per proposal: thread 0 the first pass (bins 0..31, four quarters), thread 1 the second
+    // (bins 32..48, three quarters) and the proposal record.  occ[quarter] = bank groups taken in that quarter,
+    // one byte per block load (0,0), (0,1), (1,0), (1,1); a bin's conflicts with a quarter = popc(occ & mask).
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gpos = i >> 1;
+    const int half = (int)(i & 1);
+    if (gpos >= R) return;
+    const int r = order[gpos];
+    const uint32_t key = pkey[r];
+    uint32_t* d = desc + gpos * SLOTS + half * 32;
+    if (half) {
+      const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;   // roi_heads.py:733-739
+      pinfo[gpos] = make_uint2((uint32_t)r | (((key >> 4) & 3u) << 26) | (((key >> 6) & 3u) << 28), __float_as_uint(sc));
+    }
+    const int b_lo = half ? 32 : 0, b_hi = half ? 49 : 32;
+    const int phase = key_phase(key);
+    if (phase == PH_FALLBACK) {          // lane slot = output bin (the fallback scan recomputes its edges)
+      for (int q = 0; q < 32; ++q) d[q] = b_lo + q < 49 ? 0u : kDescIdle;
+      return;
+    }
+    const uint32_t* ax = axtab + (int64_t)r * 14;
+    const uint32_t kh = (uint32_t)phase_kh(phase), kw = (uint32_t)phase_kw(phase);
+    const uint32_t WP = (uint32_t)(W + kPad);
+    uint32_t occ0 = 0, occ1 = 0, occ2 = 0, occ3 = 0;
+    uint32_t fill = half ? 0x8000u : 0u;   // four nibbles: lanes taken in each quarter (the second pass has three)
+    uint32_t written = 0;                  // lane slots of this pass that received a bin
+    int ph = b_lo / 7, pw = b_lo - ph * 7;
+    uint32_t re = __ldg(ax + ph);
+    for (int bin = b_lo; bin < b_hi; ++bin) {
+      const uint32_t dd = combine_desc(re, __ldg(ax + 7 + pw), bin, H, W);
+      const uint32_t c0 = dd & 0xffffu, lh = (dd >> 16) & 15u, lw = (dd >> 20) & 15u;
+      const uint32_t ro = min(kh, lh) * WP, co = min(kw, lw);
+      uint32_t m = 1u << (c0 & 7u);
+      if (lw) m |= 0x100u << ((c0 + co) & 7u);
+      if (lh) m |= 0x10000u << ((c0 + ro) & 7u);
+      if (lw && lh) m |= 0x1000000u << ((c0 + ro + co) & 7u);
+      // first fit: fewest occupied bank groups, ties to the fuller quarter (full quarters are out)
+      int best_q = 0, best_key = 1 << 30;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t o = q == 0 ? occ0 : q == 1 ? occ1 : q == 2 ? occ2 : occ3;
+        const int f = (int)((fill >> (4 * q)) & 15u);
+        const int k = f >= 8 ? (1 << 29) : (__popc(o & m) << 4) + (8 - f);
+        if (k < best_key) { best_key = k; best_q = q; }
+      }
+      const int slot = best_q * 8 + (int)((fill >> (4 * best_q)) & 15u);
+      d[slot] = dd;
+      written |= 1u << slot;
+      fill += 1u << (4 * best_q);
+      occ0 |= best_q == 0 ? m : 0u; occ1 |= best_q == 1 ? m : 0u; occ2 |= best_q == 2 ? m : 0u; occ3 |= best_q == 3 ? m : 0u;
+      if (++pw == 7) { pw = 0; ++ph; re = __ldg(ax + (ph < 7 ? ph : 6)); }
+    }
+    for (int q = 0; q < 32; ++q)
+      if (!((written >> q) & 1u)) d[q] = kDescIdle;
   }
 }
 
@@ -545,13 +614,15 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   const unsigned parts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(R, 2048)));
   pyr_order_kernel<<<dim3((unsigned)N, parts), 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.cursor, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
-  const int slots = cb == 4 ? kSlots : 49;
-  if (cb == 4)
-    pyr_bins_kernel<kSlots><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
-                                                                               row_scale_bias, w.pinfo, w.desc);
+  if (cb == 4 && tune(TUNE_POOL_GROUP))
+    pyr_bins_kernel<kSlots, true><<<(unsigned)ceil_div(R * 2, 128), 128, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
+                                                                                   row_scale_bias, w.pinfo, w.desc);
+  else if (cb == 4)
+    pyr_bins_kernel<kSlots, false><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
+                                                                                      row_scale_bias, w.pinfo, w.desc);
   else
-    pyr_bins_kernel<49><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
-                                                                           row_scale_bias, w.pinfo, w.desc);
+    pyr_bins_kernel<49, false><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
+                                                                                  row_scale_bias, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
   p.input = input; p.rois = rois; p.scale = scale;
