@@ -116,8 +116,10 @@ int wsovod_b200_align_fwd(const float* x, const float* classifier, int64_t M, in
                           float* logits, float* probs,
                           void* workspace, size_t workspace_bytes, void* stream);
 size_t wsovod_b200_align_bwd_workspace(int64_t M, int64_t D, int64_t K);
-/* backward of align_fwd w.r.t. x (grad_x [M,D]) and optionally the classifier (grad_classifier [K,D],
- * may be NULL -- a buffer in every shipped config) given grad_logits [M,K+bg]. fp32. */
+/* backward of align_fwd given grad_logits [M,K+bg], fp32: w.r.t. x (grad_x [M,D], may be NULL) and w.r.t. the
+ * classifier (grad_classifier [K,D], may be NULL: the text embeddings are a buffer in every shipped config and a
+ * Parameter only with weight_path "rand", open_vocabulary_classifier.py:62-65); includes the Jacobian of the
+ * weight normalisation when norm_weight == 1.  Deterministic (fixed-order split-M sums). */
 int wsovod_b200_align_bwd(const float* grad_logits, const float* x, const float* classifier,
                           int64_t M, int64_t D, int64_t K, float temperature, int norm_weight,
                           int append_background, float* grad_x, float* grad_classifier,

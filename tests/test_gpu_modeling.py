@@ -165,3 +165,67 @@ def test_training_slice_matches_pytorch():
     assert abs(lm1 - lm2) <= 1e-5 * abs(lm2) + 1e-7
     assert abs(lr1 - lr2) <= 1e-4 * abs(lr2) + 1e-6
     torch.testing.assert_close(g1, g2, rtol=2e-3, atol=2e-6)
+
+
+def test_classifier_state_dict_layout_and_rand_gradient():
+    """class_weight keeps the reference's (D, K) layout (open_vocabulary_classifier.py:47-65: Parameter for
+    "rand"), a reference-shaped state_dict loads, and the "rand" Parameter receives the gradient torch.mm gives"""
+    K, D, Fdim = 12, 32, 20
+    torch.manual_seed(3)
+    m = OpenVocabularyClassifier(Fdim, num_classes=K, weight_path="rand", weight_dim=D, precision=ops.ALIGN_FP32).to(DEV)
+    assert tuple(m.class_weight.shape) == (D, K) and isinstance(m.class_weight, torch.nn.Parameter)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["class_weight"] = F.normalize(torch.randn(D, K, device=DEV), p=2, dim=0)
+    m.load_state_dict(sd)
+    x = torch.randn(50, Fdim, device=DEV)
+    logits = m(x, None, append_background=True)
+    go = torch.randn_like(logits)
+    logits.backward(go)
+    got = m.class_weight.grad.clone()
+    xp = m.projection(x).detach()
+    wr = m.class_weight.detach().clone().requires_grad_(True)
+    ref = torch.mm(m.norm_temperature * F.normalize(xp, p=2, dim=1), torch.cat([wr, wr.new_zeros(D, 1)], 1))  # :91-102
+    torch.testing.assert_close(logits.detach(), ref.detach(), rtol=0, atol=5e-5)
+    ref.backward(go)
+    torch.testing.assert_close(got, wr.grad, rtol=1e-4, atol=1e-5)
+    # buffer form: eval-time classifier passed in, stored weights untouched
+    m.eval()
+    with torch.no_grad():
+        a = m(x, None, append_background=False)
+        b = m(x, None, append_background=False)       # cached (K, D) copy
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("R,batch,frac", [(5000, 4096, 1.0), (600, 512, 0.25), (300, 512, 0.25), (300, 4096, 1.0)])
+def test_label_proposals_subsampling_matches_reference_rng(R, batch, frac):
+    """_sample_proposals_wsl -> detectron2 subsample_labels (roi_heads.py:1597-1610): same labels AND same torch
+    RNG stream as the reference's two randperm draws per image, for R above / below the budget and for
+    positive_fraction < 1 (an image below the budget can still hold more positives than int(B * frac))"""
+    from oracle.d2_shim import subsample_labels
+    g = synth.gen(R + batch)
+    K = 20
+    shapes = [(480, 640), (480, 640)]
+    boxes = [synth.proposals(R, 480, 640, g), synth.proposals(R // 2, 480, 640, g)]
+    props = _proposals(boxes, shapes)
+    gts = [torch.tensor([1, 5, 9]), torch.tensor([2])]
+    goff = torch.tensor([0, 3, 4], device=DEV)
+    off = torch.tensor([0, R, R + R // 2], device=DEV)
+    seed_rows = [torch.tensor([10, 20, 30]), torch.tensor([5])]
+    seeds = dict(seed_boxes=torch.cat([b[r] for b, r in zip(boxes, seed_rows)]).to(DEV), seed_classes=torch.cat(gts).to(DEV),
+                 seed_scores=torch.rand(4, generator=g).to(DEV), seed_weights=torch.rand(4, generator=g).to(DEV),
+                 seed_offsets=goff, seed_count=torch.tensor([3, 1], device=DEV))
+    torch.manual_seed(77)
+    lab, a = label_proposals_wsl(props, seeds, K, 0.5, batch_size_per_image=batch, positive_fraction=frac)
+    after = torch.cuda.get_rng_state(0).clone()
+    torch.manual_seed(77)
+    for n, (lo, hi) in enumerate(((0, R), (R, R + R // 2))):
+        cls = a["gt_classes"][lo:hi]
+        fg, bg = subsample_labels(cls, batch, frac, K)
+        exp = torch.full_like(cls, -1)
+        idx = torch.cat([fg, bg])
+        exp[idx] = cls[idx]
+        assert torch.equal(lab[n].gt_classes, exp)
+        assert int((exp != -1).sum()) <= batch
+    assert torch.equal(torch.cuda.get_rng_state(0), after)
+    if frac < 1.0:
+        assert int(((lab[0].gt_classes != -1) & (lab[0].gt_classes != K)).sum()) <= int(batch * frac)

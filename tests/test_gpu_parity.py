@@ -208,6 +208,39 @@ def test_align_backward():
     torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("M,D,K,mode,bg", [(200, 96, 20, 1, True), (5024, 768, 80, 1, True), (333, 100, 130, 2, False),
+                                           (64, 64, 5, 0, True), (1000, 512, 1203, 1, True)])
+def test_align_backward_classifier(M, D, K, mode, bg):
+    """gradient w.r.t. the classifier (the "rand" Parameter of open_vocabulary_classifier.py:62-65) and w.r.t. x
+    against autograd through the reference's own expression (:85-104), all three norm modes"""
+    g = synth.gen(M + K)
+    x = synth.region_embeddings(M, D, g).add_(0.01)
+    x[3] = 0
+    t = synth.text_embeddings(K, D, g)
+    if mode == 2:
+        t = torch.nn.functional.normalize(t, p=2, dim=1)
+    xg, tg = x.to(DEV).requires_grad_(True), t.to(DEV).requires_grad_(True)
+    lg, _ = ops.align(xg, tg, 50.0, mode, bg, None, ops.ALIGN_FP32, True, False)
+    go = torch.randn(lg.shape, generator=g)
+    lg.backward(go.to(DEV))
+    xr, tr = x.double().requires_grad_(True), t.double().requires_grad_(True)
+    w = tr.permute(1, 0)
+    if mode == 1:
+        w = torch.nn.functional.normalize(w, p=2, dim=0)
+    xn = 50.0 * torch.nn.functional.normalize(xr, p=2, dim=1) if mode else xr
+    if bg:
+        w = torch.cat([w, w.new_zeros(D, 1)], 1)
+    torch.mm(xn, w).backward(go.double())
+    sw, sx = tr.grad.abs().max().item(), xr.grad.abs().max().item()
+    assert (tg.grad.cpu().double() - tr.grad).abs().max().item() <= 2e-5 * sw
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() <= 1e-4 * sx
+    # classifier-only request (x detached): the x half is skipped
+    tg2 = t.to(DEV).requires_grad_(True)
+    lg2, _ = ops.align(x.to(DEV), tg2, 50.0, mode, bg, None, ops.ALIGN_FP32, True, False)
+    lg2.backward(go.to(DEV))
+    assert torch.equal(tg2.grad, tg.grad)        # deterministic: fixed-order split-M sums
+
+
 def test_mil_golden_and_oracle(golden):
     for name, c in golden("mil").items():
         off = torch.tensor(_offs(c["sizes"]), dtype=torch.int64, device=DEV)

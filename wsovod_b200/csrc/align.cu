@@ -134,6 +134,98 @@ __global__ void align_bwd_rows_kernel(const float* __restrict__ x, const float* 
   for (int d = lane; d < D; d += 32) dx[r * D + d] = s * (gr[d] - xr[d] * proj);
 }
 
+// backward w.r.t. the classifier (the "rand" weights of open_vocabulary_classifier.py:62-65 are a Parameter):
+//   dW^[k, d] = sum_m g[m, k] * s_m * x[m, d],  s_m = T / max(||x_m||, eps)  (1 without normalisation)
+// (1) per-row scale, (2) split-M partial products straight from the row-major operands (a tile of 16 rows of g
+// and of x is already reduction-major for this product), (3) fixed-order sum of the partials and, for
+// norm_weight == 1, the Jacobian of w^ = w / max(||w||, eps):  dW = (dW^ - w^ <w^, dW^>) / max(||w||, eps).
+__global__ void align_rowscale_kernel(const float* __restrict__ x, int64_t M, int D, float temperature, int norm,
+                                      float* __restrict__ rowscale) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= M) return;
+  float ss = 0.f;
+  if (norm)
+    for (int d = lane; d < D; d += 32) { const float v = x[r * D + d]; ss += v * v; }
+  ss = warp_sum(ss);
+  if (lane == 0) rowscale[r] = norm ? temperature / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+}
+
+constexpr int WM = 16;   // rows of g / x per shared-memory step
+__global__ void __launch_bounds__(256) align_bwd_w_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x,
+                                                          const float* __restrict__ rowscale, int64_t M, int K, int D,
+                                                          int64_t rows_per_split, float* __restrict__ part) {
+  __shared__ float Gs[WM][64 + 4];
+  __shared__ float Xs[WM][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int d0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int64_t m_lo = (int64_t)blockIdx.z * rows_per_split, m_hi = min(M, m_lo + rows_per_split);
+  const int lrow = tid >> 4, lcol = (tid & 15) * 4;     // 16 rows x 64 columns, four consecutive columns per thread
+  float acc[4][4] = {};
+  for (int64_t m0 = m_lo; m0 < m_hi; m0 += WM) {
+    const int64_t m = m0 + lrow;
+    const bool in = m < m_hi;
+    const float sc = in ? __ldg(rowscale + m) : 0.f;
+    float gv[4], xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gv[i] = (in && k0 + lcol + i < K) ? __ldg(g + m * ldg + k0 + lcol + i) : 0.f;
+      xv[i] = (in && d0 + lcol + i < D) ? __ldg(x + m * D + d0 + lcol + i) * sc : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { Gs[lrow][lcol + i] = gv[i]; Xs[lrow][lcol + i] = xv[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < WM; ++mm) {
+      const float4 av = *reinterpret_cast<const float4*>(&Gs[mm][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Xs[mm][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+  float* out = part + (int64_t)blockIdx.z * K * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + tx * 4 + j;
+      if (d < D) out[(int64_t)k * D + d] = acc[i][j];
+    }
+  }
+}
+
+__global__ void align_bwd_w_finish_kernel(const float* __restrict__ part, int S, const float* __restrict__ w, int K, int D,
+                                          int norm, float* __restrict__ grad_w) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  float ss = 0.f, dot = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float a = 0.f;
+    for (int z = 0; z < S; ++z) a += part[((int64_t)z * K + k) * D + d];   // fixed order: deterministic
+    grad_w[(int64_t)k * D + d] = a;
+    const float v = w[(int64_t)k * D + d];
+    ss += v * v;
+    dot += v * a;
+  }
+  if (norm != 1) return;
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float nrm = sqrtf(ss), den = fmaxf(nrm, 1e-12f);
+  const float proj = nrm > 1e-12f ? dot / (den * den) : 0.f;     // <w^, dW^> / den
+  __syncwarp();
+  for (int d = lane; d < D; d += 32) {
+    const float a = grad_w[(int64_t)k * D + d];
+    grad_w[(int64_t)k * D + d] = (a - w[(int64_t)k * D + d] * proj) / den;
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out) {
   // out[c, r] = in[r, c]   (tiny: the K x D text matrix)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,6 +243,11 @@ AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward
   w.what = take(sizeof(float) * (size_t)(w.Kp * w.Dp));            // normalised text matrix
   w.wt = take(backward ? sizeof(float) * (size_t)(K * D) : 0);     // its transpose (backward)
   w.dy = take(backward ? sizeof(float) * (size_t)(M * D) : 0);     // backward scratch
+  // classifier gradient: per-row scales and split-M partial products
+  const int64_t tiles = std::max<int64_t>(1, ceil_div(D, 64) * ceil_div(K, 64));
+  w.wsplit = backward ? std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, ceil_div(M, 64)), ceil_div(2 * kNumSMs, tiles))) : 0;
+  w.rowscale = take(backward ? sizeof(float) * (size_t)M : 0);
+  w.wpart = take(backward ? sizeof(float) * (size_t)(w.wsplit * K * D) : 0);
   w.rowstat = take(precision == WSOVOD_B200_ALIGN_TF32 && K + 1 > 256 ? sizeof(float) * 2 * (size_t)M : 0);
   w.bytes = o;
   return w;
@@ -215,9 +312,11 @@ WSOVOD_API int wsovod_b200_align_bwd(const float* grad_logits, const float* x, c
                                      float* grad_classifier, void* workspace, size_t workspace_bytes,
                                      void* stream) {
   if (M < 0 || D < 0 || K < 0) return WSOVOD_B200_EINVAL;
-  if (grad_classifier) return WSOVOD_B200_EUNSUPPORTED;   // text embeddings are a buffer in every shipped config
-  if (M == 0 || D == 0) return 0;
-  if (!grad_logits || !x || !grad_x || (K > 0 && !classifier)) return WSOVOD_B200_EINVAL;
+  if (M == 0 || D == 0) {
+    if (grad_classifier && K > 0 && D > 0) return (int)cudaMemsetAsync(grad_classifier, 0, sizeof(float) * (size_t)(K * D), (cudaStream_t)stream);
+    return 0;
+  }
+  if (!grad_logits || !x || (!grad_x && !grad_classifier) || (K > 0 && !classifier)) return WSOVOD_B200_EINVAL;
   const AlignWs w = align_plan(M, D, K, WSOVOD_B200_ALIGN_FP32, true);
   if (!workspace || workspace_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -227,7 +326,21 @@ WSOVOD_API int wsovod_b200_align_bwd(const float* grad_logits, const float* x, c
   float* dy = (float*)(ws + w.dy);
   const int64_t KO = K + (append_background ? 1 : 0);
   int rc;
-  if (K == 0) return (int)cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)(M * D), st);
+  if (K == 0) return grad_x ? (int)cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)(M * D), st) : 0;
+  if (grad_classifier) {
+    float* rowscale = (float*)(ws + w.rowscale);
+    float* part = (float*)(ws + w.wpart);
+    const int S = (int)w.wsplit;
+    const int64_t per = ceil_div(ceil_div(M, S), WM) * WM;
+    align_rowscale_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(x, M, (int)D, temperature, norm_weight, rowscale);
+    if ((rc = after_launch())) return rc;
+    align_bwd_w_kernel<<<dim3((unsigned)ceil_div(D, 64), (unsigned)ceil_div(K, 64), (unsigned)S), 256, 0, st>>>(
+        grad_logits, KO, x, rowscale, M, (int)K, (int)D, per, part);
+    if ((rc = after_launch())) return rc;
+    align_bwd_w_finish_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(part, S, classifier, (int)K, (int)D, norm_weight, grad_classifier);
+    if ((rc = after_launch())) return rc;
+    if (!grad_x) return 0;
+  }
   align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)D, norm_weight == 1, what);
   if ((rc = after_launch())) return rc;
   transpose_kernel<<<(unsigned)ceil_div(K * D, 256), 256, 0, st>>>(what, (int)K, (int)D, (int)D, wt);   // wt [D,K]

@@ -5,7 +5,8 @@
 namespace wsovod {
 
 struct AlignWs {
-  size_t what, wt, dy, rowstat, bytes;
+  size_t what, wt, dy, rowstat, rowscale, wpart, bytes;
+  int64_t wsplit;   // split-M factor of the classifier-gradient partial products
   int64_t Dp, Kp;   // padded reduction length / padded number of weight rows (TF32 path)
 };
 AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward);

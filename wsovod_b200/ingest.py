@@ -19,6 +19,7 @@ Mirrors, with the same numpy calls where their tie behaviour matters:
 `batch()` turns the prepared images into the (M, 5) roi tensor / offsets / objectness vector the pooling op
 takes (poolers.py:81-108).
 """
+import os
 import pickle
 
 import numpy as np
@@ -39,11 +40,46 @@ def load_proposal_file(path):
     return d
 
 
+def _index(pfile):
+    """str(image id) -> position in the file's lists, built once per loaded file (build.py:156)"""
+    if "_index" not in pfile:
+        pfile["_index"] = {str(i): k for k, i in enumerate(pfile["ids"])}
+    return pfile["_index"]
+
+
 def image_proposals(pfile, image_id):
     """build.py:153-171 -- (boxes, objectness_logits) of one image, sorted by score descending"""
-    index = {str(i): k for k, i in enumerate(pfile["ids"])}
-    k = index[str(image_id)]
+    k = _index(pfile)[str(image_id)]
     boxes, logits = pfile["boxes"][k], pfile["objectness_logits"][k]
+    inds = logits.argsort()[::-1]
+    return boxes[inds], logits[inds]
+
+
+def load_proposals_into_dataset(dataset_dicts, proposal_file):
+    """build.py:112-173 with its three forms of `proposal_file`: "" leaves the records alone (:134-135); a
+    directory only records the per-image path `<dir>/<image_id>.pkl` (:137-142; `image_proposals_from_dir`
+    reads such a file); a pickle file attaches proposal_boxes / proposal_objectness_logits /
+    proposal_bbox_mode, score-sorted, to every record (:144-171)."""
+    if proposal_file == "":
+        return dataset_dicts
+    if os.path.isdir(proposal_file):
+        for record in dataset_dicts:
+            record["proposal_file"] = proposal_file + "/" + str(record["image_id"]) + ".pkl"
+        return dataset_dicts
+    pfile = load_proposal_file(proposal_file)
+    for record in dataset_dicts:
+        boxes, logits = image_proposals(pfile, record["image_id"])
+        record["proposal_boxes"] = boxes
+        record["proposal_objectness_logits"] = logits
+        record["proposal_bbox_mode"] = pfile["bbox_mode"]
+    return dataset_dicts
+
+
+def image_proposals_from_dir(record):
+    """one image's `<image_id>.pkl` of the directory form (same dict layout, lists of length one, as
+    tools/generate_sam_proposals_cuda.py writes per image): (boxes, objectness_logits), score-sorted"""
+    pfile = load_proposal_file(record["proposal_file"])
+    boxes, logits = pfile["boxes"][0], pfile["objectness_logits"][0]
     inds = logits.argsort()[::-1]
     return boxes[inds], logits[inds]
 

@@ -289,11 +289,13 @@ def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_i
 
 @torch.no_grad()
 def label_proposals_wsl(proposals, seeds, num_classes, iou_threshold=0.5, batch_size_per_image=4096,
-                        positive_fraction=1.0):
+                        positive_fraction=1.0, skip_noop_sampling=False):
     """label_and_sample_proposals_wsl + _sample_proposals_wsl (roi_heads.py:1566-1610,1722-1825): IoU ->
-    argmax -> label -> class / gathered seed box, score, loss weight in one kernel for all images; the
-    random subsampling to BATCH_SIZE_PER_IMAGE stays in PyTorch (torch RNG, :1597-1610) and only runs
-    when an image has more candidates than the budget."""
+    argmax -> label -> class / gathered seed box, score, loss weight in one kernel for all images.  The
+    random subsampling to BATCH_SIZE_PER_IMAGE stays in PyTorch and follows detectron2's subsample_labels call
+    for call (two randperm draws per image, :1597-1602), so labels AND the torch RNG stream match the reference
+    under the same seed.  ``skip_noop_sampling`` drops the draws for images where they cannot change a label
+    (at most batch_size_per_image proposals and positive_fraction >= 1): same labels, RNG not advanced."""
     dev = seeds["seed_boxes"].device
     off, sizes = _offsets(proposals, dev)
     boxes = torch.cat([p.proposal_boxes.tensor for p in proposals], 0)
@@ -304,16 +306,18 @@ def label_proposals_wsl(proposals, seeds, num_classes, iou_threshold=0.5, batch_
     for n, p in enumerate(proposals):
         sl = slice(o[n], o[n + 1])
         cls = a["gt_classes"][sl]
-        if sizes[n] > batch_size_per_image:                    # subsample_labels semantics
+        if not (skip_noop_sampling and sizes[n] <= batch_size_per_image and positive_fraction >= 1.0):
             pos = torch.nonzero((cls != -1) & (cls != num_classes), as_tuple=True)[0]
             neg = torch.nonzero(cls == num_classes, as_tuple=True)[0]
             num_pos = min(pos.numel(), int(batch_size_per_image * positive_fraction))
             num_neg = min(neg.numel(), batch_size_per_image - num_pos)
-            keep = torch.cat([pos[torch.randperm(pos.numel(), device=dev)[:num_pos]],
-                              neg[torch.randperm(neg.numel(), device=dev)[:num_neg]]])
-            sampled = torch.full_like(cls, -1)
-            sampled[keep] = cls[keep]
-            cls = sampled
+            perm1 = torch.randperm(pos.numel(), device=dev)[:num_pos]
+            perm2 = torch.randperm(neg.numel(), device=dev)[:num_neg]
+            if num_pos < pos.numel() or num_neg < neg.numel():
+                keep = torch.cat([pos[perm1], neg[perm2]])
+                sampled = torch.full_like(cls, -1)
+                sampled[keep] = cls[keep]
+                cls = sampled
         q = Instances(p.image_size, proposal_boxes=p.proposal_boxes, gt_classes=cls,
                       gt_boxes=Boxes(a["gt_boxes"][sl]), gt_scores=a["gt_scores"][sl], gt_weights=a["gt_weights"][sl])
         if hasattr(p, "has") and p.has("objectness_logits"):

@@ -274,25 +274,28 @@ def _(x, classifier, temperature, norm_weight, append_background, bias, precisio
 
 @torch.library.custom_op("wsovod_b200::align_backward", mutates_args=())
 def _align_backward(grad_logits: torch.Tensor, x: torch.Tensor, classifier: torch.Tensor,
-                    temperature: float, norm_weight: int, append_background: bool) -> torch.Tensor:
+                    temperature: float, norm_weight: int, append_background: bool, need_x: bool,
+                    need_classifier: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     _need_cuda(grad_logits, x, classifier)
     grad_logits, x, classifier = _f32c(grad_logits), _f32c(x), _f32c(classifier)
     M, D = x.shape
     K = classifier.size(0)
     with torch.cuda.device(x.device):
-        gx = torch.empty_like(x)
+        gx = torch.empty_like(x) if need_x else x.new_empty((0,))
+        gw = torch.empty_like(classifier) if need_classifier else x.new_empty((0,))
         L = _lib.lib()
         ws = _workspace(L.wsovod_b200_align_bwd_workspace(M, D, K), x.device)
         rc = L.wsovod_b200_align_bwd(_ptr(grad_logits), _ptr(x), _ptr(classifier), M, D, K, temperature,
-                                     int(norm_weight), int(append_background), _ptr(gx), c_p(0), _ptr(ws),
-                                     ws.numel(), _stream(x))
+                                     int(norm_weight), int(append_background), _ptr(gx if need_x else None),
+                                     _ptr(gw if need_classifier else None), _ptr(ws), ws.numel(), _stream(x))
     _lib.check(rc, "align_bwd")
-    return gx
+    return gx, gw
 
 
 @_align_backward.register_fake
-def _(grad_logits, x, classifier, temperature, norm_weight, append_background):
-    return torch.empty_like(x)
+def _(grad_logits, x, classifier, temperature, norm_weight, append_background, need_x, need_classifier):
+    return (torch.empty_like(x) if need_x else x.new_empty((0,)),
+            torch.empty_like(classifier) if need_classifier else x.new_empty((0,)))
 
 
 def _align_setup(ctx, inputs, output):
@@ -310,9 +313,14 @@ def _align_bwd(ctx, g_logits, g_probs):
         g = gp if g is None else g + gp
     if g is None:
         return (None,) * 9
-    gx = torch.ops.wsovod_b200.align_backward(g, x, classifier, temperature, norm_weight, append_background)
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    gx = gw = None
+    if need_x or need_w:
+        gx, gw = torch.ops.wsovod_b200.align_backward(g, x, classifier, temperature, norm_weight, append_background,
+                                                      bool(need_x), bool(need_w))
+        gx, gw = (gx if need_x else None), (gw if need_w else None)
     gb = g.sum().reshape(1) if has_bias else None
-    return gx, None, None, None, None, gb, None, None, None
+    return gx, gw, None, None, None, gb, None, None, None
 
 
 _align.register_autograd(_align_bwd, setup_context=_align_setup)
