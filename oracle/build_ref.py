@@ -8,7 +8,13 @@
   wsovod_ref_cpu.so a 12-line pybind shim (written here, not reference code) that exposes the
                     reference's ROILoopPool_forward_cpu / _backward_cpu (ROILoopPool_cpu.cpp:125-232),
                     which the reference compiles but never dispatches to: the CPU oracle of ROIPool.
-No reference source is copied into the repository; the compiler reads the files in place.
+  py/               the reference's hot-path PYTHON files, byte for byte (wsovod/modeling/roi_heads/roi_heads.py,
+                    fast_rcnn_open_vocabulary.py, class_heads/open_vocabulary_classifier.py, poolers.py,
+                    layers/roi_loop_pool.py, layers/csc.py): /root/reference does not exist on the GPU box, so the
+                    drop-in test (tests/test_gpu_dropin.py) and `bench.py --impl reference` import the
+                    reference from here through oracle/d2_shim.py.
+No reference source is copied into the repository's history (oracle/_ref/ is git-ignored); the compiler reads the
+native files in place.
 """
 import argparse
 import os
@@ -28,6 +34,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 '''
 
 
+PY_FILES = [
+    "wsovod/modeling/roi_heads/roi_heads.py",
+    "wsovod/modeling/roi_heads/fast_rcnn_open_vocabulary.py",
+    "wsovod/modeling/class_heads/open_vocabulary_classifier.py",
+    "wsovod/modeling/poolers.py",
+    "wsovod/layers/roi_loop_pool.py",
+    "wsovod/layers/csc.py",
+]
+
+
+def ship_python(reference):
+    for rel in PY_FILES:
+        dst = os.path.join(OUT, "py", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(reference, rel), dst)
+    print("shipped", len(PY_FILES), "reference python files to", os.path.join(OUT, "py"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -38,6 +62,7 @@ def main():
         print("reference not present; nothing to build")
         return 0
     os.makedirs(OUT, exist_ok=True)
+    ship_python(a.reference)
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
     from torch.utils.cpp_extension import load
     build = os.path.join("/tmp", "wsovod_ref_build")

@@ -8,7 +8,9 @@ modules plus namespace packages for ``wsovod``/``wsovod.modeling``/``wsovod.mode
 that the detectron2-heavy ``__init__``s of the reference do not run, after which e.g.
 ``import wsovod.modeling.roi_heads.fast_rcnn_open_vocabulary`` executes the reference file itself.
 
-Used only by oracle/make_golden.py (in the build container, where /root/reference exists).
+Used by oracle/make_golden.py (in the build container, where /root/reference exists) and -- through the
+byte-for-byte copies oracle/build_ref.py ships under the git-ignored oracle/_ref/py/ -- by the drop-in test and
+`bench.py --impl reference` on the GPU box.
 """
 import importlib.util
 import math
@@ -323,6 +325,29 @@ def smooth_l1_loss(input, target, beta, reduction="none"):
     return loss
 
 
+class ROIAlign(nn.Module):
+    """detectron2.layers.ROIAlign as poolers.py:169-182 constructs it: torchvision's compiled roi_align"""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio, aligned=True):
+        super().__init__()
+        self.output_size = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+        self.spatial_scale, self.sampling_ratio, self.aligned = spatial_scale, sampling_ratio, aligned
+
+    def forward(self, input, rois):
+        assert rois.dim() == 2 and rois.size(1) == 5
+        return torchvision.ops.roi_align(input, rois.to(dtype=input.dtype), self.output_size, self.spatial_scale,
+                                         self.sampling_ratio, self.aligned)
+
+
+def default_reference_root():
+    """/root/reference in the build container; the shipped copies (oracle/_ref/py) on the GPU box; None if neither"""
+    import os
+    if os.path.isdir("/root/reference/wsovod"):
+        return "/root/reference"
+    shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "py")
+    return shipped if os.path.isdir(os.path.join(shipped, "wsovod")) else None
+
+
 def _mod(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -330,16 +355,20 @@ def _mod(name, **attrs):
     return m
 
 
-def install(reference_root="/root/reference"):
+def install(reference_root=None):
     """Register the fake modules; afterwards the reference hot-path files import verbatim."""
     if "detectron2" in sys.modules and getattr(sys.modules["detectron2"], "_wsovod_shim", False):
         return
+    if reference_root is None:
+        reference_root = default_reference_root()
+    if reference_root is None:
+        raise RuntimeError("no reference tree: neither /root/reference nor oracle/_ref/py (run oracle/build_ref.py)")
     d2 = _mod("detectron2", _wsovod_shim=True)
     d2.__path__ = []
     _mod("detectron2.config", configurable=configurable, CfgNode=CfgNode)
     _mod("detectron2.layers", ShapeSpec=ShapeSpec, cat=cat, nonzero_tuple=nonzero_tuple,
          batched_nms=batched_nms, cross_entropy=cross_entropy, Linear=nn.Linear,
-         ciou_loss=_unavailable, diou_loss=_unavailable, ROIAlign=_unavailable,
+         ciou_loss=_unavailable, diou_loss=_unavailable, ROIAlign=ROIAlign,
          ROIAlignRotated=_unavailable)
     _mod("detectron2.structures", Boxes=Boxes, Instances=Instances, pairwise_iou=pairwise_iou,
          ImageList=object, PolygonMasks=object)
@@ -385,5 +414,23 @@ def install(reference_root="/root/reference"):
     sys.modules[spec.name] = ovc
     spec.loader.exec_module(ovc)
     sys.modules["wsovod.modeling.class_heads"].OpenVocabularyClassifier = ovc.OpenVocabularyClassifier
-    # wsovod.layers (ROILoopPool) is needed by poolers.py only; give it a placeholder
-    _mod("wsovod.layers", ROILoopPool=type("ROILoopPool", (nn.Module,), {}))
+    # wsovod.layers (ROILoopPool) is needed by poolers.py only: the reference's own wrapper over its own compiled
+    # extension when oracle/_ref/wsovod_ref_C.so exists (`from wsovod import _C`, roi_loop_pool.py:6), else a
+    # placeholder class (the CPU container has no GPU to run it on anyway)
+    layers = _mod("wsovod.layers", ROILoopPool=type("ROILoopPool", (nn.Module,), {}))
+    layers.__path__ = [f"{reference_root}/wsovod/layers"]
+    try:
+        import os
+        from . import ref
+        ext = ref.cuda() if os.path.exists(f"{reference_root}/wsovod/layers/roi_loop_pool.py") else None
+        if ext is not None:
+            sys.modules["wsovod"]._C = ext
+            sys.modules["wsovod._C"] = ext
+            spec = importlib.util.spec_from_file_location("wsovod.layers.roi_loop_pool",
+                                                          f"{reference_root}/wsovod/layers/roi_loop_pool.py")
+            rlp = importlib.util.module_from_spec(spec)
+            sys.modules[spec.name] = rlp
+            spec.loader.exec_module(rlp)
+            layers.ROILoopPool = rlp.ROILoopPool
+    except Exception:  # noqa: BLE001  (no libtorch_cuda / no extension: keep the placeholder)
+        pass

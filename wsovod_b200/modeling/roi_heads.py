@@ -53,9 +53,11 @@ class ObjectMiningOutputLayers(nn.Module):
     ``class_head`` (an OpenVocabularyClassifier) is supplied -- the fused "alignment + MIL" variant of
     the commented-out line roi_heads.py:588-589."""
 
-    def __init__(self, input_size, num_classes, class_head=None):
+    def __init__(self, input_size, num_classes, class_head=None, loss_weight=None, mean_loss=True):
         super().__init__()
         self.num_classes = num_classes
+        self.loss_weight = loss_weight or {}
+        self.mean_loss = mean_loss
         self.det = nn.Linear(input_size, num_classes)
         nn.init.xavier_uniform_(self.det.weight)
         nn.init.constant_(self.det.bias, 0)
@@ -88,6 +90,18 @@ class ObjectMiningOutputLayers(nn.Module):
         else:
             off, _ = _offsets(proposals, C.device)
         return ops.mil(C, D, off)                             # (scores, clamped image-level scores)
+
+    def losses(self, predictions, proposals, gt_classes_img_oh):
+        """:392-427 -- image-level BCE of the MIL head (plain PyTorch: N x K numbers; the image-level scores come
+        out of the MIL kernel with their autograd formula): {"loss_cls_object_mining": ...}"""
+        img = self.predict_probs_img(predictions, proposals)
+        assert gt_classes_img_oh.dim() == 2 and img.dim() == 2
+        if self.mean_loss:
+            loss = nn.functional.binary_cross_entropy(img.float(), gt_classes_img_oh.float(), reduction="mean")
+        else:
+            loss = nn.functional.binary_cross_entropy(img.float(), gt_classes_img_oh.float(),
+                                                      reduction="sum") / (1.0 * gt_classes_img_oh.size(0))
+        return {"loss_cls_object_mining": loss * self.loss_weight.get("loss_cls_object_mining", 1.0)}
 
     def predict_probs_img(self, predictions, proposals):
         """:604-618 -- clamp(sum over the image's proposals of scores, 1e-6, 1-1e-6)"""
