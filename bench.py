@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- proposals/s of WSOVOD's region-scoring hot path on B200 (one process per GPU).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5                 # our arm
-    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # N ranks, weak scaling
-    python bench.py --impl reference --steps 3 --warmup 1          # the reference's CPU path (host cores)
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our arm: headline c2 + one line per other config
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # N ranks, weak scaling (DDP in the training configs)
+    python bench.py --config c3                                    # make another BASELINE config the headline
+    python bench.py --impl reference --steps 3 --warmup 1          # the reference's own CPU path (host cores)
 
-Workload (BASELINE.json configs[1], "c2"): COCO WSOVOD_WSR_18_DC5 inference, 8 images / GPU of
-688x1024 (res5 map 512x86x128, stride 8), 4000 proposals / image, 80 concepts + background, D=768,
-T=50, score_thresh 1e-5, nms 0.3, 100 detections / image.  Synthetic, seeded (wsovod_b200/synth.py).
+Headline workload (BASELINE.json configs[1], "c2"): COCO WSOVOD_WSR_18_DC5 inference, 8 images / GPU of 688x1024
+(res5 map 512x86x128, stride 8), 4000 proposals / image, 80 concepts + background, D=768, T=50, score_thresh 1e-5,
+nms 0.3, 100 detections / image.  Synthetic, seeded (wsovod_b200/synth.py).
 
-One step = ROI pool (+objectness scale) -> [box-head FCs: out of scope, embeddings are synthetic]
--> region x concept alignment + softmax (tcgen05 TF32) -> per-class NMS + top-100  for the GPU's 8
-images.  `value`: inputs resident in HBM.  `e2e`: the same step through the C-ABI host entry point
-(wsovod_b200_infer_host) from pinned HOST buffers, H2D/D2H inside the timed region.
+One inference step (c1, c2, c4) = ROI pool (+objectness scale) -> [box-head FCs: out of scope, embeddings are
+synthetic] -> region x concept alignment + softmax (tcgen05 TF32) -> per-class NMS + top-100.
+One training step (c3, c5) = WSOVODROIHeads.forward in training mode + backward (wsovod_b200/steps.py): pool -> MIL ->
+seeds -> assignment -> alignment -> weighted losses, forward and backward, under DistributedDataParallel when N > 1 with
+a stand-in parameter of the FC layers' size so the reference's 0.5 / 1.7 GB gradient all-reduce is in the step.
+`value`: inputs resident in HBM.  `e2e`: the c2 step through the C-ABI host entry point (wsovod_b200_infer_host)
+from pinned HOST buffers, H2D/D2H inside the timed region.  `configs`: the other BASELINE configs, same run.
 """
 import argparse
 import ctypes
@@ -30,14 +34,31 @@ sys.path.insert(0, ROOT)
 
 METRIC = "proposals/sec of region-scoring path"
 UNIT = "proposals/s"
+WORKLOADS = {
+    "c1": "c1: VOC WSR_18_DC5 inference slice, 1 img x 2000 proposals, K=20, D=768",
+    "c2": "c2: COCO WSR_18_DC5 inference slice, 8 img x 4000 proposals/GPU, K=80, D=768",
+    "c3": "c3: COCO WSR_50_DC5 training step (MIL + refinement + alignment loss, fwd+bwd), 1 img x 5024 proposals/GPU, C=2048, K=80",
+    "c4": "c4: open-vocabulary eval, 8 img x 4000 proposals/GPU, K=1203 LVIS-scale concepts, D=768",
+    "c5": "c5: mixed VOC+COCO training step + inference pass (refinement + NMS), 1 img x 5000 proposals/GPU, C=512, K=20|80",
+}
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+        m = json.load(open(p))
+        d = dict(hbm_gbs=m["hbm_gbs"], bf16_tflops=m["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    # TF32 tensor peak: MEASURED_PEAKS.json has none; tools/measure_tf32_peak.py measures torch.matmul (cuBLAS TF32) the
+    # same way the driver measures BF16 and commits the result under profiles/
+    t = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.exists(t):
+        d["tf32_tflops"] = json.load(open(t))["tf32_tflops"]
+        d["tf32_source"] = "measured (profiles/tf32_peak.json, cuBLAS TF32 8192^3)"
+    else:
+        d["tf32_tflops"] = 1100.0
+        d["tf32_source"] = "nominal dense TF32 (B200_PROFILING.md)"
+    return d
 
 
 def load_traffic(with_arg):
@@ -104,46 +125,216 @@ class ClockSampler:
                     samples=len(sm), samples_in_timed_region=len(inside), reasons=sorted(reasons))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation of the path (the arm the driver times beside ours; also `cpu_baseline`)
+# ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(w, budget_s=20.0):
-    """The reference's CPU path (oracle/cpu_path.py) on a bounded sample of the same workload."""
-    from oracle import cpu_path
+    """the reference's own code on a bounded sample of the workload: oracle/ref_path.py drives the reference's Python
+    (shipped byte for byte under oracle/_ref/py) when present ("reference"), else the port oracle/cpu_path.py"""
+    from oracle import ref_path
+    impl, kind = ref_path.get()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     # size the sample from a tiny probe so that one pass costs ~10-30 s at most
-    dt, n, *_ = cpu_path.run_slice(w, images=1, proposals=100)
+    dt, n, *_ = impl.run_slice(w, images=1, proposals=100)
     per_prop = dt / n
     props = int(max(200, min(w["R"], budget_s / max(per_prop, 1e-9))))
     images = 1
     if props >= w["R"]:
         props = w["R"]
         images = int(max(1, min(w["N"], budget_s / max(per_prop * props, 1e-9))))
-    return cpu_path, cores, images, props
+    return impl, kind, cores, images, props
 
 
 def run_reference(args, w, rank):
     if rank != 0:
         return
     # the whole --steps K run has to end within a few minutes: ~150 s of CPU work in total
-    cpu_path, cores, images, props = cpu_reference_leg(w, budget_s=max(2.0, min(20.0, 150.0 / max(args.steps, 1))))
+    impl, kind, cores, images, props = cpu_reference_leg(w, budget_s=max(2.0, min(20.0, 150.0 / max(args.steps, 1))))
     for _ in range(args.warmup):
-        cpu_path.run_slice(w, images=1, proposals=min(props, 200))
+        impl.run_slice(w, images=1, proposals=min(props, 200))
     t, n = 0.0, 0
     for _ in range(args.steps):
-        dt, k, *_ = cpu_path.run_slice(w, images=images, proposals=props)
+        dt, k, *_ = impl.run_slice(w, images=images, proposals=props)
         t += dt
         n += k
     v = n / t
-    sample = f"{images} image(s) x {props} proposals of c2 per step (pool+scale, align+softmax, NMS+top100)"
+    sample = (f"{images} image(s) x {props} proposals of {args.config} per step; " + impl.DESCRIPTION)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: COCO WSR_18_DC5 inference slice, 8 img x 4000 proposals/GPU, K=80, D=768",
-                   "device": "cpu"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS[args.config]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def ktime(fn, iters):
+    """device time of one call of `fn`: `iters` calls captured in a CUDA graph and replayed, so that the
+    sub-100-us ops are not timed at the pace of their Python wrappers; plain loop if capture fails"""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b) / iters
+            best = t if best is None else min(best, t)
+        del g
+        return best
+    except Exception:  # noqa: BLE001
+        torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def timed_steps(step, steps, warmup, shard, dev):
+    """W untimed steps, then exactly K steps between barrier + synchronize, CUDA events, max over ranks -> ms total"""
+    out = None
+    for _ in range(warmup):
+        out = step()
+    torch.cuda.synchronize()
+    shard.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    shard.barrier()
+    return shard.max_over_ranks(e0.elapsed_time(e1), dev), out, (t0, t1)
+
+
+def hbm(entry, peaks):
+    entry["GBps"] = entry["algorithmic_bytes"] / (entry["ms"] * 1e-3) / 1e9
+    entry["frac_hbm"] = entry["GBps"] / peaks["hbm_gbs"]
+    return entry
+
+
+def inference_kernels(st, w, peaks, it, with_arg):
+    """per-kernel device times of the inference slice (CUDA-graph replays), SURVEY 8d bytes"""
+    from wsovod_b200 import ops
+    N, C, R, K, D = (w[k] for k in "NCRKD")
+    M = N * R
+    probs = st.align()
+    out_bytes = M * C * 49 * 4
+    fixed = st.feat.numel() * 4 + M * 20
+    k = {}
+    k["roi_pool"] = hbm({"ms": ktime(lambda: st.pool(with_arg), it), "algorithmic_bytes": out_bytes * (2 if with_arg else 1) + fixed}, peaks)
+    k["roi_pool+argmax"] = hbm({"ms": ktime(lambda: st.pool(True), it), "algorithmic_bytes": 2 * out_bytes + fixed}, peaks)
+    k["align_tf32+softmax"] = hbm({"ms": ktime(st.align, it), "algorithmic_bytes": M * D * 4 + M * (K + 1) * 4 + K * D * 4}, peaks)
+    k["align_tf32+softmax"]["TFLOPs"] = 2.0 * M * D * (K + 1) / (k["align_tf32+softmax"]["ms"] * 1e-3) / 1e12
+    k["align_tf32+softmax"]["frac_tf32"] = k["align_tf32+softmax"]["TFLOPs"] / peaks["tf32_tflops"]
+    k["nms+top100"] = {"ms": ktime(lambda: st.detections(probs), it), "candidates": int((probs[:, :-1] > w["score_thresh"]).sum()),
+                       "algorithmic_bytes": M * (K + 1) * 4 + M * 16}
+    return k
+
+
+def extra_kernels(w2, st2, peaks, it, dev):
+    """kernels that are not in the c2 step: ROILoopPool / ROIAlign at c2, the training kernels at c3's shapes
+    (5024 proposals of one image, K = 80), the K = 1203 contraction of c4"""
+    from wsovod_b200 import ops, synth
+    k = {}
+    M2, C2 = w2["N"] * w2["R"], w2["C"]
+    out_bytes = M2 * C2 * 49 * 4
+    fixed = st2.feat.numel() * 4 + M2 * 20
+    sc = w2["spatial_scale"]
+    k["roi_loop_pool+argmax"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, st2.rois, sc, 7, st2.obj, 1.0, True), max(it // 3, 2)),
+                                     "algorithmic_bytes": 6 * out_bytes + fixed}, peaks)
+    k["roi_loop_pool"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, st2.rois, sc, 7, st2.obj, 1.0, False), max(it // 3, 2)),
+                              "algorithmic_bytes": 3 * out_bytes + fixed}, peaks)
+    k["roi_align"] = hbm({"ms": ktime(lambda: ops.roi_align(st2.feat, st2.rois, sc, 7, 0, True, st2.obj, 1.0), max(it // 3, 2)),
+                          "algorithmic_bytes": out_bytes + fixed}, peaks)
+    # training kernels: one image of 5024 proposals (c3), K = 80, D = 768
+    g = synth.gen(99)
+    M, K, D = 5024, 80, 768
+    Cl, Dl = (t.to(dev) for t in synth.mil_logits(M, K, g))
+    off = torch.tensor([0, M], dtype=torch.int64, device=dev)
+    k["mil_fwd"] = hbm({"ms": ktime(lambda: ops.mil(Cl, Dl, off), it), "algorithmic_bytes": 3 * 4 * K * M + 4 * K}, peaks)
+    s_mil, img = ops.mil(Cl, Dl, off)
+    gs, gi = torch.randn_like(s_mil), torch.randn_like(img)
+    k["mil_bwd"] = hbm({"ms": ktime(lambda: torch.ops.wsovod_b200.mil_backward(gs, gi, Cl, Dl, off), it),
+                        "algorithmic_bytes": 5 * 4 * K * M}, peaks)
+    boxes = synth.proposals(M, 800, 1216, g).to(dev)
+    gt = synth.image_labels(1, K, g, 8)[0].to(dev)
+    goff = torch.tensor([0, gt.numel()], dtype=torch.int64, device=dev)
+
+    def refine():
+        sd = ops.pgt_top1(s_mil, boxes, off, gt, goff, img)
+        return ops.refine_assign(boxes, off, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"], sd["seed_weights"], goff,
+                                 sd["seed_count"], K, 0.5)
+    a = refine()
+    k["pgt_top1+refine_assign"] = hbm({"ms": ktime(refine, it), "algorithmic_bytes": M * 57 + 28 * int(gt.numel()) + 4 * M * int(gt.numel())}, peaks)
+    logits = torch.randn(M, K + 1, device=dev) * 3
+    deltas = torch.randn(M, 4, device=dev) * 0.1
+    fwd = lambda: torch.ops.wsovod_b200.refine_losses(logits, deltas, a["gt_classes"], a["gt_weights"], boxes, a["gt_boxes"], K,  # noqa: E731
+                                                      10.0, 10.0, 5.0, 5.0, 0.0)
+    out, lse = fwd()
+    go = torch.ones(2, device=dev)
+    k["refine_loss_fwd"] = hbm({"ms": ktime(fwd, it), "algorithmic_bytes": M * (4 * (K + 1) + 8 + 4 + 16 + 16 + 16)}, peaks)
+    k["refine_loss_bwd"] = hbm({"ms": ktime(lambda: torch.ops.wsovod_b200.refine_losses_backward(
+        go, out, lse, logits, deltas, a["gt_classes"], a["gt_weights"], boxes, a["gt_boxes"], K, 10.0, 10.0, 5.0, 5.0, 0.0), it),
+        "algorithmic_bytes": M * (2 * 4 * (K + 1) + 8 + 4 + 16 + 16 + 32)}, peaks)
+    x = synth.region_embeddings(M, D, g).to(dev)
+    t = synth.text_embeddings(K, D, g).to(dev)
+    gl = torch.randn(M, K + 1, device=dev)
+    k["align_tf32_fwd_c3"] = hbm({"ms": ktime(lambda: ops.align(x, t, 50.0, 1, True, None, ops.ALIGN_TF32, True, False), it),
+                                  "algorithmic_bytes": M * D * 4 + M * (K + 1) * 4 + K * D * 4}, peaks)
+    k["align_bwd_c3"] = hbm({"ms": ktime(lambda: torch.ops.wsovod_b200.align_backward(gl, x, t, 50.0, 1, True, True, False), it),
+                             "algorithmic_bytes": 2 * M * D * 4 + M * (K + 1) * 4 + K * D * 4}, peaks)
+    k["align_bwd_c3"]["TFLOPs"] = 2.0 * M * D * K / (k["align_bwd_c3"]["ms"] * 1e-3) / 1e12
+    # c4: K = 1203 concepts on the c2 embeddings (59 GFLOP): tensor-bound
+    K4 = 1203
+    t4 = synth.text_embeddings(K4, w2["D"], g).to(dev)
+    ms = ktime(lambda: ops.align(st2.emb, t4, 50.0, 1, True, None, ops.ALIGN_TF32, False, True), max(it // 2, 2))
+    tf = 2.0 * M2 * w2["D"] * (K4 + 1) / (ms * 1e-3) / 1e12
+    k["align_tf32_c4"] = {"ms": ms, "TFLOPs": tf, "frac_tf32": tf / peaks["tf32_tflops"], "tf32_peak": peaks["tf32_tflops"],
+                          "tf32_peak_source": peaks["tf32_source"], "flops": 2.0 * M2 * w2["D"] * (K4 + 1)}
+    return k
+
+
+def bench_config(name, args, shard, dev, rank, world, steps, warmup):
+    """value of one more BASELINE config in the same run (device-resident, same timing rules)"""
+    from wsovod_b200 import steps as S, synth
+    w = synth.workload(name, seed=1234, rank=rank)
+    st = S.make(name, w, dev, world)
+    ms_total, out, _ = timed_steps(st, steps, warmup, shard, dev)
+    res = {"workload": WORKLOADS[name], "kind": "training" if name in S.TRAIN_CONFIGS else "inference", "steps": steps,
+           "warmup": warmup, "ms_per_step": ms_total / steps, "value": world * st.proposals * steps / (ms_total * 1e-3),
+           "unit": UNIT, "proposals_per_step_per_gpu": st.proposals}
+    if name in S.TRAIN_CONFIGS:
+        res["grad_bytes"] = st.grad_bytes()
+        res["losses"] = {k: (float(v) if torch.is_tensor(v) else v) for k, v in out.items()}
+        if world > 1:
+            ms_ns, _, _ = timed_steps(lambda: st(sync=False), steps, 2, shard, dev)
+            res["ms_per_step_no_allreduce"] = ms_ns / steps
+            res["exposed_allreduce_ms"] = max(res["ms_per_step"] - ms_ns / steps, 0.0)
+            res["allreduce_busbw_GBps"] = (2.0 * (world - 1) / world * res["grad_bytes"] / 1e9
+                                           / max(res["exposed_allreduce_ms"] * 1e-3, 1e-9))
+    del st
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -152,11 +343,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2")
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--pool-argmax", type=int, default=0,
                     help="1: the pooling kernel also emits argmax (training with a trainable backbone); the "
                          "reference's frozen-backbone inference never reads it (SURVEY fact 6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", action="store_true", help="skip the other BASELINE configs and the extra per-kernel timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -167,7 +359,7 @@ def main():
         run_reference(args, w, rank)
         return
 
-    from wsovod_b200 import _lib, ops
+    from wsovod_b200 import _lib, steps as S
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl ours) needs a CUDA device: wsovod_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -187,27 +379,20 @@ def main():
         os.close(saved_fd)
     N, C, H, W, R, K, D = (w[k] for k in "NCHWRKD")
     M = N * R
-    feat, rois, obj = w["features"].to(dev), w["rois"].to(dev), w["objectness"].to(dev)
-    emb, text = w["region_emb"].to(dev), w["text_emb"].to(dev)
-    off = torch.tensor(w["offsets"], dtype=torch.int64, device=dev)
-    sizes = w["image_sizes"].to(dev)
-    boxes = rois[:, 1:].contiguous()
+    training = args.config in S.TRAIN_CONFIGS
     with_arg = bool(args.pool_argmax)
-
-    def step():
-        pooled, _ = ops.roi_pool(feat, rois, w["spatial_scale"], 7, obj, 1.0, with_arg)
-        _, probs = ops.align(emb, text, w["temperature"], 1, True, None, ops.ALIGN_TF32, False, True)
-        det = ops.detections(probs, boxes, off, sizes, R, w["score_thresh"], w["nms_thresh"], w["topk"],
-                             ops.IOU_TV_CUDA)
-        return pooled, det
+    st = S.make(args.config, w, dev, world)
+    if not training:
+        st.with_argmax = with_arg
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        out = step()
-    torch.cuda.synchronize()
+    launches0 = None
     # ---- timed region: exactly `steps` steps, device time, barrier + synchronize on both sides ------
+    for _ in range(args.warmup):
+        out = st()
+    torch.cuda.synchronize()
     shard.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
@@ -215,75 +400,92 @@ def main():
     t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        out = step()
+        out = st()
     e1.record()
     torch.cuda.synchronize()
     sampler.window(t_wall0, time.time())
     shard.barrier()
     ms_total = shard.max_over_ranks(e0.elapsed_time(e1), dev)
     launches = _lib.launch_count() - launches0
-    value = world * M * args.steps / (ms_total * 1e-3)
+    value = world * st.proposals * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel device times (CUDA events on the launching stream), same inputs ----------------
-    def ktime(fn, iters):
-        """device time of one call of `fn`: `iters` calls captured in a CUDA graph and replayed, so that the
-        sub-100-us ops are not timed at the pace of their Python wrappers; plain loop if capture fails"""
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _ in range(iters):
-                    fn()
-            g.replay()
-            torch.cuda.synchronize()
-            best = None
-            for _ in range(3):
-                a.record()
-                g.replay()
-                b.record()
-                torch.cuda.synchronize()
-                t = a.elapsed_time(b) / iters
-                best = t if best is None else min(best, t)
-            del g
-            return best
-        except Exception:  # noqa: BLE001
-            torch.cuda.synchronize()
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
-
     it = max(args.steps // 2, 3)
-    probs = ops.align(emb, text, w["temperature"], 1, True, None, ops.ALIGN_TF32, False, True)[1]
-    t_pool = ktime(lambda: ops.roi_pool(feat, rois, w["spatial_scale"], 7, obj, 1.0, with_arg), it)
-    t_pool_arg = ktime(lambda: ops.roi_pool(feat, rois, w["spatial_scale"], 7, obj, 1.0, True), it)
-    t_align = ktime(lambda: ops.align(emb, text, w["temperature"], 1, True, None, ops.ALIGN_TF32, False, True), it)
-    t_det = ktime(lambda: ops.detections(probs, boxes, off, sizes, R, w["score_thresh"], w["nms_thresh"], w["topk"],
-                                         ops.IOU_TV_CUDA), it)
-    clocks = sampler.stop() if rank == 0 else None
     peaks = load_peaks()
-    out_bytes = M * C * 49 * 4
-    pool_bytes = out_bytes * (2 if with_arg else 1) + feat.numel() * 4 + M * 20      # DESIGN.md "Kernel 1"
-    pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
-    kernels = {
-        "roi_pool": {"ms": t_pool, "algorithmic_bytes": pool_bytes, "GBps": pool_gbs, "frac_hbm": pool_gbs / peaks["hbm_gbs"]},
-        "roi_pool+argmax": {"ms": t_pool_arg, "algorithmic_bytes": 2 * out_bytes + feat.numel() * 4 + M * 20,
-                            "GBps": (2 * out_bytes + feat.numel() * 4 + M * 20) / (t_pool_arg * 1e-3) / 1e9},
-        "align_tf32+softmax": {"ms": t_align, "algorithmic_bytes": M * D * 4 + M * (K + 1) * 4 + K * D * 4,
-                               "GBps": (M * D * 4 + M * (K + 1) * 4 + K * D * 4) / (t_align * 1e-3) / 1e9,
-                               "TFLOPs": 2.0 * M * D * (K + 1) / (t_align * 1e-3) / 1e12},
-        "nms+top100": {"ms": t_det, "candidates": int((probs[:, :-1] > w["score_thresh"]).sum()),
-                       "algorithmic_bytes": M * (K + 1) * 4 + M * 16},
+    pool_st = st if not training else S.InferenceStep(w, dev)
+    kernels = inference_kernels(pool_st, w, peaks, it, with_arg)
+    if training:
+        for k in ("align_tf32+softmax", "nms+top100"):
+            kernels[k]["note"] = "inference-slice kernel at this config's shapes (not in the training step)"
+    t_pool = kernels["roi_pool"]["ms"]
+    pool_gbs = kernels["roi_pool"]["GBps"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (pool, softmax, MIL, assignment, losses, NMS) / tf32 (alignment contraction)", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config]},
+        "roofline": {"bound": "hbm", "kernel": "roi_pool7_pyr_kernel (ROI max-pool, block-max planes)", "achieved": pool_gbs,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
+                     "peak_source": peaks["source"], "traffic": load_traffic(with_arg) if args.config == "c2" else None,
+                     "share_of_step": t_pool / (ms_total / args.steps)},
+        "kernels": kernels,
+        "gpu_launches": int(launches),
     }
-    for k in ("roi_pool+argmax", "align_tf32+softmax"):
-        kernels[k]["frac_hbm"] = kernels[k]["GBps"] / peaks["hbm_gbs"]
+    info = {"global_proposals_per_step": world * st.proposals, "pool_argmax": with_arg,
+            "l2": "inputs+outputs per step exceed the 126 MB L2; no flush needed",
+            "parallelism": f"dp{world} (images sharded, " + ("DDP gradient all-reduce over NCCL)" if training else "no data-path collective)")}
+    if training:
+        info["grad_bytes"] = st.grad_bytes()
+        info["out_of_scope"] = ("box-head FCs stubbed (strided slice of the pooled tensor, width 256); a stand-in parameter of "
+                                "fc1+fc2's size receives a zero gradient at the end of backward so DDP all-reduces their bytes")
+        line["losses"] = {k: (float(v) if torch.is_tensor(v) else v) for k, v in out.items()}
+        if world > 1:
+            ms_ns, _, _ = timed_steps(lambda: st(sync=False), args.steps, 2, shard, dev)
+            line["ddp"] = {"ms_per_step_no_allreduce": ms_ns / args.steps,
+                           "exposed_allreduce_ms": max(ms_total / args.steps - ms_ns / args.steps, 0.0),
+                           "grad_bytes": st.grad_bytes()}
 
-    # ---- e2e: host buffers through the C-ABI entry point --------------------------------------------
+    # ---- e2e: host buffers through the C-ABI entry point (inference configs) --------------------------
+    if not training:
+        line["e2e"] = e2e_inference(w, st, out, dev, shard, world, args, with_arg)
+    else:
+        # training: the step's inputs (feature map, proposals, labels) from pinned host memory every step, loss read back
+        line["e2e"] = e2e_training(w, st, dev, shard, world, args)
+
+    # ---- the other BASELINE configs and the kernels outside the c2 step, same run ------------------------
+    if not args.only:
+        others = {}
+        for name in sorted(WORKLOADS):
+            if name == args.config:
+                continue
+            k_steps = max(min(args.steps, 10), 3)
+            others[name] = bench_config(name, args, shard, dev, rank, world, k_steps, 3)
+        line["configs"] = others
+        w2 = w if args.config == "c2" else synth.workload("c2", seed=1234, rank=rank)
+        st2 = st if args.config == "c2" else S.InferenceStep(w2, dev)
+        line["kernels"].update(extra_kernels(w2, st2, peaks, it, dev))
+    clocks = sampler.stop() if rank == 0 else None
+    line["clocks"] = clocks
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        impl, kind, cores, images, props = cpu_reference_leg(w, budget_s=12.0)
+        dt, n, *_ = impl.run_slice(w, images=images, proposals=props)
+        cpu_base = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                    "sample": f"{images} image(s) x {props} proposals of {args.config}, one pass; " + impl.DESCRIPTION}
+    if rank == 0:
+        line["config"].update(info)
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def e2e_inference(w, st, out, dev, shard, world, args, with_arg):
+    from wsovod_b200 import _lib
+    N, C, H, W, R, K, D = (w[k] for k in "NCHWRKD")
+    M = N * R
     L = _lib.lib()
     pin = lambda t: t.contiguous().pin_memory()  # noqa: E731
     h_feat, h_rois, h_obj = pin(w["features"]), pin(w["rois"]), pin(w["objectness"])
@@ -325,44 +527,46 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = shard.max_over_ranks(a.elapsed_time(b), dev)
     e2e_wall = time.perf_counter() - t0
-    e2e_value = world * M * e2e_steps / (e2e_ms * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in (h_feat, h_rois, h_obj, h_emb, h_text, h_sizes, h_off))
     d2h = sum(t.numel() * t.element_size() for t in (h_db, h_ds, h_dc, h_dr, h_cnt))
     # device-resident and host-buffer paths must agree on the detections
     same = bool(torch.equal(out[1]["det_scores"].cpu(), h_ds) and torch.equal(out[1]["det_rows"].cpu(), h_dr))
+    return {"value": world * M * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": 1e3 * e2e_wall / e2e_steps,
+            "h2d_GBps_per_rank": h2d / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+            "matches_device_path": same, "detections_last_step": ndet}
 
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_path, cores, images, props = cpu_reference_leg(w, budget_s=12.0)
-        dt, n, *_ = cpu_path.run_slice(w, images=images, proposals=props)
-        cpu_base = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{images} image(s) x {props} proposals of c2, one pass: torchvision CPU roi_pool + "
-                              f"objectness scale, ATen normalize/mm/softmax, torchvision CPU batched_nms + top100"}
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (pool, softmax, NMS) / tf32 (alignment contraction)", "data": "synthetic",
-            "config": {"workload": "c2: COCO WSR_18_DC5 inference slice, 8 img x 4000 proposals/GPU, K=80, D=768",
-                       "global_proposals_per_step": world * M, "pool_argmax": with_arg,
-                       "l2": "inputs+outputs per step (3.5 GB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "roofline": {"bound": "hbm", "kernel": "roi_pool7_pyr_kernel (ROI max-pool, block-max planes)", "achieved": pool_gbs,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
-                         "peak_source": peaks["source"], "traffic": load_traffic(with_arg),
-                         "share_of_step": t_pool / (ms_total / args.steps)},
-            "kernels": kernels,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": 1e3 * e2e_wall / e2e_steps,
-                    "matches_device_path": same, "detections_last_step": ndet},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        if cpu_base:
-            line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+
+def e2e_training(w, st, dev, shard, world, args):
+    """the training step with its inputs copied from pinned host memory inside the timed region and the summed loss
+    read back by the host every step"""
+    h_feat, h_rois, h_obj = (t.contiguous().pin_memory() for t in (w["features"], w["rois"], w["objectness"]))
+    d_feat = st.features["res5"]
+    d_boxes = torch.cat([p.proposal_boxes.tensor for p in st.props])
+    d_obj = torch.cat([p.objectness_logits for p in st.props])
+    h_loss = torch.empty(1).pin_memory()
+
+    def step():
+        d_feat.copy_(h_feat, non_blocking=True)
+        d_boxes.copy_(h_rois[:, 1:], non_blocking=True)
+        d_obj.copy_(h_obj, non_blocking=True)
+        off = 0
+        for p in st.props:
+            n = len(p)
+            p.proposal_boxes.tensor.copy_(d_boxes[off:off + n])
+            p.objectness_logits.copy_(d_obj[off:off + n])
+            off += n
+        out = st()
+        total = sum(v for k, v in out.items() if torch.is_tensor(v))
+        h_loss.copy_(total.reshape(1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(h_loss)
+
+    e2e_steps = max(args.steps // 2, 3)
+    ms, _, _ = timed_steps(step, e2e_steps, 2, shard, dev)
+    h2d = sum(t.numel() * t.element_size() for t in (h_feat, h_rois, h_obj))
+    return {"value": world * st.proposals * e2e_steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": 4, "ms_per_step": ms / e2e_steps}
 
 
 if __name__ == "__main__":

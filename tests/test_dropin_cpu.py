@@ -81,3 +81,19 @@ def test_reference_forward_box_vs_oracle_composition(R, batch):
         assert c == len(i.scores)
         assert torch.equal(det["det_boxes"][n, :c], i.pred_boxes.tensor) and torch.equal(det["det_scores"][n, :c], i.scores)
         assert torch.equal(det["det_classes"][n, :c], i.pred_classes) and torch.equal(det["det_rows"][n, :c], i.pred_inds)
+
+
+def test_reference_arm_of_the_bench_is_the_reference_code():
+    """bench.py --impl reference / cpu_baseline: oracle/ref_path.py runs the reference's own classes; same numbers as
+    the port (oracle/cpu_path.py) and as the oracle's kernels"""
+    from oracle import cpu_path, ref_path
+    from wsovod_b200 import synth
+    w = synth.workload("c1")
+    impl, kind = ref_path.get()
+    assert kind == "reference" and impl is ref_path
+    _, n, pooled, probs, inst = impl.run_slice(w, images=1, proposals=400)
+    _, n2, pooled2, probs2, dets2 = cpu_path.run_slice(w, images=1, proposals=400)
+    assert n == n2 == 400 and torch.equal(pooled, pooled2) and torch.equal(probs, probs2)
+    assert torch.equal(inst[0].scores, dets2[0][1]) and torch.equal(inst[0].pred_inds, dets2[0][3])
+    o, _ = oracle.roi_pool(w["features"], w["rois"][:400], w["spatial_scale"], 7)
+    assert torch.equal(pooled, o * (w["objectness"][:400] + 1).view(-1, 1, 1, 1))
