@@ -143,6 +143,22 @@ int wsovod_b200_mil_bwd(const float* grad_scores, const float* grad_img, const f
                         float* grad_cls, float* grad_det,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* North-star kernel 2 in one call: alignment on tensor cores FUSED with the MIL two-stream score -- replaces
+ * ObjectMiningOutputLayers.forward + predict_probs_img when `cls` is the open-vocabulary class head
+ * (roi_heads/fast_rcnn_open_vocabulary.py:280-285,318-367,604-618; the head variant of roi_heads.py:588-590):
+ *   C = align_fwd(x, classifier) without background column (tcgen05 kind::tf32, |dlogit| <= 5e-2),
+ *   scores[r,k] = softmax(C[r,:])[k] * softmax over the image's rows of det[:,k],  img_scores as mil_fwd.
+ * The TMEM epilogue emits the row softmax and per-(image, class) column (max, sum exp) partials of `det` in one
+ * pass; a second light launch applies the column softmax in place and sums the image scores (deterministic).
+ * x [M,D] (16-byte aligned, D % 4 == 0), classifier [K,D] with K <= 256, det/scores [M,K], offsets device int64 [N+1],
+ * img_scores [N,K] (may be NULL), logits [M,K] (may be NULL; the backward pass is mil_bwd on them, then align_bwd). */
+size_t wsovod_b200_align_mil_fused_workspace(int64_t M, int64_t N, int64_t D, int64_t K);
+int wsovod_b200_align_mil_fused_fwd(const float* x, const float* classifier, const float* det,
+                                    const int64_t* offsets, int64_t M, int64_t N, int64_t D, int64_t K,
+                                    float temperature, int norm_weight, const float* bias, float* scores,
+                                    float* img_scores, float* logits, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) refinement pseudo-label assignment.
  * ---------------------------------------------------------------------------------------------- */

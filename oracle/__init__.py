@@ -135,6 +135,16 @@ def mil(cls, det, offsets):
     return scores, img
 
 
+def align_mil(x, classifier, det, offsets, temperature=50.0, norm_weight=True, bias=None):
+    """ObjectMiningOutputLayers.forward with `cls` = the open-vocabulary class head
+    (fast_rcnn_open_vocabulary.py:280-285,318-367; roi_heads.py:588-590): the alignment logits WITHOUT background
+    column (open_vocabulary_classifier.py:79-105, append_background default False) feed the MIL two-stream score.
+    Returns (scores, img, logits)."""
+    logits, _ = align(x, classifier, temperature, norm_weight, False, bias, want_probs=False)
+    scores, img = mil(logits, det, offsets)
+    return scores, img, logits
+
+
 def pgt_top1(scores, boxes, offsets, gt_classes, gt_offsets, img_scores):
     s, sp = _f(scores)
     b, bp = _f(boxes)

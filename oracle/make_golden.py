@@ -118,6 +118,28 @@ def main():
                            probs_bg=torch.cat(pb, 0))
     torch.save(cases, os.path.join(GOLD, "mil.pt"))
 
+    # ---- (2) fused alignment + MIL: ObjectMiningOutputLayers with the open-vocabulary class head (roi_heads.py:588-590) ---
+    cases = {}
+    g_main, g = g, torch.Generator().manual_seed(20261018)       # own stream: the sections after this one keep theirs
+    for name, (sizes, K, D) in dict(two=((150, 97), 20, 64), one=((300,), 80, 96), tiny=((5, 1, 40), 7, 32)).items():
+        Fdim = D
+        ovc = OpenVocabularyClassifier(ShapeSpec(channels=Fdim), num_classes=K, weight_path="rand", weight_dim=D,
+                                       norm_temperature=50.0)
+        ovc.projection = nn.Identity()
+        om = fr.ObjectMiningOutputLayers(ShapeSpec(channels=Fdim), box2box_transform=Box2BoxTransform((10, 10, 5, 5)),
+                                         num_classes=K, class_head=ovc, loss_weight={})
+        x = torch.relu(torch.randn(sum(sizes), Fdim, generator=g))
+        x[::29] = 0
+        props = [list(range(s)) for s in sizes]
+        with torch.no_grad():
+            om.det.weight.mul_(8.0)
+            scores, _ = om(x, props)
+            img = om.predict_probs_img((scores, None), props)
+            cases[name] = dict(x=x, class_weight=ovc.class_weight.detach().clone(), det=om.det(x), sizes=list(sizes),
+                               T=50.0, logits=ovc(x), scores=scores, img=img)
+    torch.save(cases, os.path.join(GOLD, "align_mil.pt"))
+    g = g_main
+
     # ---- (4) fast_rcnn_inference (filter + clip + batched_nms + top-k) -----------------------------
     sizes, K = (300, 260), 20
     img_shapes = [(240, 320), (200, 304)]

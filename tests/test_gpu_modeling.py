@@ -229,3 +229,33 @@ def test_label_proposals_subsampling_matches_reference_rng(R, batch, frac):
     assert torch.equal(torch.cuda.get_rng_state(0), after)
     if frac < 1.0:
         assert int(((lab[0].gt_classes != -1) & (lab[0].gt_classes != K)).sum()) <= int(batch * frac)
+
+
+def test_object_miner_with_class_head_uses_fused_kernel(golden):
+    """ObjectMiningOutputLayers(cfg, shape, class_head) (roi_heads.py:588-590): the mirror routes through
+    ops.align_mil; reference golden from the reference's own class"""
+    for name, c in golden("align_mil").items():
+        D, K = c["class_weight"].shape
+        ovc = OpenVocabularyClassifier(D, num_classes=K, weight_path="rand", weight_dim=D, precision=ops.ALIGN_TF32)
+        ovc.projection = torch.nn.Identity()
+        m = ObjectMiningOutputLayers(D, K, class_head=ovc).to(DEV)
+        with torch.no_grad():
+            m.cls.class_weight.copy_(c["class_weight"].to(DEV))
+        props = [list(range(s)) for s in c["sizes"]]
+        # det is a Linear in the module: feed the golden's det logits by making it the identity on an augmented input
+        det = c["det"].to(DEV)
+        m.det = _Fixed(det)
+        scores, deltas = m(c["x"].to(DEV), props)
+        img = m.predict_probs_img((scores, deltas), props)
+        assert (scores.cpu() - c["scores"]).abs().max().item() <= 2.5e-2 * c["scores"].max().item() + 1e-6, name
+        assert (img.cpu() - c["img"]).abs().max().item() <= 2.5e-2, name
+        assert deltas.shape == (scores.shape[0], 4)
+
+
+class _Fixed(torch.nn.Module):
+    def __init__(self, out):
+        super().__init__()
+        self.out = out
+
+    def forward(self, x):
+        return self.out

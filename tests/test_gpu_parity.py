@@ -241,6 +241,67 @@ def test_align_backward_classifier(M, D, K, mode, bg):
     assert torch.equal(tg2.grad, tg.grad)        # deterministic: fixed-order split-M sums
 
 
+def test_align_mil_fused_golden_and_oracle(golden):
+    """north star kernel 2, fused: against the reference's ObjectMiningOutputLayers(class_head=OpenVocabularyClassifier)
+    golden and the oracle composition align -> mil, at the stated TF32 tolerance on the logits"""
+    for name, c in golden("align_mil").items():
+        off = torch.tensor(_offs(c["sizes"]), dtype=torch.int64, device=DEV)
+        w = c["class_weight"].t().contiguous().to(DEV)                 # stored (D, K) -> (K, D)
+        s, img, lg = ops.align_mil(c["x"].to(DEV), w, c["det"].to(DEV), off, c["T"], 2, None, True)
+        assert (lg.cpu() - c["logits"]).abs().max().item() <= TF32_LOGIT_TOL, name
+        # the score is compared against the two-stream formula on OUR logits at 1e-5 (fp32 softmaxes), and against
+        # the reference's fp32 result at the error the logit tolerance allows (|d softmax| <= |d logit| / 2)
+        so, io = oracle.mil(lg.cpu(), c["det"], _offs(c["sizes"]))
+        torch.testing.assert_close(s.cpu(), so, rtol=1e-5, atol=1e-10)
+        torch.testing.assert_close(img.cpu(), io, rtol=1e-5, atol=1e-8)
+        assert (s.cpu() - c["scores"]).abs().max().item() <= 0.5 * TF32_LOGIT_TOL * c["scores"].max().item() + 1e-6, name
+        assert (img.cpu() - c["img"]).abs().max().item() <= 0.5 * TF32_LOGIT_TOL, name
+    g = synth.gen(31)
+    for sizes, K, D in (([4000, 1, 2500, 0, 333], 80, 768), ([5024], 80, 768), ([130, 126, 1], 255, 64), ([7, 0, 0, 9], 3, 32)):
+        M = sum(sizes)
+        x = synth.region_embeddings(M, D, g)
+        t = synth.text_embeddings(K, D, g)
+        det = synth.mil_logits(M, K, g)[1]
+        off = _offs(sizes)
+        s, img, lg = ops.align_mil(x.to(DEV), t.to(DEV), det.to(DEV), torch.tensor(off, device=DEV), 50.0, 1, None, True)
+        so, io, lo = oracle.align_mil(x, t, det, off, 50.0, 1)
+        assert (lg.cpu() - lo).abs().max().item() <= TF32_LOGIT_TOL
+        s2, i2 = oracle.mil(lg.cpu(), det, off)
+        torch.testing.assert_close(s.cpu(), s2, rtol=1e-5, atol=1e-12)
+        keep = [i for i, n in enumerate(sizes) if n > 0]
+        torch.testing.assert_close(img.cpu()[keep], i2[keep], rtol=1e-5, atol=1e-8)
+        empty = [i for i, n in enumerate(sizes) if n == 0]
+        assert (img.cpu()[empty] == 1e-6).all()
+        # equals the unfused pair of ops on the same logits, and is deterministic
+        s3, i3 = ops.mil(lg, det.to(DEV), torch.tensor(off, device=DEV))
+        torch.testing.assert_close(s, s3, rtol=1e-5, atol=1e-12)
+        s4, i4, _ = ops.align_mil(x.to(DEV), t.to(DEV), det.to(DEV), torch.tensor(off, device=DEV), 50.0, 1, None, False)
+        assert torch.equal(s, s4) and torch.equal(img, i4)
+
+
+def test_align_mil_fused_backward():
+    g = synth.gen(41)
+    sizes, K, D = [200, 77], 20, 96
+    M = sum(sizes)
+    x = synth.region_embeddings(M, D, g).add_(0.01)
+    t = synth.text_embeddings(K, D, g)
+    det = synth.mil_logits(M, K, g)[1]
+    off = torch.tensor(_offs(sizes), device=DEV)
+    xg, tg, dg = (v.to(DEV).requires_grad_(True) for v in (x, t, det))
+    s, img, _ = ops.align_mil(xg, tg, dg, off, 50.0, 1)
+    gs, gi = torch.randn(s.shape, generator=g).to(DEV), torch.randn(img.shape, generator=g).to(DEV)
+    (s * gs).sum().add((img * gi).sum()).backward()
+    # reference expression in fp64 on the SAME (TF32) logits is not available to autograd: compare with the fp32
+    # composition of the two ops (align fp32 -> mil), whose backward kernels are the ones this op reuses
+    xr, tr, dr = (v.to(DEV).requires_grad_(True) for v in (x, t, det))
+    lg, _ = ops.align(xr, tr, 50.0, 1, False, None, ops.ALIGN_FP32, True, False)
+    s2, i2 = ops.mil(lg, dr, off)
+    (s2 * gs).sum().add((i2 * gi).sum()).backward()
+    for a, b in ((xg.grad, xr.grad), (tg.grad, tr.grad), (dg.grad, dr.grad)):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-2 * scale          # TF32 logits vs fp32 logits in the saved activations
+
+
 def test_mil_golden_and_oracle(golden):
     for name, c in golden("mil").items():
         off = torch.tensor(_offs(c["sizes"]), dtype=torch.int64, device=DEV)

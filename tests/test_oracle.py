@@ -165,3 +165,16 @@ def test_refine_losses_oracle_matches_reference_golden(golden):
         torch.testing.assert_close(logits.grad, c["grad_logits"], rtol=1e-6, atol=1e-9)
         if deltas is not None:
             torch.testing.assert_close(deltas.grad, c["grad_deltas"], rtol=1e-6, atol=1e-9)
+
+
+def test_align_mil_composition_vs_reference_class_head_miner(golden):
+    """oracle.align_mil (align without background -> mil) against the reference's own
+    ObjectMiningOutputLayers(class_head=OpenVocabularyClassifier) (fast_rcnn_open_vocabulary.py:280-285,318-367)"""
+    for name, c in golden("align_mil").items():
+        off = [0]
+        for s in c["sizes"]:
+            off.append(off[-1] + s)
+        s, img, lg = oracle.align_mil(c["x"], c["class_weight"].t().contiguous(), c["det"], off, c["T"], 2)
+        assert (lg - c["logits"]).abs().max().item() <= 5e-5, name
+        torch.testing.assert_close(s, c["scores"], rtol=2e-4, atol=1e-7)
+        torch.testing.assert_close(img, c["img"], rtol=2e-4, atol=1e-7)

@@ -47,6 +47,9 @@ SIGNATURES = {
     "wsovod_b200_mil_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_sz, c_p]),
     "wsovod_b200_mil_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_sz,
                                     c_p]),
+    "wsovod_b200_align_mil_fused_workspace": (c_sz, [c_i64, c_i64, c_i64, c_i64]),
+    "wsovod_b200_align_mil_fused_fwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_p, c_p,
+                                                c_p, c_p, c_p, c_sz, c_p]),
     "wsovod_b200_pgt_top1": (c_int, [c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "wsovod_b200_refine_assign": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64,

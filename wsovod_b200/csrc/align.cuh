@@ -16,8 +16,19 @@ __global__ void align_wnorm_kernel(const float* __restrict__ w, int K, int D, in
 __global__ void row_softmax_kernel(const float* __restrict__ logits, int64_t M, int KO,
                                    float* __restrict__ probs);
 
+// fused alignment + MIL (align_mil.cu): image-aligned row tiles and the detection stream whose column statistics the
+// epilogue reduces on the way out
+struct AlignMilFuse {
+  const int4* tiles;        // [ntiles_max] (first row, rows, image, -)
+  const int* ntiles_dev;    // valid entries
+  int ntiles_max;
+  const float* det;         // [M, K]
+  float2* colpart;          // [ntiles_max * 4, K]
+};
+
 int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D, int64_t K,
                    float temperature, int norm_weight, int append_background, const float* bias,
-                   float* logits, float* probs, const AlignWs& w, char* ws, cudaStream_t st);
+                   float* logits, float* probs, const AlignWs& w, char* ws, cudaStream_t st,
+                   const AlignMilFuse* mil = nullptr);
 
 }  // namespace wsovod

@@ -107,7 +107,21 @@ struct TcParams {
   int write_logits;   // 0: only probabilities are wanted and they come straight from TMEM
   float temperature;
   uint32_t tmem_cols;
+  // fused alignment + MIL (align_mil.cu): row tiles come from a table so that every tile lies inside ONE image
+  // (x = first row, y = rows, z = image); the epilogue then also reduces the detection stream's column softmax
+  // statistics of its rows: colpart[(tile * 4 + warp) * KO + k] = (max, sum exp) over the warp's <= 32 rows
+  const int4* tiles;          // null: tile t = rows [128 t, 128 t + 128)
+  const int* ntiles_dev;      // number of valid table entries (device-side: offsets never visit the host)
+  const float* det;           // [M, KO] detection-stream logits (MIL mode)
+  float2* colpart;
 };
+
+struct TcTile { int row0, rows; };
+__device__ __forceinline__ TcTile tc_tile(const TcParams& p, int tile) {
+  if (p.tiles) { const int4 t = __ldg(p.tiles + tile); return TcTile{t.x, t.y}; }
+  const int64_t r0 = (int64_t)tile * TC_BM;
+  return TcTile{(int)r0, (int)min((int64_t)TC_BM, p.M - r0)};
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -150,26 +164,29 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int ntiles = p.ntiles_dev ? min(__ldg(p.ntiles_dev), p.ntiles) : p.ntiles;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tc_tile(p, tile).row0;
         for (int c = 0; c < p.nchunks; ++c)
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], a_bytes + b_bytes);
-            tma_load_2d(&map_x, sa + (size_t)stage * a_bytes, &full[stage], kb * TC_BK, tile * TC_BM);
+            tma_load_2d(&map_x, sa + (size_t)stage * a_bytes, &full[stage], kb * TC_BK, row0);
             tma_load_2d(&map_w, sb + (size_t)stage * b_bytes, &full[stage], kb * TC_BK, c * p.BN);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int c = 0; c < p.nchunks; ++c, ++it) {
           const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
           mbar_wait(&tempty[buf], aphase ^ 1);
@@ -193,7 +210,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ===== norm warps: ||x_r||^2 from the very stages the MMA consumes (x crosses HBM once) =====
     const int t = (warp - 2) * 32 + lane;        // 0..63, rows t and t + 64 of the tile
     int stage = 0; uint32_t phase = 0; uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       float ss0 = 0.f, ss1 = 0.f;
       for (int c = 0; c < p.nchunks; ++c) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -233,8 +250,10 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     float* st = stage_out + wq * 32 * 33;        // [32 rows][33]
     const float bias = p.bias ? __ldg(p.bias) : 0.f;
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
-      const int64_t wrow0 = (int64_t)tile * TC_BM + wq * 32;     // first row of this warp
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const TcTile tt = tc_tile(p, tile);
+      const int64_t wrow0 = (int64_t)tt.row0 + wq * 32;          // first row of this warp
+      const int wrows = min(32, tt.rows - wq * 32);              // rows of the tile this warp owns (<= 0: none)
       const uint32_t nb = tcount & 1, nphase = (tcount >> 1) & 1;
       mbar_wait(&nfull[nb], nphase);
       float scale = 1.f;
@@ -272,7 +291,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int cc = col0 + j + lane;
           if (p.write_logits && cc < p.KO)
             for (int rr = 0; rr < 32; ++rr)
-              if (wrow0 + rr < p.M) p.logits[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+              if (rr < wrows) p.logits[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
           __syncwarp();
         }
         if (p.probs && p.nchunks == 1) {
@@ -284,16 +303,29 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int i = 0; i < 32; ++i) st[lane * 33 + i] = expf(fmaf(v[i], scale, bias) - run_m) * inv;
             __syncwarp();
             const int cc = j + lane;
-            if (cc < p.KO)
+            if (cc < p.KO) {
+              // lane == output column: 128-byte row segments; in MIL mode the same walk reduces the detection
+              // stream's column statistics over this warp's rows (online max / sum of exp, row order)
+              float dm = -FLT_MAX, ds = 0.f;
               for (int rr = 0; rr < 32; ++rr)
-                if (wrow0 + rr < p.M) p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+                if (rr < wrows) {
+                  p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+                  if (p.det) {
+                    const float d = __ldg(p.det + (wrow0 + rr) * p.KO + cc);
+                    const float nm = fmaxf(dm, d);
+                    ds = ds * expf(dm - nm) + expf(d - nm);
+                    dm = nm;
+                  }
+                }
+              if (p.det) p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
+            }
             __syncwarp();
           }
         }
         tc_fence_before();
         mbar_arrive(&tempty[buf]);               // accumulator buffer may be overwritten
       }
-      if (p.rowstat && wrow0 + lane < p.M) {
+      if (p.rowstat && lane < wrows) {
         // multi-chunk: (max, 1/sum) per row for the streaming normalisation kernel that follows
         p.rowstat[2 * (wrow0 + lane)] = run_m;
         p.rowstat[2 * (wrow0 + lane) + 1] = 1.f / run_s;
@@ -359,7 +391,7 @@ static int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t 
 
 int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D, int64_t K, float temperature,
                    int norm_weight, int append_background, const float* bias, float* logits, float* probs,
-                   const AlignWs& w, char* ws, cudaStream_t st) {
+                   const AlignWs& w, char* ws, cudaStream_t st, const AlignMilFuse* mil) {
   if ((D & 3) || ((uintptr_t)x & 15)) return WSOVOD_B200_EALIGN;   // TMA: 16-byte rows
   if (M > 0x7fffffffLL - TC_BM) return WSOVOD_B200_ETOOBIG;
   const int64_t KO = K + (append_background ? 1 : 0);
@@ -374,11 +406,17 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   TcParams p;
   p.x = x; p.bias = bias; p.logits = logits ? logits : probs; p.probs = probs;
   p.rowstat = nullptr;
+  p.tiles = nullptr; p.ntiles_dev = nullptr; p.det = nullptr; p.colpart = nullptr;
   p.M = M; p.D = (int)D; p.KO = (int)KO; p.Kp = (int)w.Kp;
   p.BN = (int)std::min<int64_t>(w.Kp, 256);
   p.nchunks = (int)ceil_div(KO, p.BN);
   p.kblocks = (int)ceil_div(D, TC_BK);
   p.ntiles = (int)ceil_div(M, TC_BM);
+  if (mil) {
+    if (p.nchunks != 1 || !probs) return WSOVOD_B200_EUNSUPPORTED;   // the column statistics ride on the single-chunk sweep
+    p.tiles = mil->tiles; p.ntiles_dev = mil->ntiles_dev; p.ntiles = mil->ntiles_max;
+    p.det = mil->det; p.colpart = mil->colpart;
+  }
   p.norm = norm_weight; p.temperature = temperature;
   p.write_logits = (logits != nullptr || p.nchunks > 1) ? 1 : 0;
   if (probs && p.nchunks > 1) p.rowstat = (float*)(ws + w.rowstat);

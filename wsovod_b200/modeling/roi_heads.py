@@ -77,11 +77,29 @@ class ObjectMiningOutputLayers(nn.Module):
         else:
             if x.dim() > 2:
                 x = torch.flatten(x, start_dim=1)
+            fused = self._fused(x, proposals)
+            if fused is not None:
+                self._last = fused
+                return fused[0], torch.zeros(fused[0].shape[0], 4, dtype=fused[0].dtype, device=fused[0].device)
             C, D = self.cls(x), self.det(x)
         scores, img = self.score(C, D, proposals)
         self._last = (scores, img)          # the image-level scores come out of the same kernel pass
         deltas = torch.zeros(scores.shape[0], 4, dtype=scores.dtype, device=scores.device)
         return scores, deltas
+
+    def _fused(self, x, proposals):
+        """the class-head variant (roi_heads.py:588-590) through the fused alignment + MIL kernel: `cls` is an
+        OpenVocabularyClassifier on its tensor-core path with at most 256 concepts and stored weights"""
+        from .class_heads import OpenVocabularyClassifier
+        c = self.cls
+        if not (isinstance(c, OpenVocabularyClassifier) and c.precision == ops.ALIGN_TF32 and x.is_cuda
+                and 1 < self.num_classes <= 256):
+            return None
+        off = (torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device) if proposals is None
+               else _offsets(proposals, x.device)[0])
+        scores, img, _ = ops.align_mil(c.projection(x), c._stored_kd(), self.det(x), off, c.norm_temperature,
+                                       2 if c.norm_weight else 0, c.cls_bias if c.use_bias else None)
+        return scores, img
 
     @staticmethod
     def score(C, D, proposals=None):

@@ -411,6 +411,78 @@ def mil(cls, det, offsets):
     return torch.ops.wsovod_b200.mil(cls, det, offsets)
 
 
+@torch.library.custom_op("wsovod_b200::align_mil", mutates_args=())
+def _align_mil(x: torch.Tensor, classifier: torch.Tensor, det: torch.Tensor, offsets: torch.Tensor, temperature: float,
+               norm_weight: int, bias: Optional[torch.Tensor], want_logits: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _need_cuda(x, classifier, det, offsets, bias)
+    x, classifier, det = _f32c(x), _f32c(classifier), _f32c(det)
+    if x.dim() != 2 or classifier.dim() != 2 or x.size(1) != classifier.size(1) or det.shape != (x.size(0), classifier.size(0)) \
+            or offsets.dtype != torch.int64:
+        raise RuntimeError("wsovod_b200::align_mil expects x (M,D), classifier (K,D), det (M,K), int64 offsets (N+1)")
+    M, D = x.shape
+    K = classifier.size(0)
+    N = offsets.numel() - 1
+    b = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x.device):
+        scores = torch.empty((M, K), dtype=torch.float32, device=x.device)
+        img = torch.empty((N, K), dtype=torch.float32, device=x.device)
+        logits = torch.empty((M, K) if want_logits else (0,), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        ws = _workspace(L.wsovod_b200_align_mil_fused_workspace(M, N, D, K), x.device)
+        rc = L.wsovod_b200_align_mil_fused_fwd(_ptr(x), _ptr(classifier), _ptr(det), _ptr(offsets), M, N, D, K, temperature,
+                                               int(norm_weight), _ptr(b), _ptr(scores), _ptr(img),
+                                               _ptr(logits if want_logits else None), _ptr(ws), ws.numel(), _stream(x))
+    _lib.check(rc, "align_mil_fused_fwd")
+    return scores, img, logits
+
+
+@_align_mil.register_fake
+def _(x, classifier, det, offsets, temperature, norm_weight, bias, want_logits):
+    M, K = det.shape
+    return x.new_empty((M, K)), x.new_empty((offsets.numel() - 1, K)), x.new_empty((M, K) if want_logits else (0,))
+
+
+def _align_mil_setup(ctx, inputs, output):
+    x, classifier, det, offsets, temperature, norm_weight, bias, want_logits = inputs
+    ctx.save_for_backward(x, classifier, det, offsets, output[1], output[2])
+    ctx.cfg = (temperature, norm_weight, bias is not None, want_logits)
+    ctx.mark_non_differentiable(output[2])
+
+
+def _align_mil_bwd(ctx, g_scores, g_img, _g_logits):
+    x, classifier, det, offsets, img, logits = ctx.saved_tensors
+    temperature, norm_weight, has_bias, want_logits = ctx.cfg
+    if not want_logits:
+        raise RuntimeError("wsovod_b200::align_mil: backward needs want_logits=True in the forward call")
+    if g_scores is None and g_img is None:
+        return (None,) * 8
+    if g_img is not None:   # clamp(min=1e-6, max=1-1e-6) passes gradient only strictly inside
+        g_img = g_img * ((img > 1e-6) & (img < 1.0 - 1e-6)).to(g_img.dtype)
+    gc, gd = torch.ops.wsovod_b200.mil_backward(g_scores, g_img, logits, det, offsets)
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    gx = gw = None
+    if need_x or need_w:
+        gx, gw = torch.ops.wsovod_b200.align_backward(gc, x, classifier, temperature, norm_weight, False, bool(need_x),
+                                                      bool(need_w))
+        gx, gw = (gx if need_x else None), (gw if need_w else None)
+    gb = gc.sum().reshape(1) if has_bias else None
+    return gx, gw, (gd if ctx.needs_input_grad[2] else None), None, None, None, gb, None
+
+
+_align_mil.register_autograd(_align_mil_bwd, setup_context=_align_mil_setup)
+
+
+def align_mil(x, classifier, det, offsets, temperature=50.0, norm_weight=True, bias=None, want_logits=None):
+    """Fused alignment + MIL (north star kernel 2): scores (M,K) = softmax_k(T normalize(x) normalize(W)^T) *
+    per-image softmax_r(det), image scores (N,K); the alignment logits come back too when ``want_logits`` (default:
+    whenever autograd will need them).  TF32 contraction, K <= 256."""
+    if want_logits is None:
+        want_logits = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, classifier, det, bias))
+    s, img, lg = torch.ops.wsovod_b200.align_mil(x, classifier, det, offsets, float(temperature), int(norm_weight), bias,
+                                                 bool(want_logits))
+    return s, img, lg
+
+
 # ------------------------------------------------------------------------------------------------
 # (3) refinement
 # ------------------------------------------------------------------------------------------------
