@@ -24,13 +24,14 @@ import torch
 
 from . import ops
 from .modeling import (OpenVocabularyClassifier, ROIPooler, fast_rcnn_inference, get_pgt_top_k, label_proposals_wsl)
+from .modeling.roi_heads import _offsets_tensor
 
 
 def _offsets(proposals, device):
     off = [0]
     for p in proposals:
         off.append(off[-1] + len(p))
-    return torch.tensor(off, dtype=torch.int64, device=device)
+    return _offsets_tensor(off, device)
 
 
 def _miner_forward(self, x, proposals=None, context=False):
@@ -44,8 +45,7 @@ def _miner_forward(self, x, proposals=None, context=False):
     if self.num_classes == 1:                                                  # :338-340
         C = torch.cat((C, torch.zeros_like(C)), dim=1)
         D = torch.cat((D, torch.zeros_like(D)), dim=1)
-    off = (torch.tensor([0, C.shape[0]], dtype=torch.int64, device=C.device) if proposals is None
-           else _offsets(proposals, C.device))
+    off = _offsets_tensor([0, C.shape[0]], C.device) if proposals is None else _offsets(proposals, C.device)
     scores, img = ops.mil(C, D, off)
     if self.num_classes == 1:                                                  # :356-357
         scores, _ = torch.split(scores, 1, dim=1)

@@ -39,12 +39,37 @@ def apply_deltas(deltas, boxes, weights=(10.0, 10.0, 5.0, 5.0), scale_clamp=math
     return out.reshape(deltas.shape)
 
 
+_OFFSET_CACHE = {}
+
+
+def _offsets_tensor(off, device):
+    """int64 device tensor of a host offsets list.  A pageable host->device copy synchronises the stream, and the
+    same per-image counts recur step after step (4000 proposals / image), so the tensors are cached."""
+    key = (tuple(off), str(device))
+    t = _OFFSET_CACHE.get(key)
+    if t is None:
+        if len(_OFFSET_CACHE) >= 64:
+            _OFFSET_CACHE.clear()
+        t = _OFFSET_CACHE[key] = torch.tensor(off, dtype=torch.int64, device=device)
+    return t
+
+
+def _sizes_tensor(image_shapes, device):
+    key = (tuple((float(h), float(w)) for h, w in image_shapes), str(device), "hw")
+    t = _OFFSET_CACHE.get(key)
+    if t is None:
+        if len(_OFFSET_CACHE) >= 64:
+            _OFFSET_CACHE.clear()
+        t = _OFFSET_CACHE[key] = torch.tensor([list(k) for k in key[0]], dtype=torch.float32, device=device).reshape(-1, 2)
+    return t
+
+
 def _offsets(proposals, device):
     sizes = [len(p) for p in proposals]
     off = [0]
     for s in sizes:
         off.append(off[-1] + s)
-    return torch.tensor(off, dtype=torch.int64, device=device), sizes
+    return _offsets_tensor(off, device), sizes
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,8 +120,7 @@ class ObjectMiningOutputLayers(nn.Module):
         if not (isinstance(c, OpenVocabularyClassifier) and c.precision == ops.ALIGN_TF32 and x.is_cuda
                 and 1 < self.num_classes <= 256):
             return None
-        off = (torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device) if proposals is None
-               else _offsets(proposals, x.device)[0])
+        off = _offsets_tensor([0, x.shape[0]], x.device) if proposals is None else _offsets(proposals, x.device)[0]
         scores, img, _ = ops.align_mil(c.projection(x), c._stored_kd(), self.det(x), off, c.norm_temperature,
                                        2 if c.norm_weight else 0, c.cls_bias if c.use_bias else None)
         return scores, img
@@ -104,7 +128,7 @@ class ObjectMiningOutputLayers(nn.Module):
     @staticmethod
     def score(C, D, proposals=None):
         if proposals is None:
-            off = torch.tensor([0, C.shape[0]], dtype=torch.int64, device=C.device)
+            off = _offsets_tensor([0, C.shape[0]], C.device)
         else:
             off, _ = _offsets(proposals, C.device)
         return ops.mil(C, D, off)                             # (scores, clamped image-level scores)
@@ -250,8 +274,8 @@ def fast_rcnn_inference(boxes: List[torch.Tensor], scores: List[torch.Tensor], i
         off.append(off[-1] + s)
     probs = scores[0] if len(scores) == 1 else torch.cat(list(scores), 0)
     bx = boxes[0] if len(boxes) == 1 else torch.cat(list(boxes), 0)
-    r = ops.detections(probs, bx, torch.tensor(off, dtype=torch.int64, device=dev),
-                       torch.tensor([[float(h), float(w)] for h, w in image_shapes], dtype=torch.float32, device=dev),
+    r = ops.detections(probs, bx, _offsets_tensor(off, dev),
+                       _sizes_tensor(image_shapes, dev),
                        max(sizes), score_thresh, nms_thresh, topk_per_image, iou_mode)
     counts = r["det_count"].tolist()
     instances, kept = [], []
@@ -294,9 +318,11 @@ def get_image_level_gt(targets, num_classes):
 
 @torch.no_grad()
 def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits,
-                  num_classes):
+                  num_classes, build_targets=True):
     """roi_heads.py:1043-1343 with top_k=1, thres=0, need_weight=True, sam=None: one seed per image-level
-    class.  Returns (targets: list[Instances{gt_boxes, gt_classes, gt_scores, gt_weights}], flat seeds)."""
+    class.  Returns (targets: list[Instances{gt_boxes, gt_classes, gt_scores, gt_weights}], flat seeds).
+    ``build_targets=False`` returns (None, seeds): slicing the per-image Instances needs the seed counts on the
+    host (one device->host read); the assignment kernel only takes the flat seeds."""
     dev = prev_pred_boxes[0].device
     off, sizes = _offsets(proposals, dev)
     scores = prev_pred_scores if isinstance(prev_pred_scores, torch.Tensor) else torch.cat(list(prev_pred_scores), 0)
@@ -305,10 +331,12 @@ def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_i
     goff = [0]
     for s in gsz:
         goff.append(goff[-1] + s)
-    goff_t = torch.tensor(goff, dtype=torch.int64, device=dev)
+    goff_t = _offsets_tensor(goff, dev)
     seeds = ops.pgt_top1(scores, boxes, off, torch.cat(list(gt_classes_img_int)).to(dev), goff_t,
                          pred_class_img_logits)
     seeds["seed_offsets"] = goff_t
+    if not build_targets:
+        return None, seeds
     counts = seeds["seed_count"].tolist()
     targets = []
     for n, p in enumerate(proposals):
@@ -334,7 +362,9 @@ def label_proposals_wsl(proposals, seeds, num_classes, iou_threshold=0.5, batch_
     a = ops.refine_assign(boxes, off, seeds["seed_boxes"], seeds["seed_classes"], seeds["seed_scores"],
                           seeds["seed_weights"], seeds["seed_offsets"], seeds["seed_count"], num_classes, iou_threshold)
     out = []
-    o = off.tolist()
+    o = [0]
+    for n in sizes:
+        o.append(o[-1] + n)
     for n, p in enumerate(proposals):
         sl = slice(o[n], o[n + 1])
         cls = a["gt_classes"][sl]

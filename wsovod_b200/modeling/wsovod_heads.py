@@ -178,7 +178,7 @@ class WSOVODROIHeads(nn.Module):
                                               self.pred_class_img_logits, self.num_classes)
             else:
                 targets, seeds = get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, self.gt_classes_img_int,
-                                               self.pred_class_img_logits, self.num_classes)
+                                               self.pred_class_img_logits, self.num_classes, build_targets=False)
             if not self.sampling_on:
                 raise NotImplementedError("WSOVOD.SAMPLING.SAMPLING_ON False (detectron2's GT-style sampling, :812-813) is "
                                           "not used by the shipped configs")
