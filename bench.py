@@ -348,6 +348,8 @@ def main():
                     help="1: the pooling kernel also emits argmax (training with a trainable backbone); the "
                          "reference's frozen-backbone inference never reads it (SURVEY fact 6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the inference step's launches from Python every step "
+                    "instead of replaying them from a CUDA graph")
     ap.add_argument("--only", action="store_true", help="skip the other BASELINE configs and the extra per-kernel timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -381,9 +383,11 @@ def main():
     M = N * R
     training = args.config in S.TRAIN_CONFIGS
     with_arg = bool(args.pool_argmax)
-    st = S.make(args.config, w, dev, world)
+    st = S.make(args.config, w, dev, world, graph=False)
     if not training:
         st.with_argmax = with_arg
+        if not args.no_graph:
+            st.capture()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -407,6 +411,8 @@ def main():
     shard.barrier()
     ms_total = shard.max_over_ranks(e0.elapsed_time(e1), dev)
     launches = _lib.launch_count() - launches0
+    if getattr(st, "_graph", None) is not None:      # replays do not pass through the library's host-side counter
+        launches = st.launches_per_step * args.steps
     value = world * st.proposals * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel device times (CUDA events on the launching stream), same inputs ----------------
@@ -432,6 +438,8 @@ def main():
         "gpu_launches": int(launches),
     }
     info = {"global_proposals_per_step": world * st.proposals, "pool_argmax": with_arg,
+            "launch": ("training step issued from Python (torch-RNG subsampling reads counts on the host)" if training
+                       else "eager Python launches" if args.no_graph else "step replayed from a CUDA graph"),
             "l2": "inputs+outputs per step exceed the 126 MB L2; no flush needed",
             "parallelism": f"dp{world} (images sharded, " + ("DDP gradient all-reduce over NCCL)" if training else "no data-path collective)")}
     if training:
