@@ -264,6 +264,18 @@ int wsovod_b200_detections(const float* probs, const float* boxes, const int64_t
                            int64_t* det_rows, int64_t* det_count,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* replaces wsovod._C.csc_forward (wsovod/layers/vision.cpp:12, wsovod/layers/csc/csc.h:22-33,
+ * csc_cuda.cu:183-531; call site proposal_generator/proposal_utils.py:272-291): W [R,K], the proposals' frame-vs-context
+ * contrast of the class peak response maps cpgs [B,K,H,W], for the classes with labels[b,k] >= 0.5, normalised to
+ * [-1, 1] and blended with preds [B,K]; columns of classes without a positive label are 1.  rois [R,5] in MAP pixels
+ * (the batch index is not read, as upstream: every positive (image, class) pair rewrites the whole column, the last
+ * image wins).  The reference's tau / mass_threshold / density_threshold arguments do not reach its arithmetic
+ * (csc_cuda.cu:424-426,443-444,322) and are not part of this entry.  Stream-ordered (the reference blocks the host). */
+size_t wsovod_b200_csc_workspace(int64_t K, int64_t H, int64_t W);
+int wsovod_b200_csc_fwd(const float* cpgs, const float* labels, const float* preds, const float* rois,
+                        int64_t B, int64_t K, int64_t H, int64_t W, int64_t R, float fg_threshold, int area_sqrt,
+                        float context_scale, float* W_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer convenience for the reference-facing end-to-end call (bench.py's `e2e`): the inference
  * slice pool -> align+softmax -> detections on pinned HOST buffers; copies in, launches, copies the

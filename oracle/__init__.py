@@ -265,3 +265,77 @@ def detections(probs, boxes, offsets, image_sizes, score_thresh, nms_thresh, top
                                        _p(db[n]), _p(ds[n]), _p(dc[n]), _p(dr[n]))
         cnt[n] = k
     return dict(det_boxes=db, det_scores=ds, det_classes=dc, det_rows=dr, det_count=cnt)
+
+
+def csc(cpgs, labels, preds, rois, fg_threshold=0.1, area_sqrt=True, context_scale=1.8):
+    """csc_forward restated in numpy, statement for statement (wsovod/layers/csc/csc_cuda.cu:183-531): the host loop
+    over (image, class) with a positive label, `binary_and_integral_cpu` (:117-147), `CSCPool` with its int / float /
+    double mix (:200-306), the max / min normalisation (:466-505) and the blend with `preds` (:506-509).  float32
+    scalars are numpy float32 so every operation rounds where the reference's `T = float` rounds."""
+    import numpy as np
+    f32 = np.float32
+    M = cpgs.detach().cpu().numpy().astype(np.float32)
+    X = labels.detach().cpu().numpy().astype(np.float32)
+    Y = preds.detach().cpu().numpy().astype(np.float32)
+    Rr = rois.detach().cpu().numpy().astype(np.float32)
+    B, K, H, Wd = M.shape
+    R = Rr.shape[0]
+    Wout = np.ones((R, K), np.float32)
+    cs = f32(context_scale)
+
+    def rnd(v):                       # C round(): half away from zero
+        return np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5))
+
+    def box(I, ws, hs, we, he):
+        a1 = I[he, we]
+        a2 = np.where(ws - 1 >= 0, I[he, np.maximum(ws - 1, 0)], f32(0))
+        a3 = np.where(hs - 1 >= 0, I[np.maximum(hs - 1, 0), we], f32(0))
+        a4 = np.where((hs - 1 >= 0) & (ws - 1 >= 0), I[np.maximum(hs - 1, 0), np.maximum(ws - 1, 0)], f32(0))
+        return ((a1 - a2).astype(f32) - a3).astype(f32) + a4
+
+    for b in range(B):
+        for c in range(K):
+            if X[b, c] < 0.5:
+                continue
+            thr = f32(1.0) * f32(fg_threshold)
+            binm = (M[b, c] >= thr).astype(np.float32)
+            I = np.cumsum(np.cumsum(binm, axis=1, dtype=np.float32), axis=0, dtype=np.float32)     # exact integer counts
+            ws = np.clip(rnd(Rr[:, 1]).astype(np.int64), 0, Wd - 1)
+            hs = np.clip(rnd(Rr[:, 2]).astype(np.int64), 0, H - 1)
+            we = np.clip(rnd(Rr[:, 3]).astype(np.int64), 0, Wd - 1)
+            he = np.clip(rnd(Rr[:, 4]).astype(np.int64), 0, H - 1)
+            wr, hr = (we - ws).astype(f32), (he - hs).astype(f32)
+            wi, hi = (wr.astype(np.float64) / np.float64(cs)).astype(f32), (hr.astype(np.float64) / np.float64(cs)).astype(f32)
+            wo, ho = (wr.astype(np.float64) * np.float64(cs)).astype(f32), (hr.astype(np.float64) * np.float64(cs)).astype(f32)
+            wc, hc = ((we + ws) / 2.0).astype(f32), ((he + hs) / 2.0).astype(f32)
+            d = np.float64
+            ws_i = rnd(wc.astype(d) - wi.astype(d) / 2.0).astype(np.int64)
+            hs_i = rnd(hc.astype(d) - hi.astype(d) / 2.0).astype(np.int64)
+            we_i = np.minimum(rnd(wc.astype(d) + wi.astype(d) / 2.0).astype(np.int64), Wd - 1)
+            he_i = np.minimum(rnd(hc.astype(d) + hi.astype(d) / 2.0).astype(np.int64), H - 1)
+            ws_o = rnd(np.maximum(wc.astype(d) - wo.astype(d) / 2.0, 0.0)).astype(np.int64)
+            hs_o = rnd(np.maximum(hc.astype(d) - ho.astype(d) / 2.0, 0.0)).astype(np.int64)
+            we_o = rnd(np.minimum(wc.astype(d) + wo.astype(d) / 2.0, Wd - 1.0)).astype(np.int64)
+            he_o = rnd(np.minimum(hc.astype(d) + ho.astype(d) / 2.0, H - 1.0)).astype(np.int64)
+            a_roi = ((he - hs + 1).astype(f32) * (we - ws + 1).astype(f32)).astype(f32)
+            a_in = ((he_i - hs_i + 1).astype(f32) * (we_i - ws_i + 1).astype(f32)).astype(f32)
+            a_out = ((he_o - hs_o + 1).astype(f32) * (we_o - ws_o + 1).astype(f32)).astype(f32)
+            s_roi, s_in, s_out = box(I, ws, hs, we, he), box(I, ws_i, hs_i, we_i, he_i), box(I, ws_o, hs_o, we_o, he_o)
+            a_frame, a_ctx = np.maximum(a_roi - a_in, f32(1)), np.maximum(a_out - a_roi, f32(1))
+            s_frame, s_ctx = (s_roi - s_in).astype(f32), (s_out - s_roi).astype(f32)
+            if area_sqrt:
+                score = (s_frame / np.sqrt(a_frame)).astype(f32) - (s_ctx / np.sqrt(a_ctx)).astype(f32)
+            else:
+                score = (s_frame / a_frame).astype(f32) - (s_ctx / a_ctx).astype(f32)
+            score = score.astype(f32)
+            mx = max(f32(0), score.max()) if R else f32(0)
+            mn = min(f32(0), score.min()) if R else f32(0)
+            if mx > 0 and mn < 0:
+                v = np.where(score > 0, score / mx, score / (-mn)).astype(f32)
+            elif mx > 0 and mn == 0:
+                v = (score / mx).astype(f32)
+            else:
+                v = np.ones(R, f32)
+            p = Y[b, c]
+            Wout[:, c] = ((p * v).astype(f32) + ((f32(1) - p) * f32(1))).astype(f32)
+    return torch.from_numpy(Wout)

@@ -287,6 +287,43 @@ def main():
                            boxes=[r.proposal_boxes.tensor for r in res], scores=[r.objectness_logits for r in res])
     torch.save(cases, os.path.join(GOLD, "rpn_select.pt"))
 
+    # ---- (4c) grouped RPN selection with the CSC re-weighting: find_top_rpn_proposals_group verbatim (:146-362); its
+    #      `csc` (wsovod._C.csc_forward, GPU only) is the oracle's restatement here -- pinned against the compiled
+    #      reference extension on the GPU box (tests/test_csc.py)
+    import oracle as orc
+    g2 = torch.Generator().manual_seed(20261019)
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("find_top_rpn_proposals_group", "_is_tracing")]
+
+    def conv(box_lists):
+        return torch.cat([torch.cat((torch.full_like(b.tensor[:, :1], i), b.tensor), dim=1) for i, b in enumerate(box_lists)], dim=0)
+
+    def csc_ref(cp, lab, pr, rois, tau, dbg, fg, mass, dens, area_sqrt, ctx):
+        return orc.csc(cp, lab, pr, rois, fg, area_sqrt, ctx), lab.clone(), torch.zeros_like(lab)
+    ns = dict(torch=torch, List=_List, Tuple=_Tuple, Boxes=Boxes, Instances=Instances, cat=d2_shim.cat,
+              batched_nms=d2_shim.batched_nms, move_device_like=lambda src_, dst_: src_, csc=csc_ref,
+              convert_boxes_to_pooler_format=conv, get_event_storage=d2_shim.get_event_storage)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "proposal_utils.py", "exec"), ns)
+    cases = {}
+    for name, (Nimg, lvls, anchors, pre, post, with_cpg) in dict(plain=(2, (900, 300), (3, 3), 200, 300, False),
+                                                                csc=(2, (1200,), (3,), 300, 250, True)).items():
+        sizes = [(480, 640), (400, 600)][:Nimg]
+        props = [torch.stack([make_rois(n, 1, 480, 640, g2)[:, 1:] for _ in range(Nimg)]) for n in lvls]
+        logits = [torch.randn(Nimg, n, generator=g2) for n in lvls]
+        cpgs = strides = None
+        if with_cpg:
+            cpgs = []
+            for (h, w_) in sizes:
+                m = torch.rand(h // 8, w_ // 8, generator=g2) * 0.09
+                m[10:30, 20:50] = 0.6
+                cpgs.append(m)
+            strides = (8, 8)
+        res = ns["find_top_rpn_proposals_group"]([p.clone() for p in props], [l.clone() for l in logits], sizes, list(anchors),
+                                                 0.7, pre, post, 0.0, False, cpgs, strides)
+        cases[name] = dict(proposals=props, logits=logits, image_sizes=sizes, num_anchors=list(anchors), nms_thresh=0.7, pre=pre,
+                           post=post, cpgs=cpgs, cpg_strides=strides, boxes=[r.proposal_boxes.tensor for r in res],
+                           scores=[r.objectness_logits for r in res], level_ids=[r.level_ids for r in res])
+    torch.save(cases, os.path.join(GOLD, "rpn_group.pt"))
+
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

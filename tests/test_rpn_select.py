@@ -36,3 +36,33 @@ def test_rpn_selection_matches_reference_on_gpu(golden):
                                      c["nms_thresh"], c["pre"], c["post"], c["min_box_size"], False,
                                      nms_fn=lambda b, s, g, t: ops.batched_nms(b, s, g, t, ops.IOU_TV_CPU))
         _check(res, c)
+
+
+def _check_group(res, c):
+    for r, gb, gs, gl in zip(res, c["boxes"], c["scores"], c["level_ids"]):
+        assert torch.equal(r.objectness_logits.cpu(), gs)
+        assert torch.equal(r.proposal_boxes.tensor.cpu(), gb)
+        assert torch.equal(r.level_ids.cpu(), gl)
+
+
+def test_rpn_group_selection_matches_reference_with_oracle_kernels(golden):
+    """find_top_rpn_proposals_group (proposal_utils.py:146-362): per-(level, anchor) groups and the CSC re-weighting"""
+    from wsovod_b200.modeling.proposal_utils import find_top_rpn_proposals_group
+    for name, c in golden("rpn_group").items():
+        res = find_top_rpn_proposals_group(
+            c["proposals"], c["logits"], c["image_sizes"], c["num_anchors"], c["nms_thresh"], c["pre"], c["post"], 0.0, False,
+            c["cpgs"], c["cpg_strides"], nms_fn=lambda b, s, g, t: oracle.batched_nms(b, s, g, t, oracle.IOU_TV_CPU),
+            csc_fn=lambda cp, l, p, r: oracle.csc(cp, l, p, r, 0.1, True, 1.8))
+        _check_group(res, c)
+
+
+@pytest.mark.gpu
+def test_rpn_group_selection_on_gpu(golden):
+    from wsovod_b200.modeling.proposal_utils import find_top_rpn_proposals_group
+    for name, c in golden("rpn_group").items():
+        cp = None if c["cpgs"] is None else [m.cuda() for m in c["cpgs"]]
+        res = find_top_rpn_proposals_group(
+            [p.cuda() for p in c["proposals"]], [l.cuda() for l in c["logits"]], c["image_sizes"], c["num_anchors"],
+            c["nms_thresh"], c["pre"], c["post"], 0.0, False, cp, c["cpg_strides"],
+            nms_fn=lambda b, s, g, t: ops.batched_nms(b, s, g, t, ops.IOU_TV_CPU))
+        _check_group(res, c)

@@ -65,6 +65,9 @@ SIGNATURES = {
     "wsovod_b200_detections_workspace": (c_sz, [c_i64, c_i64, c_i64, c_i64]),
     "wsovod_b200_detections": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_f, c_d, c_i64, c_int,
                                        c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "wsovod_b200_csc_workspace": (c_sz, [c_i64, c_i64, c_i64]),
+    "wsovod_b200_csc_fwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_f, c_p, c_p, c_sz,
+                                    c_p]),
     "wsovod_b200_infer_host_arena": (c_sz, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                             c_i64, c_int]),
     "wsovod_b200_infer_host": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p,

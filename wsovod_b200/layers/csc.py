@@ -1,19 +1,26 @@
 """``CSC`` / ``CSCConstraint`` with the reference's signatures (wsovod/layers/csc.py:9-143).
 
-``csc_constraint`` is plain tensor arithmetic in the reference (csc.py:102-125) and is kept as such.
-``csc_forward`` (wsovod/layers/csc/csc_cuda.cu) is dead code in every shipped config -- its only call
-site needs ``cpgs`` that are never produced -- and is outside the region-scoring path
-this library accelerates, so ``CSC.forward`` raises instead of silently computing something else."""
+``csc`` runs ``wsovod_b200_csc_fwd`` (csrc/csc.cu): the reference's ``_C.csc_forward`` (csc_cuda.cu:183-531) as three
+stream-ordered launches instead of a host loop with a device synchronisation per (image, class).  Like ``_CSC.apply``
+it returns ``(W, PL, NL)`` with ``PL = labels.clone().detach()`` and ``NL = zeros_like(labels)`` (csc.py:25-26,43) and
+is not differentiable (:46-49).  ``tau``, ``mass_threshold`` and ``density_threshold`` are accepted and, as upstream,
+do not influence the result (their uses are commented out, csc_cuda.cu:424-426,322).  ``csc_constraint`` is plain tensor
+arithmetic in the reference (csc.py:102-125) and is kept as such."""
 import torch
 from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+from .. import ops
+
 
 def csc(cpgs, labels, preds, rois, tau=0.7, debug_info=False, fg_threshold=0.1, mass_threshold=0.2,
         density_threshold=0.0, area_sqrt=True, context_scale=1.8):
-    raise NotImplementedError(
-        "wsovod_b200: csc_forward is not on the region-scoring path (unused by every shipped WSOVOD config)")
+    PL = labels.clone().detach()
+    NL = torch.zeros(labels.size(), dtype=labels.dtype, device=labels.device)
+    with torch.no_grad():
+        W = ops.csc(cpgs, labels, preds, rois, fg_threshold, area_sqrt, context_scale)
+    return W, PL, NL
 
 
 class CSC(nn.Module):

@@ -755,3 +755,38 @@ def detections(probs, boxes, offsets, image_sizes, max_rows, score_thresh, nms_t
     r = torch.ops.wsovod_b200.detections(probs, boxes, offsets, image_sizes, int(max_rows), float(score_thresh),
                                          float(nms_thresh), int(topk), int(iou_mode))
     return dict(det_boxes=r[0], det_scores=r[1], det_classes=r[2], det_rows=r[3], det_count=r[4])
+
+
+# ------------------------------------------------------------------------------------------------
+# CSC
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("wsovod_b200::csc", mutates_args=())
+def _csc(cpgs: torch.Tensor, labels: torch.Tensor, preds: torch.Tensor, rois: torch.Tensor, fg_threshold: float,
+         area_sqrt: bool, context_scale: float) -> torch.Tensor:
+    _need_cuda(cpgs, labels, preds, rois)
+    cpgs, labels, preds, rois = _f32c(cpgs), _f32c(labels), _f32c(preds), _f32c(rois)
+    # the reference's CAFFE_ENFORCE_EQ shape checks (csc_cuda.cu:364-372)
+    if cpgs.dim() != 4 or labels.dim() != 2 or preds.dim() != 2 or rois.dim() != 2 or rois.size(1) != 5 \
+            or labels.shape != preds.shape or labels.shape != cpgs.shape[:2]:
+        raise RuntimeError("wsovod_b200::csc expects cpgs (B,K,H,W), labels (B,K), preds (B,K), rois (R,5)")
+    B, K, H, W = cpgs.shape
+    R = rois.size(0)
+    with torch.cuda.device(cpgs.device):
+        out = torch.empty((R, K), dtype=torch.float32, device=cpgs.device)
+        L = _lib.lib()
+        ws = _workspace(L.wsovod_b200_csc_workspace(K, H, W), cpgs.device)
+        rc = L.wsovod_b200_csc_fwd(_ptr(cpgs), _ptr(labels), _ptr(preds), _ptr(rois), B, K, H, W, R, fg_threshold,
+                                   int(area_sqrt), context_scale, _ptr(out), _ptr(ws), ws.numel(), _stream(cpgs))
+    _lib.check(rc, "csc_fwd")
+    return out
+
+
+@_csc.register_fake
+def _(cpgs, labels, preds, rois, fg_threshold, area_sqrt, context_scale):
+    return cpgs.new_empty((rois.size(0), cpgs.size(1)))
+
+
+def csc(cpgs, labels, preds, rois, fg_threshold=0.1, area_sqrt=True, context_scale=1.8):
+    """wsovod._C.csc_forward: W (R,K) from class peak response maps (B,K,H,W), image labels / predictions (B,K) and rois
+    (R,5) in map pixels; not differentiable (csc.py:44-47)."""
+    return torch.ops.wsovod_b200.csc(cpgs, labels, preds, rois, float(fg_threshold), bool(area_sqrt), float(context_scale))
