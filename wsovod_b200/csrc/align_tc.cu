@@ -117,12 +117,16 @@ struct TcParams {
 };
 
 struct TcTile { int row0, rows; };
+template <bool MIL>
 __device__ __forceinline__ TcTile tc_tile(const TcParams& p, int tile) {
-  if (p.tiles) { const int4 t = __ldg(p.tiles + tile); return TcTile{t.x, t.y}; }
+  if (MIL) { const int4 t = __ldg(p.tiles + tile); return TcTile{t.x, t.y}; }
   const int64_t r0 = (int64_t)tile * TC_BM;
   return TcTile{(int)r0, (int)min((int64_t)TC_BM, p.M - r0)};
 }
 
+// MIL = fused alignment + MIL flavour (tile table, detection-stream column statistics in the epilogue); the plain
+// flavour compiles to the same code as before the fusion existed
+template <bool MIL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -164,13 +168,13 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int ntiles = p.ntiles_dev ? min(__ldg(p.ntiles_dev), p.ntiles) : p.ntiles;
+  const int ntiles = MIL ? min(__ldg(p.ntiles_dev), p.ntiles) : p.ntiles;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row0 = tc_tile(p, tile).row0;
+        const int row0 = tc_tile<MIL>(p, tile).row0;
         for (int c = 0; c < p.nchunks; ++c)
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -251,7 +255,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const float bias = p.bias ? __ldg(p.bias) : 0.f;
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-      const TcTile tt = tc_tile(p, tile);
+      const TcTile tt = tc_tile<MIL>(p, tile);
       const int64_t wrow0 = (int64_t)tt.row0 + wq * 32;          // first row of this warp
       const int wrows = min(32, tt.rows - wq * 32);              // rows of the tile this warp owns (<= 0: none)
       const uint32_t nb = tcount & 1, nphase = (tcount >> 1) & 1;
@@ -310,14 +314,14 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
               for (int rr = 0; rr < 32; ++rr)
                 if (rr < wrows) {
                   p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
-                  if (p.det) {
+                  if (MIL) {
                     const float d = __ldg(p.det + (wrow0 + rr) * p.KO + cc);
                     const float nm = fmaxf(dm, d);
                     ds = ds * expf(dm - nm) + expf(d - nm);
                     dm = nm;
                   }
                 }
-              if (p.det) p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
+              if (MIL) p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
             }
             __syncwarp();
           }
@@ -430,10 +434,11 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   CUtensorMap mx, mw;
   if ((rc = make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
   if ((rc = make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
-  e = cudaFuncSetAttribute(align_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = mil ? align_tc_kernel<true> : align_tc_kernel<false>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = std::min(p.ntiles, kNumSMs);
-  align_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
+  kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   if ((rc = after_launch())) return rc;
   if (p.rowstat) {   // in place when the caller did not ask for logits (p.logits aliases probs)
     normalize_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(p.logits, p.rowstat, M, (int)KO, probs);

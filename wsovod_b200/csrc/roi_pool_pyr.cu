@@ -333,7 +333,7 @@ __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__
   }
 }
 
-// in-place doubling D[i] = max(D[i], D[i + stride]) over the first `ncell` cells.  Reads only go
+// generic in-place doubling (any stride; used where a plane row is wider than the CTA): reads only go
 // forward, so chunks are processed front to back with one barrier between a chunk's loads and its
 // stores.  Horizontal steps may wrap into the next row's pad columns, which hold the identity for the
 // strides used (1, 2 with 3 pad columns); vertical steps run into the identity tail rows.
@@ -360,6 +360,101 @@ __device__ __noinline__ void pyr_double(uint32_t sbase, int ncell, int stride) {
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * (int)blockDim.x + (int)threadIdx.x;
       if (idx < ncell) p_sts<CB>(sbase + (uint32_t)idx * CS, v[u]);
+    }
+  }
+  __syncthreads();
+}
+
+// in-place doubling D[i] = max(D[i], D[i + stride]) over the first `ncell` cells (every output from the ORIGINAL
+// values).  Round 1 read both operands and wrote the result per cell, chunk by chunk with a barrier per chunk
+// (3 shared-memory accesses per cell).  Now every thread owns a run of cells it walks front to back with the
+// operands in a register window: it first saves the `s` cells just behind its run (the head of the next run, which
+// that run's owner will overwrite), one barrier, then one load and one store per cell.
+//   horizontal (stride 1 or 2 cells): runs of kRun consecutive cells of the linear plane; kRun is odd so the 8 lanes
+//     of a quarter-warp (kRun cells apart) hit 8 different 16-byte bank groups.  A step may wrap into the next row's
+//     pad columns, which hold the identity for the strides used (3 pad columns).
+//   vertical (stride 1 or 2 rows): a thread owns a column segment, lanes are consecutive columns (conflict-free);
+//     the last segments run into the identity tail rows.
+template <int CB, int S>
+__device__ __noinline__ void pyr_double_h(uint32_t sbase, int ncell) {
+  constexpr int s = S;
+  constexpr uint32_t CS = 4u * CB;
+  const int run = max(13, (((ncell + (int)blockDim.x - 1) / (int)blockDim.x) | 1));   // odd, >= cells per thread
+  const int a = (int)threadIdx.x * run, b = min(a + run, ncell);
+  float ov0[CB], ov1[CB];
+  if (a < ncell) {
+    p_lds<CB>(sbase + (uint32_t)b * CS, ov0);
+    if (S == 2) p_lds<CB>(sbase + (uint32_t)(b + 1) * CS, ov1);     // b + 1 <= ncell + 1 < ntot: identity tail rows
+  }
+  __syncthreads();
+  if (a < ncell) {
+    float p0[CB], p1[CB], nx[CB];
+    p_lds<CB>(sbase + (uint32_t)a * CS, p0);
+    if (s == 2) {
+      if (a + 1 < b) p_lds<CB>(sbase + (uint32_t)(a + 1) * CS, p1);
+      else {
+#pragma unroll
+        for (int k = 0; k < CB; ++k) p1[k] = ov0[k];
+      }
+    }
+    for (int j = a; j < b; ++j) {
+      const int q = j + s;
+      if (q < b) p_lds<CB>(sbase + (uint32_t)q * CS, nx);
+      else {
+#pragma unroll
+        for (int k = 0; k < CB; ++k) nx[k] = (S == 2 && (q - b)) ? ov1[k] : ov0[k];
+      }
+      float o[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) o[k] = fmaxf(p0[k], nx[k]);
+      p_sts<CB>(sbase + (uint32_t)j * CS, o);
+#pragma unroll
+      for (int k = 0; k < CB; ++k) { p0[k] = s == 2 ? p1[k] : nx[k]; p1[k] = nx[k]; }
+    }
+  }
+  __syncthreads();
+}
+
+template <int CB, int S>
+__device__ __noinline__ void pyr_double_v(uint32_t sbase, int rows, int WP) {
+  constexpr int s = S;
+  constexpr uint32_t CS = 4u * CB;
+  if (WP > (int)blockDim.x) { pyr_double<CB>(sbase, rows * WP, S * WP); return; }
+  const int nseg = max(1, (int)blockDim.x / WP);                 // column segments
+  const int seg = (int)threadIdx.x / WP, w = (int)threadIdx.x - seg * WP;
+  const int per = (rows + nseg - 1) / nseg;
+  const int r0 = seg * per, r1 = min(r0 + per, rows);
+  const bool on = seg < nseg && r0 < rows;
+  const uint32_t col = sbase + (uint32_t)w * CS, pitch = (uint32_t)WP * CS;
+  float ov0[CB], ov1[CB];
+  if (on) {
+    p_lds<CB>(col + (uint32_t)r1 * pitch, ov0);
+    if (S == 2) p_lds<CB>(col + (uint32_t)(r1 + 1) * pitch, ov1);   // rows + 1 < rows + kTailRows
+  }
+  __syncthreads();
+  if (on) {
+    float p0[CB], p1[CB], nx[CB];
+    p_lds<CB>(col + (uint32_t)r0 * pitch, p0);
+    if (s == 2) {
+      if (r0 + 1 < r1) p_lds<CB>(col + (uint32_t)(r0 + 1) * pitch, p1);
+      else {
+#pragma unroll
+        for (int k = 0; k < CB; ++k) p1[k] = ov0[k];
+      }
+    }
+    for (int j = r0; j < r1; ++j) {
+      const int q = j + s;
+      if (q < r1) p_lds<CB>(col + (uint32_t)q * pitch, nx);
+      else {
+#pragma unroll
+        for (int k = 0; k < CB; ++k) nx[k] = (S == 2 && (q - r1)) ? ov1[k] : ov0[k];
+      }
+      float o[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) o[k] = fmaxf(p0[k], nx[k]);
+      p_sts<CB>(col + (uint32_t)j * pitch, o);
+#pragma unroll
+      for (int k = 0; k < CB; ++k) { p0[k] = s == 2 ? p1[k] : nx[k]; p1[k] = nx[k]; }
     }
   }
   __syncthreads();
@@ -485,15 +580,15 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
       __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
         case PH_11: pyr_stage<CB, 0>(sbase, src, nc, H, W); __syncthreads(); break;
-        case PH_21: pyr_double<CB>(sbase, ncell, WP); break;
-        case PH_22: pyr_double<CB>(sbase, ncell, 1); break;
-        case PH_42: pyr_double<CB>(sbase, ncell, 2 * WP); break;
-        case PH_44: pyr_double<CB>(sbase, ncell, 2); break;
+        case PH_21: pyr_double_v<CB, 1>(sbase, H + kPad, WP); break;
+        case PH_22: pyr_double_h<CB, 1>(sbase, ncell); break;
+        case PH_42: pyr_double_v<CB, 2>(sbase, H + kPad, WP); break;
+        case PH_44: pyr_double_h<CB, 2>(sbase, ncell); break;
         case PH_12: pyr_stage<CB, 1>(sbase, src, nc, H, W); __syncthreads(); break;
-        case PH_14: pyr_double<CB>(sbase, ncell, 2); break;
-        case PH_24: pyr_double<CB>(sbase, ncell, WP); break;
+        case PH_14: pyr_double_h<CB, 2>(sbase, ncell); break;
+        case PH_24: pyr_double_v<CB, 1>(sbase, H + kPad, WP); break;
         default:    pyr_stage<CB, 2>(sbase, src, nc, H, W); __syncthreads();
-                    pyr_double<CB>(sbase, ncell, 2 * WP); break;       // PH_41
+                    pyr_double_v<CB, 2>(sbase, H + kPad, WP); break;   // PH_41
       }
     }
     if (phase != PH_FALLBACK) {
