@@ -186,8 +186,9 @@ class WSOVODROIHeads(nn.Module):
                                                  self.batch_size_per_images[k], self.positive_sample_fractions[k])
             predictions_k = self.box_refinery[k](box_features, classifier=classifier, append_background=append_background)
             losses.update(self.box_refinery[k].losses(predictions_k, proposals_k, num_classes=self.num_classes, refine_k=k))
-            prev_pred_scores = [s.detach() for s in self.box_refinery[k].predict_probs(predictions_k, proposals_k)]
-            prev_pred_boxes = [b.detach() for b in self.box_refinery[k].predict_boxes(predictions_k, proposals_k)]
+            if k + 1 < self.refine_K or self.rpn_on:       # the next stage's (or the RPN's) seeds come from this stage (:822-828)
+                prev_pred_scores = [s.detach() for s in self.box_refinery[k].predict_probs(predictions_k, proposals_k)]
+                prev_pred_boxes = [b.detach() for b in self.box_refinery[k].predict_boxes(predictions_k, proposals_k)]
         if self.rpn_on:                                                       # pseudo targets of the RPN (:872-881)
             self.proposal_targets, _ = get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, self.gt_classes_img_int,
                                                      self.pred_class_img_logits, self.num_classes)
