@@ -204,6 +204,32 @@ def main():
         gt_scores=[p.gt_scores for p in labelled], gt_weights=[p.gt_weights for p in labelled],
     ), os.path.join(GOLD, "refine.pt"))
 
+    # ---- (3') MIST seeds: WSOVODROIHeads.get_pgt_mist verbatim (roi_heads.py:910-1040, no SAM) -------------------
+    g3 = torch.Generator().manual_seed(20261020)
+    mist_sizes = (400, 120, 30)
+    mist_shapes = [(240, 320), (200, 304), (120, 160)]
+    mp, ms_l, mb_l = [], [], []
+    for i, (s_, (ih, iw)) in enumerate(zip(mist_sizes, mist_shapes)):
+        b = make_rois(s_, 1, ih, iw, g3)[:, 1:]
+        if i == 2:
+            b[::2, 2] = b[::2, 0] + 3.0
+            b[::2, 3] = b[::2, 1] + 3.0                      # every other box has area 9 <= 20: filtered (:1090-1111)
+        inst = Instances((ih, iw))
+        inst.proposal_boxes = Boxes(b)
+        mp.append(inst)
+        mb_l.append(b)
+        sc = torch.rand(s_, K, generator=g3) ** 6            # a few scores above the 0.05 threshold, most below
+        ms_l.append(torch.cat([sc, torch.zeros(s_, 1)], 1))
+    mself = types.SimpleNamespace(num_classes=K, images=[None] * 3, gt_classes_img_int=self.gt_classes_img_int,
+                                  pred_class_img_logits=self.pred_class_img_logits)
+    mself.get_pgt_top_k = types.MethodType(rh.WSOVODROIHeads.get_pgt_top_k, mself)
+    mt = rh.WSOVODROIHeads.get_pgt_mist(mself, mb_l, ms_l, mp)
+    torch.save(dict(boxes=mb_l, scores=ms_l, sizes=list(mist_sizes), shapes=mist_shapes, num_classes=K,
+                    gt_classes_img=[t.clone() for t in self.gt_classes_img_int], img_scores=self.pred_class_img_logits,
+                    seed_boxes=[t.gt_boxes.tensor for t in mt], seed_classes=[t.gt_classes for t in mt],
+                    seed_scores=[t.gt_scores for t in mt], seed_weights=[t.gt_weights for t in mt]),
+               os.path.join(GOLD, "mist.pt"))
+
     # ---- (3b) weighted refinement losses: InstanceRefinementOutputLayers.losses verbatim ---
     cases = {}
     for name, (dcols_per, beta, reg) in dict(agnostic=(1, 0.0, True), specific=(K, 0.5, True), noreg=(1, 0.0, False)).items():

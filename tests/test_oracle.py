@@ -178,3 +178,30 @@ def test_align_mil_composition_vs_reference_class_head_miner(golden):
         assert (lg - c["logits"]).abs().max().item() <= 5e-5, name
         torch.testing.assert_close(s, c["scores"], rtol=2e-4, atol=1e-7)
         torch.testing.assert_close(img, c["img"], rtol=2e-4, atol=1e-7)
+
+
+def _mist_check(golden, device, **kw):
+    from wsovod_b200.modeling import get_pgt_mist
+    from wsovod_b200.structures import Boxes, Instances
+    f = golden("mist")
+    props = [Instances(tuple(s), proposal_boxes=Boxes(b.to(device))) for b, s in zip(f["boxes"], f["shapes"])]
+    targets, seeds = get_pgt_mist([b.to(device) for b in f["boxes"]], [s.to(device) for s in f["scores"]], props,
+                                  [g.to(device) for g in f["gt_classes_img"]], f["img_scores"].to(device), f["num_classes"], **kw)
+    for n, t in enumerate(targets):
+        assert torch.equal(t.gt_boxes.tensor.cpu(), f["seed_boxes"][n])
+        assert torch.equal(t.gt_classes.cpu(), f["seed_classes"][n])
+        assert torch.equal(t.gt_scores.cpu(), f["seed_scores"][n])
+        assert torch.equal(t.gt_weights.cpu(), f["seed_weights"][n])
+    assert seeds["seed_offsets"].tolist()[-1] == sum(len(t.gt_classes) for t in targets)
+
+
+def test_get_pgt_mist_vs_reference_with_oracle_nms(golden):
+    """WSOVODROIHeads.get_pgt_mist (roi_heads.py:910-1040) mirror: top 15 % per class, 0.05 threshold, class-agnostic
+    NMS at 0.2 -- with the oracle's NMS in place of the kernel (CPU)"""
+    _mist_check(golden, "cpu", nms_fn=lambda b, s, g, t: oracle.batched_nms(b, s, g, t, oracle.IOU_TV_CPU))
+
+
+@pytest.mark.gpu
+def test_get_pgt_mist_vs_reference_on_gpu(golden):
+    from wsovod_b200 import ops
+    _mist_check(golden, "cuda:0", iou_mode=ops.IOU_TV_CPU)

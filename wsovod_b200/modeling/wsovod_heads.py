@@ -28,7 +28,7 @@ from .roi_heads import get_image_level_gt, get_pgt_top_k, label_proposals_wsl
 
 @torch.no_grad()
 def get_pgt_mist(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits, num_classes,
-                 top_pro=0.15, thres=0.05, nms_thresh=0.2, iou_mode=ops.IOU_TV_CUDA):
+                 top_pro=0.15, thres=0.05, nms_thresh=0.2, iou_mode=ops.IOU_TV_CUDA, nms_fn=None):
     """roi_heads.py:910-1040 without SAM (the MIST seeds): per image and image-level class the top
     ``max(int(n * top_pro), 1)`` proposals with box area > 20 (:1090-1118), rank 0 always and the rest only with
     score >= thres (:1148-1175), then ONE class-agnostic NMS at 0.2 over the image's candidates (:930-939) -- all
@@ -44,10 +44,13 @@ def get_pgt_mist(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_in
         b, s = b[keep], s[keep][:, gt]
         num = b.size(0)
         G = gt.numel()
-        if num == 0 or G == 0:          # the reference's fallback seed (:1188-1207)
+        if G == 0:                      # no image-level class: the reference's fallback seed (:1188-1207)
             cb.append(torch.tensor([[-10000.0, -10000.0, 10000.0, 10000.0]], device=dev))
             cs.append(torch.ones(1, device=dev))
             cc.append(torch.zeros(1, dtype=gt.dtype, device=dev))
+        elif num == 0:
+            # upstream asks topk for max(int(0 * top_pro), 1) = 1 row of an empty matrix (:1116-1125) and fails
+            raise RuntimeError("selected index k out of range (image %d has no proposal with box area > 20)" % n)
         else:
             k = max(int(num * top_pro), 1) if 0 < top_pro < 1 else min(num, max(int(top_pro), 1))
             v, i = torch.topk(s, k, dim=0)                                   # (k, G), scores descending per class
@@ -59,8 +62,11 @@ def get_pgt_mist(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_in
         cg.append(torch.full((cs[-1].numel(),), n, dtype=torch.int64, device=dev))
         per_img.append(cs[-1].numel())
     B, S, C, Gr = torch.cat(cb), torch.cat(cs), torch.cat(cc), torch.cat(cg)
-    keep, num_keep = torch.ops.wsovod_b200.batched_nms(B, S, Gr, len(proposals), float(nms_thresh), int(iou_mode))
-    keep = keep[: int(num_keep.item())]
+    if nms_fn is None:
+        keep, num_keep = torch.ops.wsovod_b200.batched_nms(B, S, Gr, len(proposals), float(nms_thresh), int(iou_mode))
+        keep = keep[: int(num_keep.item())]
+    else:
+        keep = nms_fn(B, S, Gr, nms_thresh)
     # per image, score-descending (batched_nms returns the kept indices of all groups sorted by score)
     kg = Gr[keep]
     order = torch.sort(kg, stable=True).indices
