@@ -200,15 +200,16 @@ __global__ void __launch_bounds__(256) align_bwd_w_kernel(const float* __restric
   }
 }
 
-__global__ void align_bwd_w_finish_kernel(const float* __restrict__ part, int S, const float* __restrict__ w, int K, int D,
-                                          int norm, float* __restrict__ grad_w) {
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (k >= K) return;
+// one CTA per class: the split-M partials are added in a fixed order (deterministic); <w, dW^> and ||w||^2 by a block
+// reduction, then the Jacobian of the weight normalisation
+__global__ void __launch_bounds__(256) align_bwd_w_finish_kernel(const float* __restrict__ part, int S, const float* __restrict__ w,
+                                                                 int K, int D, int norm, float* __restrict__ grad_w) {
+  const int k = blockIdx.x;
+  __shared__ float s_ss[8], s_dot[8];
   float ss = 0.f, dot = 0.f;
-  for (int d = lane; d < D; d += 32) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float a = 0.f;
-    for (int z = 0; z < S; ++z) a += part[((int64_t)z * K + k) * D + d];   // fixed order: deterministic
+    for (int z = 0; z < S; ++z) a += __ldg(part + ((int64_t)z * K + k) * D + d);
     grad_w[(int64_t)k * D + d] = a;
     const float v = w[(int64_t)k * D + d];
     ss += v * v;
@@ -217,10 +218,13 @@ __global__ void align_bwd_w_finish_kernel(const float* __restrict__ part, int S,
   if (norm != 1) return;
   ss = warp_sum(ss);
   dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) { s_ss[threadIdx.x >> 5] = ss; s_dot[threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  ss = dot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ss += s_ss[i]; dot += s_dot[i]; }
   const float nrm = sqrtf(ss), den = fmaxf(nrm, 1e-12f);
   const float proj = nrm > 1e-12f ? dot / (den * den) : 0.f;     // <w^, dW^> / den
-  __syncwarp();
-  for (int d = lane; d < D; d += 32) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float a = grad_w[(int64_t)k * D + d];
     grad_w[(int64_t)k * D + d] = (a - w[(int64_t)k * D + d] * proj) / den;
   }
@@ -337,7 +341,7 @@ WSOVOD_API int wsovod_b200_align_bwd(const float* grad_logits, const float* x, c
     align_bwd_w_kernel<<<dim3((unsigned)ceil_div(D, 64), (unsigned)ceil_div(K, 64), (unsigned)S), 256, 0, st>>>(
         grad_logits, KO, x, rowscale, M, (int)K, (int)D, per, part);
     if ((rc = after_launch())) return rc;
-    align_bwd_w_finish_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(part, S, classifier, (int)K, (int)D, norm_weight, grad_classifier);
+    align_bwd_w_finish_kernel<<<(unsigned)K, 256, 0, st>>>(part, S, classifier, (int)K, (int)D, norm_weight, grad_classifier);
     if ((rc = after_launch())) return rc;
     if (!grad_x) return 0;
   }

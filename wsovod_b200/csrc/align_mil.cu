@@ -5,14 +5,15 @@
 // i.e. ObjectMiningOutputLayers.forward / predict_probs_img with `cls` = the open-vocabulary class head
 // (fast_rcnn_open_vocabulary.py:280-285,318-367,604-618; the variant of roi_heads.py:588-590).
 //
-// Three launches after the weight normalisation:
+// Four launches after the weight normalisation:
 //   (1) mil_tiles_kernel   -- device-side table of row tiles, every tile inside ONE image (offsets stay on the device)
 //   (2) align_tc_kernel    -- tcgen05 TF32 contraction; the TMEM epilogue turns the accumulator into the row softmax
 //                             p[r, :] (written to `scores`) and, on the same transposed walk that writes it, reduces
 //                             the detection stream's column softmax statistics (max, sum exp) of its <= 32 rows
-//   (3) mil_fused_finish   -- one CTA per tile: merges the image's partial statistics (fixed order), applies the
-//                             column softmax in place, sums the tile's columns; the last CTA of an image (ticket)
-//                             adds the tile sums in tile order and clamps: deterministic, no float atomics.
+//   (3) mil_fused_merge    -- one warp per (image, class) merges the partial statistics (fixed tree)
+//   (4) mil_fused_finish   -- one CTA per tile: applies the column softmax in place, sums the tile's columns; the last
+//                             CTA of an image (ticket) adds the tile sums in tile order and clamps: deterministic, no
+//                             float atomics.
 #include "align.cuh"
 
 #include <algorithm>
@@ -38,9 +39,34 @@ __global__ void mil_tiles_kernel(const int64_t* __restrict__ offsets, int N, int
   *ntiles = t;
 }
 
+// one warp per (image, class): the image's partial statistics (tile-major, four per tile), 32 at a time, combined with
+// the online-softmax merge -- a fixed tree, so the result does not depend on scheduling
+__global__ void __launch_bounds__(256) mil_fused_merge_kernel(const int* __restrict__ tile_first, const float2* __restrict__ colpart,
+                                                              int N, int K, float2* __restrict__ colstat) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= N * K) return;
+  const int n = wid / K, k = wid - n * K;
+  const int q0 = __ldg(tile_first + n) * 4, q1 = __ldg(tile_first + n + 1) * 4;
+  float m = -FLT_MAX, s = 0.f;
+  for (int q = q0 + lane; q < q1; q += 32) {
+    const float2 pq = __ldg(colpart + (size_t)q * K + k);
+    const float nm = fmaxf(m, pq.x);
+    s = s * expf(m - nm) + pq.y * expf(pq.x - nm);
+    m = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = s * expf(m - nm) + os * expf(om - nm);
+    m = nm;
+  }
+  if (lane == 0) colstat[(size_t)n * K + k] = make_float2(m, 1.f / s);
+}
+
 __global__ void __launch_bounds__(128) mil_fused_finish_kernel(
     const int4* __restrict__ tiles, const int* __restrict__ tile_first, const int* __restrict__ ntiles,
-    const float2* __restrict__ colpart, const float* __restrict__ det, int K, float* __restrict__ scores,
+    const float2* __restrict__ colstat, const float* __restrict__ det, int K, float* __restrict__ scores,
     float* __restrict__ tilesum, int* __restrict__ tickets, float* __restrict__ img) {
   extern __shared__ float sm[];
   float* cmax = sm;             // [K]
@@ -52,39 +78,35 @@ __global__ void __launch_bounds__(128) mil_fused_finish_kernel(
   const int4 t = __ldg(tiles + tile);
   const int n = t.z;
   const int t0 = __ldg(tile_first + n), t1 = __ldg(tile_first + n + 1);
-  // (a) the image's column statistics: partials in (tile, warp) order
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float m = -FLT_MAX, s = 0.f;
-    for (int q = t0 * 4; q < t1 * 4; ++q) {
-      const float2 pq = __ldg(colpart + (size_t)q * K + k);
-      const float nm = fmaxf(m, pq.x);
-      s = s * expf(m - nm) + pq.y * expf(pq.x - nm);
-      m = nm;
-    }
-    cmax[k] = m;
-    cinv[k] = 1.f / s;
+    const float2 cs = __ldg(colstat + (size_t)n * K + k);
+    cmax[k] = cs.x;
+    cinv[k] = cs.y;
   }
   __syncthreads();
-  // (b) scores = p * softmax_col(det) in place; lane == column, a warp walks its 32 rows in order
+  // scores = p * softmax_col(det) in place; lane == column, a warp walks its 32 rows in order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t wrow0 = (int64_t)t.x + warp * 32;
   const int wrows = min(32, t.y - warp * 32);
   for (int k0 = 0; k0 < K; k0 += 32) {
     const int k = k0 + lane;
     float acc = 0.f;
-    if (k < K)
+    if (k < K) {
+      const float cm = cmax[k], ci = cinv[k];
+#pragma unroll 8
       for (int rr = 0; rr < wrows; ++rr) {
         const size_t e = (size_t)(wrow0 + rr) * K + k;
-        const float v = scores[e] * (expf(__ldg(det + e) - cmax[k]) * cinv[k]);
+        const float v = scores[e] * (expf(__ldg(det + e) - cm) * ci);
         scores[e] = v;
         acc += v;
       }
-    if (k < K) wsum[warp * K + k] = acc;
+      wsum[warp * K + k] = acc;
+    }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     tilesum[(size_t)tile * K + k] = (wsum[k] + wsum[K + k]) + (wsum[2 * K + k] + wsum[3 * K + k]);
-  // (c) the last tile of the image adds the tile sums in tile order
+  // the last tile of the image adds the tile sums in tile order
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1) == (t1 - t0 - 1);
@@ -106,7 +128,7 @@ __global__ void mil_empty_images_kernel(const int* __restrict__ tile_first, int 
   if (tile_first[n + 1] == tile_first[n]) img[i] = 1e-6f;
 }
 
-struct MilFuseWs { size_t tiles, tile_first, ntiles, tickets, colpart, tilesum, align, bytes; int ntiles_max; };
+struct MilFuseWs { size_t tiles, tile_first, ntiles, tickets, colpart, colstat, tilesum, align, bytes; int ntiles_max; };
 
 static MilFuseWs mil_fuse_plan(int64_t M, int64_t N, int64_t D, int64_t K) {
   MilFuseWs w;
@@ -118,6 +140,7 @@ static MilFuseWs mil_fuse_plan(int64_t M, int64_t N, int64_t D, int64_t K) {
   w.ntiles = take(sizeof(int));
   w.tickets = take(sizeof(int) * (size_t)std::max<int64_t>(N, 1));
   w.colpart = take(sizeof(float2) * (size_t)w.ntiles_max * 4 * (size_t)K);
+  w.colstat = take(sizeof(float2) * (size_t)std::max<int64_t>(N, 1) * (size_t)K);
   w.tilesum = take(sizeof(float) * (size_t)w.ntiles_max * (size_t)K);
   w.align = take(align_plan(M, D, K, WSOVOD_B200_ALIGN_TF32, false).bytes);
   w.bytes = o;
@@ -153,6 +176,7 @@ WSOVOD_API int wsovod_b200_align_mil_fused_fwd(const float* x, const float* clas
   int* ntiles = (int*)(ws + w.ntiles);
   int* tickets = (int*)(ws + w.tickets);
   float2* colpart = (float2*)(ws + w.colpart);
+  float2* colstat = (float2*)(ws + w.colstat);
   float* tilesum = (float*)(ws + w.tilesum);
   int rc;
   mil_tiles_kernel<<<1, 32, 0, st>>>(offsets, (int)N, M, tiles, tile_first, ntiles, tickets);
@@ -163,8 +187,10 @@ WSOVOD_API int wsovod_b200_align_mil_fused_fwd(const float* x, const float* clas
   rc = align_fwd_tf32(x, classifier, M, D, K, temperature, norm_weight, /*append_background=*/0, bias, logits, scores, aw,
                       ws + w.align, st, &mf);
   if (rc) return rc;
+  mil_fused_merge_kernel<<<(unsigned)ceil_div(N * K, 8), 256, 0, st>>>(tile_first, colpart, (int)N, (int)K, colstat);
+  if ((rc = after_launch())) return rc;
   const size_t smem = sizeof(float) * (size_t)(6 * K);
-  mil_fused_finish_kernel<<<(unsigned)w.ntiles_max, 128, smem, st>>>(tiles, tile_first, ntiles, colpart, det, (int)K, scores,
+  mil_fused_finish_kernel<<<(unsigned)w.ntiles_max, 128, smem, st>>>(tiles, tile_first, ntiles, colstat, det, (int)K, scores,
                                                                       tilesum, tickets, img_scores);
   if ((rc = after_launch())) return rc;
   if (img_scores) {

@@ -310,18 +310,20 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (cc < p.KO) {
               // lane == output column: 128-byte row segments; in MIL mode the same walk reduces the detection
               // stream's column statistics over this warp's rows (online max / sum of exp, row order)
-              float dm = -FLT_MAX, ds = 0.f;
+              if (MIL) {
+                // 32 independent loads, then max and sum-exp as two passes without a dependent rescale chain
+                float dv[32];
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) dv[rr] = rr < wrows ? __ldg(p.det + (wrow0 + rr) * p.KO + cc) : -FLT_MAX;
+                float dm = -FLT_MAX, ds = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) dm = fmaxf(dm, dv[rr]);
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) ds += rr < wrows ? expf(dv[rr] - dm) : 0.f;
+                p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
+              }
               for (int rr = 0; rr < 32; ++rr)
-                if (rr < wrows) {
-                  p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
-                  if (MIL) {
-                    const float d = __ldg(p.det + (wrow0 + rr) * p.KO + cc);
-                    const float nm = fmaxf(dm, d);
-                    ds = ds * expf(dm - nm) + expf(d - nm);
-                    dm = nm;
-                  }
-                }
-              if (MIL) p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
+                if (rr < wrows) p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
             }
             __syncwarp();
           }
@@ -344,19 +346,26 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
-// probs[r, :] = exp(logits[r, :] - max_r) * inv_r   (K > 256: the row spans several accumulator chunks)
-__global__ void normalize_rows_kernel(const float* __restrict__ logits, const float* __restrict__ rowstat, int64_t M,
-                                      int KO, float* __restrict__ probs) {
-  const int64_t total = M * KO;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total;
-       i += (int64_t)gridDim.x * blockDim.x * 4) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t e = i + j;
-      if (e < total) {
-        const int64_t r = e / KO;
-        probs[e] = expf(logits[e] - __ldg(rowstat + 2 * r)) * __ldg(rowstat + 2 * r + 1);
+// probs[r, :] = exp(logits[r, :] - max_r) * inv_r   (K > 256: the row spans several accumulator chunks).  One warp per
+// row (its two statistics are loaded once), 16-byte accesses when the row pitch allows.
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ logits, const float* __restrict__ rowstat,
+                                                             int64_t M, int KO, float* __restrict__ probs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += nwarps) {
+    const float mx = __ldg(rowstat + 2 * r), inv = __ldg(rowstat + 2 * r + 1);
+    const float* src = logits + r * KO;
+    float* dst = probs + r * KO;
+    if ((KO & 3) == 0 && (((uintptr_t)logits | (uintptr_t)probs) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int i = lane; i < KO / 4; i += 32) {
+        float4 v = s4[i];
+        v.x = expf(v.x - mx) * inv; v.y = expf(v.y - mx) * inv; v.z = expf(v.z - mx) * inv; v.w = expf(v.w - mx) * inv;
+        d4[i] = v;
       }
+    } else {
+      for (int i = lane; i < KO; i += 32) dst[i] = expf(src[i] - mx) * inv;
     }
   }
 }
@@ -441,7 +450,7 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   if ((rc = after_launch())) return rc;
   if (p.rowstat) {   // in place when the caller did not ask for logits (p.logits aliases probs)
-    normalize_rows_kernel<<<kNumSMs * 8, 256, 0, st>>>(p.logits, p.rowstat, M, (int)KO, probs);
+    normalize_rows_kernel<<<kNumSMs * 16, 256, 0, st>>>(p.logits, p.rowstat, M, (int)KO, probs);
     if ((rc = after_launch())) return rc;
   }
   return 0;
