@@ -93,12 +93,22 @@ __global__ void __launch_bounds__(128) mil_fused_finish_kernel(
     float acc = 0.f;
     if (k < K) {
       const float cm = cmax[k], ci = cinv[k];
-#pragma unroll 8
-      for (int rr = 0; rr < wrows; ++rr) {
-        const size_t e = (size_t)(wrow0 + rr) * K + k;
-        const float v = scores[e] * (expf(__ldg(det + e) - cm) * ci);
-        scores[e] = v;
-        acc += v;
+      for (int r0 = 0; r0 < wrows; r0 += 8) {          // eight rows in flight: `scores` is read and written in place,
+        float pv[8], dv[8];                            // so the loads are issued before any of the stores
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool in = r0 + u < wrows;
+          const size_t e = (size_t)(wrow0 + r0 + (in ? u : 0)) * K + k;
+          pv[u] = in ? scores[e] : 0.f;
+          dv[u] = in ? __ldg(det + e) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (r0 + u < wrows) {
+            const float v = pv[u] * (expf(dv[u] - cm) * ci);
+            scores[(size_t)(wrow0 + r0 + u) * K + k] = v;
+            acc += v;
+          }
       }
       wsum[warp * K + k] = acc;
     }

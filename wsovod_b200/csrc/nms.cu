@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(kBlkThreads) nms_blocked_kernel(
   const int g = blockIdx.x;
   const int s0 = starts[g], n = starts[g + 1] - s0;
   if (n <= 0 || n > kBlkCap) return;             // larger groups: nms_segment_kernel (launched for them by the host)
-  int npad = 1;
+  int npad = 2;                                    // even: the float4 array behind the keys stays 16-byte aligned
   while (npad < n) npad <<= 1;
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);                       // [npad]
   float4* sbox = reinterpret_cast<float4*>(sm + sizeof(unsigned long long) * (size_t)npad);   // [n] in sorted order
@@ -876,7 +876,18 @@ __global__ void __launch_bounds__(kBlkThreads) nms_blocked_kernel(
       bool dead = c >= nb;
       if (!dead) {
         const float4 bc = sbox[p0 + c];
-        for (int k = q; k < nk && !dead; k += 4) {
+        int k = q;
+        for (; k + 12 < nk && !dead; k += 16) {       // four kept boxes in flight per step: the loop is latency-bound
+          const float4 b0 = sbox[kpos[k]], b1 = sbox[kpos[k + 4]], b2 = sbox[kpos[k + 8]], b3 = sbox[kpos[k + 12]];
+          const int f0 = suppresses_fast<MODE>(b0, area_rn(b0), bc, thr), f1 = suppresses_fast<MODE>(b1, area_rn(b1), bc, thr);
+          const int f2 = suppresses_fast<MODE>(b2, area_rn(b2), bc, thr), f3 = suppresses_fast<MODE>(b3, area_rn(b3), bc, thr);
+          if ((f0 | f1 | f2 | f3) == 0) continue;      // four sure "no": the common case
+          dead = (f0 == 2 ? suppresses<MODE>(b0, area_rn(b0), bc, thr) : f0 == 1) ||
+                 (f1 == 2 ? suppresses<MODE>(b1, area_rn(b1), bc, thr) : f1 == 1) ||
+                 (f2 == 2 ? suppresses<MODE>(b2, area_rn(b2), bc, thr) : f2 == 1) ||
+                 (f3 == 2 ? suppresses<MODE>(b3, area_rn(b3), bc, thr) : f3 == 1);
+        }
+        for (; k < nk && !dead; k += 4) {
           const float4 bk = sbox[kpos[k]];
           dead = sup_exact<MODE>(bk, area_rn(bk), bc, thr);
         }
@@ -1116,7 +1127,7 @@ WSOVOD_API int wsovod_b200_batched_nms(const float* boxes, const float* scores, 
   // skips what the blocked kernel took -- `min_n`)
   {
     const int64_t nmax = std::min<int64_t>(M, kBlkCap);
-    int64_t npad2 = 1;
+    int64_t npad2 = 2;
     while (npad2 < nmax) npad2 <<= 1;
     const size_t bsmem = (size_t)npad2 * sizeof(unsigned long long) + (size_t)nmax * (sizeof(float4) + sizeof(uint16_t)) + 16;
     auto bk = iou_mode == 0 ? nms_blocked_kernel<0> : nms_blocked_kernel<1>;
