@@ -90,6 +90,12 @@ int wsovod_b200_roi_align_fwd(const float* input, int64_t N, int64_t C, int64_t 
                               const float* row_scale, float row_scale_bias,
                               float* output, void* workspace, size_t workspace_bytes, void* stream);
 
+/* backward of roi_align_fwd (torchvision _roi_align_backward): every sample scatters grad * w / count to its four taps.
+ * grad_output [R,C,PH,PW]; grad_input [N,C,H,W] must be zero-filled by the caller; fp32 atomics. */
+int wsovod_b200_roi_align_bwd(const float* grad_output, const float* rois, int64_t R, int64_t N, int64_t C,
+                              int64_t H, int64_t W, float spatial_scale, int pooled_h, int pooled_w,
+                              int sampling_ratio, int aligned, float* grad_input, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) region x concept alignment and the MIL two-stream score.
  * ---------------------------------------------------------------------------------------------- */

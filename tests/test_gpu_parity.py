@@ -678,3 +678,25 @@ def test_roi_pool_blockmax_empty_images_and_single_class():
             ref, _ = oracle.roi_pool(feat, r, 1 / 8, 7)
             out, _ = ops.roi_pool(feat.to(DEV), r.to(DEV), 1 / 8, 7, with_argmax=False)
             assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("sr,aligned", [(0, False), (0, True), (2, True)])
+def test_roi_align_backward_vs_torchvision(sr, aligned):
+    """ROIAlign backward (round 2) against torchvision's compiled op on the same GPU, incl. the folded objectness scale"""
+    import torchvision  # noqa: F401
+    g = synth.gen(61)
+    feat = synth.features(2, 5, 30, 40, g, relu=False)
+    boxes = [synth.proposals(150, 240, 320, g, stress=False) for _ in range(2)]
+    boxes[0][:10] += 90.0                                     # partly outside the map
+    rois, _ = synth.rois_from(boxes)
+    obj = synth.objectness(300, g)
+    x1 = feat.to(DEV).requires_grad_(True)
+    out = ops.roi_align(x1, rois.to(DEV), 1 / 8, 7, sr, aligned, obj.to(DEV), 1.0)
+    go = torch.randn(out.shape, generator=g).to(DEV)
+    out.backward(go)
+    x2 = feat.to(DEV).requires_grad_(True)
+    ref = torch.ops.torchvision.roi_align(x2, rois.to(DEV), 1 / 8, 7, 7, sr, aligned) * (obj.to(DEV) + 1).view(-1, 1, 1, 1)
+    ref.backward(go)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    scale = x2.grad.abs().max().item()
+    assert (x1.grad - x2.grad).abs().max().item() <= 1e-5 * scale

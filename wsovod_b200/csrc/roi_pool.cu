@@ -769,6 +769,52 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const fl
   }
 }
 
+// backward of ROIAlign (torchvision roi_align backward, reached through detectron2's ROIAlign, poolers.py:169-182):
+// every sample of every bin scatters grad * w_i / count to its four taps.  Same sample positions and weights as the
+// forward above (each operation individually rounded); accumulation with fp32 atomics like torchvision's kernel.
+__global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois, int64_t total,
+                                     int N, int C, int H, int W, int PH, int PW, float scale, int sampling_ratio,
+                                     int aligned, float* __restrict__ grad_in) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(i % PW), ph = (int)((i / PW) % PH);
+    const int c = (int)((i / ((int64_t)PW * PH)) % C);
+    const int64_t r = i / ((int64_t)PW * PH * C);
+    const float* roi = rois + r * 5;
+    int b = (int)roi[0];
+    b = min(max(b, 0), N - 1);
+    const float off = aligned ? 0.5f : 0.f;
+    const float sw = __fsub_rn(__fmul_rn(roi[1], scale), off), sh = __fsub_rn(__fmul_rn(roi[2], scale), off);
+    const float ew = __fsub_rn(__fmul_rn(roi[3], scale), off), eh = __fsub_rn(__fmul_rn(roi[4], scale), off);
+    float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+    if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+    const float bh = __fdiv_rn(rh, (float)PH), bw = __fdiv_rn(rw, (float)PW);
+    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)PH));
+    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)PW));
+    const float count = (float)max(gh * gw, 1);
+    const float g = grad_out[i];
+    float* gi = grad_in + ((int64_t)b * C + c) * H * W;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float yy = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn((float)iy + .5f, bh), (float)gh));
+      for (int ix = 0; ix < gw; ++ix) {
+        const float xx = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn((float)ix + .5f, bw), (float)gw));
+        float y = yy, x = xx;
+        if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+        if (y <= 0) y = 0;
+        if (x <= 0) x = 0;
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+        const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+        atomicAdd(gi + yl * W + xl, __fdiv_rn(__fmul_rn(g, __fmul_rn(hy, hx)), count));
+        atomicAdd(gi + yl * W + xh, __fdiv_rn(__fmul_rn(g, __fmul_rn(hy, lx)), count));
+        atomicAdd(gi + yh * W + xl, __fdiv_rn(__fmul_rn(g, __fmul_rn(ly, hx)), count));
+        atomicAdd(gi + yh * W + xh, __fdiv_rn(__fmul_rn(g, __fmul_rn(ly, lx)), count));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1027,6 +1073,20 @@ WSOVOD_API int wsovod_b200_roi_align_fwd(const float* input, int64_t N, int64_t 
   return pool_common(MODE_ALIGN, input, N, C, H, W, rois, R, spatial_scale, PH, PW, sampling_ratio,
                      aligned, row_scale, row_scale_bias, output, nullptr, workspace, workspace_bytes,
                      stream);
+}
+
+WSOVOD_API int wsovod_b200_roi_align_bwd(const float* grad_output, const float* rois, int64_t R, int64_t N, int64_t C,
+                                         int64_t H, int64_t W, float spatial_scale, int PH, int PW, int sampling_ratio,
+                                         int aligned, float* grad_input, void* stream) {
+  if (R < 0 || N <= 0 || C < 0 || H <= 0 || W <= 0 || PH <= 0 || PW <= 0) return WSOVOD_B200_EINVAL;
+  const int64_t total = R * C * PH * PW;
+  if (total == 0) return 0;
+  if (!grad_output || !rois || !grad_input) return WSOVOD_B200_EINVAL;
+  if (H > 32767 || W > 32767 || N >= (1LL << 31) || C >= (1LL << 31)) return WSOVOD_B200_ETOOBIG;
+  const int64_t blocks = std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 32);
+  roi_align_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_output, rois, total, (int)N, (int)C, (int)H, (int)W,
+                                                                           PH, PW, spatial_scale, sampling_ratio, aligned, grad_input);
+  return after_launch();
 }
 
 WSOVOD_API int wsovod_b200_roi_pool_bwd(const float* grad_output, const float* rois,

@@ -228,6 +228,44 @@ def _(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned, r
     return input.new_empty((rois.size(0), input.size(1), pooled_h, pooled_w))
 
 
+@torch.library.custom_op("wsovod_b200::roi_align_backward", mutates_args=())
+def _roi_align_backward(grad: torch.Tensor, rois: torch.Tensor, spatial_scale: float, sampling_ratio: int, aligned: bool,
+                        N: int, C: int, H: int, W: int) -> torch.Tensor:
+    _need_cuda(grad, rois)
+    grad, rois = _f32c(grad), _f32c(rois)
+    ph, pw = grad.shape[-2:]
+    with torch.cuda.device(grad.device):
+        gi = torch.zeros((N, C, H, W), dtype=torch.float32, device=grad.device)
+        rc = _lib.lib().wsovod_b200_roi_align_bwd(_ptr(grad), _ptr(rois), rois.size(0), N, C, H, W, spatial_scale, ph, pw,
+                                                  sampling_ratio, int(aligned), _ptr(gi), _stream(grad))
+    _lib.check(rc, "roi_align_bwd")
+    return gi
+
+
+@_roi_align_backward.register_fake
+def _(grad, rois, spatial_scale, sampling_ratio, aligned, N, C, H, W):
+    return grad.new_empty((N, C, H, W))
+
+
+def _roi_align_setup(ctx, inputs, output):
+    input, rois, spatial_scale, ph, pw, sampling_ratio, aligned, row_scale, bias = inputs
+    ctx.shape = tuple(input.shape)
+    ctx.cfg = (spatial_scale, sampling_ratio, aligned, bias, row_scale is not None)
+    ctx.save_for_backward(rois, row_scale)
+
+
+def _roi_align_bwd(ctx, grad_out):
+    rois, row_scale = ctx.saved_tensors
+    spatial_scale, sampling_ratio, aligned, bias, has_scale = ctx.cfg
+    g = grad_out * (row_scale + bias).view(-1, 1, 1, 1) if has_scale else grad_out
+    N, C, H, W = ctx.shape
+    gi = torch.ops.wsovod_b200.roi_align_backward(g, rois, spatial_scale, sampling_ratio, aligned, N, C, H, W)
+    return gi, None, None, None, None, None, None, None, None
+
+
+_roi_align.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
+
+
 def roi_align(input, rois, spatial_scale, output_size, sampling_ratio=0, aligned=False, row_scale=None,
               row_scale_bias=0.0):
     ph, pw = _pair(output_size)
