@@ -5,6 +5,7 @@ implementation and, where the reference op is differentiable, an autograd formul
 matching ``*_bwd`` kernel.  CPU tensors are rejected like the reference's own ops do
 (wsovod/layers/ROILoopPool/ROILoopPool.h:62 "Not compiled with CPU support").
 """
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -47,6 +48,49 @@ def _workspace(nbytes, device):
 
 def _pair(v):
     return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+# Eager fast path.  Every op below is registered as a torch custom op (torch.ops.wsovod_b200.*: schema, fake kernel,
+# autograd formula -- what torch.compile / export see).  The dispatcher's Python layers cost 50-100 us per call, which
+# is the price of a dozen of these kernels; in plain eager mode the public functions therefore call the op's body
+# directly and, where autograd is needed, through a torch.autograd.Function built from the SAME setup / backward
+# functions the custom op registers.  WSOVOD_B200_EAGER_FAST=0 routes everything through torch.ops again.
+_FAST = os.environ.get("WSOVOD_B200_EAGER_FAST", "1") != "0"
+_FAST_FN = {}
+
+
+def _body(op):
+    return op._init_fn
+
+
+def _fast_function(op, setup, backward):
+    body = _body(op)
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *inputs):
+            out = body(*inputs)
+            setup(ctx, inputs, out)
+            return tuple(out) if isinstance(out, (list, tuple)) else out
+
+        @staticmethod
+        def backward(ctx, *grads):
+            return backward(ctx, *grads)
+
+    Fn.__name__ = "Fast_" + op._opoverload.name().replace("::", "_") if hasattr(op, "_opoverload") else "Fast"
+    return Fn
+
+
+def _call(op, *args):
+    """run custom op `op` on `args`: torch.ops dispatch under tracing / compile (or WSOVOD_B200_EAGER_FAST=0), else its
+    body directly, wrapped in the op's autograd formula when a tensor argument requires grad"""
+    if not _FAST or torch.compiler.is_compiling():
+        return op(*args)
+    fn = _FAST_FN.get(op)
+    if fn is not None and torch.is_grad_enabled() and any(isinstance(a, torch.Tensor) and a.requires_grad for a in args):
+        return fn.apply(*args)
+    with torch.no_grad():
+        return _body(op)(*args)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -125,11 +169,12 @@ def _roi_pool_bwd(ctx, grad_out, _grad_arg):
     if ctx.has_scale:
         g = g * (row_scale + ctx.bias).view(-1, 1, 1, 1)
     N, C, H, W = ctx.shape
-    gi = torch.ops.wsovod_b200.roi_pool_backward(g, rois, argmax, N, C, H, W, False)
+    gi = _call(_roi_pool_backward, g, rois, argmax, N, C, H, W, False)
     return gi, None, None, None, None, None, None, None
 
 
 _roi_pool.register_autograd(_roi_pool_bwd, setup_context=_roi_pool_setup)
+_FAST_FN[_roi_pool] = _fast_function(_roi_pool, _roi_pool_setup, _roi_pool_bwd)
 
 
 def roi_pool(input, rois, spatial_scale, output_size, row_scale=None, row_scale_bias=0.0,
@@ -140,7 +185,7 @@ def roi_pool(input, rois, spatial_scale, output_size, row_scale=None, row_scale_
     ph, pw = _pair(output_size)
     if with_argmax is None:
         with_argmax = bool(input.requires_grad and torch.is_grad_enabled())
-    return torch.ops.wsovod_b200.roi_pool(input, rois, float(spatial_scale), ph, pw, row_scale,
+    return _call(_roi_pool, input, rois, float(spatial_scale), ph, pw, row_scale,
                                           float(row_scale_bias), bool(with_argmax))
 
 
@@ -186,18 +231,19 @@ def _roi_loop_pool_bwd(ctx, grad_out, _grad_arg):
         s = (row_scale + ctx.bias)
         g = g * torch.cat([s, s, s]).view(-1, 1, 1, 1)
     N, C, H, W = ctx.shape
-    gi = torch.ops.wsovod_b200.roi_pool_backward(g, rois, argmax, N, C, H, W, True)
+    gi = _call(_roi_pool_backward, g, rois, argmax, N, C, H, W, True)
     return gi, None, None, None, None, None, None, None
 
 
 _roi_loop_pool.register_autograd(_roi_loop_pool_bwd, setup_context=_roi_pool_setup)
+_FAST_FN[_roi_loop_pool] = _fast_function(_roi_loop_pool, _roi_pool_setup, _roi_loop_pool_bwd)
 
 
 def roi_loop_pool(input, rois, spatial_scale, output_size, row_scale=None, row_scale_bias=0.0,
                   with_argmax=True):
     """wsovod._C.roi_loop_pool_forward semantics: (3R,C,P,P) = roi | frame | context."""
     ph, pw = _pair(output_size)
-    return torch.ops.wsovod_b200.roi_loop_pool(input, rois, float(spatial_scale), ph, pw, row_scale,
+    return _call(_roi_loop_pool, input, rois, float(spatial_scale), ph, pw, row_scale,
                                                float(row_scale_bias), bool(with_argmax))
 
 
@@ -259,17 +305,18 @@ def _roi_align_bwd(ctx, grad_out):
     spatial_scale, sampling_ratio, aligned, bias, has_scale = ctx.cfg
     g = grad_out * (row_scale + bias).view(-1, 1, 1, 1) if has_scale else grad_out
     N, C, H, W = ctx.shape
-    gi = torch.ops.wsovod_b200.roi_align_backward(g, rois, spatial_scale, sampling_ratio, aligned, N, C, H, W)
+    gi = _call(_roi_align_backward, g, rois, spatial_scale, sampling_ratio, aligned, N, C, H, W)
     return gi, None, None, None, None, None, None, None, None
 
 
 _roi_align.register_autograd(_roi_align_bwd, setup_context=_roi_align_setup)
+_FAST_FN[_roi_align] = _fast_function(_roi_align, _roi_align_setup, _roi_align_bwd)
 
 
 def roi_align(input, rois, spatial_scale, output_size, sampling_ratio=0, aligned=False, row_scale=None,
               row_scale_bias=0.0):
     ph, pw = _pair(output_size)
-    return torch.ops.wsovod_b200.roi_align(input, rois, float(spatial_scale), ph, pw, int(sampling_ratio),
+    return _call(_roi_align, input, rois, float(spatial_scale), ph, pw, int(sampling_ratio),
                                            bool(aligned), row_scale, float(row_scale_bias))
 
 
@@ -354,7 +401,7 @@ def _align_bwd(ctx, g_logits, g_probs):
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     gx = gw = None
     if need_x or need_w:
-        gx, gw = torch.ops.wsovod_b200.align_backward(g, x, classifier, temperature, norm_weight, append_background,
+        gx, gw = _call(_align_backward, g, x, classifier, temperature, norm_weight, append_background,
                                                       bool(need_x), bool(need_w))
         gx, gw = (gx if need_x else None), (gw if need_w else None)
     gb = g.sum().reshape(1) if has_bias else None
@@ -362,13 +409,14 @@ def _align_bwd(ctx, g_logits, g_probs):
 
 
 _align.register_autograd(_align_bwd, setup_context=_align_setup)
+_FAST_FN[_align] = _fast_function(_align, _align_setup, _align_bwd)
 
 
 def align(x, classifier, temperature=50.0, norm_weight=True, append_background=True, bias=None,
           precision=ALIGN_TF32, want_logits=True, want_probs=False):
     """Contraction part of OpenVocabularyClassifier.forward (+ optional fused row softmax).
     Returns (logits, probs); a tensor that was not requested is empty."""
-    return torch.ops.wsovod_b200.align(x, classifier, float(temperature), int(norm_weight),
+    return _call(_align, x, classifier, float(temperature), int(norm_weight),
                                        bool(append_background), bias, int(precision), bool(want_logits),
                                        bool(want_probs))
 
@@ -437,16 +485,17 @@ def _mil_bwd(ctx, g_scores, g_img):
     cls, det, offsets, img = ctx.saved_tensors
     if g_img is not None:   # clamp(min=1e-6, max=1-1e-6) passes gradient only strictly inside
         g_img = g_img * ((img > 1e-6) & (img < 1.0 - 1e-6)).to(g_img.dtype)
-    gc, gd = torch.ops.wsovod_b200.mil_backward(g_scores, g_img, cls, det, offsets)
+    gc, gd = _call(_mil_backward, g_scores, g_img, cls, det, offsets)
     return gc, gd, None
 
 
 _mil.register_autograd(_mil_bwd, setup_context=_mil_setup)
+_FAST_FN[_mil] = _fast_function(_mil, _mil_setup, _mil_bwd)
 
 
 def mil(cls, det, offsets):
     """Two-stream MIL scores (M,K) and clamped image-level scores (N,K); offsets: int64 (N+1) on GPU."""
-    return torch.ops.wsovod_b200.mil(cls, det, offsets)
+    return _call(_mil, cls, det, offsets)
 
 
 @torch.library.custom_op("wsovod_b200::align_mil", mutates_args=())
@@ -496,11 +545,11 @@ def _align_mil_bwd(ctx, g_scores, g_img, _g_logits):
         return (None,) * 8
     if g_img is not None:   # clamp(min=1e-6, max=1-1e-6) passes gradient only strictly inside
         g_img = g_img * ((img > 1e-6) & (img < 1.0 - 1e-6)).to(g_img.dtype)
-    gc, gd = torch.ops.wsovod_b200.mil_backward(g_scores, g_img, logits, det, offsets)
+    gc, gd = _call(_mil_backward, g_scores, g_img, logits, det, offsets)
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     gx = gw = None
     if need_x or need_w:
-        gx, gw = torch.ops.wsovod_b200.align_backward(gc, x, classifier, temperature, norm_weight, False, bool(need_x),
+        gx, gw = _call(_align_backward, gc, x, classifier, temperature, norm_weight, False, bool(need_x),
                                                       bool(need_w))
         gx, gw = (gx if need_x else None), (gw if need_w else None)
     gb = gc.sum().reshape(1) if has_bias else None
@@ -508,6 +557,7 @@ def _align_mil_bwd(ctx, g_scores, g_img, _g_logits):
 
 
 _align_mil.register_autograd(_align_mil_bwd, setup_context=_align_mil_setup)
+_FAST_FN[_align_mil] = _fast_function(_align_mil, _align_mil_setup, _align_mil_bwd)
 
 
 def align_mil(x, classifier, det, offsets, temperature=50.0, norm_weight=True, bias=None, want_logits=None):
@@ -516,7 +566,7 @@ def align_mil(x, classifier, det, offsets, temperature=50.0, norm_weight=True, b
     whenever autograd will need them).  TF32 contraction, K <= 256."""
     if want_logits is None:
         want_logits = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, classifier, det, bias))
-    s, img, lg = torch.ops.wsovod_b200.align_mil(x, classifier, det, offsets, float(temperature), int(norm_weight), bias,
+    s, img, lg = _call(_align_mil, x, classifier, det, offsets, float(temperature), int(norm_weight), bias,
                                                  bool(want_logits))
     return s, img, lg
 
@@ -559,7 +609,7 @@ def _(scores, boxes, offsets, gt_classes, gt_offsets, img_scores):
 
 
 def pgt_top1(scores, boxes, offsets, gt_classes, gt_offsets, img_scores):
-    sb, sc, ss, sw, sr, cnt = torch.ops.wsovod_b200.pgt_top1(scores, boxes, offsets, gt_classes, gt_offsets,
+    sb, sc, ss, sw, sr, cnt = _call(_pgt_top1, scores, boxes, offsets, gt_classes, gt_offsets,
                                                              img_scores)
     return dict(seed_boxes=sb, seed_classes=sc, seed_scores=ss, seed_weights=sw, seed_rows=sr, seed_count=cnt)
 
@@ -604,7 +654,7 @@ def _(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_weights, seed_
 
 def refine_assign(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_weights, seed_offsets,
                   seed_count, num_classes, iou_thresh=0.5):
-    r = torch.ops.wsovod_b200.refine_assign(boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_weights,
+    r = _call(_refine_assign, boxes, offsets, seed_boxes, seed_classes, seed_scores, seed_weights,
                                             seed_offsets, seed_count, int(num_classes), float(iou_thresh))
     return dict(matched_idx=r[0], matched_label=r[1], matched_iou=r[2], gt_classes=r[3], gt_boxes=r[4],
                 gt_scores=r[5], gt_weights=r[6])
@@ -694,12 +744,13 @@ def _refine_losses_setup(ctx, inputs, output):
 def _refine_losses_bwd(ctx, g_out, g_lse):
     out, lse, logits, gt_classes, gt_weights = ctx.saved_tensors[:5]
     deltas, pb, gb = ctx.saved_tensors[5:] if ctx.has_deltas else (None, None, None)
-    gl, gd = torch.ops.wsovod_b200.refine_losses_backward(g_out[:2].contiguous(), out, lse, logits, deltas, gt_classes,
+    gl, gd = _call(_refine_losses_backward, g_out[:2].contiguous(), out, lse, logits, deltas, gt_classes,
                                                           gt_weights, pb, gb, *ctx.consts)
     return (gl, gd if ctx.has_deltas else None) + (None,) * 10
 
 
 _refine_losses.register_autograd(_refine_losses_bwd, setup_context=_refine_losses_setup)
+_FAST_FN[_refine_losses] = _fast_function(_refine_losses, _refine_losses_setup, _refine_losses_bwd)
 
 
 def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes=None, gt_boxes=None, num_classes=None,
@@ -709,7 +760,7 @@ def refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes=None, g
     to `logits` and `deltas`; `deltas=None` (refine_reg off) gives loss_box_reg = 0."""
     K = int(num_classes) if num_classes is not None else logits.size(1) - 1
     wx, wy, ww, wh = (float(v) for v in box_weights)
-    out, _ = torch.ops.wsovod_b200.refine_losses(logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, K,
+    out, _ = _call(_refine_losses, logits, deltas, gt_classes, gt_weights, proposal_boxes, gt_boxes, K,
                                                  wx, wy, ww, wh, float(smooth_l1_beta))
     return out[0], out[1]
 
@@ -749,7 +800,7 @@ def batched_nms(boxes, scores, idxs, iou_threshold, iou_mode=IOU_TV_CUDA):
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
     uniq, dense = torch.unique(idxs, return_inverse=True)
-    keep, num = torch.ops.wsovod_b200.batched_nms(boxes.float(), scores, dense, int(uniq.numel()),
+    keep, num = _call(_batched_nms, boxes.float(), scores, dense, int(uniq.numel()),
                                                   float(iou_threshold), int(iou_mode))
     return keep[: int(num.item())]
 
@@ -790,7 +841,7 @@ def _(probs, boxes, offsets, image_sizes, max_rows, score_thresh, nms_thresh, to
 def detections(probs, boxes, offsets, image_sizes, max_rows, score_thresh, nms_thresh, topk,
                iou_mode=IOU_TV_CUDA):
     """Fused fast_rcnn_inference tail for class-agnostic boxes, batched over images (padded outputs)."""
-    r = torch.ops.wsovod_b200.detections(probs, boxes, offsets, image_sizes, int(max_rows), float(score_thresh),
+    r = _call(_detections, probs, boxes, offsets, image_sizes, int(max_rows), float(score_thresh),
                                          float(nms_thresh), int(topk), int(iou_mode))
     return dict(det_boxes=r[0], det_scores=r[1], det_classes=r[2], det_rows=r[3], det_count=r[4])
 
@@ -827,4 +878,4 @@ def _(cpgs, labels, preds, rois, fg_threshold, area_sqrt, context_scale):
 def csc(cpgs, labels, preds, rois, fg_threshold=0.1, area_sqrt=True, context_scale=1.8):
     """wsovod._C.csc_forward: W (R,K) from class peak response maps (B,K,H,W), image labels / predictions (B,K) and rois
     (R,5) in map pixels; not differentiable (csc.py:44-47)."""
-    return torch.ops.wsovod_b200.csc(cpgs, labels, preds, rois, float(fg_threshold), bool(area_sqrt), float(context_scale))
+    return _call(_csc, cpgs, labels, preds, rois, float(fg_threshold), bool(area_sqrt), float(context_scale))
