@@ -296,6 +296,26 @@ def extra_kernels(w2, st2, peaks, it, dev):
     k["refine_loss_bwd"] = hbm({"ms": ktime(lambda: torch.ops.wsovod_b200.refine_losses_backward(
         go, out, lse, logits, deltas, a["gt_classes"], a["gt_weights"], boxes, a["gt_boxes"], K, 10.0, 10.0, 5.0, 5.0, 0.0), it),
         "algorithmic_bytes": M * (2 * 4 * (K + 1) + 8 + 4 + 16 + 16 + 32)}, peaks)
+    # the same two kernels batched over a whole c2 batch (8 images x 4000 rows) and over 64 images: one image of 5024 rows
+    # moves 1.6 MB per tensor and is latency-bound by nature ("report both per-image and batched")
+    for tag, (nimg, rows) in dict(c2=(8, 4000), x64=(64, 4000)).items():
+        Mb = nimg * rows
+        Cb, Db = (t_.to(dev) for t_ in synth.mil_logits(Mb, K, g))
+        offb = torch.arange(0, Mb + 1, rows, dtype=torch.int64, device=dev)
+        k[f"mil_fwd_{tag}"] = hbm({"ms": ktime(lambda: ops.mil(Cb, Db, offb), it), "algorithmic_bytes": 3 * 4 * K * Mb + 4 * K * nimg}, peaks)
+        sb_, imgb = ops.mil(Cb, Db, offb)
+        bb = synth.proposals(Mb, 688, 1024, g).to(dev)
+        lab = synth.image_labels(nimg, K, synth.gen(5), 8)
+        gtb = torch.cat(lab).to(dev)
+        goffb = torch.tensor([0] + torch.tensor([len(x_) for x_ in lab]).cumsum(0).tolist(), dtype=torch.int64, device=dev)
+
+        def refine_b():
+            sd = ops.pgt_top1(sb_, bb, offb, gtb, goffb, imgb)
+            return ops.refine_assign(bb, offb, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"], sd["seed_weights"], goffb,
+                                     sd["seed_count"], K, 0.5)
+        k[f"pgt_top1+refine_assign_{tag}"] = hbm({"ms": ktime(refine_b, it),
+                                                  "algorithmic_bytes": Mb * 57 + 28 * int(gtb.numel()) + 4 * Mb * int(gtb.numel()) // nimg}, peaks)
+        del Cb, Db, sb_, imgb, bb
     x = synth.region_embeddings(M, D, g).to(dev)
     t = synth.text_embeddings(K, D, g).to(dev)
     gl = torch.randn(M, K + 1, device=dev)
