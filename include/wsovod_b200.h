@@ -38,6 +38,7 @@ uint64_t wsovod_b200_launch_count(void);
  * reference's interface; results never depend on them.  Returns the previous value (or EINVAL). */
 #define WSOVOD_B200_TUNE_POOL_PATH 0  /* 0 library's choice (default), 1 scan kernels, 2 block-max planes */
 #define WSOVOD_B200_TUNE_POOL_GROUP 1 /* 1 bank-conflict-aware lane order of the block-max path (default), 0 row-major */
+#define WSOVOD_B200_TUNE_ALIGN_PAIR 2 /* 1 CTA-pair (cta_group::2) contraction for K + 1 > 256 (default), 0 one CTA per tile */
 int wsovod_b200_tune(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------

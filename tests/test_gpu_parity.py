@@ -192,6 +192,35 @@ def test_align_vs_oracle(M, D, K, precision):
     assert (lg3.cpu() - lo3).abs().max().item() <= (1e-5 if precision == ops.ALIGN_FP32 else 4e-3) * scale
 
 
+@pytest.mark.parametrize("M,D,K", [(257, 768, 1203), (1, 64, 300), (700, 100, 513), (2049, 768, 1203), (130, 32, 256),
+                                   (5000, 512, 1000)])
+def test_align_cta_pair_kernel(M, D, K):
+    """K + 1 > 256: the CTA-pair kernel (cta_group::2, units dealt across pairs, per-chunk row statistics) against the
+    oracle at the stated TF32 tolerance and against the one-CTA-per-tile kernel (same TF32 products in the same order:
+    identical logits; probabilities at 1e-5, the chunk statistics are merged in another order)"""
+    from wsovod_b200 import _lib
+    g = synth.gen(M + K + 1)
+    x = synth.region_embeddings(M, D, g)
+    x[0] = 0
+    t = synth.text_embeddings(K, D, g)
+    lo, po = oracle.align(x, t, 50.0, True, True)
+    xd, td = x.to(DEV), t.to(DEV)
+    assert _lib.tune(_lib.TUNE_ALIGN_PAIR, 1) == 1
+    lg, pr = ops.align(xd, td, 50.0, True, True, None, ops.ALIGN_TF32, True, True)
+    _, pr_only = ops.align(xd, td, 50.0, True, True, None, ops.ALIGN_TF32, False, True)
+    lg_only, _ = ops.align(xd, td, 50.0, True, True, None, ops.ALIGN_TF32, True, False)
+    _lib.tune(_lib.TUNE_ALIGN_PAIR, 0)
+    try:
+        lg1, pr1 = ops.align(xd, td, 50.0, True, True, None, ops.ALIGN_TF32, True, True)
+    finally:
+        _lib.tune(_lib.TUNE_ALIGN_PAIR, 1)
+    assert (lg.cpu() - lo).abs().max().item() <= TF32_LOGIT_TOL
+    assert torch.equal(lg, lg1) and torch.equal(lg_only, lg)
+    torch.testing.assert_close(pr, torch.softmax(lg, -1), rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(pr, pr1, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(pr_only, pr, rtol=1e-6, atol=1e-9)
+
+
 def test_align_backward():
     g = synth.gen(5)
     x = synth.region_embeddings(200, 96, g).add_(0.01)

@@ -29,6 +29,28 @@ def short(name):
     return name.replace("void ", "").replace("wsovod::", "").split("(")[0]
 
 
+def launches_md(launches, tag, out):
+    """ncu launch list (gpu__time_duration per launch) -> profiles/<tag>_launches.md: per-kernel share of the run"""
+    rows = list(csv.reader(open(launches)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= vi:
+            continue
+        a = agg.setdefault(short(r[ki])[:70], [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi]) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`)\n\n")
+        f.write(f"source: `{os.path.basename(launches)}`; {sum(v[0] for v in agg.values())} launches, {tot:.0f} us in total "
+                "(cold-cache, serialised: compare shares, not absolutes)\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {v[1] / tot:.3f} |\n")
+
+
 def main():
     rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
     out = os.path.join(ROOT, "profiles")
@@ -58,24 +80,7 @@ def main():
     traffic["source"] = f"ncu --set full, {os.path.basename(rep)}, config c2, dram__bytes_read.sum + dram__bytes_write.sum per launch"
     json.dump(traffic, open(os.path.join(out, "roofline_traffic.json"), "w"), indent=1)
 
-    rows = list(csv.reader(open(launches)))
-    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-    hdr = rows[hi]
-    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    agg = collections.OrderedDict()
-    for r in rows[hi + 1:]:
-        if len(r) <= vi:
-            continue
-        a = agg.setdefault(short(r[ki])[:70], [0, 0.0])
-        a[0] += 1
-        a[1] += float(r[vi]) / 1e3
-    tot = sum(v[1] for v in agg.values())
-    with open(os.path.join(out, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`)\n\n")
-        f.write(f"source: `{os.path.basename(launches)}`; {sum(v[0] for v in agg.values())} launches, {tot:.0f} us in total "
-                "(cold-cache, serialised: compare shares, not absolutes)\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
-        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {v[1] / tot:.3f} |\n")
+    launches_md(launches, tag, out)
     print("wrote", out)
 
 

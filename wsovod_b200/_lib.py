@@ -108,7 +108,7 @@ def launch_count():
     return int(lib().wsovod_b200_launch_count())
 
 
-TUNE_POOL_PATH, TUNE_POOL_GROUP = 0, 1
+TUNE_POOL_PATH, TUNE_POOL_GROUP, TUNE_ALIGN_PAIR = 0, 1, 2
 POOL_AUTO, POOL_SCAN, POOL_BLOCKMAX = 0, 1, 2
 
 

@@ -3,7 +3,7 @@
 
 namespace wsovod {
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_tune[TUNE_COUNT] = {{0}, {1}};
+std::atomic<int> g_tune[TUNE_COUNT] = {{0}, {1}, {1}};
 }
 
 WSOVOD_API int wsovod_b200_tune(int key, int value) {

@@ -5,7 +5,7 @@
 namespace wsovod {
 
 struct AlignWs {
-  size_t what, wt, dy, rowstat, rowscale, wpart, bytes;
+  size_t what, tickets, tickets_bytes, wt, dy, rowstat, rowscale, wpart, bytes;
   int64_t wsplit;   // split-M factor of the classifier-gradient partial products
   int64_t Dp, Kp;   // padded reduction length / padded number of weight rows (TF32 path)
 };

@@ -15,90 +15,19 @@
 #include <cuda.h>
 
 #include "align.cuh"
+#include "tc_ptx.cuh"
 
 #include <algorithm>
 #include <mutex>
 
 namespace wsovod {
 
-constexpr int TC_BM = 128;          // rows per tile (UMMA M)
-constexpr int TC_BK = 32;           // fp32 elements per stage row = 128 B = one swizzle atom
-constexpr int TC_THREADS = 256;
-constexpr int TC_SPIN_LIMIT = 1 << 26;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  for (int spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (spin > TC_SPIN_LIMIT) __trap();   // a protocol bug must abort the launch, never hang the GPU
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* smem, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor: K-major operand, 128B swizzle, rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                              // leading byte offset (unused: one atom along K)
-  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
-  return d;
-}
-
 struct TcParams {
   const float* x;
   const float* bias;
   float* logits;      // [M, KO] (never null inside the kernel: falls back to `probs` storage)
   float* probs;       // [M, KO] or null
-  float* rowstat;     // [M, 2] (row max, 1/sum exp) when the softmax is finished by normalize_rows_kernel
+  float* rowstat;     // [M, 2] (row max, sum exp) when the softmax is finished by normalize_rows_kernel
   int64_t M;
   int D, KO, Kp;      // Kp: padded weight rows (multiple of 32)
   int BN;             // accumulator columns per chunk (multiple of 32, <= 256)
@@ -332,9 +261,9 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         mbar_arrive(&tempty[buf]);               // accumulator buffer may be overwritten
       }
       if (p.rowstat && lane < wrows) {
-        // multi-chunk: (max, 1/sum) per row for the streaming normalisation kernel that follows
+        // multi-chunk: (max, sum) per row for the streaming normalisation kernel that follows
         p.rowstat[2 * (wrow0 + lane)] = run_m;
-        p.rowstat[2 * (wrow0 + lane) + 1] = 1.f / run_s;
+        p.rowstat[2 * (wrow0 + lane) + 1] = run_s;
       }
     }
   }
@@ -346,14 +275,23 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
-// probs[r, :] = exp(logits[r, :] - max_r) * inv_r   (K > 256: the row spans several accumulator chunks).  One warp per
-// row (its two statistics are loaded once), 16-byte accesses when the row pitch allows.
+// probs[r, :] = exp(logits[r, :] - max_r) / sum_r   (K > 256: the row spans several accumulator chunks).  `rowstat`
+// holds `ns` (max, sum of exp(logit - max)) pairs per row -- one for the whole row from align_tc_kernel, one per chunk
+// from the CTA-pair kernel -- merged here.  One warp per row, 16-byte accesses when the row pitch allows.
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ logits, const float* __restrict__ rowstat,
-                                                             int64_t M, int KO, float* __restrict__ probs) {
+                                                             int ns, int64_t M, int KO, float* __restrict__ probs) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += nwarps) {
-    const float mx = __ldg(rowstat + 2 * r), inv = __ldg(rowstat + 2 * r + 1);
+    const float* rs = rowstat + 2 * r * ns;
+    float mx = __ldg(rs), sum = __ldg(rs + 1);
+    for (int c = 1; c < ns; ++c) {
+      const float m2 = __ldg(rs + 2 * c), s2 = __ldg(rs + 2 * c + 1);
+      const float nm = fmaxf(mx, m2);
+      sum = sum * expf(mx - nm) + s2 * expf(m2 - nm);
+      mx = nm;
+    }
+    const float inv = 1.f / sum;
     const float* src = logits + r * KO;
     float* dst = probs + r * KO;
     if ((KO & 3) == 0 && (((uintptr_t)logits | (uintptr_t)probs) & 15) == 0) {
@@ -388,8 +326,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                    uint32_t box_rows) {
+int tc_make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return WSOVOD_B200_EUNSUPPORTED;
   cuuint64_t dims[2] = {inner, rows};
@@ -409,12 +347,21 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   if (M > 0x7fffffffLL - TC_BM) return WSOVOD_B200_ETOOBIG;
   const int64_t KO = K + (append_background ? 1 : 0);
   float* what = (float*)(ws + w.what);                              // [Kp, Dp], rows >= K and cols >= D are zero
-  cudaError_t e = cudaMemsetAsync(what, 0, sizeof(float) * (size_t)(w.Kp * w.Dp), st);
+  // one memset: the padded text matrix and, right behind it, the pair kernel's tickets
+  cudaError_t e = cudaMemsetAsync(what, 0, w.tickets + w.tickets_bytes - w.what, st);
   if (e != cudaSuccess) return (int)e;
   int rc;
   if (K > 0) {
     align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)w.Dp, norm_weight == 1, what);
     if ((rc = after_launch())) return rc;
+  }
+  const int64_t nch2 = ceil_div(KO, 256);
+  if (!mil && nch2 > 1 && tune(TUNE_ALIGN_PAIR)) {
+    // large vocabularies: CTA pairs (align_tc2.cu), row softmax by the register-row pass that follows
+    float* lg = logits ? logits : probs;
+    if ((rc = align_tc2_launch(x, what, M, D, KO, w.Kp, w.Dp, temperature, norm_weight, bias, lg, probs,
+                               (int*)(ws + w.tickets), st))) return rc;
+    return 0;
   }
   TcParams p;
   p.x = x; p.bias = bias; p.logits = logits ? logits : probs; p.probs = probs;
@@ -441,8 +388,8 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;                                               // <= 512
   CUtensorMap mx, mw;
-  if ((rc = make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
-  if ((rc = make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
+  if ((rc = tc_make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
+  if ((rc = tc_make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
   auto kern = mil ? align_tc_kernel<true> : align_tc_kernel<false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -450,7 +397,7 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
   if ((rc = after_launch())) return rc;
   if (p.rowstat) {   // in place when the caller did not ask for logits (p.logits aliases probs)
-    normalize_rows_kernel<<<kNumSMs * 16, 256, 0, st>>>(p.logits, p.rowstat, M, (int)KO, probs);
+    normalize_rows_kernel<<<kNumSMs * 16, 256, 0, st>>>(p.logits, p.rowstat, 1, M, (int)KO, probs);
     if ((rc = after_launch())) return rc;
   }
   return 0;

@@ -24,6 +24,7 @@ extern std::atomic<uint64_t> g_launches; // kernels launched by this library (be
 // process-wide tuning / test switches (wsovod_b200_tune): never change results, only which kernel runs
 enum { TUNE_POOL_PATH = 0,    // 0 = library's choice, 1 = scan kernels, 2 = block-max planes wherever they apply
        TUNE_POOL_GROUP = 1,   // 1 = deal a pass's bins into bank-conflict-free quarter-warps (default), 0 = row-major lanes
+       TUNE_ALIGN_PAIR = 2,   // 1 = CTA-pair contraction kernel for K + 1 > 256 (default), 0 = one CTA per tile
        TUNE_COUNT = 16 };
 extern std::atomic<int> g_tune[TUNE_COUNT];
 inline int tune(int key) { return g_tune[key].load(std::memory_order_relaxed); }
