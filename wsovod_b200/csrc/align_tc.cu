@@ -360,7 +360,7 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
     // large vocabularies: CTA pairs (align_tc2.cu), row softmax by the register-row pass that follows
     float* lg = logits ? logits : probs;
     if ((rc = align_tc2_launch(x, what, M, D, KO, w.Kp, w.Dp, temperature, norm_weight, bias, lg, probs,
-                               (int*)(ws + w.tickets), st))) return rc;
+                               (int*)(ws + w.tickets), (float*)(ws + w.rowstat), st))) return rc;
     return 0;
   }
   TcParams p;

@@ -33,7 +33,7 @@ namespace wsovod {
 constexpr int TC2_BN = 256;          // accumulator columns per unit (UMMA N), both TMEM buffers = 512 columns
 constexpr int TC2_HALF = TC2_BN / 2; // text rows staged per CTA and stage
 constexpr int TC2_STAGING = 2 * 32 * 128;   // epilogue staging per warp: two [32 rows x 32 floats] boxes
-constexpr int TC2_THREADS = 384;            // 8 warps as in align_tc.cu + 4 finisher warps (row softmax of finished tiles)
+constexpr int TC2_THREADS = 384;            // 8 warps as in align_tc.cu + 4 warps that only finish row softmaxes
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -89,10 +89,13 @@ struct Tc2Params {
   int tma_out;         // logits leave through swizzled shared memory + TMA stores (row pitch a multiple of 16 bytes)
   float* probs;        // non-null: the row softmax is finished inside the kernel (needs tma_out), in place if == logits
   int* tickets;        // [ntiles * 8] zeroed: chunks of (tile, CTA rank, 32-row quarter) whose logits are in memory
+  float2* rowstat;     // [M, nchunks] (chunk max, sum of exp(logit - chunk max)) written by the epilogue for the finishers
   int64_t M;
   int KO, nchunks, kblocks, stages, ntiles;   // ntiles: 256-row tiles
   int norm;
   float temperature;
+  int dbg;
+  int interleave;      // 1: unit u runs on pair u % npairs; 0: contiguous ranges of units per pair
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
@@ -114,15 +117,20 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* tempty = tfull + 2;             // leader's: both CTAs' epilogues have drained the buffer
   uint64_t* nfull = tempty + 2;
   uint64_t* nempty = nfull + 2;
-  uint64_t* jfull = nempty + 2;              // [4] a finished 32-row block is posted to finisher warp q
-  uint64_t* jempty = jfull + 4;             // [4] ... which has taken it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(jempty + 4);
-  int* job_slot = reinterpret_cast<int*>(tmem_slot + 1);   // [4] first row of the posted block (-1: no more)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nempty + 2);
+  int* job_next = reinterpret_cast<int*>(tmem_slot + 1);      // next finishing job of this CTA
 
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int64_t U = (int64_t)p.ntiles * p.nchunks;
-  const int u0 = (int)(U * pair / npairs), u1 = (int)(U * (pair + 1) / npairs);
+  // unit i of this pair is u_first + i * u_step: interleaved (the chunks of a tile run on neighbouring pairs at the same
+  // time: the tile's x rows are fetched once for all of them and its logits are microseconds old when the softmax is
+  // finished) or a contiguous range
+  const int u_step = p.interleave ? npairs : 1;
+  const int u_first = p.interleave ? pair : (int)(U * pair / npairs);
+  const int u_count_all = p.interleave ? (int)((U - pair + npairs - 1) / npairs) : (int)(U * (pair + 1) / npairs) - u_first;
+  const int u_count = (p.dbg & 8) && warp < 8 ? 0 : u_count_all;    // dbg 8: finishers alone
+  auto tile_of = [&](int i) { return (u_first + i * u_step) / p.nchunks; };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -135,7 +143,7 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256);
       mbar_init(&nfull[b], 2); mbar_init(&nempty[b], 128);
     }
-    for (int q = 0; q < 4; ++q) { mbar_init(&jfull[q], 1); mbar_init(&jempty[q], 1); }
+    *job_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -151,7 +159,8 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = u0; u < u1; ++u) {
+      for (int i = 0; i < u_count; ++i) {
+        const int u = u_first + i * u_step;
         const int tile = u / p.nchunks, c = u - tile * p.nchunks;
         const int64_t row0 = (int64_t)tile * (2 * TC_BM) + rank * TC_BM;
         const int xr = row0 < p.M ? (int)row0 : 0;                       // a half tile past the last row: any rows do
@@ -170,8 +179,8 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-      for (int u = u0; u < u1; ++u, ++it) {
-        const int c = u % p.nchunks;
+      for (int i = 0; i < u_count; ++i, ++it) {
+        const int c = (u_first + i * u_step) % p.nchunks;
         const int nc = min(TC2_BN, (p.KO - c * TC2_BN + 15) & ~15);
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc, M = 256 (128 rows per CTA)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nc >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
@@ -197,8 +206,8 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ===== norm warps =====
     const int t = (warp - 2) * 32 + lane;        // rows t and t + 64 of this CTA's half tile
     int stage = 0; uint32_t phase = 0; uint32_t seg = 0;
-    for (int u = u0; u < u1; ++u) {
-      const bool first = (u == u0) || (u % p.nchunks == 0);     // first unit of a tile within this pair's range
+    for (int i = 0; i < u_count; ++i) {
+      const bool first = i == 0 || tile_of(i) != tile_of(i - 1);     // this pair's first unit of the tile
       float ss0 = 0.f, ss1 = 0.f;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(&cons[stage], phase);
@@ -234,14 +243,16 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     float* st = reinterpret_cast<float*>(stw);
     const float bias = p.bias ? __ldg(p.bias) : 0.f;
     const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty[0]), 0), ltempty1 = mapa_u32(smem_u32(&tempty[1]), 0);
-    uint32_t it = 0, seg = 0, sbuf = 0, jobs = 0;
+    uint32_t it = 0, seg = 0, sbuf = 0;
     int seg_units = 0;
     float scale = 1.f;
-    for (int u = u0; u < u1; ++u, ++it) {
+    for (int i = 0; i < u_count; ++i, ++it) {
+      const int u = u_first + i * u_step;
       const int tile = u / p.nchunks, c = u - tile * p.nchunks;
+      const bool seg_end = i + 1 == u_count || tile_of(i + 1) != tile;    // this pair's last unit of the tile
       const int64_t wrow0 = (int64_t)tile * (2 * TC_BM) + rank * TC_BM + wq * 32;
       const int wrows = (int)max((int64_t)0, min((int64_t)32, p.M - wrow0));
-      if (u == u0 || c == 0) {
+      if (i == 0 || tile_of(i - 1) != tile) {
         const uint32_t nb = seg & 1, nphase = (seg >> 1) & 1;
         ++seg;
         mbar_wait(&nfull[nb], nphase);
@@ -255,6 +266,7 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int col0 = c * TC2_BN;
       const int ncols = min(TC2_BN, p.KO - col0);
       float v[32];
+      float cm = -FLT_MAX, cs = 0.f;
       for (int j = 0; j < ncols; j += 32) {
         tmem_ld32(taddr + j, v);
         if (p.tma_out) {
@@ -266,17 +278,30 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           unsigned char* box = stw + sbuf * (32 * 128);
           unsigned char* dst = box + lane * 128;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o;
-            o.x = fmaf(v[4 * q], scale, bias); o.y = fmaf(v[4 * q + 1], scale, bias);
-            o.z = fmaf(v[4 * q + 2], scale, bias); o.w = fmaf(v[4 * q + 3], scale, bias);
-            *reinterpret_cast<float4*>(dst + ((q ^ (lane & 7)) << 4)) = o;
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (p.probs) {
+            // running (max, sum of exp) of this row over the unit's columns, one rescale per 32-column slab; the sums use
+            // the fast exponential (they are dominated by the terms next to the maximum, where its error is ~1e-7)
+            float m = -FLT_MAX;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) m = fmaxf(m, v[i]);
+            const float nm = fmaxf(cm, m);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) acc += __expf(v[i] - nm);
+            cs = cs * __expf(cm - nm) + acc;
+            cm = nm;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && wrows > 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(&map_out), "r"(smem_u32(box)), "r"(col0 + j), "r"((int)wrow0) : "memory");
+            // L2 policy: evict-last while the finishers still have to read the rows back, evict-first when nobody does
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                         ::"l"(&map_out), "r"(smem_u32(box)), "r"(col0 + j), "r"((int)wrow0),
+                           "l"(p.probs ? 0x14F0000000000000ull : 0x12F0000000000000ull) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           sbuf ^= 1;
@@ -294,111 +319,113 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       tc_fence_before();
       mbar_arrive_cluster(buf ? ltempty1 : ltempty0);
       ++seg_units;
-      if (p.probs && lane == 0 && (u + 1 == u1 || c + 1 == p.nchunks)) {
-        // this pair's last unit of the tile: once the logits of all chunks of these 32 rows are in memory (ours: the bulk
-        // stores have completed; another pair's: its ticket is in) the rows go to this quarter's finisher warp
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        bool last = seg_units == p.nchunks;
-        if (!last) {
-          __threadfence();
-          last = atomicAdd(p.tickets + (tile * 2 + (int)rank) * 4 + wq, seg_units) + seg_units == p.nchunks;
-          __threadfence();
-        }
-        if (last && wrows > 0) {
-          mbar_wait(&jempty[wq], (jobs & 1) ^ 1);
-          job_slot[wq] = (int)wrow0;
-          mbar_arrive(&jfull[wq]);
-          ++jobs;
-        }
+      if (p.probs) {
+        if (lane < wrows) p.rowstat[(wrow0 + lane) * p.nchunks + c] = make_float2(cm, cs);
+        __syncwarp();
       }
-      if (u + 1 == u1 || c + 1 == p.nchunks) seg_units = 0;
+      if (p.probs && lane == 0 && seg_end) {
+        // this pair's logits of these 32 rows are in memory once its bulk stores have completed: hand in the ticket
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence();
+        atomicAdd(p.tickets + (wrow0 >> 5), seg_units);
+      }
+      if (seg_end) seg_units = 0;
     }
     if (lane == 0) {
       if (p.tma_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      if (p.probs) {
-        mbar_wait(&jempty[wq], (jobs & 1) ^ 1);
-        job_slot[wq] = -1;
-        mbar_arrive(&jfull[wq]);
-      }
     }
-  } else if (warp < 12 && p.probs) {
-    // ===== finisher warps: probs[r, :] = softmax(logits[r, :]) for 32-row blocks whose chunks are all in memory.  The rows
-    // come back from L2 (they were written microseconds ago), two rows in flight per warp, each whole in registers.
-    const int fq = warp - 8;
+  }
+  // ===== finishing: probs[r, :] = exp(logits[r, :] - max_r) / sum_r for the tiles this pair is designated to finish =====
+  // A tile's softmax is finished by ONE pair, the one that runs the tile's chunk `dc` (a "last one in finishes" rule hands
+  // ever more work to a pair that has fallen behind).  Jobs are 16-row blocks of those tiles, taken in order from a
+  // shared-memory counter by whichever warp is free: the four finisher warps from the start, every other warp of the
+  // CTA once its own role is done (the tail of the kernel is all finishing).  A job waits until the tickets of all
+  // chunks of its rows are in (the other chunks run on other pairs at about the same time), merges the per-chunk
+  // statistics of its rows and streams the rows back from L2 through independent 16-byte loads, two rows in flight.
+  // The exponentials of this (TF32) path are ex2.approx: relative error ~1e-6 on probabilities whose logits carry 1e-3.
+  __syncwarp();
+  if (p.probs && !(p.dbg & 1)) {
     const int n4 = p.KO >> 2;
-    for (uint32_t jc = 0;; ++jc) {
-      mbar_wait(&jfull[fq], jc & 1);
-      const int row0 = job_slot[fq];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&jempty[fq]);
-      if (row0 < 0) break;
-      const int nrows = (int)min((int64_t)32, p.M - row0);
+    constexpr float L2E = 1.4426950408889634f;
+    int scan_i = 0, scan_jobs = 0;
+    for (;;) {
+      int j = 0;
+      if (lane == 0) j = atomicAdd(job_next, 1);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      int tile = -1;
+      while (scan_i < u_count_all) {
+        const int u = u_first + scan_i * u_step;
+        const int t = u / p.nchunks, c = u - t * p.nchunks;
+        if (c == (p.interleave ? t % p.nchunks : p.nchunks - 1) && (int64_t)t * (2 * TC_BM) + rank * TC_BM < p.M) {
+          if (j < scan_jobs + 8) { tile = t; break; }
+          scan_jobs += 8;
+        }
+        ++scan_i;
+      }
+      if (tile < 0) break;
+      const int row0 = tile * (2 * TC_BM) + (int)rank * TC_BM + (j - scan_jobs) * 16;
+      if (row0 >= p.M) continue;
+      {
+        const volatile int* tk = p.tickets + (row0 >> 5);
+        for (int spin = 0; *tk < p.nchunks && !(p.dbg & 8); ++spin) {
+          __nanosleep(200);
+          if (spin > (1 << 24)) __trap();
+        }
+        __threadfence();
+      }
+      const int nrows = (int)min((int64_t)16, p.M - row0);
+      float nb_l = 0.f, inv_l = 0.f;               // lane rr: -max * log2(e) and 1 / sum of row rr
+      if (lane < nrows) {
+        const float2* rs = p.rowstat + ((int64_t)row0 + lane) * p.nchunks;
+        float m = -FLT_MAX, sum = 0.f;
+        for (int c = 0; c < p.nchunks; ++c) {
+          const float2 st2 = __ldcg(rs + c);
+          const float nm = fmaxf(m, st2.x);
+          sum = sum * __expf(m - nm) + st2.y * __expf(st2.x - nm);
+          m = nm;
+        }
+        nb_l = -m * L2E; inv_l = 1.f / sum;
+      }
+      auto ex2 = [](float t) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t)); return r; };
       if (n4 <= 320) {
         for (int rr = 0; rr < nrows; rr += 2) {
-          const bool two = rr + 1 < nrows;
-          const float4* sa4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + rr) * p.KO);
-          const float4* sb4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + rr + (two ? 1 : 0)) * p.KO);
-          float4 a[10], b[10];
-          const float4 neg = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+          float4 a[2][10];
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const int k = i * 32 + lane;
-            a[i] = k < n4 ? __ldcg(sa4 + k) : neg;
-            b[i] = k < n4 ? __ldcg(sb4 + k) : neg;
+          for (int q = 0; q < 2; ++q) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + min(rr + q, nrows - 1)) * p.KO);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) a[q][i] = __ldcg(s4 + min(i * 32 + lane, n4 - 1));
           }
-          float ma = -FLT_MAX, mb = -FLT_MAX;
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            ma = fmaxf(ma, fmaxf(fmaxf(a[i].x, a[i].y), fmaxf(a[i].z, a[i].w)));
-            mb = fmaxf(mb, fmaxf(fmaxf(b[i].x, b[i].y), fmaxf(b[i].z, b[i].w)));
-          }
-          ma = warp_max(ma); mb = warp_max(mb);
-          float sa_ = 0.f, sb_ = 0.f;
+          for (int q = 0; q < 2; ++q) {
+            const float nb = __shfl_sync(0xffffffffu, nb_l, min(rr + q, nrows - 1));
+            const float inv = __shfl_sync(0xffffffffu, inv_l, min(rr + q, nrows - 1));
+            float4* d4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + min(rr + q, nrows - 1)) * p.KO);
 #pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            a[i].x = expf(a[i].x - ma); a[i].y = expf(a[i].y - ma); a[i].z = expf(a[i].z - ma); a[i].w = expf(a[i].w - ma);
-            b[i].x = expf(b[i].x - mb); b[i].y = expf(b[i].y - mb); b[i].z = expf(b[i].z - mb); b[i].w = expf(b[i].w - mb);
-            if (i * 32 + lane < n4) {
-              sa_ += (a[i].x + a[i].y) + (a[i].z + a[i].w);
-              sb_ += (b[i].x + b[i].y) + (b[i].z + b[i].w);
-            }
-          }
-          const float ia = 1.f / warp_sum(sa_), ib = 1.f / warp_sum(sb_);
-          float4* da4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + rr) * p.KO);
-          float4* db4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + rr + 1) * p.KO);
-#pragma unroll
-          for (int i = 0; i < 10; ++i) {
-            const int k = i * 32 + lane;
-            if (k < n4) {
-              da4[k] = make_float4(a[i].x * ia, a[i].y * ia, a[i].z * ia, a[i].w * ia);
-              if (two) db4[k] = make_float4(b[i].x * ib, b[i].y * ib, b[i].z * ib, b[i].w * ib);
+            for (int i = 0; i < 10; ++i) {
+              float4 o;
+              o.x = ex2(fmaf(a[q][i].x, L2E, nb)) * inv; o.y = ex2(fmaf(a[q][i].y, L2E, nb)) * inv;
+              o.z = ex2(fmaf(a[q][i].z, L2E, nb)) * inv; o.w = ex2(fmaf(a[q][i].w, L2E, nb)) * inv;
+              if (i * 32 + lane < n4 && rr + q < nrows && !(p.dbg & 2)) d4[i * 32 + lane] = o;
             }
           }
         }
       } else {
-        // longer rows (up to 2048 columns, checked by the host): one row at a time
         for (int rr = 0; rr < nrows; ++rr) {
+          const float nb = __shfl_sync(0xffffffffu, nb_l, rr), inv = __shfl_sync(0xffffffffu, inv_l, rr);
           const float4* s4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + rr) * p.KO);
-          float4 a[16];
-          float ma = -FLT_MAX, sa_ = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = i * 32 + lane;
-            a[i] = k < n4 ? __ldcg(s4 + k) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-            ma = fmaxf(ma, fmaxf(fmaxf(a[i].x, a[i].y), fmaxf(a[i].z, a[i].w)));
-          }
-          ma = warp_max(ma);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            a[i].x = expf(a[i].x - ma); a[i].y = expf(a[i].y - ma); a[i].z = expf(a[i].z - ma); a[i].w = expf(a[i].w - ma);
-            if (i * 32 + lane < n4) sa_ += (a[i].x + a[i].y) + (a[i].z + a[i].w);
-          }
-          const float ia = 1.f / warp_sum(sa_);
           float4* d4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + rr) * p.KO);
+          for (int k0 = 0; k0 < n4; k0 += 32 * 16) {
+            float4 a[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = i * 32 + lane;
-            if (k < n4) d4[k] = make_float4(a[i].x * ia, a[i].y * ia, a[i].z * ia, a[i].w * ia);
+            for (int i = 0; i < 16; ++i) a[i] = __ldcg(s4 + min(k0 + i * 32 + lane, n4 - 1));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float4 o;
+              o.x = ex2(fmaf(a[i].x, L2E, nb)) * inv; o.y = ex2(fmaf(a[i].y, L2E, nb)) * inv;
+              o.z = ex2(fmaf(a[i].z, L2E, nb)) * inv; o.w = ex2(fmaf(a[i].w, L2E, nb)) * inv;
+              if (k0 + i * 32 + lane < n4) d4[k0 + i * 32 + lane] = o;
+            }
           }
         }
       }
@@ -503,17 +530,18 @@ int64_t align_tc2_tickets(int64_t M) { return ceil_div(M, 2 * TC_BM) * 8; }
 
 int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, int64_t KO, int64_t Kp, int64_t Dp,
                      float temperature, int norm, const float* bias, float* logits, float* probs, int* tickets,
-                     cudaStream_t st) {
+                     float* rowstat, cudaStream_t st) {
   Tc2Params p;
   p.bias = bias; p.logits = logits; p.M = M; p.KO = (int)KO;
   p.nchunks = (int)ceil_div(KO, TC2_BN);
   p.kblocks = (int)ceil_div(D, TC_BK);
   p.ntiles = (int)ceil_div(M, 2 * TC_BM);
-  p.norm = norm; p.temperature = temperature;
+  p.norm = norm; p.temperature = temperature; p.interleave = (tune(15) & 1) ? 0 : 1; p.dbg = tune(15) >> 1;
   p.tma_out = ((KO & 3) == 0 && ((uintptr_t)logits & 15) == 0) ? 1 : 0;
-  const bool fuse = probs && p.tma_out && KO <= 2048 && ((uintptr_t)probs & 15) == 0 && tickets;
+  const bool fuse = probs && p.tma_out && KO <= 2048 && ((uintptr_t)probs & 15) == 0 && tickets && rowstat;
   p.probs = fuse ? probs : nullptr;
   p.tickets = tickets;
+  p.rowstat = reinterpret_cast<float2*>(rowstat);
   const size_t stage_bytes = (size_t)(TC_BM + TC2_HALF) * TC_BK * 4;
   const size_t extra = 4 * TC2_STAGING + 2 * TC_BM * sizeof(float) + 512;   // staging, norms, barriers + slots
   p.stages = (int)std::max<size_t>(2, std::min<size_t>(8, ((size_t)kMaxSmemOptin - 1024 - extra) / stage_bytes));

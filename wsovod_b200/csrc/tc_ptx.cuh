@@ -86,7 +86,7 @@ int tc_make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t rows
 // CTA-pair contraction for K + 1 > 256 (align_tc2.cu)
 int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, int64_t KO, int64_t Kp, int64_t Dp,
                      float temperature, int norm, const float* bias, float* logits, float* probs, int* tickets,
-                     cudaStream_t st);
+                     float* rowstat, cudaStream_t st);
 int64_t align_tc2_tickets(int64_t M);
 // probs = row softmax of logits (in place allowed), rows held in registers up to 2048 columns (align_tc2.cu)
 int softmax_rows_launch(const float* logits, int64_t M, int64_t KO, float* probs, cudaStream_t st);
