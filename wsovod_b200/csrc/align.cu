@@ -246,7 +246,7 @@ AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward
   w.Kp = precision == WSOVOD_B200_ALIGN_TF32 ? (int64_t)align_up((size_t)K + 1, 32) : K;
   w.what = take(sizeof(float) * (size_t)(w.Kp * w.Dp));            // normalised text matrix
   // completion tickets of the CTA-pair kernel (K + 1 > 256), zeroed together with `what`
-  w.tickets_bytes = precision == WSOVOD_B200_ALIGN_TF32 && K + 1 > 256 ? sizeof(int) * (size_t)(ceil_div(M, 256) * 8) : 0;
+  w.tickets_bytes = precision == WSOVOD_B200_ALIGN_TF32 && K + 1 > 256 ? sizeof(int) * (size_t)(ceil_div(M, 256) * 8 + 1) : 0;
   w.tickets = take(w.tickets_bytes);
   w.wt = take(backward ? sizeof(float) * (size_t)(K * D) : 0);     // its transpose (backward)
   w.dy = take(backward ? sizeof(float) * (size_t)(M * D) : 0);     // backward scratch

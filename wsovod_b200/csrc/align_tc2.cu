@@ -33,6 +33,7 @@ namespace wsovod {
 constexpr int TC2_BN = 256;          // accumulator columns per unit (UMMA N), both TMEM buffers = 512 columns
 constexpr int TC2_HALF = TC2_BN / 2; // text rows staged per CTA and stage
 constexpr int TC2_STAGING = 2 * 32 * 128;   // epilogue staging per warp: two [32 rows x 32 floats] boxes
+constexpr int TC2_JOBS = 16;                // finishing jobs per half tile: 8 rows each
 constexpr int TC2_THREADS = 384;            // 8 warps as in align_tc.cu + 4 warps that only finish row softmaxes
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -83,12 +84,17 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ unsigned long long g_trace[148 * 512 * 4];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ float ex2_approx(float t) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t)); return r; }
+
 struct Tc2Params {
   const float* bias;
   float* logits;       // [M, KO]
   int tma_out;         // logits leave through swizzled shared memory + TMA stores (row pitch a multiple of 16 bytes)
   float* probs;        // non-null: the row softmax is finished inside the kernel (needs tma_out), in place if == logits
-  int* tickets;        // [ntiles * 8] zeroed: chunks of (tile, CTA rank, 32-row quarter) whose logits are in memory
+  int* tickets;        // [ntiles * 8 + 1] zeroed: chunks of each 32-row block whose logits are in memory; + the job counter
   float2* rowstat;     // [M, nchunks] (chunk max, sum of exp(logit - chunk max)) written by the epilogue for the finishers
   int64_t M;
   int KO, nchunks, kblocks, stages, ntiles;   // ntiles: 256-row tiles
@@ -244,7 +250,18 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const float bias = p.bias ? __ldg(p.bias) : 0.f;
     const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty[0]), 0), ltempty1 = mapa_u32(smem_u32(&tempty[1]), 0);
     uint32_t it = 0, seg = 0, sbuf = 0;
-    int seg_units = 0;
+    int seg_units = 0, pend_ticket = -1, pend_units = 0;
+    // a pair's rows of a tile are in memory once the bulk stores (lane 0's) have completed; the ticket is a release
+    // (the lanes' statistics are ordered before it by the warp barrier), the finishers poll it with acquire loads
+    auto hand_in = [&]() {
+      if (pend_ticket < 0) return;
+      __syncwarp();                      // every lane's statistics are ordered before lane 0's release below
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.tickets + pend_ticket), "r"(pend_units) : "memory");
+      }
+      pend_ticket = -1;
+    };
     float scale = 1.f;
     for (int i = 0; i < u_count; ++i, ++it) {
       const int u = u_first + i * u_step;
@@ -262,19 +279,50 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(&tfull[buf], aphase);
       tc_fence_after();
+      const unsigned long long tr0 = (p.dbg & 16) ? gtime() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)TC2_BN;
       const int col0 = c * TC2_BN;
       const int ncols = min(TC2_BN, p.KO - col0);
       float v[32];
       float cm = -FLT_MAX, cs = 0.f;
+      long long cycA = 0, cycB = 0, cyc0 = clock64();
       for (int j = 0; j < ncols; j += 32) {
+        const long long ca = clock64();
         tmem_ld32(taddr + j, v);
-        if (p.tma_out) {
+        cycA += clock64() - ca;
+        if (p.tma_out == 2) {
+          // thread == row: its 32 logits are 128 contiguous bytes of the output row, written straight from registers as
+          // eight 16-byte stores (a warp store touches 32 rows; the L2 merges the sectors before they leave for HBM)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
+          if (lane < wrows) {
+            float4* dst = reinterpret_cast<float4*>(p.logits + (wrow0 + lane) * p.KO + col0 + j);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (j + 4 * q < ncols) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          if (p.probs) {
+            // running (max, sum of exp) of this row over the unit's columns, one rescale per 32-column slab; the sums use
+            // the fast exponential (they are dominated by the terms next to the maximum, where its error is ~1e-7)
+            float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+            const float nm = fmaxf(cm, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            const float nb = -nm * 1.4426950408889634f;
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) a4[i & 3] += ex2_approx(fmaf(v[i], 1.4426950408889634f, nb));
+            cs = cs * ex2_approx(fmaf(cm, 1.4426950408889634f, nb)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+            cm = nm;
+          }
+        } else         if (p.tma_out) {
           // thread == row: its 32 logits are 128 contiguous bytes of the output row.  They go into a [32 x 128 B] box
           // in the TMA 128B swizzle (16-byte chunk q of row r at chunk q ^ (r & 7): conflict-free for a quarter-warp),
           // and one lane sends the box; columns >= KO and rows >= M are clipped by the tensor map.
+          const long long cb = clock64();
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box two stores back has been read
           __syncwarp();
+          cycB += clock64() - cb;
           unsigned char* box = stw + sbuf * (32 * 128);
           unsigned char* dst = box + lane * 128;
 #pragma unroll
@@ -285,14 +333,15 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (p.probs) {
             // running (max, sum of exp) of this row over the unit's columns, one rescale per 32-column slab; the sums use
             // the fast exponential (they are dominated by the terms next to the maximum, where its error is ~1e-7)
-            float m = -FLT_MAX;
+            float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (j + i < ncols) m = fmaxf(m, v[i]);
-            const float nm = fmaxf(cm, m);
-            float acc = 0.f;
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+            const float nm = fmaxf(cm, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            const float nb = -nm * 1.4426950408889634f;
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (j + i < ncols) acc += __expf(v[i] - nm);
-            cs = cs * __expf(cm - nm) + acc;
+            for (int i = 0; i < 32; ++i) if (j + i < ncols) a4[i & 3] += ex2_approx(fmaf(v[i], 1.4426950408889634f, nb));
+            cs = cs * ex2_approx(fmaf(cm, 1.4426950408889634f, nb)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
             cm = nm;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -316,64 +365,58 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           __syncwarp();
         }
       }
+      const long long cycLoop = clock64() - cyc0;
       tc_fence_before();
       mbar_arrive_cluster(buf ? ltempty1 : ltempty0);
       ++seg_units;
       if (p.probs) {
         if (lane < wrows) p.rowstat[(wrow0 + lane) * p.nchunks + c] = make_float2(cm, cs);
-        __syncwarp();
-      }
-      if (p.probs && lane == 0 && seg_end) {
-        // this pair's logits of these 32 rows are in memory once its bulk stores have completed: hand in the ticket
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __threadfence();
-        atomicAdd(p.tickets + (wrow0 >> 5), seg_units);
+        if (seg_end) { pend_ticket = (int)(wrow0 >> 5); pend_units = seg_units; hand_in(); }
       }
       if (seg_end) seg_units = 0;
+      if ((p.dbg & 16) && lane == 0 && wq == 0 && i < 8) {
+        unsigned long long* tr = g_trace + ((size_t)blockIdx.x * 512 + i * 8) ;
+        tr[0] = 1; tr[1] = tr0; tr[2] = gtime(); tr[3] = u; tr[4] = cycA; tr[5] = cycB; tr[6] = cycLoop; tr[7] = clock64() - cyc0;
+      }
     }
-    if (lane == 0) {
-      if (p.tma_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
+    hand_in();
+    if (lane == 0 && p.tma_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   // ===== finishing: probs[r, :] = exp(logits[r, :] - max_r) / sum_r for the tiles this pair is designated to finish =====
-  // A tile's softmax is finished by ONE pair, the one that runs the tile's chunk `dc` (a "last one in finishes" rule hands
-  // ever more work to a pair that has fallen behind).  Jobs are 16-row blocks of those tiles, taken in order from a
-  // shared-memory counter by whichever warp is free: the four finisher warps from the start, every other warp of the
-  // CTA once its own role is done (the tail of the kernel is all finishing).  A job waits until the tickets of all
-  // chunks of its rows are in (the other chunks run on other pairs at about the same time), merges the per-chunk
-  // statistics of its rows and streams the rows back from L2 through independent 16-byte loads, two rows in flight.
+  // Jobs are 8-row blocks of the whole matrix in row order (= the order in which the interleaved units complete tiles),
+  // taken from ONE global counter by whichever warp of whichever CTA is free: the four finisher warps of every CTA
+  // from the start, every other warp once its own role is done (the tail of the kernel is all finishing, spread over
+  // all SMs).  Tying a tile's finish to the pair that produced it -- "last one in finishes", or a designated pair --
+  // left the slow pairs with the most work.  A job waits until the tickets of all chunks of its rows are in, merges the
+  // per-chunk statistics of its rows and streams the rows back from L2 through independent 16-byte loads, two rows in
+  // flight and the next two prefetched.
   // The exponentials of this (TF32) path are ex2.approx: relative error ~1e-6 on probabilities whose logits carry 1e-3.
   __syncwarp();
   if (p.probs && !(p.dbg & 1)) {
     const int n4 = p.KO >> 2;
     constexpr float L2E = 1.4426950408889634f;
-    int scan_i = 0, scan_jobs = 0;
+    int* const global_next = p.tickets + p.ntiles * 8;      // zeroed with the tickets
+    const int njobs = p.ntiles * 2 * TC2_JOBS;
     for (;;) {
       int j = 0;
-      if (lane == 0) j = atomicAdd(job_next, 1);
+      if (lane == 0) j = atomicAdd(global_next, 1);
       j = __shfl_sync(0xffffffffu, j, 0);
-      int tile = -1;
-      while (scan_i < u_count_all) {
-        const int u = u_first + scan_i * u_step;
-        const int t = u / p.nchunks, c = u - t * p.nchunks;
-        if (c == (p.interleave ? t % p.nchunks : p.nchunks - 1) && (int64_t)t * (2 * TC_BM) + rank * TC_BM < p.M) {
-          if (j < scan_jobs + 8) { tile = t; break; }
-          scan_jobs += 8;
-        }
-        ++scan_i;
-      }
-      if (tile < 0) break;
-      const int row0 = tile * (2 * TC_BM) + (int)rank * TC_BM + (j - scan_jobs) * 16;
+      if (j >= njobs) break;
+      const int row0 = j * (TC_BM / TC2_JOBS);               // jobs in row order = the order in which tiles complete
       if (row0 >= p.M) continue;
+      const unsigned long long jt0 = (p.dbg & 16) ? gtime() : 0;
       {
-        const volatile int* tk = p.tickets + (row0 >> 5);
-        for (int spin = 0; *tk < p.nchunks && !(p.dbg & 8); ++spin) {
-          __nanosleep(200);
+        const int* tk = p.tickets + (row0 >> 5);
+        for (int spin = 0; !(p.dbg & 8); ++spin) {
+          int got;
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(tk) : "memory");
+          if (got >= p.nchunks) break;
+          __nanosleep(100);
           if (spin > (1 << 24)) __trap();
         }
-        __threadfence();
       }
-      const int nrows = (int)min((int64_t)16, p.M - row0);
+      const unsigned long long jt1 = (p.dbg & 16) ? gtime() : 0;
+      const int nrows = (int)min((int64_t)(TC_BM / TC2_JOBS), p.M - row0);
       float nb_l = 0.f, inv_l = 0.f;               // lane rr: -max * log2(e) and 1 / sum of row rr
       if (lane < nrows) {
         const float2* rs = p.rowstat + ((int64_t)row0 + lane) * p.nchunks;
@@ -386,26 +429,33 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         nb_l = -m * L2E; inv_l = 1.f / sum;
       }
-      auto ex2 = [](float t) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t)); return r; };
+      auto ex2 = [](float t) { return ex2_approx(t); };
       if (n4 <= 320) {
+        // rows of up to 1280 columns, two at a time = 20 independent 16-byte loads per lane.  Rolling prefetch: as soon
+        // as an element of this pair of rows has been consumed its register is reloaded with the same element of the next
+        // pair, so the next round trip runs under this one's exponentials and stores.
+        float4 a[2][10];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4* s4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + min(q, nrows - 1)) * p.KO);
+#pragma unroll
+          for (int i = 0; i < 10; ++i) a[q][i] = __ldcg(s4 + min(i * 32 + lane, n4 - 1));
+        }
         for (int rr = 0; rr < nrows; rr += 2) {
-          float4 a[2][10];
+          const bool more = rr + 2 < nrows;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const float4* s4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + min(rr + q, nrows - 1)) * p.KO);
-#pragma unroll
-            for (int i = 0; i < 10; ++i) a[q][i] = __ldcg(s4 + min(i * 32 + lane, n4 - 1));
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float nb = __shfl_sync(0xffffffffu, nb_l, min(rr + q, nrows - 1));
-            const float inv = __shfl_sync(0xffffffffu, inv_l, min(rr + q, nrows - 1));
-            float4* d4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + min(rr + q, nrows - 1)) * p.KO);
+            const int r_this = min(rr + q, nrows - 1), r_next = min(rr + 2 + q, nrows - 1);
+            const float nb = __shfl_sync(0xffffffffu, nb_l, r_this);
+            const float inv = __shfl_sync(0xffffffffu, inv_l, r_this);
+            float4* d4 = reinterpret_cast<float4*>(p.probs + (int64_t)(row0 + r_this) * p.KO);
+            const float4* s4 = reinterpret_cast<const float4*>(p.logits + (int64_t)(row0 + r_next) * p.KO);
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
               float4 o;
               o.x = ex2(fmaf(a[q][i].x, L2E, nb)) * inv; o.y = ex2(fmaf(a[q][i].y, L2E, nb)) * inv;
               o.z = ex2(fmaf(a[q][i].z, L2E, nb)) * inv; o.w = ex2(fmaf(a[q][i].w, L2E, nb)) * inv;
+              if (more) a[q][i] = __ldcg(s4 + min(i * 32 + lane, n4 - 1));
               if (i * 32 + lane < n4 && rr + q < nrows && !(p.dbg & 2)) d4[i * 32 + lane] = o;
             }
           }
@@ -428,6 +478,10 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
           }
         }
+      }
+      if ((p.dbg & 16) && lane == 0 && j < 148 * 112) {
+        unsigned long long* tr = g_trace + ((size_t)(j / 112) * 512 + 64 + (j % 112) * 4);
+        tr[0] = 2 + ((unsigned long long)warp << 8); tr[1] = jt0; tr[2] = jt1; tr[3] = gtime();
       }
     }
   }
@@ -526,7 +580,7 @@ int softmax_rows_launch(const float* logits, int64_t M, int64_t KO, float* probs
 
 // logits[M, KO] for KO > 256 and, if asked, their row softmax (`probs` may alias `logits`); `what` is the normalised,
 // zero-padded text matrix, `tickets` ntiles * 8 zeroed ints (align_tc2_tickets)
-int64_t align_tc2_tickets(int64_t M) { return ceil_div(M, 2 * TC_BM) * 8; }
+int64_t align_tc2_tickets(int64_t M) { return ceil_div(M, 2 * TC_BM) * 8 + 1; }
 
 int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, int64_t KO, int64_t Kp, int64_t Dp,
                      float temperature, int norm, const float* bias, float* logits, float* probs, int* tickets,
@@ -537,7 +591,7 @@ int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, in
   p.kblocks = (int)ceil_div(D, TC_BK);
   p.ntiles = (int)ceil_div(M, 2 * TC_BM);
   p.norm = norm; p.temperature = temperature; p.interleave = (tune(15) & 1) ? 0 : 1; p.dbg = tune(15) >> 1;
-  p.tma_out = ((KO & 3) == 0 && ((uintptr_t)logits & 15) == 0) ? 1 : 0;
+  p.tma_out = ((KO & 3) == 0 && ((uintptr_t)logits & 15) == 0) ? ((tune(15) >> 1) & 32 ? 2 : 1) : 0;
   const bool fuse = probs && p.tma_out && KO <= 2048 && ((uintptr_t)probs & 15) == 0 && tickets && rowstat;
   p.probs = fuse ? probs : nullptr;
   p.tickets = tickets;
@@ -561,4 +615,14 @@ int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, in
   return probs && !fuse ? softmax_rows_launch(logits, M, KO, probs, st) : 0;
 }
 
+
+int align_tc2_trace(void* dst, size_t bytes) {
+  return (int)cudaMemcpyFromSymbol(dst, g_trace, std::min(bytes, sizeof(unsigned long long) * 148 * 512 * 4));
+}
+
 }  // namespace wsovod
+
+// temporary: timeline of the pair kernel (tune key 15, bit 5)
+extern "C" __attribute__((visibility("default"))) int wsovod_b200_debug_trace(void* dst, size_t bytes) {
+  return wsovod::align_tc2_trace(dst, bytes);
+}
