@@ -193,11 +193,14 @@ def test_align_vs_oracle(M, D, K, precision):
 
 
 @pytest.mark.parametrize("M,D,K", [(257, 768, 1203), (1, 64, 300), (700, 100, 513), (2049, 768, 1203), (130, 32, 256),
-                                   (5000, 512, 1000)])
+                                   (5000, 512, 1000), (3000, 64, 1023), (777, 128, 2047), (300, 64, 2051), (515, 96, 259),
+                                   (40000, 32, 1203)])
 def test_align_cta_pair_kernel(M, D, K):
-    """K + 1 > 256: the CTA-pair kernel (cta_group::2, units dealt across pairs, per-chunk row statistics) against the
-    oracle at the stated TF32 tolerance and against the one-CTA-per-tile kernel (same TF32 products in the same order:
-    identical logits; probabilities at 1e-5, the chunk statistics are merged in another order)"""
+    """K + 1 > 256: the CTA-pair kernel (cta_group::2, units interleaved over the pairs, TMA-stored logits, in-kernel
+    softmax finish behind tickets when the row pitch is a multiple of 16 bytes -- K + 1 = 1204, 1024, 2048, 260 --, plain
+    stores and a separate softmax pass otherwise, no fusion above 2048 columns) against the oracle at the stated TF32
+    tolerance and against the one-CTA-per-tile kernel (same TF32 products in the same order: identical logits;
+    probabilities at 1e-5: the chunk statistics are merged in another order, the finish uses ex2.approx)"""
     from wsovod_b200 import _lib
     g = synth.gen(M + K + 1)
     x = synth.region_embeddings(M, D, g)
@@ -217,7 +220,7 @@ def test_align_cta_pair_kernel(M, D, K):
     assert (lg.cpu() - lo).abs().max().item() <= TF32_LOGIT_TOL
     assert torch.equal(lg, lg1) and torch.equal(lg_only, lg)
     torch.testing.assert_close(pr, torch.softmax(lg, -1), rtol=1e-5, atol=1e-9)
-    torch.testing.assert_close(pr, pr1, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(pr, pr1, rtol=2e-5, atol=1e-9)          # two paths, each within 1e-5 of softmax(logits)
     torch.testing.assert_close(pr_only, pr, rtol=1e-6, atol=1e-9)
 
 

@@ -33,13 +33,3 @@ for pair in (1, 0):
     _lib.tune(_lib.TUNE_ALIGN_PAIR, pair)
     print("pair", pair, "probs-only op ms", round(timeit(f1), 4), "logits-only ms", round(timeit(f2), 4))
 _lib.tune(_lib.TUNE_ALIGN_PAIR, 1)
-_lib.tune(15, 1)
-print("pair kernel, contiguous unit ranges: probs-only op ms", round(timeit(f1), 4), "logits-only ms", round(timeit(f2), 4))
-_lib.tune(15, 0)
-for dbg in (1, 2, 8, 10):
-    _lib.tune(15, dbg << 1)
-    print("interleaved, finisher debug bits", dbg, "(1 no finishing, 2 no stores, 8 finishing alone): probs-only op ms", round(timeit(f1), 4))
-_lib.tune(15, 0)
-_lib.tune(15, 32 << 1)
-print("interleaved, logits by direct 16-byte register stores: probs-only op ms", round(timeit(f1), 4), "logits-only ms", round(timeit(f2), 4))
-_lib.tune(15, 0)

@@ -8,21 +8,28 @@
 // of four), the leader CTA's single thread issues the MMAs for both SMs, and each CTA's TMEM receives the
 // accumulator rows of its own x rows.
 //
-//   cluster = 2 CTAs (one TPC), grid = 2 x min(#units, resident clusters), persistent.
-//   unit    = (256-row tile, 256-column chunk of the vocabulary); units are dealt to the pairs as CONTIGUOUS ranges of
-//             the tile-major order, so the 148 SMs finish within one unit of each other (125 tiles x 5 chunks over 74
-//             pairs: 8 or 9 units each; whole tiles would be 1 or 2 = 84 % busy) and a pair mostly keeps streaming the
-//             chunks of one tile.  The row softmax therefore cannot be carried across chunks inside the kernel: every unit
-//             writes its rows' (chunk max, sum of exp) and `normalize_rows_kernel` merges the chunks of a row.
+//   cluster = 2 CTAs (one TPC), grid = 2 x min(#units, resident clusters), persistent, 384 threads per CTA.
+//   unit    = (256-row tile, 256-column chunk of the vocabulary).  Unit u runs on pair u % #pairs: the chunks of a tile
+//             run on neighbouring pairs at the same time (its x rows come from HBM once, its logits are complete
+//             within one accumulator step), and the 148 SMs finish within one unit of each other (125 tiles x 5 chunks
+//             over 74 pairs: 8 or 9 units each; whole tiles per pair would be 1 or 2 = 84 % busy).
 //   warp 0  TMA producer (both CTAs): x tile [128 x 32 fp32] + text half tile [128 x 32] per stage, completing on the
 //           LEADER's `full` barrier (cp.async.bulk.tensor ... .cta_group::2)
 //   warp 1  MMA issuer (leader CTA only): 4 x (M = 256, N <= 256, K = 8) per stage; `tcgen05.commit ... multicast` arrives
 //           on `cons[stage]` of BOTH CTAs, and on `tfull[buf]` of both when the accumulator is complete
 //   warps 2-3  norm warps (both CTAs): wait for `cons[stage]` (the MMAs are done with the stage, the bytes are still
-//           there), add up ||x_r||^2 while a tile's first unit streams by, then hand the stage back (`empty`)
-//   warps 4-7  epilogue (both CTAs, thread == accumulator row): logits = acc * T / ||x_r|| (+ bias) -> global, chunk
-//           statistics; releases the accumulator buffer on the leader's `tempty` (remote arrive for the peer CTA)
+//           there), add up ||x_r||^2 as the unit streams by, then hand the stage back (`empty`)
+//   warps 4-7  epilogue (both CTAs, thread == accumulator row): logits = acc * T / ||x_r|| (+ bias) into a 128B-swizzled
+//           [32 x 32] box per warp and out with a TMA store; running (max, sum of exp) of the row over the unit;
+//           releases the accumulator buffer on the leader's `tempty` (remote arrive for the peer CTA); hands in the
+//           unit's TICKET (release) once its stores have completed
+//   warps 8-11 finishers: probs = exp(logit - max_r) / sum_r for 4-row jobs taken from one global counter, each after
+//           the tickets of all chunks of its rows are in; every other warp joins them when its own role is done.
+// A row of 1204 logits never exists on chip (TMEM holds 512 columns), so its softmax needs the logits back from memory
+// once all chunks are known; done inside the kernel they come back from L2 while the tensor pipe works on later units,
+// instead of a second pass over 2 x 154 MB after it (what was measured on the way is in DESIGN.md, Kernel 2a).
 // The last chunk of the vocabulary runs with N rounded up to 16 only (K = 1203: 192 instead of 256 columns).
+// Row pitches that are not a multiple of 16 bytes (TMA) take plain stores and a separate softmax pass.
 #include "align.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,7 +40,7 @@ namespace wsovod {
 constexpr int TC2_BN = 256;          // accumulator columns per unit (UMMA N), both TMEM buffers = 512 columns
 constexpr int TC2_HALF = TC2_BN / 2; // text rows staged per CTA and stage
 constexpr int TC2_STAGING = 2 * 32 * 128;   // epilogue staging per warp: two [32 rows x 32 floats] boxes
-constexpr int TC2_JOBS = 16;                // finishing jobs per half tile: 8 rows each
+constexpr int TC2_JOBS = 32;                // finishing jobs per half tile: 4 rows each
 constexpr int TC2_THREADS = 384;            // 8 warps as in align_tc.cu + 4 warps that only finish row softmaxes
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -84,9 +91,6 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__device__ unsigned long long g_trace[148 * 512 * 4];
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-
 __device__ __forceinline__ float ex2_approx(float t) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t)); return r; }
 
 struct Tc2Params {
@@ -100,8 +104,6 @@ struct Tc2Params {
   int KO, nchunks, kblocks, stages, ntiles;   // ntiles: 256-row tiles
   int norm;
   float temperature;
-  int dbg;
-  int interleave;      // 1: unit u runs on pair u % npairs; 0: contiguous ranges of units per pair
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
@@ -124,19 +126,13 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   uint64_t* nfull = tempty + 2;
   uint64_t* nempty = nfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nempty + 2);
-  int* job_next = reinterpret_cast<int*>(tmem_slot + 1);      // next finishing job of this CTA
 
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int64_t U = (int64_t)p.ntiles * p.nchunks;
-  // unit i of this pair is u_first + i * u_step: interleaved (the chunks of a tile run on neighbouring pairs at the same
-  // time: the tile's x rows are fetched once for all of them and its logits are microseconds old when the softmax is
-  // finished) or a contiguous range
-  const int u_step = p.interleave ? npairs : 1;
-  const int u_first = p.interleave ? pair : (int)(U * pair / npairs);
-  const int u_count_all = p.interleave ? (int)((U - pair + npairs - 1) / npairs) : (int)(U * (pair + 1) / npairs) - u_first;
-  const int u_count = (p.dbg & 8) && warp < 8 ? 0 : u_count_all;    // dbg 8: finishers alone
-  auto tile_of = [&](int i) { return (u_first + i * u_step) / p.nchunks; };
+  // unit i of this pair is pair + i * npairs; npairs >= nchunks, so a pair never sees two units of one tile
+  const int u_step = npairs, u_first = pair;
+  const int u_count = (int)((U - pair + npairs - 1) / npairs);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -149,7 +145,6 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 256);
       mbar_init(&nfull[b], 2); mbar_init(&nempty[b], 128);
     }
-    *job_next = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -211,13 +206,12 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   } else if (warp < 4) {
     // ===== norm warps =====
     const int t = (warp - 2) * 32 + lane;        // rows t and t + 64 of this CTA's half tile
-    int stage = 0; uint32_t phase = 0; uint32_t seg = 0;
+    int stage = 0; uint32_t phase = 0;
     for (int i = 0; i < u_count; ++i) {
-      const bool first = i == 0 || tile_of(i) != tile_of(i - 1);     // this pair's first unit of the tile
       float ss0 = 0.f, ss1 = 0.f;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(&cons[stage], phase);
-        if (first && p.norm) {
+        if (p.norm) {
           const unsigned char* base = sa + (size_t)stage * a_bytes;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -232,15 +226,12 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (first) {
-        const uint32_t nb = seg & 1, nphase = (seg >> 1) & 1;
-        ++seg;
-        mbar_wait(&nempty[nb], nphase ^ 1);
-        snorm[nb * TC_BM + t] = ss0;
-        snorm[nb * TC_BM + t + 64] = ss1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&nfull[nb]);
-      }
+      const uint32_t nb = i & 1, nphase = (i >> 1) & 1;
+      mbar_wait(&nempty[nb], nphase ^ 1);        // the epilogue has read the previous use of this buffer
+      snorm[nb * TC_BM + t] = ss0;
+      snorm[nb * TC_BM + t + 64] = ss1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&nfull[nb]);
     }
   } else if (warp < 8) {
     // ===== epilogue warps =====
@@ -249,29 +240,15 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     float* st = reinterpret_cast<float*>(stw);
     const float bias = p.bias ? __ldg(p.bias) : 0.f;
     const uint32_t ltempty0 = mapa_u32(smem_u32(&tempty[0]), 0), ltempty1 = mapa_u32(smem_u32(&tempty[1]), 0);
-    uint32_t it = 0, seg = 0, sbuf = 0;
-    int seg_units = 0, pend_ticket = -1, pend_units = 0;
-    // a pair's rows of a tile are in memory once the bulk stores (lane 0's) have completed; the ticket is a release
-    // (the lanes' statistics are ordered before it by the warp barrier), the finishers poll it with acquire loads
-    auto hand_in = [&]() {
-      if (pend_ticket < 0) return;
-      __syncwarp();                      // every lane's statistics are ordered before lane 0's release below
-      if (lane == 0) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.tickets + pend_ticket), "r"(pend_units) : "memory");
-      }
-      pend_ticket = -1;
-    };
+    uint32_t it = 0, sbuf = 0;
     float scale = 1.f;
     for (int i = 0; i < u_count; ++i, ++it) {
       const int u = u_first + i * u_step;
       const int tile = u / p.nchunks, c = u - tile * p.nchunks;
-      const bool seg_end = i + 1 == u_count || tile_of(i + 1) != tile;    // this pair's last unit of the tile
       const int64_t wrow0 = (int64_t)tile * (2 * TC_BM) + rank * TC_BM + wq * 32;
       const int wrows = (int)max((int64_t)0, min((int64_t)32, p.M - wrow0));
-      if (i == 0 || tile_of(i - 1) != tile) {
-        const uint32_t nb = seg & 1, nphase = (seg >> 1) & 1;
-        ++seg;
+      {
+        const uint32_t nb = i & 1, nphase = (i >> 1) & 1;
         mbar_wait(&nfull[nb], nphase);
         scale = p.norm ? p.temperature / fmaxf(sqrtf(snorm[nb * TC_BM + wq * 32 + lane]), 1e-12f) : 1.f;
         mbar_arrive(&nempty[nb]);
@@ -279,50 +256,19 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(&tfull[buf], aphase);
       tc_fence_after();
-      const unsigned long long tr0 = (p.dbg & 16) ? gtime() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)TC2_BN;
       const int col0 = c * TC2_BN;
       const int ncols = min(TC2_BN, p.KO - col0);
       float v[32];
       float cm = -FLT_MAX, cs = 0.f;
-      long long cycA = 0, cycB = 0, cyc0 = clock64();
       for (int j = 0; j < ncols; j += 32) {
-        const long long ca = clock64();
         tmem_ld32(taddr + j, v);
-        cycA += clock64() - ca;
-        if (p.tma_out == 2) {
-          // thread == row: its 32 logits are 128 contiguous bytes of the output row, written straight from registers as
-          // eight 16-byte stores (a warp store touches 32 rows; the L2 merges the sectors before they leave for HBM)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], scale, bias);
-          if (lane < wrows) {
-            float4* dst = reinterpret_cast<float4*>(p.logits + (wrow0 + lane) * p.KO + col0 + j);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (j + 4 * q < ncols) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-          if (p.probs) {
-            // running (max, sum of exp) of this row over the unit's columns, one rescale per 32-column slab; the sums use
-            // the fast exponential (they are dominated by the terms next to the maximum, where its error is ~1e-7)
-            float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (j + i < ncols) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
-            const float nm = fmaxf(cm, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-            const float nb = -nm * 1.4426950408889634f;
-            float a4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (j + i < ncols) a4[i & 3] += ex2_approx(fmaf(v[i], 1.4426950408889634f, nb));
-            cs = cs * ex2_approx(fmaf(cm, 1.4426950408889634f, nb)) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
-            cm = nm;
-          }
-        } else         if (p.tma_out) {
+        if (p.tma_out) {
           // thread == row: its 32 logits are 128 contiguous bytes of the output row.  They go into a [32 x 128 B] box
           // in the TMA 128B swizzle (16-byte chunk q of row r at chunk q ^ (r & 7): conflict-free for a quarter-warp),
           // and one lane sends the box; columns >= KO and rows >= M are clipped by the tensor map.
-          const long long cb = clock64();
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box two stores back has been read
           __syncwarp();
-          cycB += clock64() - cb;
           unsigned char* box = stw + sbuf * (32 * 128);
           unsigned char* dst = box + lane * 128;
 #pragma unroll
@@ -365,25 +311,24 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           __syncwarp();
         }
       }
-      const long long cycLoop = clock64() - cyc0;
       tc_fence_before();
       mbar_arrive_cluster(buf ? ltempty1 : ltempty0);
-      ++seg_units;
       if (p.probs) {
+        // the pair's part of these 32 rows is in memory once the bulk stores (lane 0's) have completed: then the ticket
+        // goes in as a release (the lanes' statistics are ordered before it by the warp barrier); the finishers poll
+        // it with acquire loads
         if (lane < wrows) p.rowstat[(wrow0 + lane) * p.nchunks + c] = make_float2(cm, cs);
-        if (seg_end) { pend_ticket = (int)(wrow0 >> 5); pend_units = seg_units; hand_in(); }
-      }
-      if (seg_end) seg_units = 0;
-      if ((p.dbg & 16) && lane == 0 && wq == 0 && i < 8) {
-        unsigned long long* tr = g_trace + ((size_t)blockIdx.x * 512 + i * 8) ;
-        tr[0] = 1; tr[1] = tr0; tr[2] = gtime(); tr[3] = u; tr[4] = cycA; tr[5] = cycB; tr[6] = cycLoop; tr[7] = clock64() - cyc0;
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p.tickets + (wrow0 >> 5)), "r"(1) : "memory");
+        }
       }
     }
-    hand_in();
     if (lane == 0 && p.tma_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
-  // ===== finishing: probs[r, :] = exp(logits[r, :] - max_r) / sum_r for the tiles this pair is designated to finish =====
-  // Jobs are 8-row blocks of the whole matrix in row order (= the order in which the interleaved units complete tiles),
+  // ===== finishing: probs[r, :] = exp(logits[r, :] - max_r) / sum_r =====
+  // Jobs are 4-row blocks of the whole matrix in row order (= the order in which the interleaved units complete tiles),
   // taken from ONE global counter by whichever warp of whichever CTA is free: the four finisher warps of every CTA
   // from the start, every other warp once its own role is done (the tail of the kernel is all finishing, spread over
   // all SMs).  Tying a tile's finish to the pair that produced it -- "last one in finishes", or a designated pair --
@@ -392,7 +337,7 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   // flight and the next two prefetched.
   // The exponentials of this (TF32) path are ex2.approx: relative error ~1e-6 on probabilities whose logits carry 1e-3.
   __syncwarp();
-  if (p.probs && !(p.dbg & 1)) {
+  if (p.probs) {
     const int n4 = p.KO >> 2;
     constexpr float L2E = 1.4426950408889634f;
     int* const global_next = p.tickets + p.ntiles * 8;      // zeroed with the tickets
@@ -404,10 +349,9 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       if (j >= njobs) break;
       const int row0 = j * (TC_BM / TC2_JOBS);               // jobs in row order = the order in which tiles complete
       if (row0 >= p.M) continue;
-      const unsigned long long jt0 = (p.dbg & 16) ? gtime() : 0;
       {
         const int* tk = p.tickets + (row0 >> 5);
-        for (int spin = 0; !(p.dbg & 8); ++spin) {
+        for (int spin = 0;; ++spin) {
           int got;
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(tk) : "memory");
           if (got >= p.nchunks) break;
@@ -415,7 +359,6 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (spin > (1 << 24)) __trap();
         }
       }
-      const unsigned long long jt1 = (p.dbg & 16) ? gtime() : 0;
       const int nrows = (int)min((int64_t)(TC_BM / TC2_JOBS), p.M - row0);
       float nb_l = 0.f, inv_l = 0.f;               // lane rr: -max * log2(e) and 1 / sum of row rr
       if (lane < nrows) {
@@ -456,7 +399,7 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               o.x = ex2(fmaf(a[q][i].x, L2E, nb)) * inv; o.y = ex2(fmaf(a[q][i].y, L2E, nb)) * inv;
               o.z = ex2(fmaf(a[q][i].z, L2E, nb)) * inv; o.w = ex2(fmaf(a[q][i].w, L2E, nb)) * inv;
               if (more) a[q][i] = __ldcg(s4 + min(i * 32 + lane, n4 - 1));
-              if (i * 32 + lane < n4 && rr + q < nrows && !(p.dbg & 2)) d4[i * 32 + lane] = o;
+              if (i * 32 + lane < n4 && rr + q < nrows) d4[i * 32 + lane] = o;
             }
           }
         }
@@ -478,10 +421,6 @@ align_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
           }
         }
-      }
-      if ((p.dbg & 16) && lane == 0 && j < 148 * 112) {
-        unsigned long long* tr = g_trace + ((size_t)(j / 112) * 512 + 64 + (j % 112) * 4);
-        tr[0] = 2 + ((unsigned long long)warp << 8); tr[1] = jt0; tr[2] = jt1; tr[3] = gtime();
       }
     }
   }
@@ -590,8 +529,8 @@ int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, in
   p.nchunks = (int)ceil_div(KO, TC2_BN);
   p.kblocks = (int)ceil_div(D, TC_BK);
   p.ntiles = (int)ceil_div(M, 2 * TC_BM);
-  p.norm = norm; p.temperature = temperature; p.interleave = (tune(15) & 1) ? 0 : 1; p.dbg = tune(15) >> 1;
-  p.tma_out = ((KO & 3) == 0 && ((uintptr_t)logits & 15) == 0) ? ((tune(15) >> 1) & 32 ? 2 : 1) : 0;
+  p.norm = norm; p.temperature = temperature;
+  p.tma_out = ((KO & 3) == 0 && ((uintptr_t)logits & 15) == 0) ? 1 : 0;
   const bool fuse = probs && p.tma_out && KO <= 2048 && ((uintptr_t)probs & 15) == 0 && tickets && rowstat;
   p.probs = fuse ? probs : nullptr;
   p.tickets = tickets;
@@ -616,13 +555,5 @@ int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, in
 }
 
 
-int align_tc2_trace(void* dst, size_t bytes) {
-  return (int)cudaMemcpyFromSymbol(dst, g_trace, std::min(bytes, sizeof(unsigned long long) * 148 * 512 * 4));
-}
-
 }  // namespace wsovod
 
-// temporary: timeline of the pair kernel (tune key 15, bit 5)
-extern "C" __attribute__((visibility("default"))) int wsovod_b200_debug_trace(void* dst, size_t bytes) {
-  return wsovod::align_tc2_trace(dst, bytes);
-}
