@@ -696,6 +696,20 @@ def test_roi_pool_blockmax_path(N, C, H, W, R, seed):
     assert torch.equal(scan, out)
     got = out_s.cpu()
     assert torch.equal(torch.where(torch.isfinite(ref), got, torch.zeros_like(got)), sc)
+    # + argmax (planes of (value, index) pairs): the FIRST maximal cell of the row-major scan, -1 where nothing beats
+    # -FLT_MAX; also on a map with few distinct values, where almost every bin has ties
+    for f in (feat, torch.where(torch.isfinite(feat), (feat * 2).round() / 2, feat)):
+        ref_v, ref_a = oracle.roi_pool(f, rois, 1 / 8, 7)
+        with _pool_variant(scan=True):
+            sv, sa = ops.roi_pool(f.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)
+        with _pool_variant(scan=False):
+            bv, ba = ops.roi_pool(f.to(DEV), rois.to(DEV), 1 / 8, 7, with_argmax=True)
+            bvs, bas = ops.roi_pool(f.to(DEV), rois.to(DEV), 1 / 8, 7, row_scale=obj.to(DEV), row_scale_bias=1.0,
+                                    with_argmax=True)
+        assert torch.equal(bv.cpu(), ref_v) and torch.equal(ba.cpu().to(ref_a.dtype), ref_a)
+        assert torch.equal(sv, bv) and torch.equal(sa, ba) and torch.equal(bas, ba)
+        fin_v = torch.where(torch.isfinite(ref_v), ref_v, torch.zeros_like(ref_v)) * (obj + 1).view(-1, 1, 1, 1)
+        assert torch.equal(torch.where(torch.isfinite(ref_v), bvs.cpu(), torch.zeros_like(ref_v)), fin_v)
 
 
 def test_roi_pool_blockmax_empty_images_and_single_class():

@@ -23,9 +23,9 @@ enum { MODE_POOL = 0, MODE_LOOP = 1, MODE_ALIGN = 2 };
 
 // roi_pool_pyr.cu: block-max fast path (7x7, values only)
 size_t pool7_pyr_workspace(int64_t N, int64_t R);
-int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R);
+int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R, bool with_argmax);
 int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, const float* rois, int64_t R,
-              float scale, const float* row_scale, float row_scale_bias, float* output, void* workspace,
+              float scale, const float* row_scale, float row_scale_bias, float* output, int32_t* argmax, void* workspace,
               cudaStream_t st);
 
 struct PoolParams {
@@ -973,9 +973,9 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   if (!workspace || ws_bytes < w.bytes) return WSOVOD_B200_EWORKSPACE;
   w = carve(workspace, mode, N, R, PH, PW);
   cudaStream_t st = (cudaStream_t)stream;
-  // values-only 7x7 max-pool: block-max planes (roi_pool_pyr.cu) when the padded plane fits shared memory
-  if (mode == MODE_POOL && PH == 7 && PW == 7 && !argmax && pool_use_blockmax(N, R) && pool7_pyr_cb(C, H, W, R))
-    return pool7_pyr(input, N, C, H, W, rois, R, scale, row_scale, row_scale_bias, output, w.pyr, st);
+  // 7x7 max-pool (+ argmax): block-max planes (roi_pool_pyr.cu) when the padded plane fits shared memory
+  if (mode == MODE_POOL && PH == 7 && PW == 7 && pool_use_blockmax(N, R) && pool7_pyr_cb(C, H, W, R, argmax != nullptr))
+    return pool7_pyr(input, N, C, H, W, rois, R, scale, row_scale, row_scale_bias, output, argmax, w.pyr, st);
   cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;
   const int pt = 128;

@@ -266,6 +266,7 @@ struct PyrParams {
   const float* rois;
   float scale;
   float* output;
+  int32_t* argmax;      // ARG flavour only
   const int32_t* img_start;
   const int32_t* bucket_off;
   const uint2* pinfo;
@@ -274,19 +275,52 @@ struct PyrParams {
   int32_t CG, S;
 };
 
-template <int CB> __device__ __forceinline__ void p_lds(uint32_t addr, float* f);
-template <> __device__ __forceinline__ void p_lds<4>(uint32_t addr, float* f) {
+// A plane cell holds CB channel values; the ARG flavour (argmax requested: training with a trainable backbone,
+// ROILoopPool_cuda.cu:206-248 reads it back) holds CB (value, index) pairs instead, index = h * W + w of the cell the
+// value came from.  Blocks are merged by  "greater value, or equal value and smaller index": the maximum over a set of
+// cells then carries the FIRST cell of the row-major scan that attains it, which is what `v > maxval` leaves behind in
+// the reference's scan (ROILoopPool_cpu.cpp:52-79, torchvision roi_pool) whatever the order the blocks are visited in.
+// Cells that can never win the reference's comparison (NaN, -inf, -FLT_MAX itself) are staged as (-FLT_MAX, -1), like
+// the pad cells: a bin of only such cells returns (-FLT_MAX, -1) as the reference does.
+// Cell size: 4 * CB bytes, ARG: 8 * CB (CB = 2 only: 16-byte cells, the same descriptors and lane order as CB = 4).
+template <int CB, bool ARG> struct CellT { static constexpr uint32_t CS = (ARG ? 8u : 4u) * CB; };
+
+template <int CB, bool ARG> __device__ __forceinline__ void p_lds(uint32_t addr, float* f, int* a);
+template <> __device__ __forceinline__ void p_lds<4, false>(uint32_t addr, float* f, int*) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr));
 }
-template <> __device__ __forceinline__ void p_lds<2>(uint32_t addr, float* f) {
+template <> __device__ __forceinline__ void p_lds<2, false>(uint32_t addr, float* f, int*) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f[0]), "=f"(f[1]) : "r"(addr));
 }
-template <int CB> __device__ __forceinline__ void p_sts(uint32_t addr, const float* f);
-template <> __device__ __forceinline__ void p_sts<4>(uint32_t addr, const float* f) {
+template <> __device__ __forceinline__ void p_lds<2, true>(uint32_t addr, float* f, int* a) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=r"(a[0]), "=r"(a[1]) : "r"(addr));
+}
+template <int CB, bool ARG> __device__ __forceinline__ void p_sts(uint32_t addr, const float* f, const int* a);
+template <> __device__ __forceinline__ void p_sts<4, false>(uint32_t addr, const float* f, const int*) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
 }
-template <> __device__ __forceinline__ void p_sts<2>(uint32_t addr, const float* f) {
+template <> __device__ __forceinline__ void p_sts<2, false>(uint32_t addr, const float* f, const int*) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(f[0]), "f"(f[1]) : "memory");
+}
+template <> __device__ __forceinline__ void p_sts<2, true>(uint32_t addr, const float* f, const int* a) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[0]), "f"(f[1]), "r"(a[0]), "r"(a[1]) : "memory");
+}
+// m <- merge(m, f)
+template <int CB, bool ARG> __device__ __forceinline__ void p_max(float* m, int* ma, const float* f, const int* a) {
+#pragma unroll
+  for (int k = 0; k < CB; ++k) {
+    if (ARG) {
+      const bool take = f[k] > m[k] || (f[k] == m[k] && a[k] < ma[k]);
+      m[k] = take ? f[k] : m[k];
+      ma[k] = take ? a[k] : ma[k];
+    } else {
+      m[k] = fmaxf(m[k], f[k]);
+    }
+  }
+}
+template <int CB, bool ARG> __device__ __forceinline__ void p_copy(float* m, int* ma, const float* f, const int* a) {
+#pragma unroll
+  for (int k = 0; k < CB; ++k) { m[k] = f[k]; if (ARG) ma[k] = a[k]; }
 }
 
 // D <- plane of the map (MODE 0), max with the right neighbour (1: block 1x2) or the lower neighbour
@@ -295,9 +329,9 @@ template <> __device__ __forceinline__ void p_sts<2>(uint32_t addr, const float*
 // A warp takes whole rows of the padded plane (row hh = warp, warp + #warps, ...), lanes walk the columns
 // 32 at a time: addresses are (row pointer of the channel) + column, the only predicates are the row /
 // column borders, and up to 8 x CB loads per lane are in flight.
-template <int CB, int MODE>
+template <int CB, int MODE, bool ARG>
 __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W) {
-  constexpr uint32_t CS = 4u * CB;
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
   const int WP = W + kPad, HP = H + kPad, HW = H * W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int hh = wid; hh < HP; hh += nw) {
@@ -324,9 +358,22 @@ __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__
       for (int u = 0; u < 2; ++u) {
         const int ww = ww0 + u * 32 + lane;
         if (ww < WP) {
+          int fa[CB], ga[CB];
+          if (ARG) {
+            const int idx = h * W + (ww - kPad);                 // only used where the cell is a real one
 #pragma unroll
-          for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
-          p_sts<CB>(srow + (uint32_t)ww * CS, f[u]);
+            for (int k = 0; k < CB; ++k) {
+              fa[k] = f[u][k] > -FLT_MAX ? idx : -1;             // false for NaN too
+              ga[k] = g[u][k] > -FLT_MAX ? idx + (MODE == 1 ? 1 : W) : -1;
+              f[u][k] = fmaxf(f[u][k], -FLT_MAX);
+              g[u][k] = fmaxf(g[u][k], -FLT_MAX);
+            }
+            p_max<CB, ARG>(f[u], fa, g[u], ga);
+          } else {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
+          }
+          p_sts<CB, ARG>(srow + (uint32_t)ww * CS, f[u], fa);
         }
       }
     }
@@ -337,29 +384,30 @@ __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__
 // forward, so chunks are processed front to back with one barrier between a chunk's loads and its
 // stores.  Horizontal steps may wrap into the next row's pad columns, which hold the identity for the
 // strides used (1, 2 with 3 pad columns); vertical steps run into the identity tail rows.
-template <int CB>
+template <int CB, bool ARG>
 __device__ __noinline__ void pyr_double(uint32_t sbase, int ncell, int stride) {
-  constexpr uint32_t CS = 4u * CB;
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
   constexpr int U = 4;
   const uint32_t sb = (uint32_t)stride * CS;
   for (int base = 0; base < ncell; base += (int)blockDim.x * U) {
     float v[U][CB];
+    int va[U][CB];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * (int)blockDim.x + (int)threadIdx.x;
       if (idx < ncell) {
         float b[CB];
-        p_lds<CB>(sbase + (uint32_t)idx * CS, v[u]);
-        p_lds<CB>(sbase + (uint32_t)idx * CS + sb, b);
-#pragma unroll
-        for (int k = 0; k < CB; ++k) v[u][k] = fmaxf(v[u][k], b[k]);
+        int ba[CB];
+        p_lds<CB, ARG>(sbase + (uint32_t)idx * CS, v[u], va[u]);
+        p_lds<CB, ARG>(sbase + (uint32_t)idx * CS + sb, b, ba);
+        p_max<CB, ARG>(v[u], va[u], b, ba);
       }
     }
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * (int)blockDim.x + (int)threadIdx.x;
-      if (idx < ncell) p_sts<CB>(sbase + (uint32_t)idx * CS, v[u]);
+      if (idx < ncell) p_sts<CB, ARG>(sbase + (uint32_t)idx * CS, v[u], va[u]);
     }
   }
   __syncthreads();
@@ -375,51 +423,49 @@ __device__ __noinline__ void pyr_double(uint32_t sbase, int ncell, int stride) {
 //     pad columns, which hold the identity for the strides used (3 pad columns).
 //   vertical (stride 1 or 2 rows): a thread owns a column segment, lanes are consecutive columns (conflict-free);
 //     the last segments run into the identity tail rows.
-template <int CB, int S>
+template <int CB, int S, bool ARG>
 __device__ __noinline__ void pyr_double_h(uint32_t sbase, int ncell) {
   constexpr int s = S;
-  constexpr uint32_t CS = 4u * CB;
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
   const int run = max(13, (((ncell + (int)blockDim.x - 1) / (int)blockDim.x) | 1));   // odd, >= cells per thread
   const int a = (int)threadIdx.x * run, b = min(a + run, ncell);
   float ov0[CB], ov1[CB];
+  int oa0[CB], oa1[CB];
   if (a < ncell) {
-    p_lds<CB>(sbase + (uint32_t)b * CS, ov0);
-    if (S == 2) p_lds<CB>(sbase + (uint32_t)(b + 1) * CS, ov1);     // b + 1 <= ncell + 1 < ntot: identity tail rows
+    p_lds<CB, ARG>(sbase + (uint32_t)b * CS, ov0, oa0);
+    if (S == 2) p_lds<CB, ARG>(sbase + (uint32_t)(b + 1) * CS, ov1, oa1);     // b + 1 <= ncell + 1 < ntot: identity tail rows
   }
   __syncthreads();
   if (a < ncell) {
     float p0[CB], p1[CB], nx[CB];
-    p_lds<CB>(sbase + (uint32_t)a * CS, p0);
+    int a0[CB], a1[CB], na[CB];
+    p_lds<CB, ARG>(sbase + (uint32_t)a * CS, p0, a0);
     if (s == 2) {
-      if (a + 1 < b) p_lds<CB>(sbase + (uint32_t)(a + 1) * CS, p1);
-      else {
-#pragma unroll
-        for (int k = 0; k < CB; ++k) p1[k] = ov0[k];
-      }
+      if (a + 1 < b) p_lds<CB, ARG>(sbase + (uint32_t)(a + 1) * CS, p1, a1);
+      else p_copy<CB, ARG>(p1, a1, ov0, oa0);
     }
     for (int j = a; j < b; ++j) {
       const int q = j + s;
-      if (q < b) p_lds<CB>(sbase + (uint32_t)q * CS, nx);
-      else {
-#pragma unroll
-        for (int k = 0; k < CB; ++k) nx[k] = (S == 2 && (q - b)) ? ov1[k] : ov0[k];
-      }
+      if (q < b) p_lds<CB, ARG>(sbase + (uint32_t)q * CS, nx, na);
+      else if (S == 2 && (q - b)) p_copy<CB, ARG>(nx, na, ov1, oa1);
+      else p_copy<CB, ARG>(nx, na, ov0, oa0);
       float o[CB];
-#pragma unroll
-      for (int k = 0; k < CB; ++k) o[k] = fmaxf(p0[k], nx[k]);
-      p_sts<CB>(sbase + (uint32_t)j * CS, o);
-#pragma unroll
-      for (int k = 0; k < CB; ++k) { p0[k] = s == 2 ? p1[k] : nx[k]; p1[k] = nx[k]; }
+      int oa[CB];
+      p_copy<CB, ARG>(o, oa, p0, a0);
+      p_max<CB, ARG>(o, oa, nx, na);
+      p_sts<CB, ARG>(sbase + (uint32_t)j * CS, o, oa);
+      if (s == 2) p_copy<CB, ARG>(p0, a0, p1, a1); else p_copy<CB, ARG>(p0, a0, nx, na);
+      p_copy<CB, ARG>(p1, a1, nx, na);
     }
   }
   __syncthreads();
 }
 
-template <int CB, int S>
+template <int CB, int S, bool ARG>
 __device__ __noinline__ void pyr_double_v(uint32_t sbase, int rows, int WP) {
   constexpr int s = S;
-  constexpr uint32_t CS = 4u * CB;
-  if (WP > (int)blockDim.x) { pyr_double<CB>(sbase, rows * WP, S * WP); return; }
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
+  if (WP > (int)blockDim.x) { pyr_double<CB, ARG>(sbase, rows * WP, S * WP); return; }
   const int nseg = max(1, (int)blockDim.x / WP);                 // column segments
   const int seg = (int)threadIdx.x / WP, w = (int)threadIdx.x - seg * WP;
   const int per = (rows + nseg - 1) / nseg;
@@ -427,69 +473,69 @@ __device__ __noinline__ void pyr_double_v(uint32_t sbase, int rows, int WP) {
   const bool on = seg < nseg && r0 < rows;
   const uint32_t col = sbase + (uint32_t)w * CS, pitch = (uint32_t)WP * CS;
   float ov0[CB], ov1[CB];
+  int oa0[CB], oa1[CB];
   if (on) {
-    p_lds<CB>(col + (uint32_t)r1 * pitch, ov0);
-    if (S == 2) p_lds<CB>(col + (uint32_t)(r1 + 1) * pitch, ov1);   // rows + 1 < rows + kTailRows
+    p_lds<CB, ARG>(col + (uint32_t)r1 * pitch, ov0, oa0);
+    if (S == 2) p_lds<CB, ARG>(col + (uint32_t)(r1 + 1) * pitch, ov1, oa1);   // rows + 1 < rows + kTailRows
   }
   __syncthreads();
   if (on) {
     float p0[CB], p1[CB], nx[CB];
-    p_lds<CB>(col + (uint32_t)r0 * pitch, p0);
+    int a0[CB], a1[CB], na[CB];
+    p_lds<CB, ARG>(col + (uint32_t)r0 * pitch, p0, a0);
     if (s == 2) {
-      if (r0 + 1 < r1) p_lds<CB>(col + (uint32_t)(r0 + 1) * pitch, p1);
-      else {
-#pragma unroll
-        for (int k = 0; k < CB; ++k) p1[k] = ov0[k];
-      }
+      if (r0 + 1 < r1) p_lds<CB, ARG>(col + (uint32_t)(r0 + 1) * pitch, p1, a1);
+      else p_copy<CB, ARG>(p1, a1, ov0, oa0);
     }
     for (int j = r0; j < r1; ++j) {
       const int q = j + s;
-      if (q < r1) p_lds<CB>(col + (uint32_t)q * pitch, nx);
-      else {
-#pragma unroll
-        for (int k = 0; k < CB; ++k) nx[k] = (S == 2 && (q - r1)) ? ov1[k] : ov0[k];
-      }
+      if (q < r1) p_lds<CB, ARG>(col + (uint32_t)q * pitch, nx, na);
+      else if (S == 2 && (q - r1)) p_copy<CB, ARG>(nx, na, ov1, oa1);
+      else p_copy<CB, ARG>(nx, na, ov0, oa0);
       float o[CB];
-#pragma unroll
-      for (int k = 0; k < CB; ++k) o[k] = fmaxf(p0[k], nx[k]);
-      p_sts<CB>(col + (uint32_t)j * pitch, o);
-#pragma unroll
-      for (int k = 0; k < CB; ++k) { p0[k] = s == 2 ? p1[k] : nx[k]; p1[k] = nx[k]; }
+      int oa[CB];
+      p_copy<CB, ARG>(o, oa, p0, a0);
+      p_max<CB, ARG>(o, oa, nx, na);
+      p_sts<CB, ARG>(col + (uint32_t)j * pitch, o, oa);
+      if (s == 2) p_copy<CB, ARG>(p0, a0, p1, a1); else p_copy<CB, ARG>(p0, a0, nx, na);
+      p_copy<CB, ARG>(p1, a1, nx, na);
     }
   }
   __syncthreads();
 }
-
-template <int CB> struct PV;
-template <> struct PV<4> { using T = float4; };
-template <> struct PV<2> { using T = float2; };
-__device__ __forceinline__ void pv_max(float* m, const float4& v) {
-  m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); m[2] = fmaxf(m[2], v.z); m[3] = fmaxf(m[3], v.w);
-}
-__device__ __forceinline__ void pv_max(float* m, const float2& v) { m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); }
-__device__ __forceinline__ void pv_set(float* m, const float4& v) { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
-__device__ __forceinline__ void pv_set(float* m, const float2& v) { m[0] = v.x; m[1] = v.y; }
 
 // One bucket slice = `total` lane slots (kSlots = 64 per proposal, 15 of them idle) whose proposals all need
 // at most CH x CW blocks per bin.  A lane handles TWO slots per pass (f and f + stride: independent LDS
 // chains hide each other's latency); per slot it reads one descriptor word (coalesced) and its
 // proposal's (id, scale) pair, both fetched one pass ahead, issues up to CH*CW LDS (a block is skipped
 // where it would repeat the previous one: the bin is not larger than the blocks before it) and stores
-// CB scalars.  Passes are aligned to proposals (f is a multiple of 32, a proposal of 64 slots).
-template <int CB, int SLOTS, int CH, int CW, bool FULL>
+// CB scalars (ARG: and CB indices).  Passes are aligned to proposals (f is a multiple of 32, a proposal of 64 slots).
+// plain C++ loads in the hot loop (ptxas schedules them freely; the asm wrappers above are volatile)
+template <int CB, bool ARG> struct PV;
+template <> struct PV<4, false> { using T = float4; };
+template <> struct PV<2, false> { using T = float2; };
+template <> struct PV<2, true> { using T = float4; };
+__device__ __forceinline__ void pv_get(float* m, int*, const float4& v, const PV<4, false>&) { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+__device__ __forceinline__ void pv_get(float* m, int*, const float2& v, const PV<2, false>&) { m[0] = v.x; m[1] = v.y; }
+__device__ __forceinline__ void pv_get(float* m, int* a, const float4& v, const PV<2, true>&) {
+  m[0] = v.x; m[1] = v.y; a[0] = __float_as_int(v.z); a[1] = __float_as_int(v.w);
+}
+
+template <int CB, bool ARG, int SLOTS, int CH, int CW, bool FULL>
 __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pitch, uint32_t khp, uint32_t kwb,
                                         const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
-                                        int total, float* __restrict__ outc, uint32_t c49, int nc, int flat0,
-                                        int stride) {
-  using V = typename PV<CB>::T;
-  constexpr uint32_t CS = 4u * CB;
+                                        int total, float* __restrict__ outc, int32_t* __restrict__ argc, uint32_t c49,
+                                        int nc, int flat0, int stride) {
+  using V = typename PV<CB, ARG>::T;
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
   auto one = [&](const uint32_t d, const uint2 pi) {
     if (d & kDescIdle) return;                 // slots 49..63 of a proposal
     const uint32_t a0 = (d & 0xffffu) * CS;
     const uint32_t lhp = ((d >> 16) & 15u) * pitch, lwb = ((d >> 20) & 15u) * CS;
     // the plane holds no NaN / -inf (pyr_stage clamps at -FLT_MAX), so the first block seeds the maximum
     float m[CB];
-    pv_set(m, *reinterpret_cast<const V*>(plane + a0));
+    int ma[CB];
+    pv_get(m, ma, *reinterpret_cast<const V*>(plane + a0), PV<CB, ARG>());
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
@@ -499,14 +545,22 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
         if (i == 0 && j == 0) continue;
         const uint32_t co = j == 0 ? 0u : min((uint32_t)j * kwb, lwb);
         const bool nj = j == 0 || (uint32_t)(j - 1) * kwb < lwb;
-        if (ni && nj) pv_max(m, *reinterpret_cast<const V*>(plane + a0 + ro + co));
+        if (ni && nj) {
+          float f[CB];
+          int fa[CB];
+          pv_get(f, fa, *reinterpret_cast<const V*>(plane + a0 + ro + co), PV<CB, ARG>());
+          p_max<CB, ARG>(m, ma, f, fa);
+        }
       }
     }
     const float sc = __uint_as_float(pi.y);   // 1.0f without a row scale: exact
-    float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + ((d >> 24) & 63u);
+    const size_t oo = (size_t)(pi.x & 0x3ffffffu) * c49 + ((d >> 24) & 63u);
 #pragma unroll
     for (int k = 0; k < CB; ++k)
-      if (FULL || k < nc) __stcs(o + k * 49, __fmul_rn(m[k], sc));
+      if (FULL || k < nc) {
+        __stcs(outc + oo + k * 49, __fmul_rn(m[k], sc));
+        if (ARG) __stcs(argc + oo + k * 49, ma[k]);
+      }
   };
   const int step = 2 * stride;
   int f = flat0;
@@ -528,12 +582,12 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
   }
 }
 
-template <int CB>
+template <int CB, bool ARG>
 __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int BINS = 49;
-  constexpr int SLOTS = CB == 4 ? kSlots : 49;   // lane slots per proposal in the descriptor stream
-  constexpr uint32_t CS = 4u * CB;
+  constexpr uint32_t CS = CellT<CB, ARG>::CS;
+  constexpr int SLOTS = CS == 16 ? kSlots : 49;   // lane slots per proposal in the descriptor stream
   const int H = p.H, W = p.W, HW = H * W;
   const int WP = W + kPad, ncell = (H + kPad) * WP, ntot = (H + kPad + kTailRows) * WP;
   const int bid = blockIdx.x;
@@ -553,17 +607,19 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
   }
   {  // identity tail rows and the all-zero cell empty bins point at (never written again)
     float id[CB];
+    int ida[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) id[k] = -FLT_MAX;
-    for (int i = ncell + (int)threadIdx.x; i < ntot; i += blockDim.x) p_sts<CB>(sbase + (uint32_t)i * CS, id);
+    for (int k = 0; k < CB; ++k) { id[k] = -FLT_MAX; ida[k] = -1; }
+    for (int i = ncell + (int)threadIdx.x; i < ntot; i += blockDim.x) p_sts<CB, ARG>(sbase + (uint32_t)i * CS, id, ida);
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < CB; ++k) id[k] = 0.f;
-      p_sts<CB>(sbase + (uint32_t)ntot * CS, id);
+      p_sts<CB, ARG>(sbase + (uint32_t)ntot * CS, id, ida);       // empty bin: value 0, argmax -1
     }
   }
   const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
   float* outc = p.output + (size_t)c0 * BINS;
+  int32_t* argc = ARG ? p.argmax + (size_t)c0 * BINS : nullptr;
   const uint32_t c49 = (uint32_t)p.C * BINS;
   const uint32_t pitch = (uint32_t)WP * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -579,16 +635,16 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     if (rem > 0 && phase != PH_FALLBACK) {
       __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
-        case PH_11: pyr_stage<CB, 0>(sbase, src, nc, H, W); __syncthreads(); break;
-        case PH_21: pyr_double_v<CB, 1>(sbase, H + kPad, WP); break;
-        case PH_22: pyr_double_h<CB, 1>(sbase, ncell); break;
-        case PH_42: pyr_double_v<CB, 2>(sbase, H + kPad, WP); break;
-        case PH_44: pyr_double_h<CB, 2>(sbase, ncell); break;
-        case PH_12: pyr_stage<CB, 1>(sbase, src, nc, H, W); __syncthreads(); break;
-        case PH_14: pyr_double_h<CB, 2>(sbase, ncell); break;
-        case PH_24: pyr_double_v<CB, 1>(sbase, H + kPad, WP); break;
-        default:    pyr_stage<CB, 2>(sbase, src, nc, H, W); __syncthreads();
-                    pyr_double_v<CB, 2>(sbase, H + kPad, WP); break;   // PH_41
+        case PH_11: pyr_stage<CB, 0, ARG>(sbase, src, nc, H, W); __syncthreads(); break;
+        case PH_21: pyr_double_v<CB, 1, ARG>(sbase, H + kPad, WP); break;
+        case PH_22: pyr_double_h<CB, 1, ARG>(sbase, ncell); break;
+        case PH_42: pyr_double_v<CB, 2, ARG>(sbase, H + kPad, WP); break;
+        case PH_44: pyr_double_h<CB, 2, ARG>(sbase, ncell); break;
+        case PH_12: pyr_stage<CB, 1, ARG>(sbase, src, nc, H, W); __syncthreads(); break;
+        case PH_14: pyr_double_h<CB, 2, ARG>(sbase, ncell); break;
+        case PH_24: pyr_double_v<CB, 1, ARG>(sbase, H + kPad, WP); break;
+        default:    pyr_stage<CB, 2, ARG>(sbase, src, nc, H, W); __syncthreads();
+                    pyr_double_v<CB, 2, ARG>(sbase, H + kPad, WP); break;   // PH_41
       }
     }
     if (phase != PH_FALLBACK) {
@@ -605,8 +661,8 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         const uint2* pin = p.pinfo + gstart + slo;
 #define PYR_CASE(CH, CW) \
   case ((CH - 1) + (CW - 1) * 4): \
-    if (nc == CB) pyr_run<CB, SLOTS, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
-    else pyr_run<CB, SLOTS, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, c49, nc, flat0, stride); \
+    if (nc == CB) pyr_run<CB, ARG, SLOTS, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
+    else pyr_run<CB, ARG, SLOTS, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
     break;
         switch (sub) {
           PYR_CASE(2, 2) PYR_CASE(4, 2) PYR_CASE(2, 4) PYR_CASE(4, 4)
@@ -636,38 +692,44 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         bin_edges(aw, pw, W, ws, we);
         const bool empty = he <= hs || we <= ws;
         float m[CB];
+        int ma[CB];
 #pragma unroll
-        for (int k = 0; k < CB; ++k) m[k] = empty ? 0.f : -FLT_MAX;
+        for (int k = 0; k < CB; ++k) { m[k] = empty ? 0.f : -FLT_MAX; ma[k] = -1; }
         if (!empty) {
           for (int h = hs; h < he; ++h) {
             uint32_t a = sbase + (uint32_t)((h + kPad) * WP + ws + kPad) * CS;
             for (int w = ws; w < we; ++w, a += CS) {
               float f[CB];
-              p_lds<CB>(a, f);
-#pragma unroll
-              for (int k = 0; k < CB; ++k) m[k] = fmaxf(m[k], f[k]);
+              int fa[CB];
+              p_lds<CB, ARG>(a, f, fa);
+              p_max<CB, ARG>(m, ma, f, fa);
             }
           }
         }
-        float* o = outc + (size_t)(pi.x & 0x3ffffffu) * c49 + bin;
+        const size_t oo = (size_t)(pi.x & 0x3ffffffu) * c49 + bin;
 #pragma unroll
         for (int k = 0; k < CB; ++k)
-          if (k < nc) __stcs(o + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
+          if (k < nc) {
+            __stcs(outc + oo + k * BINS, __fmul_rn(m[k], __uint_as_float(pi.y)));
+            if (ARG) __stcs(argc + oo + k * BINS, ma[k]);
+          }
       }
     }
   }
 }
 
-// shared memory of the padded plane (+ identity tail rows)
-static size_t pyr_smem(int64_t H, int64_t W, int cb) {
-  return ((size_t)(H + kPad + kTailRows) * (size_t)(W + kPad) + 1) * 4u * (size_t)cb;   // + the zero cell
+// shared memory of the padded plane (+ identity tail rows) at `cell` bytes per cell
+static size_t pyr_smem(int64_t H, int64_t W, int cell) {
+  return ((size_t)(H + kPad + kTailRows) * (size_t)(W + kPad) + 1) * (size_t)cell;   // + the zero cell
 }
 
-// channels per CTA the pyramid path would use for this map (0: does not apply)
-int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R) {
+// channels per CTA the pyramid path would use for this map (0: does not apply); with argmax a cell holds two
+// (value, index) pairs
+int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R, bool with_argmax) {
   if ((H + kPad + kTailRows) * (W + kPad) >= 65535 || R >= (1 << 26) || C * 49 >= (1LL << 32)) return 0;
-  if (C >= 3 && pyr_smem(H, W, 4) + 1024 <= (size_t)kMaxSmemOptin) return 4;   // + static shared memory
-  if (pyr_smem(H, W, 2) + 1024 <= (size_t)kMaxSmemOptin) return 2;
+  if (with_argmax) return (H * W < (1LL << 31) && pyr_smem(H, W, 16) + 1024 <= (size_t)kMaxSmemOptin) ? 2 : 0;
+  if (C >= 3 && pyr_smem(H, W, 16) + 1024 <= (size_t)kMaxSmemOptin) return 4;   // + static shared memory
+  if (pyr_smem(H, W, 8) + 1024 <= (size_t)kMaxSmemOptin) return 2;
   return 0;
 }
 
@@ -677,9 +739,9 @@ static int64_t pyr_split(int64_t units, int64_t proposals_per_image) {
   return std::max<int64_t>(1, std::min<int64_t>(fill, proposals_per_image / 1500));
 }
 
-template <int CB>
+template <int CB, bool ARG>
 static int pyr_launch_main(PyrParams& p, int64_t R, cudaStream_t st) {
-  const size_t smem = pyr_smem(p.H, p.W, CB);
+  const size_t smem = pyr_smem(p.H, p.W, (int)CellT<CB, ARG>::CS);
   p.CG = (int)ceil_div(p.C, CB);
   // every CTA of an image rebuilds all planes, so an image's proposals are only split over several CTAs
   // when the (image, channel group) units cannot even fill most of one wave (one image of C = 512 gives
@@ -687,19 +749,20 @@ static int pyr_launch_main(PyrParams& p, int64_t R, cudaStream_t st) {
   const int64_t units = (int64_t)p.N * p.CG;
   p.S = (int)pyr_split(units, R / std::max<int64_t>(p.N, 1));
   if (units * p.S > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
-  auto kern = roi_pool7_pyr_kernel<CB>;
+  auto kern = roi_pool7_pyr_kernel<CB, ARG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<(unsigned)(units * p.S), 1024, smem, st>>>(p);
   return after_launch();
 }
 
-// values-only ROI max-pool 7x7 through the block-max planes; `workspace` holds pool7_pyr_workspace() bytes
+// ROI max-pool 7x7 through the block-max planes (argmax: optional); `workspace` holds pool7_pyr_workspace() bytes
 int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, const float* rois, int64_t R,
-              float scale, const float* row_scale, float row_scale_bias, float* output, void* workspace,
+              float scale, const float* row_scale, float row_scale_bias, float* output, int32_t* argmax, void* workspace,
               cudaStream_t st) {
-  const int cb = pool7_pyr_cb(C, H, W, R);
+  const int cb = pool7_pyr_cb(C, H, W, R, argmax != nullptr);
   if (!cb) return WSOVOD_B200_EINVAL;
+  const bool cell16 = cb == 4 || argmax;            // 16-byte cells: 64 lane slots per proposal
   PyrWs w = pyr_carve(workspace, N, R);
   cudaError_t e = cudaMemsetAsync(w.hist, 0, sizeof(int32_t) * (size_t)N * kBuckets * 2, st);   // histogram + cursors
   if (e != cudaSuccess) return (int)e;
@@ -709,10 +772,10 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   const unsigned parts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(R, 2048)));
   pyr_order_kernel<<<dim3((unsigned)N, parts), 512, 0, st>>>(w.bidx, w.pkey, w.hist, w.cursor, (int)N, R, w.order, w.img_start, w.bucket_off);
   if ((rc = after_launch())) return rc;
-  if (cb == 4 && tune(TUNE_POOL_GROUP))
+  if (cell16 && tune(TUNE_POOL_GROUP))
     pyr_bins_kernel<kSlots, true><<<(unsigned)ceil_div(R * 2, 128), 128, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
                                                                                    row_scale_bias, w.pinfo, w.desc);
-  else if (cb == 4)
+  else if (cell16)
     pyr_bins_kernel<kSlots, false><<<(unsigned)ceil_div(R * 8, 256), 256, 0, st>>>(R, (int)H, (int)W, w.order, w.pkey, w.axtab, row_scale,
                                                                                       row_scale_bias, w.pinfo, w.desc);
   else
@@ -721,9 +784,10 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
   if ((rc = after_launch())) return rc;
   PyrParams p;
   p.input = input; p.rois = rois; p.scale = scale;
-  p.output = output; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
+  p.output = output; p.argmax = argmax; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
-  return cb == 4 ? pyr_launch_main<4>(p, R, st) : pyr_launch_main<2>(p, R, st);
+  if (argmax) return pyr_launch_main<2, true>(p, R, st);
+  return cb == 4 ? pyr_launch_main<4, false>(p, R, st) : pyr_launch_main<2, false>(p, R, st);
 }
 
 }  // namespace wsovod
