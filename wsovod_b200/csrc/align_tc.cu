@@ -200,6 +200,89 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)p.BN;
         const int col0 = c * p.BN;
         const int ncols = min(p.BN, p.KO - col0);        // valid output columns in this chunk
+        if (p.nchunks == 1 && ncols <= 96) {
+          // Up to 96 classes (VOC 20, COCO 80 + background): the whole logit row of this thread lives in registers.
+          // One pass over TMEM, the accumulator buffer goes back to the MMA warp at once, and max / exp / sum /
+          // normalise never leave the register file.  (The three-sweep code below with accurate expf was what bounded
+          // the K = 80 kernel: ~10 us of epilogue per 128-row tile against 9 us of HBM time for its x rows.)  The
+          // exponentials of this TF32 path are ex2.approx: ~1e-6 relative on probabilities whose logits carry 1e-3.
+          float w[3][32];
+          const int ns = (ncols + 31) >> 5;
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < ns) tmem_ld32(taddr + 32 * q, w[q]);
+          tc_fence_before();
+          mbar_arrive(&tempty[buf]);
+          constexpr float L2E = 1.4426950408889634f;
+          float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < ns) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                w[q][i] = fmaf(w[q][i], scale, bias);
+                if (q * 32 + i < ncols) m4[i & 3] = fmaxf(m4[i & 3], w[q][i]);
+              }
+            }
+          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          if (p.write_logits) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (q < ns) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) st[lane * 33 + i] = w[q][i];
+                __syncwarp();
+                const int cc = q * 32 + lane;
+                if (cc < p.KO)
+                  for (int rr = 0; rr < 32; ++rr)
+                    if (rr < wrows) p.logits[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+                __syncwarp();
+              }
+          }
+          if (p.probs) {
+            const float nb = -mx * L2E;
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (q < ns) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  float e;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(w[q][i], L2E, nb)));
+                  w[q][i] = e;
+                  if (q * 32 + i < ncols) a4[i & 3] += e;
+                }
+              }
+            const float inv = 1.f / ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (q < ns) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) st[lane * 33 + i] = w[q][i] * inv;
+                __syncwarp();
+                const int cc = q * 32 + lane;
+                if (cc < p.KO) {
+                  if (MIL) {
+                    // lane == output column: the same walk reduces the detection stream's column statistics over this
+                    // warp's rows (32 independent loads, then max and sum of exp as two passes)
+                    float dv[32];
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) dv[rr] = rr < wrows ? __ldg(p.det + (wrow0 + rr) * p.KO + cc) : -FLT_MAX;
+                    float dm = -FLT_MAX, ds = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) dm = fmaxf(dm, dv[rr]);
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) ds += rr < wrows ? expf(dv[rr] - dm) : 0.f;
+                    p.colpart[((size_t)tile * 4 + wq) * p.KO + cc] = make_float2(dm, ds);
+                  }
+                  for (int rr = 0; rr < 32; ++rr)
+                    if (rr < wrows) p.probs[(wrow0 + rr) * p.KO + cc] = st[rr * 33 + lane];
+                }
+                __syncwarp();
+              }
+          }
+          continue;
+        }
         float v[32];
         // sweep A: chunk maximum
         float cm = -FLT_MAX;
@@ -347,17 +430,15 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   if (M > 0x7fffffffLL - TC_BM) return WSOVOD_B200_ETOOBIG;
   const int64_t KO = K + (append_background ? 1 : 0);
   float* what = (float*)(ws + w.what);                              // [Kp, Dp], rows >= K and cols >= D are zero
-  // one memset: the padded text matrix and, right behind it, the pair kernel's tickets
-  cudaError_t e = cudaMemsetAsync(what, 0, w.tickets + w.tickets_bytes - w.what, st);
-  if (e != cudaSuccess) return (int)e;
+  // the normalised text matrix, zero-padded to [Kp, Dp] (the appended background column is a zero row, :97-100)
+  align_wnorm_kernel<<<(unsigned)ceil_div(w.Kp, 8), 256, 0, st>>>(classifier, (int)K, (int)w.Kp, (int)D, (int)w.Dp, norm_weight == 1, what);
   int rc;
-  if (K > 0) {
-    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)D, (int)w.Dp, norm_weight == 1, what);
-    if ((rc = after_launch())) return rc;
-  }
+  if ((rc = after_launch())) return rc;
   const int64_t nch2 = ceil_div(KO, 256);
   if (!mil && nch2 > 1 && tune(TUNE_ALIGN_PAIR)) {
-    // large vocabularies: CTA pairs (align_tc2.cu), row softmax by the register-row pass that follows
+    cudaError_t e0 = cudaMemsetAsync(ws + w.tickets, 0, w.tickets_bytes, st);
+    if (e0 != cudaSuccess) return (int)e0;
+    // large vocabularies: CTA pairs (align_tc2.cu), row softmax finished inside the kernel where the row pitch allows
     float* lg = logits ? logits : probs;
     if ((rc = align_tc2_launch(x, what, M, D, KO, w.Kp, w.Dp, temperature, norm_weight, bias, lg, probs,
                                (int*)(ws + w.tickets), (float*)(ws + w.rowstat), st))) return rc;
@@ -391,7 +472,7 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   if ((rc = tc_make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
   if ((rc = tc_make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
   auto kern = mil ? align_tc_kernel<true> : align_tc_kernel<false>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = std::min(p.ntiles, kNumSMs);
   kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, p);
