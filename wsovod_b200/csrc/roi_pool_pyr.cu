@@ -562,12 +562,16 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
         if (ARG) __stcs(argc + oo + k * 49, ma[k]);
       }
   };
+  // 64-slot stream: a warp takes BOTH halves of a proposal (lane l: slots l and 32 + l, i.e. bins l and 32 + l), so every
+  // warp -- and every SM sub-partition's scheduler -- carries the same 32 + 17 bins per pass.  (With the halves dealt to
+  // alternating warps, the even warps = two of the four schedulers had twice the issue load of the others.)
+  const int second = SLOTS == 64 ? 32 : stride;
   const int step = 2 * stride;
-  int f = flat0;
+  int f = SLOTS == 64 ? 2 * (flat0 & ~31) + (flat0 & 31) : flat0;
   uint32_t d0 = kDescIdle, d1 = kDescIdle;
   uint2 p0 = make_uint2(0u, 0u), p1 = p0;
   if (f < total) { d0 = __ldg(dsc + f); p0 = __ldg(pin + (uint32_t)f / (uint32_t)SLOTS); }
-  if (f + stride < total) { d1 = __ldg(dsc + f + stride); p1 = __ldg(pin + (uint32_t)(f + stride) / (uint32_t)SLOTS); }
+  if (f + second < total) { d1 = __ldg(dsc + f + second); p1 = __ldg(pin + (uint32_t)(f + second) / (uint32_t)SLOTS); }
   while (f < total) {
     const uint32_t c0 = d0, c1 = d1;
     const uint2 q0 = p0, q1 = p1;
@@ -575,7 +579,7 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
     d0 = kDescIdle;
     d1 = kDescIdle;
     if (g < total) { d0 = __ldg(dsc + g); p0 = __ldg(pin + (uint32_t)g / (uint32_t)SLOTS); }
-    if (g + stride < total) { d1 = __ldg(dsc + g + stride); p1 = __ldg(pin + (uint32_t)(g + stride) / (uint32_t)SLOTS); }
+    if (g + second < total) { d1 = __ldg(dsc + g + second); p1 = __ldg(pin + (uint32_t)(g + second) / (uint32_t)SLOTS); }
     one(c0, q0);
     one(c1, q1);
     f = g;
