@@ -42,12 +42,14 @@ def main():
                 v, u = float(m.get(x, 0) or 0), units.get(x, "").lower()
                 return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
             tot = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-            if k.startswith("roi_pool7_pyr_kernel<4>") or k.startswith("roi_pool7_pyr_kernel<(int)4>"):
-                traffic.setdefault("roi_pool", tot)
+            if k.startswith("roi_pool7_pyr_kernel<4, 0>") or k.startswith("roi_pool7_pyr_kernel<(int)4, (bool)0>"):
+                traffic.setdefault("roi_pool", tot)             # values-only pooling of bench.py: block-max planes
+            if k.startswith("roi_pool7_pyr_kernel<2, 1>") or k.startswith("roi_pool7_pyr_kernel<(int)2, (bool)1>"):
+                traffic.setdefault("roi_pool+argmax", tot)      # block-max planes of (value, index) pairs
             if k.startswith("roi_pool7_kernel<4, 0>") or k.startswith("roi_pool7_kernel<(int)4, (bool)0>"):
                 traffic.setdefault("roi_pool_scan", tot)
             if k.startswith("roi_pool7_kernel<4, 1>") or k.startswith("roi_pool7_kernel<(int)4, (bool)1>"):
-                traffic.setdefault("roi_pool+argmax", tot)
+                traffic.setdefault("roi_pool+argmax_scan", tot)
     traffic["source"] = (f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum (and the rest of {os.path.basename(out)}), "
                          f"{os.path.basename(src)}, config c2, per launch")
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)

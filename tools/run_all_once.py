@@ -44,7 +44,9 @@ for _ in range(reps):
     torch.ops.wsovod_b200.roi_pool_backward(out[:4000], rois[:4000], arg[:4000], 8, 512, 86, 128, False)
     del out, arg
     ops.roi_loop_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
-    ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)
+    ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)
+    torch.ops.wsovod_b200.roi_align_backward(ra[:4000].contiguous(), rois[:4000].contiguous(), 1 / 8, 0, True, 8, 512, 86, 128)
+    del ra
     _, probs = ops.align(x, t, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)
     ops.align(x, t4, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)        # c4: K = 1203
     ops.detections(probs, boxes, off, sizes, w["R"], 1e-5, 0.3, 100, ops.IOU_TV_CUDA)
