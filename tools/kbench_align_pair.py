@@ -33,3 +33,7 @@ for pair in (1, 0):
     _lib.tune(_lib.TUNE_ALIGN_PAIR, pair)
     print("pair", pair, "probs-only op ms", round(timeit(f1), 4), "logits-only ms", round(timeit(f2), 4))
 _lib.tune(_lib.TUNE_ALIGN_PAIR, 1)
+for K2 in (200, 255):
+    t2 = synth.text_embeddings(K2, D, g).cuda()
+    f3 = lambda: ops.align(x, t2, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)
+    print("K =", K2, "(one chunk, three-sweep epilogue) probs-only op ms", round(timeit(f3), 4))

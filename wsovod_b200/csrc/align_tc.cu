@@ -45,6 +45,13 @@ struct TcParams {
   float2* colpart;
 };
 
+// exp of the TF32 path's softmax: ex2.approx (1e-6 relative on probabilities whose logits carry 1e-3)
+__device__ __forceinline__ float tc_exp(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+
 struct TcTile { int row0, rows; };
 template <bool MIL>
 __device__ __forceinline__ TcTile tc_tile(const TcParams& p, int tile) {
@@ -55,7 +62,8 @@ __device__ __forceinline__ TcTile tc_tile(const TcParams& p, int tile) {
 
 // MIL = fused alignment + MIL flavour (tile table, detection-stream column statistics in the epilogue); the plain
 // flavour compiles to the same code as before the fusion existed
-template <bool MIL>
+// REGROW: the single-chunk, <= 96-column flavour whose epilogue keeps the thread's logit row in registers
+template <bool MIL, bool REGROW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -200,7 +208,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * (uint32_t)p.BN;
         const int col0 = c * p.BN;
         const int ncols = min(p.BN, p.KO - col0);        // valid output columns in this chunk
-        if (p.nchunks == 1 && ncols <= 96) {
+        if (REGROW) {
           // Up to 96 classes (VOC 20, COCO 80 + background): the whole logit row of this thread lives in registers.
           // One pass over TMEM, the accumulator buffer goes back to the MMA warp at once, and max / exp / sum /
           // normalise never leave the register file.  (The three-sweep code below with accurate expf was what bounded
@@ -292,7 +300,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           for (int i = 0; i < 32; ++i) if (j + i < ncols) cm = fmaxf(cm, fmaf(v[i], scale, bias));
         }
         const float new_m = fmaxf(run_m, cm);
-        run_s *= expf(run_m - new_m);
+        run_s *= tc_exp(run_m - new_m);
         run_m = new_m;
         // sweep B: logits (staged, then written as 128-byte row segments), running sum of exp
         for (int j = 0; j < ncols; j += 32) {
@@ -300,7 +308,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float l = fmaf(v[i], scale, bias);
-            if (j + i < ncols) run_s += expf(l - run_m);
+            if (j + i < ncols) run_s += tc_exp(l - run_m);
             st[lane * 33 + i] = l;
           }
           __syncwarp();
@@ -316,7 +324,7 @@ align_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           for (int j = 0; j < ncols; j += 32) {
             tmem_ld32(taddr + j, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) st[lane * 33 + i] = expf(fmaf(v[i], scale, bias) - run_m) * inv;
+            for (int i = 0; i < 32; ++i) st[lane * 33 + i] = tc_exp(fmaf(v[i], scale, bias) - run_m) * inv;
             __syncwarp();
             const int cc = j + lane;
             if (cc < p.KO) {
@@ -471,7 +479,9 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   CUtensorMap mx, mw;
   if ((rc = tc_make_map(&mx, x, (uint64_t)D, (uint64_t)M, (uint64_t)D, TC_BM))) return rc;
   if ((rc = tc_make_map(&mw, what, (uint64_t)w.Dp, (uint64_t)w.Kp, (uint64_t)w.Dp, (uint32_t)p.BN))) return rc;
-  auto kern = mil ? align_tc_kernel<true> : align_tc_kernel<false>;
+  const bool regrow = p.nchunks == 1 && p.BN <= 96;
+  auto kern = mil ? (regrow ? align_tc_kernel<true, true> : align_tc_kernel<true, false>)
+                  : (regrow ? align_tc_kernel<false, true> : align_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = std::min(p.ntiles, kNumSMs);

@@ -549,7 +549,17 @@ int align_tc2_launch(const float* x, const float* what, int64_t M, int64_t D, in
   if (e != cudaSuccess) return (int)e;
   const int64_t units = (int64_t)p.ntiles * p.nchunks;
   const int pairs = (int)std::max<int64_t>(1, std::min<int64_t>(units, pair_slots(smem)));
-  align_tc2_kernel<<<2 * pairs, TC2_THREADS, smem, st>>>(mx, mw, mo, p);
+  // The finishing warps wait for tickets of OTHER CTAs of this grid, so every CTA must be resident: a cooperative launch
+  // is gang-scheduled (it starts when all 2 x pairs CTAs fit at once; with another kernel of the caller holding SMs -- a
+  // second stream -- it waits instead of starting half of the grid, which could then wait for the other half forever)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, align_tc2_kernel, mx, mw, mo, p);
+  if (e != cudaSuccess) return (int)e;
   if ((rc = after_launch())) return rc;
   return probs && !fuse ? softmax_rows_launch(logits, M, KO, probs, st) : 0;
 }
