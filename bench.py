@@ -72,7 +72,7 @@ def load_traffic(with_arg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / clock-event (throttle) reasons sampled DURING the timed region (NVML, the numbers nvidia-smi prints)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -81,6 +81,19 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        # NVML in a thread (a sample every ~1 ms: the timed region of an inference config is 20-30 ms); the nvidia-smi
+        # subprocess (one line per 20 ms) is the fallback when the NVML bindings are missing
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            self.proc = "nvml"
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -89,6 +102,25 @@ class ClockSampler:
             self.t.start()
         except Exception:  # noqa: BLE001
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            mx = 0
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                r = int(get_reasons(self.h))
+                act = lambda k: "Active" if r & bits[k] else "Not Active"  # noqa: E731
+                self.rows.append((time.time(), [str(sm), str(mx), "", act("hw_slowdown"), act("hw_thermal_slowdown"),
+                                                act("sw_thermal_slowdown"), act("sw_power_cap")]))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -100,11 +132,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
+        if self.proc == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
         inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
