@@ -224,6 +224,28 @@ def test_align_cta_pair_kernel(M, D, K):
     torch.testing.assert_close(pr_only, pr, rtol=1e-6, atol=1e-9)
 
 
+def test_align_cta_pair_kernel_two_streams():
+    """the pair kernel's finishing warps wait for tickets of other CTAs of the grid, so it is launched cooperatively
+    (gang-scheduled): two instances issued on two streams at once must both complete, with identical results, instead of
+    each holding half of the SMs and waiting for the other half forever"""
+    g = synth.gen(4242)
+    x = synth.region_embeddings(32000, 256, g).to(DEV)
+    t = synth.text_embeddings(1203, 256, g).to(DEV)
+    x2 = x.clone()
+    ref = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)[1].clone()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            a = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)[1]
+        with torch.cuda.stream(s2):
+            b = ops.align(x2, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)[1]
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, ref) and torch.equal(b, ref) for a, b in outs)
+
+
 def test_align_backward():
     g = synth.gen(5)
     x = synth.region_embeddings(200, 96, g).add_(0.01)
