@@ -17,7 +17,9 @@ namespace wsovod {
 // w^[k,:] = w[k,:] / max(||w[k,:]||, 1e-12)  (F.normalize(..., dim=0) on the D x K transpose, :89-90); rows K..Kp-1 and
 // columns D..Dp-1 of the padded output are written as zeros (grid covers Kp rows: no separate memset)
 __global__ void align_wnorm_kernel(const float* __restrict__ w, int K, int Kp, int D, int Dp, int norm,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, int* __restrict__ zero, int nzero) {
+  // `zero`: ints the caller wants cleared on the same launch (the pair kernel's tickets: one memset node less)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (k >= Kp) return;
@@ -300,7 +302,7 @@ WSOVOD_API int wsovod_b200_align_fwd(const float* x, const float* classifier, in
     return align_fwd_tf32(x, classifier, M, D, K, temperature, norm_weight, append_background, bias, logits,
                           probs, w, ws, st);
   if (K > 0) {
-    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)K, (int)D, (int)D, norm_weight == 1, what);
+    align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)K, (int)D, (int)D, norm_weight == 1, what, nullptr, 0);
     if ((rc = after_launch())) return rc;
   }
   // logits go to `logits` when given, else straight into `probs` and are normalised in place
@@ -353,7 +355,7 @@ WSOVOD_API int wsovod_b200_align_bwd(const float* grad_logits, const float* x, c
     if ((rc = after_launch())) return rc;
     if (!grad_x) return 0;
   }
-  align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)K, (int)D, (int)D, norm_weight == 1, what);
+  align_wnorm_kernel<<<(unsigned)ceil_div(K, 8), 256, 0, st>>>(classifier, (int)K, (int)K, (int)D, (int)D, norm_weight == 1, what, nullptr, 0);
   if ((rc = after_launch())) return rc;
   transpose_kernel<<<(unsigned)ceil_div(K * D, 256), 256, 0, st>>>(what, (int)K, (int)D, (int)D, wt);   // wt [D,K]
   if ((rc = after_launch())) return rc;

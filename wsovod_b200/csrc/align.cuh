@@ -12,7 +12,7 @@ struct AlignWs {
 AlignWs align_plan(int64_t M, int64_t D, int64_t K, int precision, bool backward);
 
 __global__ void align_wnorm_kernel(const float* __restrict__ w, int K, int Kp, int D, int Dp, int norm,
-                                   float* __restrict__ out);
+                                   float* __restrict__ out, int* __restrict__ zero = nullptr, int nzero = 0);
 __global__ void row_softmax_kernel(const float* __restrict__ logits, int64_t M, int KO,
                                    float* __restrict__ probs);
 

@@ -439,13 +439,14 @@ int align_fwd_tf32(const float* x, const float* classifier, int64_t M, int64_t D
   const int64_t KO = K + (append_background ? 1 : 0);
   float* what = (float*)(ws + w.what);                              // [Kp, Dp], rows >= K and cols >= D are zero
   // the normalised text matrix, zero-padded to [Kp, Dp] (the appended background column is a zero row, :97-100)
-  align_wnorm_kernel<<<(unsigned)ceil_div(w.Kp, 8), 256, 0, st>>>(classifier, (int)K, (int)w.Kp, (int)D, (int)w.Dp, norm_weight == 1, what);
+  const int64_t nch2 = ceil_div(KO, 256);
+  const bool pair = !mil && nch2 > 1 && tune(TUNE_ALIGN_PAIR);
+  align_wnorm_kernel<<<(unsigned)ceil_div(w.Kp, 8), 256, 0, st>>>(classifier, (int)K, (int)w.Kp, (int)D, (int)w.Dp, norm_weight == 1, what,
+                                                                  pair ? (int*)(ws + w.tickets) : nullptr,
+                                                                  pair ? (int)(w.tickets_bytes / sizeof(int)) : 0);
   int rc;
   if ((rc = after_launch())) return rc;
-  const int64_t nch2 = ceil_div(KO, 256);
-  if (!mil && nch2 > 1 && tune(TUNE_ALIGN_PAIR)) {
-    cudaError_t e0 = cudaMemsetAsync(ws + w.tickets, 0, w.tickets_bytes, st);
-    if (e0 != cudaSuccess) return (int)e0;
+  if (pair) {
     // large vocabularies: CTA pairs (align_tc2.cu), row softmax finished inside the kernel where the row pitch allows
     float* lg = logits ? logits : probs;
     if ((rc = align_tc2_launch(x, what, M, D, KO, w.Kp, w.Dp, temperature, norm_weight, bias, lg, probs,
