@@ -182,6 +182,13 @@ def cpu_reference_leg(w, budget_s=20.0):
     return impl, kind, cores, images, props
 
 
+def workload_config(args, w, world):
+    """the `config` object both arms print (the workload, nothing about how an arm runs it)"""
+    return {"workload": WORKLOADS[args.config], "global_proposals_per_step": int(world * w["N"] * w["R"] * (2 if args.config == "c5" else 1)),
+            "pool_argmax": bool(args.pool_argmax),
+            "l2": "inputs+outputs per step exceed the 126 MB L2; no flush needed"}
+
+
 def run_reference(args, w, rank):
     if rank != 0:
         return
@@ -200,7 +207,7 @@ def run_reference(args, w, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config]},
+        "config": workload_config(args, w, max(args.gpus, 1)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -485,7 +492,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (pool, softmax, MIL, assignment, losses, NMS) / tf32 (alignment contraction)", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config]},
+        "config": workload_config(args, w, world),
         "roofline": {"bound": "hbm", "kernel": "roi_pool7_pyr_kernel (ROI max-pool, block-max planes)", "achieved": pool_gbs,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / peaks["hbm_gbs"],
                      "peak_source": peaks["source"], "traffic": load_traffic(with_arg) if args.config == "c2" else None,
@@ -493,10 +500,8 @@ def main():
         "kernels": kernels,
         "gpu_launches": int(launches),
     }
-    info = {"global_proposals_per_step": world * st.proposals, "pool_argmax": with_arg,
-            "launch": ("training step issued from Python (torch-RNG subsampling reads counts on the host)" if training
+    info = {"launch": ("training step issued from Python (torch-RNG subsampling reads counts on the host)" if training
                        else "eager Python launches" if args.no_graph else "step replayed from a CUDA graph"),
-            "l2": "inputs+outputs per step exceed the 126 MB L2; no flush needed",
             "parallelism": f"dp{world} (images sharded, " + ("DDP gradient all-reduce over NCCL)" if training else "no data-path collective)")}
     if training:
         info["grad_bytes"] = st.grad_bytes()
@@ -538,7 +543,7 @@ def main():
         cpu_base = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
                     "sample": f"{images} image(s) x {props} proposals of {args.config}, one pass; " + impl.DESCRIPTION}
     if rank == 0:
-        line["config"].update(info)
+        line["run"] = info          # how THIS arm ran the workload (`config` is the workload itself, identical in both arms)
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
