@@ -24,11 +24,25 @@ _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
 b = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]
 _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
 assert torch.equal(a, b)
-ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
+va, ia = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)                  # scan kernel with argmax
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
+vb, ib = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)                  # (value, index) planes
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
+assert torch.equal(va, vb) and torch.equal(ia, ib)
+ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)
 ops.roi_loop_pool(feat, rois, 1 / 8, 7, with_argmax=False)
 x, t = synth.region_embeddings(N * R, D, g).to(DEV), synth.text_embeddings(K, D, g).to(DEV)
 _, probs = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)
 ops.align(x, t, 50.0, True, True, None, ops.ALIGN_FP32, True, True)
+# K + 1 > 256: the CTA-pair kernel (cluster barriers, multicast commits, TMA stores, tickets, in-kernel finish), K + 1 a
+# multiple of 4 (TMA-stored logits) and not (plain stores + softmax pass); and the one-CTA multi-chunk kernel
+for K3 in (299, 300):
+    t3 = synth.text_embeddings(K3, D, g).to(DEV)
+    l2, p2 = ops.align(x, t3, 50.0, True, True, None, ops.ALIGN_TF32, True, True)
+    _lib.tune(_lib.TUNE_ALIGN_PAIR, 0)
+    l1, p1 = ops.align(x, t3, 50.0, True, True, None, ops.ALIGN_TF32, True, True)
+    _lib.tune(_lib.TUNE_ALIGN_PAIR, 1)
+    assert torch.equal(l1, l2) and torch.allclose(p1, p2, rtol=2e-5, atol=1e-9)
 offd = torch.tensor(off, device=DEV)
 sizes = torch.tensor([[H * 8.0, W * 8.0]] * N, device=DEV)
 bx = rois[:, 1:].contiguous()
