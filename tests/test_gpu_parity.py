@@ -633,6 +633,28 @@ def test_detections_topk_merge_shapes(K, topk, sizes):
         assert torch.equal(r[k].cpu(), o[k]), k
 
 
+@pytest.mark.parametrize("K,topk,thr,quant", [(1203, 100, 1e-5, 0.0), (1203, 100, 1e-5, 2e-3), (400, 10, 1e-4, 1e-3),
+                                             (150, 100, 0.02, 0.0), (1203, 100, 0.5, 0.0)])
+def test_detections_image_pruning_threshold(K, topk, thr, quant):
+    """K >= topk: candidates below tau = the topk-th largest per-class maximum of their image are dropped before the per-class
+    NMS (det_tau_kernel; exact: the best box of a class is never suppressed, so topk kept boxes at or above tau exist).
+    LVIS-sized class counts, scores quantised so that many tie with tau, a score threshold that leaves fewer than topk
+    non-empty classes (tau = 0), images of 5 and 0 proposals, row tiles that straddle two images -- bit-exact vs the oracle."""
+    g = synth.gen(700 + K + topk)
+    sizes = [700, 333, 0, 5]
+    shapes = [(480, 640)] * len(sizes)
+    boxes = [synth.proposals(s, 480, 640, g) if s else torch.zeros(0, 4) for s in sizes]
+    probs = [torch.softmax(torch.randn(s, K + 1, generator=g) * 3.0, -1) for s in sizes]
+    if quant:
+        probs = [(p / quant).round() * quant for p in probs]
+    off = _offs(sizes)
+    r = ops.detections(torch.cat(probs).to(DEV), torch.cat(boxes).to(DEV), torch.tensor(off, device=DEV),
+                       torch.tensor(shapes, dtype=torch.float32, device=DEV), max(sizes), thr, 0.4, topk, ops.IOU_TV_CUDA)
+    o = oracle.detections(torch.cat(probs), torch.cat(boxes), off, shapes, thr, 0.4, topk, ops.IOU_TV_CUDA)
+    for k in o:
+        assert torch.equal(r[k].cpu(), o[k]), k
+
+
 @pytest.mark.parametrize("mode", [ops.IOU_TV_CPU, ops.IOU_TV_CUDA])
 def test_detections_prefix_fallback_and_long_columns(mode):
     """Columns longer than 2048 candidates take the histogram pre-selection; when the selected prefix
