@@ -293,29 +293,52 @@ constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == hist
 // drops candidates below tau before sorting them -- exact, and at LVIS scale (1203 classes, 100 detections) it removes
 // almost all of the 4000 x 1203 candidates.  Fewer than topk non-empty classes give tau = 0 (the zeros of cmax).
 // One CTA per image: 4-pass radix select on the float bits (probabilities: non-negative, bit order = value order).
-__global__ void __launch_bounds__(256) det_tau_kernel(const unsigned* __restrict__ cmax, int K, int topk, float* __restrict__ tau) {
+__global__ void __launch_bounds__(1024) det_tau_kernel(const unsigned* __restrict__ cmax, int K, int topk, float* __restrict__ tau) {
+  extern __shared__ unsigned s_val[];           // the image's K maxima (one global read)
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_remaining;
   const unsigned* v = cmax + (size_t)blockIdx.x * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_val[k] = __ldg(v + k);
   if (threadIdx.x == 0) { s_prefix = 0u; s_remaining = (unsigned)topk; }
   for (int shift = 24; shift >= 0; shift -= 8) {
-    hist[threadIdx.x] = 0u;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
     __syncthreads();
     const unsigned prefix = s_prefix, himask = shift == 24 ? 0u : 0xffffffffu << (shift + 8);
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      const unsigned x = v[k];
+      const unsigned x = s_val[k];
       if ((x & himask) == (prefix & himask)) atomicAdd(&hist[(x >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned cum = 0, rem = s_remaining;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (cum + hist[b] >= rem) break;
-        cum += hist[b];
+    if (threadIdx.x < 32) {
+      // digit = the largest b with (number of values whose digit is >= b) >= remaining; lane l owns bins 8l .. 8l + 7
+      const int lane = threadIdx.x;
+      unsigned h[8], own = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; own += h[i]; }
+      unsigned suf = own;                         // inclusive suffix sum over the lanes: values in bins >= 8 * lane
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += t;
       }
-      s_prefix = prefix | ((unsigned)b << shift);       // b == 0: fewer than `rem` values above: the answer's digit is 0
-      s_remaining = rem - cum;
+      const unsigned above = suf - own;           // values in the bins of higher lanes
+      const unsigned rem = s_remaining;
+      int digit = -1;
+      unsigned cum_before = 0;
+      if (above < rem && suf >= rem) {            // the answer's bin is one of this lane's eight
+        unsigned cum = above;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+          if (digit < 0 && cum + h[i] >= rem) { digit = lane * 8 + i; cum_before = cum; }
+          if (digit < 0) cum += h[i];
+        }
+      }
+      const unsigned found = __ballot_sync(0xffffffffu, digit >= 0);
+      if (found == 0) {
+        if (lane == 0) s_remaining = rem;         // fewer than `rem` values in range: digit 0 (prefix unchanged)
+      } else if (digit >= 0) {
+        s_prefix = prefix | ((unsigned)digit << shift);
+        s_remaining = rem - cum_before;
+      }
     }
     __syncthreads();
   }
@@ -1267,12 +1290,12 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     float* scoresT = (float*)(ws + w.scoresT);
     // pruning needs at least topk classes (else the threshold is 0) and non-negative candidates (score bits ordered like
     // values: any threshold >= 0, the reference's 1e-5 / 0.05, guarantees that)
-    const bool prune = K >= topk && score_thresh >= 0.f;
+    const bool prune = K >= topk && K <= 8192 && score_thresh >= 0.f;
     det_rows_kernel<<<(unsigned)ceil_div(M, kRtRows), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes, scoresT,
                                                                       score_thresh, prune ? (unsigned*)(ws + w.cmax) : nullptr);
     if ((rc = after_launch())) return rc;
     if (prune) {
-      det_tau_kernel<<<(unsigned)N, 256, 0, st>>>((const unsigned*)(ws + w.cmax), (int)K, (int)topk, (float*)(ws + w.tau));
+      det_tau_kernel<<<(unsigned)N, 1024, sizeof(unsigned) * (size_t)K, st>>>((const unsigned*)(ws + w.cmax), (int)K, (int)topk, (float*)(ws + w.tau));
       if ((rc = after_launch())) return rc;
     }
     auto kern = iou_mode == 0 ? det_class_kernel<0> : det_class_kernel<1>;
