@@ -1,12 +1,13 @@
 // align_tc2.cu -- the alignment contraction for large vocabularies (K + 1 > 256: LVIS, c4) on CTA PAIRS:
 // tcgen05.mma.cta_group::2 kind::tf32, one 256 x 256 accumulator step per SM pair.
 //
-// Why a second kernel: with one CTA per 128 x 256 tile (align_tc.cu) every SM pulls 48 KB of operands through TMA per
-// 2.1 MFLOP; at K = 1203 that kernel runs the tensor pipe 40 % of the time with nothing else saturated (ncu:
-// L2 -> SM 8 TB/s = 24 % of its peak, four 48 KB stages in flight per SM).  A CTA pair shares the text tile: each CTA
-// stages its own 128 rows of x and HALF of the 256 text rows (32 KB per stage instead of 48 KB, six stages instead
-// of four), the leader CTA's single thread issues the MMAs for both SMs, and each CTA's TMEM receives the
-// accumulator rows of its own x rows.
+// Why a second kernel: at K = 1203 the one-CTA-per-tile kernel (align_tc.cu) ran the tensor pipe 40 % of the time with
+// nothing saturated.  A CTA pair shares the text tile -- each CTA stages its own 128 rows of x and HALF of the 256 text
+// rows (32 KB per stage instead of 48 KB, six stages instead of four), the leader CTA's single thread issues the MMAs
+// for both SMs, each CTA's TMEM receives the accumulator rows of its own x rows -- but what actually bounded that
+// kernel was its epilogue (four warps, three TMEM sweeps, accurate expf, scalar row-segment stores): with the epilogue
+// below the main loop runs at the TF32 peak, and the row softmax, which cannot be completed before the last chunk of a
+// row exists, is finished inside the kernel instead of by a second pass over the matrix.
 //
 //   cluster = 2 CTAs (one TPC), grid = 2 x min(#units, resident clusters), persistent, 384 threads per CTA.
 //   unit    = (256-row tile, 256-column chunk of the vocabulary).  Unit u runs on pair u % #pairs: the chunks of a tile
@@ -30,6 +31,7 @@
 // instead of a second pass over 2 x 154 MB after it (what was measured on the way is in DESIGN.md, Kernel 2a).
 // The last chunk of the vocabulary runs with N rounded up to 16 only (K = 1203: 192 instead of 256 columns).
 // Row pitches that are not a multiple of 16 bytes (TMA) take plain stores and a separate softmax pass.
+// Launched cooperatively: the finishing warps wait for tickets of other CTAs, so the whole grid must be resident.
 #include "align.cuh"
 #include "tc_ptx.cuh"
 
