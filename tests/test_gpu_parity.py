@@ -637,7 +637,8 @@ def test_detections_topk_merge_shapes(K, topk, sizes):
                                              (150, 100, 0.02, 0.0), (1203, 100, 0.5, 0.0)])
 def test_detections_image_pruning_threshold(K, topk, thr, quant):
     """K >= topk: candidates below tau = the topk-th largest per-class maximum of their image are dropped before the per-class
-    NMS (det_tau_kernel; exact: the best box of a class is never suppressed, so topk kept boxes at or above tau exist).
+    NMS (det_scan / det_tau / det_compact kernels; exact: the best box of a class is never suppressed, so topk kept boxes at
+    or above tau exist).
     LVIS-sized class counts, scores quantised so that many tie with tau, a score threshold that leaves fewer than topk
     non-empty classes (tau = 0), images of 5 and 0 proposals, row tiles that straddle two images -- bit-exact vs the oracle."""
     g = synth.gen(700 + K + topk)
@@ -647,6 +648,14 @@ def test_detections_image_pruning_threshold(K, topk, thr, quant):
     probs = [torch.softmax(torch.randn(s, K + 1, generator=g) * 3.0, -1) for s in sizes]
     if quant:
         probs = [(p / quant).round() * quant for p in probs]
+    else:
+        # rows the finite filter drops (:178-182), among them the image's best score: the front end of the pruned path
+        # accumulates class maxima while it checks a row and must take a dropped row's contribution back
+        best = int(probs[0][:, :K].max(1).values.argmax())
+        probs[0][best, K // 2] = float("nan")
+        probs[0][13, 3] = float("inf")
+        boxes[1][40, 2] = float("inf")
+        probs[1][int(probs[1][:, :K].max(1).values.argmax()), 0] = float("-inf")
     off = _offs(sizes)
     r = ops.detections(torch.cat(probs).to(DEV), torch.cat(boxes).to(DEV), torch.tensor(off, device=DEV),
                        torch.tensor(shapes, dtype=torch.float32, device=DEV), max(sizes), thr, 0.4, topk, ops.IOU_TV_CUDA)

@@ -48,7 +48,9 @@ for _ in range(reps):
     torch.ops.wsovod_b200.roi_align_backward(ra[:4000].contiguous(), rois[:4000].contiguous(), 1 / 8, 0, True, 8, 512, 86, 128)
     del ra
     _, probs = ops.align(x, t, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)
-    ops.align(x, t4, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)        # c4: K = 1203
+    _, probs4 = ops.align(x, t4, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)   # c4: K = 1203 (CTA-pair kernel)
+    ops.detections(probs4, boxes, off, sizes, w["R"], 1e-5, 0.3, 100, ops.IOU_TV_CUDA)  # c4 tail: det_tau pruning threshold
+    del probs4
     ops.detections(probs, boxes, off, sizes, w["R"], 1e-5, 0.3, 100, ops.IOU_TV_CUDA)
     ops.align(x3, t3, 50.0, 1, True, None, ops.ALIGN_FP32, True, False)
     gl = torch.randn(M3, K + 1, device=DEV)

@@ -170,13 +170,9 @@ constexpr int kRtRows = 32, kRtCols = 128;
 __global__ void __launch_bounds__(256) det_rows_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
                                                        const int64_t* __restrict__ offsets, const float* __restrict__ image_sizes,
                                                        int64_t M, int N, int K1, float4* __restrict__ cboxes,
-                                                       float* __restrict__ scoresT, float score_thr,
-                                                       unsigned* __restrict__ cmax) {
-  // cmax[n][k] (zeroed by the caller) <- bits of the largest candidate score (> score_thr, finite row) of class k in
-  // image n, or stays 0: det_tau_kernel turns the K maxima of an image into its pruning threshold
+                                                       float* __restrict__ scoresT) {
   __shared__ float tile[kRtRows][kRtCols + 1];
   __shared__ uint8_t s_ok[kRtRows];
-  __shared__ int s_img[kRtRows];
   const int64_t rb = (int64_t)blockIdx.x * kRtRows;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;      // 8 warps, 4 rows each
 #pragma unroll
@@ -195,10 +191,9 @@ __global__ void __launch_bounds__(256) det_rows_kernel(const float* __restrict__
         const float ih = image_sizes[2 * lo], iw = image_sizes[2 * lo + 1];
         cboxes[r] = make_float4(fminf(fmaxf(b.x, 0.f), iw), fminf(fmaxf(b.y, 0.f), ih),
                                 fminf(fmaxf(b.z, 0.f), iw), fminf(fmaxf(b.w, 0.f), ih));
-        s_img[rl] = lo;
       }
     }
-    if (lane == 0) { s_ok[rl] = ok ? 1 : 0; if (r >= M) s_img[rl] = -1; }
+    if (lane == 0) s_ok[rl] = ok ? 1 : 0;
   }
   __syncthreads();
   const int K = K1 - 1;
@@ -214,26 +209,8 @@ __global__ void __launch_bounds__(256) det_rows_kernel(const float* __restrict__
     }
     __syncthreads();
     const int64_t r = rb + lane;
-    const int img = s_img[lane];
-    const bool uniform = s_img[0] == s_img[kRtRows - 1] || s_img[kRtRows - 1] < 0;   // one image (or the ragged last tile)
-    if (!cmax) {                                                                      // no pruning for this call
-      if (r < M)
-        for (int c = wid; c < kRtCols && kb + c < K; c += 8) scoresT[(int64_t)(kb + c) * M + r] = tile[lane][c];
-    } else
-    for (int c = wid; c < kRtCols && kb + c < K; c += 8) {                            // warp-uniform trip count
-      const float v = tile[lane][c];
-      if (r < M) scoresT[(int64_t)(kb + c) * M + r] = v;
-      const unsigned cand = (r < M && v > score_thr && v > 0.f) ? __float_as_uint(v) : 0u;   // positive: bits order like values
-      if (uniform && s_img[0] == img) {
-        const unsigned m = __reduce_max_sync(0xffffffffu, cand);
-        if (lane == 0 && m) atomicMax(cmax + (size_t)s_img[0] * K + kb + c, m);
-      } else if (uniform) {
-        const unsigned m = __reduce_max_sync(0xffffffffu, img == s_img[0] ? cand : 0u);
-        if (lane == 0 && m) atomicMax(cmax + (size_t)s_img[0] * K + kb + c, m);
-      } else if (cand) {
-        atomicMax(cmax + (size_t)img * K + kb + c, cand);
-      }
-    }
+    if (r < M)
+      for (int c = wid; c < kRtCols && kb + c < K; c += 8) scoresT[(int64_t)(kb + c) * M + r] = tile[lane][c];
     __syncthreads();
   }
 }
@@ -287,6 +264,118 @@ constexpr int kMaxRunClasses = 2048;    // the run table / run merge of det_topk
 constexpr int kSelectBins = 2048;     // histogram over the 11 leading key bits (quarter octaves of the score)
 constexpr int kSelectShift = 53;
 constexpr int kSelectCap = 1024;      // selected-prefix capacity (keys) == histogram storage (8 KB)
+// ---- front end of the pruned path (K >= topk): no class-major copy of the score matrix ------------------------------------
+// With the image threshold tau of det_tau_kernel almost nothing survives (c4: a few hundred of 4.8 M scores per image), so
+// the scores are read twice in their own row-major layout instead of being transposed for det_class: det_scan_kernel =
+// det_rows' finite filter + box clip + the per-(image, class) maxima tau is made from; det_compact_kernel = the rows that
+// survive (score > thr, score >= tau, finite row), appended per (image, class) as row indices into the space the
+// transposed matrix would have taken.  det_class then gathers its few candidates' scores from the row-major matrix.
+constexpr int kScanRows = 64;
+__device__ __forceinline__ int det_image_of(const int64_t* __restrict__ offsets, int N, int64_t r) {
+  int lo = 0, hi = N - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= r) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+__global__ void __launch_bounds__(256) det_scan_kernel(const float* __restrict__ probs, const float* __restrict__ boxes,
+                                                       const int64_t* __restrict__ offsets, const float* __restrict__ image_sizes,
+                                                       int64_t M, int N, int K1, float4* __restrict__ cboxes,
+                                                       uint8_t* __restrict__ rowok, float score_thr, unsigned* __restrict__ cmax) {
+  extern __shared__ unsigned s_cm[];            // [K] maxima of this tile's rows of ONE image
+  __shared__ int s_i0, s_i1, s_bad;
+  const int K = K1 - 1;
+  const int64_t rb = (int64_t)blockIdx.x * kScanRows, re = min(M, rb + kScanRows);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_i0 = det_image_of(offsets, N, rb); s_i1 = det_image_of(offsets, N, re - 1); }
+  __syncthreads();
+  for (int img = s_i0; img <= s_i1; ++img) {
+    const int64_t a = max(rb, offsets[img]), b = min(re, offsets[img + 1]);
+    if (a >= b) continue;                                        // an image without proposals
+    const float ih = image_sizes[2 * img], iw = image_sizes[2 * img + 1];
+    // One pass per row in the common case: the maxima are accumulated while the row is checked for non-finite entries.
+    // A row that fails the check has already contributed, so a tile that saw one (s_bad) clears its maxima and repeats
+    // the accumulation with the flags known (second attempt: `speculate` false).
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      const bool speculate = attempt == 0;
+      for (int k = threadIdx.x; k < K; k += blockDim.x) s_cm[k] = 0u;
+      if (threadIdx.x == 0) s_bad = 0;
+      __syncthreads();
+      for (int64_t r = a + wid; r < b; r += 8) {
+        const float* row = probs + r * K1;
+        bool ok = true;
+        if (speculate) {
+          const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + r);
+          ok = isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w);
+          if (lane == 0)
+            cboxes[r] = make_float4(fminf(fmaxf(bx.x, 0.f), iw), fminf(fmaxf(bx.y, 0.f), ih),
+                                    fminf(fmaxf(bx.z, 0.f), iw), fminf(fmaxf(bx.w, 0.f), ih));
+        } else if (!rowok[r]) {
+          continue;
+        }
+        for (int k0 = 0; k0 < K1; k0 += 32 * 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 32 + lane;
+            v[u] = k < K1 ? __ldg(row + k) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 32 + lane;
+            ok &= isfinite(v[u]);
+            if (k < K && v[u] > score_thr && v[u] > 0.f && isfinite(v[u])) atomicMax(&s_cm[k], __float_as_uint(v[u]));
+          }
+        }
+        if (speculate) {
+          ok = __all_sync(0xffffffffu, ok);
+          if (lane == 0) { rowok[r] = ok ? 1 : 0; if (!ok) s_bad = 1; }
+        }
+      }
+      __syncthreads();
+      if (!s_bad) break;
+      __syncthreads();
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+      if (s_cm[k]) atomicMax(cmax + (size_t)img * K + k, s_cm[k]);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) det_compact_kernel(const float* __restrict__ probs, const int64_t* __restrict__ offsets,
+                                                          int64_t M, int N, int K1, const uint8_t* __restrict__ rowok,
+                                                          float score_thr, const float* __restrict__ tau,
+                                                          int32_t* __restrict__ ccnt, int32_t* __restrict__ cand) {
+  __shared__ int s_i0;
+  const int K = K1 - 1;
+  const int64_t rb = (int64_t)blockIdx.x * kScanRows, re = min(M, rb + kScanRows);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_i0 = det_image_of(offsets, N, rb);
+  __syncthreads();
+  int img = s_i0;
+  for (int64_t r = rb + wid; r < re; r += 8) {
+    if (!rowok[r]) continue;
+    while (r >= offsets[img + 1]) ++img;
+    const float t = fmaxf(__ldg(tau + img), 0.f);
+    const int64_t i0 = offsets[img];
+    const float* row = probs + r * K1;
+    for (int k0 = 0; k0 < K; k0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 32 + lane;
+        v[u] = k < K ? __ldg(row + k) : -1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 32 + lane;
+        if (v[u] > score_thr && v[u] >= t) {                       // the padding (-1) fails: t >= 0
+          const int slot = atomicAdd(ccnt + (size_t)img * K + k, 1);
+          cand[(int64_t)k * M + i0 + slot] = (int32_t)(r - i0);
+        }
+      }
+    }
+  }
+}
+
 // The topk best detections of an image all score at least tau = the topk-th largest of its per-class maxima: the best
 // candidate of a class is never suppressed, so an image with topk or more non-empty classes already has topk kept
 // boxes at or above tau, and nothing below tau can reach the final list (:207-208 keeps the topk best).  det_class then
@@ -366,7 +455,8 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
     const float* __restrict__ scoresT, int64_t M, const int64_t* __restrict__ offsets,
     const float4* __restrict__ cboxes, int K, float score_thr, float thr, int limit, int npad_cap, bool fixed_runs,
     int32_t* __restrict__ img_cnt, unsigned long long* __restrict__ img_kept, int64_t kept_stride,
-    int2* __restrict__ runs, const float* __restrict__ tau) {
+    int2* __restrict__ runs, const float* __restrict__ tau, const int32_t* __restrict__ cand,
+    const int32_t* __restrict__ ccnt, const float* __restrict__ probs) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ int s_n, s_base, s_sel, s_bstar, s_m, s_fitsel, s_fitb;
   __shared__ int s_new[2];
@@ -385,10 +475,21 @@ __global__ void __launch_bounds__(kDcThreads, 5) det_class_kernel(
   const float img_tau = tau ? __ldg(tau + n) : -INFINITY;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  // the column is one contiguous run of scoresT (rows that failed the finite filter hold -inf)
-  const float* col = scoresT + (int64_t)k * M + r0;
   const int nrows = (int)(r1 - r0);
+  if (cand) {
+    // pruned path: the survivors of this (class, image) were listed by det_compact_kernel; their scores come from the
+    // row-major matrix (a handful of gathers)
+    const int nc0 = __ldg(ccnt + (int64_t)n * K + k);
+    const int32_t* lst = cand + (int64_t)k * M + r0;
+    for (int i = threadIdx.x; i < nc0; i += kDcThreads) {
+      const int rl = __ldg(lst + i);
+      skey[i] = make_key(__ldg(probs + (r0 + rl) * (int64_t)(K + 1) + k), (uint32_t)rl);
+    }
+    if (threadIdx.x == 0) s_n = nc0;
+  } else
+  // the column is one contiguous run of scoresT (rows that failed the finite filter hold -inf)
   for (int rb = threadIdx.x; rb - lane < nrows; rb += 4 * kDcThreads) {      // warp-uniform trip count
+    const float* col = scoresT + (int64_t)k * M + r0;
     float s[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) s[u] = rb + u * kDcThreads < nrows ? __ldg(col + rb + u * kDcThreads) : -INFINITY;
@@ -1130,7 +1231,7 @@ static size_t det_topk_smem(int64_t K, int G, int64_t topk) {
   return sizeof(unsigned long long) * ((size_t)topk + (size_t)(cap + (cap + 1) / 2) * (size_t)topk + (size_t)cap);
 }
 
-struct DetWs { size_t cboxes, img_cnt, cmax, tau, zero_end, img_kept, runs, scoresT, part, part_len, bytes; int64_t kept_stride; int G; };
+struct DetWs { size_t cboxes, img_cnt, cmax, tau, ccnt, zero_end, img_kept, runs, scoresT, rowok, part, part_len, bytes; int64_t kept_stride; int G; };
 static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   DetWs w;
   size_t o = 0;
@@ -1143,10 +1244,12 @@ static DetWs det_plan(int64_t M, int64_t N, int64_t K, int64_t topk) {
   w.img_cnt = take(sizeof(int32_t) * (size_t)(2 * N + 1));      // per-image kept counters, then the top-k tickets
   w.cmax = take(sizeof(unsigned) * (size_t)(N * std::max<int64_t>(K, 1)));   // per (image, class) best candidate score
   w.tau = take(sizeof(float) * (size_t)N);                       // per-image pruning threshold
+  w.ccnt = take(sizeof(int32_t) * (size_t)(N * std::max<int64_t>(K, 1)));    // survivors per (image, class) (pruned path)
   w.zero_end = o;                                                // img_cnt .. tau are cleared by one memset
   w.img_kept = take(sizeof(unsigned long long) * (size_t)(N * w.kept_stride));
   w.runs = take(sizeof(int2) * (size_t)(N * std::max<int64_t>(K, 1)));
-  w.scoresT = take(sizeof(float) * (size_t)(M * K));
+  w.scoresT = take(sizeof(float) * (size_t)(M * K));             // class-major scores, or (pruned path) the survivors' row lists
+  w.rowok = take((size_t)M);                                     // pruned path: finite-row flags
   w.part = take(sizeof(unsigned long long) * (size_t)(N * std::max(w.G, 1) * std::max<int64_t>(topk, 0)));
   w.part_len = take(sizeof(int) * (size_t)(N * std::max(w.G, 1)));
   w.bytes = o;
@@ -1291,11 +1394,18 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     // pruning needs at least topk classes (else the threshold is 0) and non-negative candidates (score bits ordered like
     // values: any threshold >= 0, the reference's 1e-5 / 0.05, guarantees that)
     const bool prune = K >= topk && K <= 8192 && score_thresh >= 0.f;
-    det_rows_kernel<<<(unsigned)ceil_div(M, kRtRows), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes, scoresT,
-                                                                      score_thresh, prune ? (unsigned*)(ws + w.cmax) : nullptr);
-    if ((rc = after_launch())) return rc;
     if (prune) {
+      const unsigned tiles = (unsigned)ceil_div(M, kScanRows);
+      det_scan_kernel<<<tiles, 256, sizeof(unsigned) * (size_t)K, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes,
+                                                                       (uint8_t*)(ws + w.rowok), score_thresh, (unsigned*)(ws + w.cmax));
+      if ((rc = after_launch())) return rc;
       det_tau_kernel<<<(unsigned)N, 1024, sizeof(unsigned) * (size_t)K, st>>>((const unsigned*)(ws + w.cmax), (int)K, (int)topk, (float*)(ws + w.tau));
+      if ((rc = after_launch())) return rc;
+      det_compact_kernel<<<tiles, 256, 0, st>>>(probs, offsets, M, (int)N, (int)K + 1, (const uint8_t*)(ws + w.rowok), score_thresh,
+                                                (const float*)(ws + w.tau), (int32_t*)(ws + w.ccnt), (int32_t*)scoresT);
+      if ((rc = after_launch())) return rc;
+    } else {
+      det_rows_kernel<<<(unsigned)ceil_div(M, kRtRows), 256, 0, st>>>(probs, boxes, offsets, image_sizes, M, (int)N, (int)K + 1, cboxes, scoresT);
       if ((rc = after_launch())) return rc;
     }
     auto kern = iou_mode == 0 ? det_class_kernel<0> : det_class_kernel<1>;
@@ -1306,7 +1416,8 @@ WSOVOD_API int wsovod_b200_detections(const float* probs, const float* boxes, co
     dim3 grid((unsigned)K, (unsigned)N);
     kern<<<grid, kDcThreads, smem, st>>>(scoresT, M, offsets, cboxes, (int)K, score_thresh,
                                          cmp_threshold(nms_thresh, iou_mode), limit, npad_cap, use_runs, img_cnt, img_kept, w.kept_stride, runs,
-                                         prune ? (const float*)(ws + w.tau) : nullptr);
+                                         prune ? (const float*)(ws + w.tau) : nullptr, prune ? (const int32_t*)scoresT : nullptr,
+                                         (const int32_t*)(ws + w.ccnt), probs);
     if ((rc = after_launch())) return rc;
   }
   // final ordering: sort the image's kept list in shared memory when it fits (K * topk <= 16384 keys)
