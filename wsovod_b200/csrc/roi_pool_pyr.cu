@@ -510,7 +510,20 @@ __device__ __noinline__ void pyr_double_v(uint32_t sbase, int rows, int WP) {
 // proposal's (id, scale) pair, both fetched one pass ahead, issues up to CH*CW LDS (a block is skipped
 // where it would repeat the previous one: the bin is not larger than the blocks before it) and stores
 // CB scalars (ARG: and CB indices).  Passes are aligned to proposals (f is a multiple of 32, a proposal of 64 slots).
-// plain C++ loads in the hot loop (ptxas schedules them freely; the asm wrappers above are volatile)
+// shared-space loads from a 32-bit address in the hot loop: NOT volatile (ptxas schedules and predicates them freely; the
+// wrappers above are volatile), and no generic -> shared conversion of the plane pointer per bin (it cost four uniform
+// instructions per lane slot).  The plane does not change between the barriers that bracket a bin phase.
+template <class V> __device__ __forceinline__ V lds_plane(uint32_t addr);
+template <> __device__ __forceinline__ float4 lds_plane<float4>(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <> __device__ __forceinline__ float2 lds_plane<float2>(uint32_t addr) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 template <int CB, bool ARG> struct PV;
 template <> struct PV<4, false> { using T = float4; };
 template <> struct PV<2, false> { using T = float2; };
@@ -522,7 +535,7 @@ __device__ __forceinline__ void pv_get(float* m, int* a, const float4& v, const 
 }
 
 template <int CB, bool ARG, int SLOTS, int CH, int CW, bool FULL>
-__device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pitch, uint32_t khp, uint32_t kwb,
+__device__ __forceinline__ void pyr_run(uint32_t plane, uint32_t pitch, uint32_t khp, uint32_t kwb,
                                         const uint32_t* __restrict__ dsc, const uint2* __restrict__ pin,
                                         int total, float* __restrict__ outc, int32_t* __restrict__ argc, uint32_t c49,
                                         int nc, int flat0, int stride) {
@@ -535,7 +548,7 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
     // the plane holds no NaN / -inf (pyr_stage clamps at -FLT_MAX), so the first block seeds the maximum
     float m[CB];
     int ma[CB];
-    pv_get(m, ma, *reinterpret_cast<const V*>(plane + a0), PV<CB, ARG>());
+    pv_get(m, ma, lds_plane<V>(plane + a0), PV<CB, ARG>());
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const uint32_t ro = i == 0 ? 0u : min((uint32_t)i * khp, lhp);
@@ -548,7 +561,7 @@ __device__ __forceinline__ void pyr_run(const unsigned char* plane, uint32_t pit
         if (ni && nj) {
           float f[CB];
           int fa[CB];
-          pv_get(f, fa, *reinterpret_cast<const V*>(plane + a0 + ro + co), PV<CB, ARG>());
+          pv_get(f, fa, lds_plane<V>(plane + a0 + ro + co), PV<CB, ARG>());
           p_max<CB, ARG>(m, ma, f, fa);
         }
       }
@@ -665,8 +678,8 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
         const uint2* pin = p.pinfo + gstart + slo;
 #define PYR_CASE(CH, CW) \
   case ((CH - 1) + (CW - 1) * 4): \
-    if (nc == CB) pyr_run<CB, ARG, SLOTS, CH, CW, true>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
-    else pyr_run<CB, ARG, SLOTS, CH, CW, false>(smem_raw, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
+    if (nc == CB) pyr_run<CB, ARG, SLOTS, CH, CW, true>(sbase, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
+    else pyr_run<CB, ARG, SLOTS, CH, CW, false>(sbase, pitch, khp, kwb, dsc, pin, total, outc, argc, c49, nc, flat0, stride); \
     break;
         switch (sub) {
           PYR_CASE(2, 2) PYR_CASE(4, 2) PYR_CASE(2, 4) PYR_CASE(4, 4)
