@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 namespace wsovod {
@@ -51,6 +52,35 @@ WSOVOD_API size_t wsovod_b200_infer_host_arena(int64_t N, int64_t C, int64_t H, 
   return arena_plan(N, C, H, W, R_total, D, K, pooled, topk, with_argmax, WSOVOD_B200_ALIGN_TF32).bytes;
 }
 
+// Events of this entry point: a per-thread, per-device pool created on first use and reused by every later call (the
+// entry point needs up to 2 N + 2 of them per call; creating and destroying them each time cost ~40 us of host time).
+// Re-recording an event whose earlier cudaStreamWaitEvent is still pending is fine: a wait binds to the record that
+// preceded it.  The pool is never destroyed (process lifetime).
+namespace {
+struct EventPool {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  cudaError_t next(cudaEvent_t* out) {
+    if (used == ev.size()) {
+      cudaEvent_t e = nullptr;
+      const cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (rc != cudaSuccess) return rc;
+      ev.push_back(e);
+    }
+    *out = ev[used++];
+    return cudaSuccess;
+  }
+};
+EventPool& event_pool() {
+  thread_local std::map<int, EventPool> pools;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  EventPool& p = pools[dev];
+  p.used = 0;
+  return p;
+}
+}  // namespace
+
 WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_t C, int64_t H, int64_t W,
                                       const float* h_rois, const float* h_objectness, int64_t R,
                                       const int64_t* h_offsets, const float* h_image_sizes,
@@ -84,18 +114,15 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
   int rc = 0;
   cudaEvent_t ev_start = nullptr, ev_small = nullptr;
   std::vector<cudaEvent_t> ev((size_t)N, nullptr);
-  auto cleanup = [&]() {
-    if (ev_start) cudaEventDestroy(ev_start);
-    if (ev_small) cudaEventDestroy(ev_small);
-    for (auto x : ev) if (x) cudaEventDestroy(x);
-  };
+  EventPool& pool = event_pool();
+  auto cleanup = [&]() {};
 #define CK(call) do { e = (call); if (e != cudaSuccess) { cleanup(); return (int)e; } } while (0)
 #define RC(call) do { rc = (call); if (rc) { cleanup(); return rc; } } while (0)
   auto h2d = [&](size_t off, const void* src, size_t bytes) {
     return bytes ? cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
   };
   if (piped) {   // the copy stream must not overwrite the arena before earlier work on `stream` is done
-    CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CK(pool.next(&ev_start));
     CK(cudaEventRecord(ev_start, st));
     CK(cudaStreamWaitEvent(cs, ev_start, 0));
   }
@@ -106,7 +133,7 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
   CK(h2d(a.sizes, h_image_sizes, sizeof(float) * 2 * (size_t)N));
   CK(h2d(a.text, h_text_emb, sizeof(float) * (size_t)(K * D)));
   if (piped) {
-    CK(cudaEventCreateWithFlags(&ev_small, cudaEventDisableTiming));
+    CK(pool.next(&ev_small));
     CK(cudaEventRecord(ev_small, cs));
     CK(cudaStreamWaitEvent(st, ev_small, 0));
   }
@@ -117,13 +144,13 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
   // has landed (the big kernels overlap the rest of the copies); alignment only needs the embeddings, so
   // what is left after the LAST byte arrives is one alignment launch + the detections, not a pooling.
   std::vector<cudaEvent_t> ev_emb((size_t)N, nullptr);
-  auto cleanup2 = [&]() { for (auto x : ev_emb) if (x) cudaEventDestroy(x); };
+  auto cleanup2 = [&]() {};
 #define CK2(call) do { e = (call); if (e != cudaSuccess) { cleanup2(); cleanup(); return (int)e; } } while (0)
 #define RC2(call) do { rc = (call); if (rc) { cleanup2(); cleanup(); return rc; } } while (0)
   for (int64_t n = 0; n < N; ++n) {
     CK2(h2d(a.feat + plane * (size_t)n, h_features + (size_t)n * (size_t)(C * H * W), plane));
     if (piped) {
-      CK2(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
+      CK2(pool.next(&ev[n]));
       CK2(cudaEventRecord(ev[n], cs));
     }
   }
@@ -131,7 +158,7 @@ WSOVOD_API int wsovod_b200_infer_host(const float* h_features, int64_t N, int64_
     const int64_t r0 = h_offsets[n], rn = h_offsets[n + 1] - r0;
     CK2(h2d(a.emb + sizeof(float) * (size_t)(r0 * D), h_region_emb + r0 * D, sizeof(float) * (size_t)(rn * D)));
     if (piped) {
-      CK2(cudaEventCreateWithFlags(&ev_emb[n], cudaEventDisableTiming));
+      CK2(pool.next(&ev_emb[n]));
       CK2(cudaEventRecord(ev_emb[n], cs));
     }
   }
