@@ -823,10 +823,13 @@ __global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const f
 // image for every map / batch shape tried (tools/kbench_pool_sweep.py: 8 x 4000 proposals 1.45 vs 2.51 ms,
 // 1 x 2000 on a 60x80 map 0.135 vs 0.166 ms, 8 x 500 0.63 vs 0.40 ms).  Test / bench hook:
 // wsovod_b200_tune(WSOVOD_B200_TUNE_POOL_PATH, 1) forces the scan kernels, 2 the block-max path wherever it applies.
-static bool pool_use_blockmax(int64_t N, int64_t R) {
+static bool pool_use_blockmax(int64_t N, int64_t R, int64_t C, bool with_argmax) {
   const int v = tune(TUNE_POOL_PATH);
   if (v == 1) return false;
   if (v == 2) return true;
+  // with argmax a CTA owns two channels: one image of C = 512 is 256 CTAs = 1.7 waves of 148, where the scan kernel's
+  // 128 four-channel CTAs are faster (c1: 0.199 vs 0.216 ms); from three waves on the planes win (c2: 2.5 vs 3.7 ms)
+  if (with_argmax && N * ceil_div(C, 2) < 3 * kNumSMs) return false;
   return R >= 1200 * N;
 }
 
@@ -974,7 +977,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   w = carve(workspace, mode, N, R, PH, PW);
   cudaStream_t st = (cudaStream_t)stream;
   // 7x7 max-pool (+ argmax): block-max planes (roi_pool_pyr.cu) when the padded plane fits shared memory
-  if (mode == MODE_POOL && PH == 7 && PW == 7 && pool_use_blockmax(N, R) && pool7_pyr_cb(C, H, W, R, argmax != nullptr))
+  if (mode == MODE_POOL && PH == 7 && PW == 7 && pool_use_blockmax(N, R, C, argmax != nullptr) && pool7_pyr_cb(C, H, W, R, argmax != nullptr))
     return pool7_pyr(input, N, C, H, W, rois, R, scale, row_scale, row_scale_bias, output, argmax, w.pyr, st);
   cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)(N + 1), st);
   if (e != cudaSuccess) return (int)e;
