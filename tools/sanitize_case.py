@@ -53,6 +53,14 @@ bx2 = synth.proposals(R2, 480, 640, g).to(DEV)
 pr2 = torch.softmax(torch.randn(R2, K2 + 1, generator=g) * 2.0, -1).to(DEV)
 det2 = ops.detections(pr2, bx2, torch.tensor([0, R2], device=DEV), torch.tensor([[480.0, 640.0]], device=DEV), R2, 1e-5,
                       0.3, 100, ops.IOU_TV_CPU)
+# K >= topk: the pruned front end (scan / tau / compact, gather in det_class), rows dropped by the finite filter included
+R3, K3 = 333, 150
+bx3 = synth.proposals(R3, 480, 640, g).to(DEV)
+pr3 = torch.softmax(torch.randn(R3, K3 + 1, generator=g) * 3.0, -1)
+pr3[5, 7] = float("nan")
+pr3[int(pr3[:, :K3].max(1).values.argmax()), 2] = float("inf")
+det3 = ops.detections(pr3.to(DEV), bx3, torch.tensor([0, 200, R3], device=DEV), torch.tensor([[480.0, 640.0]] * 2, device=DEV), 200,
+                      1e-5, 0.3, 10, ops.IOU_TV_CUDA)
 Cl, Dl = synth.mil_logits(N * R, K, g)
 s, img = ops.mil(Cl.to(DEV), Dl.to(DEV), offd)
 gts = synth.image_labels(N, K, g)
@@ -63,4 +71,4 @@ sd = ops.pgt_top1(s, bx, offd, torch.cat(gts).to(DEV), torch.tensor(goff, device
 ops.refine_assign(bx, offd, sd["seed_boxes"], sd["seed_classes"], sd["seed_scores"], sd["seed_weights"],
                   torch.tensor(goff, device=DEV), sd["seed_count"], K, 0.5)
 torch.cuda.synchronize()
-print("sanitize case ok", int(det["det_count"].sum()), int(det2["det_count"].sum()))
+print("sanitize case ok", int(det["det_count"].sum()), int(det2["det_count"].sum()), int(det3["det_count"].sum()))
