@@ -17,6 +17,8 @@ What stands in for the out-of-scope parts in the training step (north star: the 
     gradient at the end of backward, where fc1's real gradient becomes ready, so DDP all-reduces the same bytes
     at the same point of the step; the small real Linears (cls / det / bbox_pred / projection MLP) train normally.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -151,7 +153,12 @@ class TrainStep:
         self.model = self.heads
         if world > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
-            self.model = DDP(self.heads, device_ids=[dev.index], find_unused_parameters=mixed, gradient_as_bucket_view=True)
+            # Buckets: the FC-sized gradients become ready last, nothing is left to overlap them with, and NCCL moves one
+            # 1.7 GB message faster than 68 buckets of 25 MB (N = 2, c3: 8.0 -> 7.0 ms per step); WSOVOD_BUCKET_MB overrides.
+            # The mixed-dataset step keeps DDP's default: with unused parameters (the other dataset's miner) in one
+            # bucket with used ones the reducer rejects the undefined gradients.
+            self.model = DDP(self.heads, device_ids=[dev.index], find_unused_parameters=mixed, gradient_as_bucket_view=True,
+                             bucket_cap_mb=int(os.environ.get("WSOVOD_BUCKET_MB", "25" if mixed else "2048")))
         self.features = {"res5": w["features"].to(dev)}
         self.props = _proposals(w, dev)
         self.texts = [synth.text_embeddings(k, D, g).to(dev) for k in self.classes]
