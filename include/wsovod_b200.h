@@ -85,6 +85,9 @@ int wsovod_b200_roi_loop_pool_bwd(const float* grad_output, const float* rois, c
  * (wsovod/modeling/poolers.py:169-182): bilinear, sampling_ratio<=0 -> ceil(roi/P) samples per bin,
  * aligned!=0 -> half-pixel offset ("ROIAlignV2"). */
 size_t wsovod_b200_roi_align_workspace(int64_t N, int64_t R, int pooled_h, int pooled_w);
+/* workspace that also holds the separable tap tables of the 7x7 adaptive-grid kernel for an H x W map (the forward
+ * takes that kernel when workspace_bytes allows it, the per-sample kernel otherwise; same results to 1e-5 rel). */
+size_t wsovod_b200_roi_align_workspace_hw(int64_t N, int64_t R, int pooled_h, int pooled_w, int64_t H, int64_t W);
 int wsovod_b200_roi_align_fwd(const float* input, int64_t N, int64_t C, int64_t H, int64_t W,
                               const float* rois, int64_t R, float spatial_scale,
                               int pooled_h, int pooled_w, int sampling_ratio, int aligned,

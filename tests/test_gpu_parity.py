@@ -152,6 +152,33 @@ def test_roi_align(sr, aligned, golden):
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("N,C,H,W,R,aligned", [(2, 5, 30, 40, 300, True), (1, 3, 86, 128, 500, False),
+                                               (1, 6, 100, 152, 400, True), (3, 2, 17, 9, 120, True), (1, 4, 1, 33, 50, True)])
+def test_roi_align_separable_kernel(N, C, H, W, R, aligned):
+    """7x7, adaptive grid: the separable tap-table kernel (roi_align_sep.cu; four channels per CTA, two on the 100x152
+    map) against the oracle and against the per-sample kernel, wild boxes and the objectness scale included"""
+    from wsovod_b200 import _lib
+    feat, rois = _pool_case(N, C, H, W, R, seed=33 + H, wild=True)
+    obj = synth.objectness(rois.size(0), synth.gen(5))
+    fd, rd, od = feat.to(DEV), rois.to(DEV), obj.to(DEV)
+    n0 = _lib.launch_count()
+    out = ops.roi_align(fd, rd, 1 / 8, 7, 0, aligned)
+    n_sep = _lib.launch_count() - n0
+    ref = oracle.roi_align(feat, rois, 1 / 8, 7, 0, aligned)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    scaled = ops.roi_align(fd, rd, 1 / 8, 7, 0, aligned, od, 1.0)
+    torch.testing.assert_close(scaled.cpu(), ref * (obj + 1).view(-1, 1, 1, 1), rtol=1e-5, atol=1e-5)
+    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+    try:
+        n0 = _lib.launch_count()
+        scan = ops.roi_align(fd, rd, 1 / 8, 7, 0, aligned)
+        n_scan = _lib.launch_count() - n0
+    finally:
+        _lib.tune(_lib.TUNE_POOL_PATH, old)
+    torch.testing.assert_close(out, scan, rtol=1e-5, atol=1e-5)
+    assert n_sep == n_scan + 1 or C == 1      # the tap-table prologue: proof that the separable kernel is what ran
+
+
 # ------------------------------------------------------------------------------------------------ (2)
 TF32_LOGIT_TOL = 5e-2      # stated tolerance (SURVEY A.3): T*2*2^-11 worst case at T=50
 

@@ -35,6 +35,7 @@ SIGNATURES = {
     "wsovod_b200_roi_loop_pool_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                               c_int, c_p, c_p]),
     "wsovod_b200_roi_align_workspace": (c_sz, [c_i64, c_i64, c_int, c_int]),
+    "wsovod_b200_roi_align_workspace_hw": (c_sz, [c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "wsovod_b200_roi_align_fwd": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_f, c_int, c_int,
                                           c_int, c_int, c_p, c_f, c_p, c_p, c_sz, c_p]),
     "wsovod_b200_roi_align_bwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_int, c_int, c_int, c_p,

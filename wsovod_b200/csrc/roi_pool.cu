@@ -28,6 +28,13 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
               float scale, const float* row_scale, float row_scale_bias, float* output, int32_t* argmax, void* workspace,
               cudaStream_t st);
 
+// roi_align_sep.cu: ROIAlign 7x7, adaptive sample grid, separable tap tables
+size_t align7_sep_workspace(int64_t R, int64_t H, int64_t W);
+int align7_sep_cb(int64_t C, int64_t H, int64_t W);
+int align7_sep(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, int64_t R, const int32_t* counts,
+               const int32_t* order, const float* alignp, const float* row_scale, float row_scale_bias, float* output,
+               void* workspace, cudaStream_t st);
+
 struct PoolParams {
   const float* input;
   const float* rois;
@@ -835,10 +842,11 @@ static bool pool_use_blockmax(int64_t N, int64_t R, int64_t C, bool with_argmax)
 
 struct PoolWs {
   int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; uint2* rects;
-  void* pyr; size_t bytes;
+  void* pyr; void* asep; size_t bytes;
 };
 
-static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
+// H, W > 0 (ROIAlign only): room for the separable tap tables of roi_align_sep.cu behind the common part
+static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW, int64_t H = 0, int64_t W = 0) {
   PoolWs w;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 256); return o; };
@@ -854,6 +862,7 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
                        : seven && mode == MODE_LOOP ? sizeof(uint2) * 98 * (size_t)R : 0);
   size_t o_rects = take(seven && mode == MODE_LOOP ? sizeof(uint2) * 2 * (size_t)R : 0);
   size_t o_pyr = take(seven && mode == MODE_POOL ? pool7_pyr_workspace(N, R) : 0);
+  size_t o_asep = take(seven && mode == MODE_ALIGN && H > 0 && W > 0 ? align7_sep_workspace(R, H, W) : 0);
   w.counts = (int32_t*)(base + o_counts);
   w.bidx = (int32_t*)(base + o_bidx);
   w.order = (int32_t*)(base + o_order);
@@ -862,6 +871,7 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW) {
   w.bins = (uint2*)(base + o_bins);
   w.rects = (uint2*)(base + o_rects);
   w.pyr = base + o_pyr;
+  w.asep = base + o_asep;
   w.bytes = off;
   return w;
 }
@@ -1012,6 +1022,13 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
   p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+  // ROIAlign 7x7 with the adaptive grid: separable tap tables when the caller's workspace has room for them
+  // (wsovod_b200_roi_align_workspace_hw) and the scan kernels are not forced
+  if (mode == MODE_ALIGN && PH == 7 && PW == 7 && sampling_ratio <= 0 && tune(TUNE_POOL_PATH) != 1 &&
+      align7_sep_cb(C, H, W) && ws_bytes >= carve(nullptr, mode, N, R, PH, PW, H, W).bytes) {
+    const PoolWs w2 = carve(workspace, mode, N, R, PH, PW, H, W);
+    return align7_sep(input, N, C, H, W, R, w.counts, w.order, w.alignp, row_scale, row_scale_bias, output, w2.asep, st);
+  }
   if (loop7) return loop7_cb4 ? launch_loop7<4>(p, w.bins, w.rects, R, st) : launch_loop7<2>(p, w.bins, w.rects, R, st);
   if (fast7) return fast7_cb4 ? launch_pool7<4>(p, w.bins, R, argmax != nullptr, st)
                              : launch_pool7<2>(p, w.bins, R, argmax != nullptr, st);
@@ -1047,6 +1064,11 @@ WSOVOD_API size_t wsovod_b200_roi_loop_pool_workspace(int64_t N, int64_t R, int 
 }
 WSOVOD_API size_t wsovod_b200_roi_align_workspace(int64_t N, int64_t R, int PH, int PW) {
   return carve(nullptr, MODE_ALIGN, N, R, PH, PW).bytes;
+}
+
+WSOVOD_API size_t wsovod_b200_roi_align_workspace_hw(int64_t N, int64_t R, int PH, int PW, int64_t H, int64_t W) {
+  if (H <= 0 || W <= 0 || H > 32767 || W > 32767) return carve(nullptr, MODE_ALIGN, N, R, PH, PW).bytes;
+  return carve(nullptr, MODE_ALIGN, N, R, PH, PW, H, W).bytes;
 }
 
 WSOVOD_API int wsovod_b200_roi_pool_fwd(const float* input, int64_t N, int64_t C, int64_t H, int64_t W,

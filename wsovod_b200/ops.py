@@ -261,7 +261,7 @@ def _roi_align(input: torch.Tensor, rois: torch.Tensor, spatial_scale: float, po
     with torch.cuda.device(input.device):
         out = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.float32, device=input.device)
         L = _lib.lib()
-        ws = _workspace(L.wsovod_b200_roi_align_workspace(N, R, pooled_h, pooled_w), input.device)
+        ws = _workspace(L.wsovod_b200_roi_align_workspace_hw(N, R, pooled_h, pooled_w, H, W), input.device)
         rc = L.wsovod_b200_roi_align_fwd(_ptr(input), N, C, H, W, _ptr(rois), R, spatial_scale, pooled_h,
                                          pooled_w, sampling_ratio, int(aligned), _ptr(rs), row_scale_bias,
                                          _ptr(out), _ptr(ws), ws.numel(), _stream(input))
