@@ -81,6 +81,23 @@ int wsovod_b200_roi_loop_pool_bwd(const float* grad_output, const float* rois, c
                                   int64_t R, int64_t N, int64_t C, int64_t H, int64_t W,
                                   int pooled_h, int pooled_w, float* grad_input, void* stream);
 
+/* the same two entry points for the reference's other dtypes (ROILoopPool_cuda.cu:294,364:
+ * AT_DISPATCH_FLOATING_TYPES_AND_HALF): input, rois, output, grad tensors all of `dtype`, box arithmetic rounded the
+ * way the reference's template rounds it for that T (c10::Half products and quotients rounded to half, the clamp bound
+ * T(1.0 * width / spatial_scale), double throughout for double).  Values and argmax, no fused row scale.  F32 is accepted
+ * too and gives the results of wsovod_b200_roi_loop_pool_fwd.  The backward accumulates in T with atomics. */
+#define WSOVOD_B200_F32 0
+#define WSOVOD_B200_F16 1
+#define WSOVOD_B200_F64 2
+size_t wsovod_b200_roi_loop_pool_dtype_workspace(int64_t N, int64_t R, int pooled_h, int pooled_w);
+int wsovod_b200_roi_loop_pool_dtype_fwd(int dtype, const void* input, int64_t N, int64_t C, int64_t H, int64_t W,
+                                        const void* rois, int64_t R, float spatial_scale,
+                                        int pooled_h, int pooled_w, void* output, int32_t* argmax,
+                                        void* workspace, size_t workspace_bytes, void* stream);
+int wsovod_b200_roi_loop_pool_dtype_bwd(int dtype, const void* grad_output, const void* rois, const int32_t* argmax,
+                                        int64_t R, int64_t N, int64_t C, int64_t H, int64_t W,
+                                        int pooled_h, int pooled_w, void* grad_input, void* stream);
+
 /* replaces torch.ops.torchvision.roi_align reached through detectron2's ROIAlign
  * (wsovod/modeling/poolers.py:169-182): bilinear, sampling_ratio<=0 -> ceil(roi/P) samples per bin,
  * aligned!=0 -> half-pixel offset ("ROIAlignV2"). */

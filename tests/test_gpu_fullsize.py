@@ -37,17 +37,28 @@ def test_c2_pool_equals_torchvision_cuda(c2):
     assert torch.equal(out4, out[perm])
 
 
-def test_c2_roi_align_equals_torchvision_cuda(c2):
-    """ROIAlignV2 (aligned, adaptive grid) at c2 through the separable tap-table kernel against torchvision's CUDA op
-    (per-sample loop, the reference's own GPU path): 1e-5 relative on 0.8 G outputs; the objectness epilogue is linear"""
+def test_c2_roi_align_separable_kernel_full_size(c2):
+    """ROIAlignV2 (aligned, adaptive grid) at c2 through the separable tap-table kernel: within 1e-5 of the per-sample
+    kernel (torchvision's CPU operation order, the order the goldens pin) on all 0.8 G outputs; against torchvision's
+    CUDA op within 1e-5 relative + 5e-5 absolute -- that kernel contracts `start + ph * bin` into an FMA, which moves a
+    sample coordinate near 100 by one ulp (7.6e-6) and with it the bilinear weights, so torchvision's own two
+    implementations are that far apart; the objectness epilogue is linear."""
     import torchvision  # noqa: F401
+    from wsovod_b200 import _lib
     d = c2["d"]
     out = ops.roi_align(d["features"], d["rois"], 1 / 8, 7, 0, True)
+    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+    try:
+        ref = ops.roi_align(d["features"], d["rois"], 1 / 8, 7, 0, True)
+    finally:
+        _lib.tune(_lib.TUNE_POOL_PATH, old)
+    err = (out - ref).abs_()
+    assert bool((err <= ref.abs_().mul_(1e-5).add_(1e-5)).all())
+    del ref, err
     tv = torch.ops.torchvision.roi_align(d["features"], d["rois"], 1 / 8, 7, 7, 0, True)
     err = (out - tv).abs_()
-    tol = tv.abs_().mul_(1e-5).add_(1e-5)
-    assert bool((err <= tol).all())
-    del tv, err, tol
+    assert bool((err <= tv.abs_().mul_(1e-5).add_(5e-5)).all())
+    del tv, err
     out2 = ops.roi_align(d["features"], d["rois"], 1 / 8, 7, 0, True, d["objectness"], 1.0)
     assert torch.equal(out2, out * (d["objectness"] + 1).view(-1, 1, 1, 1))
 

@@ -34,6 +34,11 @@ SIGNATURES = {
                                               c_int, c_p, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "wsovod_b200_roi_loop_pool_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
                                               c_int, c_p, c_p]),
+    "wsovod_b200_roi_loop_pool_dtype_workspace": (c_sz, [c_i64, c_i64, c_int, c_int]),
+    "wsovod_b200_roi_loop_pool_dtype_fwd": (c_int, [c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_f, c_int,
+                                                    c_int, c_p, c_p, c_p, c_sz, c_p]),
+    "wsovod_b200_roi_loop_pool_dtype_bwd": (c_int, [c_int, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int,
+                                                    c_int, c_p, c_p]),
     "wsovod_b200_roi_align_workspace": (c_sz, [c_i64, c_i64, c_int, c_int]),
     "wsovod_b200_roi_align_workspace_hw": (c_sz, [c_i64, c_i64, c_int, c_int, c_i64, c_i64]),
     "wsovod_b200_roi_align_fwd": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_f, c_int, c_int,
@@ -109,6 +114,7 @@ def launch_count():
     return int(lib().wsovod_b200_launch_count())
 
 
+F32, F16, F64 = 0, 1, 2
 TUNE_POOL_PATH, TUNE_POOL_GROUP, TUNE_ALIGN_PAIR = 0, 1, 2
 POOL_AUTO, POOL_SCAN, POOL_BLOCKMAX = 0, 1, 2
 

@@ -29,6 +29,7 @@ struct AlignSepParams {
   int32_t capy, capx;
   int32_t N, C, H, W;
   int32_t CG, S;
+  int32_t pitch;           // cells per staged row: W made odd, so that equal columns of different rows fall into different bank groups
 };
 
 // prologue: one thread per (proposal, axis)
@@ -84,8 +85,10 @@ __global__ void __launch_bounds__(1024, 1) roi_align7_sep_kernel(const AlignSepP
       float f[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
-      if (CB == 4) reinterpret_cast<float4*>(sp)[i] = make_float4(f[0], f[1], f[2 % CB], f[3 % CB]);
-      else reinterpret_cast<float2*>(sp)[i] = make_float2(f[0], f[1]);
+      const int y = i / W;
+      const int j = i + y * (p.pitch - W);
+      if (CB == 4) reinterpret_cast<float4*>(sp)[j] = make_float4(f[0], f[1], f[2 % CB], f[3 % CB]);
+      else reinterpret_cast<float2*>(sp)[j] = make_float2(f[0], f[1]);
     }
   }
   __syncthreads();
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(1024, 1) roi_align7_sep_kernel(const AlignSepP
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  const uint32_t pitch = (uint32_t)W * CS;
+  const uint32_t pitch = (uint32_t)p.pitch * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(1024, 1) roi_align7_sep_kernel(const AlignSepP
       const int ph = bin_n / 7, pw = bin_n - ph * 7;
       hy_n = __ldg(p.hdr + (int64_t)r_n * 14 + ph);
       hx_n = __ldg(p.hdr + (int64_t)r_n * 14 + 7 + pw);
-      cnt_n = __ldg(p.alignp + (int64_t)r_n * 8 + 6);
+      cnt_n = __ldg(p.alignp + (int64_t)r_n * 8 + 7);   // 1 / count
       if (p.row_scale) sc_n = __fadd_rn(__ldg(p.row_scale + r_n), p.row_scale_bias);
     }
   };
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(1024, 1) roi_align7_sep_kernel(const AlignSepP
     float acc[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) acc[k] = 0.f;
-    const uint32_t cell = sbase + (uint32_t)(y0 * W + x0) * CS;
+    const uint32_t cell = sbase + (uint32_t)(y0 * p.pitch + x0) * CS;
     for (int xc = 0; xc < nx; xc += 4) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(wxp + xc));
       const int m = nx - xc;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(1024, 1) roi_align7_sep_kernel(const AlignSepP
 #pragma unroll
     for (int k = 0; k < CB; ++k)
       if (k < nc) {
-        const float v = __fdiv_rn(acc[k], count);
+        const float v = __fmul_rn(acc[k], count);        // count holds 1 / (gh * gw): one more rounding, inside the stated 1e-5
         __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(v, scale) : v);
       }
   }
@@ -182,8 +185,10 @@ size_t align7_sep_workspace(int64_t R, int64_t H, int64_t W) {
 }
 
 // channels per CTA the separable kernel would use for this map (0: it does not apply)
+static int sep_pitch(int64_t W) { return (int)(W | 1); }
+
 int align7_sep_cb(int64_t C, int64_t H, int64_t W) {
-  const size_t plane = (size_t)H * W * sizeof(float);
+  const size_t plane = (size_t)H * sep_pitch(W) * sizeof(float);
   if (C >= 3 && 4 * plane <= (size_t)kMaxSmemOptin) return 4;
   if (C >= 2 && 2 * plane <= (size_t)kMaxSmemOptin) return 2;
   return 0;
@@ -191,7 +196,8 @@ int align7_sep_cb(int64_t C, int64_t H, int64_t W) {
 
 template <int CB>
 static int launch_sep(AlignSepParams& p, int64_t R, cudaStream_t st) {
-  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float);
+  p.pitch = sep_pitch(p.W);
+  const size_t smem = CB * (size_t)p.H * p.pitch * sizeof(float);
   p.CG = (int)ceil_div(p.C, CB);
   int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
   per_sm = std::max(per_sm, 1);

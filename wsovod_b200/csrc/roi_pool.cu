@@ -159,7 +159,7 @@ __global__ void roi_prepare_kernel(const float* __restrict__ rois, int64_t R, in
     float* a = alignp + r * 8;
     a[0] = sw; a[1] = sh; a[2] = bw; a[3] = bh;
     a[4] = __int_as_float(gh); a[5] = __int_as_float(gw);
-    a[6] = (float)max(gh * gw, 1); a[7] = 0.f;
+    a[6] = (float)max(gh * gw, 1); a[7] = __fdiv_rn(1.f, a[6]);
   }
 }
 
@@ -291,6 +291,12 @@ __global__ void roi_order_kernel(const int32_t* __restrict__ bidx, const int32_t
     if (tid == 0) s_base += tot;
     __syncthreads();
   }
+}
+
+// for roi_loop_dtype.cu
+int launch_roi_order(const int32_t* bidx, const int32_t* counts, int64_t R, int N, int32_t* order, cudaStream_t st) {
+  roi_order_kernel<<<(unsigned)N, 256, 0, st>>>(bidx, counts, R, N, order);
+  return after_launch();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -133,6 +133,17 @@ def _(input, rois, spatial_scale, pooled_h, pooled_w, row_scale, row_scale_bias,
 def _roi_pool_backward(grad: torch.Tensor, rois: torch.Tensor, argmax: torch.Tensor, N: int, C: int,
                        H: int, W: int, three_way: bool) -> torch.Tensor:
     _need_cuda(grad, rois, argmax)
+    if three_way and grad.dtype in _LOOP_DTYPES:
+        if rois.dtype != grad.dtype:
+            raise RuntimeError("expected scalar type %s but found %s" % (grad.dtype, rois.dtype))
+        grad, rois, argmax = grad.contiguous(), rois.contiguous(), argmax.contiguous()
+        ph, pw = grad.shape[-2:]
+        with torch.cuda.device(grad.device):
+            gi = torch.zeros((N, C, H, W), dtype=grad.dtype, device=grad.device)
+            rc = _lib.lib().wsovod_b200_roi_loop_pool_dtype_bwd(_LOOP_DTYPES[grad.dtype], _ptr(grad), _ptr(rois), _ptr(argmax),
+                                                                rois.size(0), N, C, H, W, ph, pw, _ptr(gi), _stream(grad))
+        _lib.check(rc, "roi_loop_pool_dtype_bwd")
+        return gi
     grad, rois = _f32c(grad), _f32c(rois)
     argmax = argmax.contiguous()
     R = rois.size(0)
@@ -189,14 +200,43 @@ def roi_pool(input, rois, spatial_scale, output_size, row_scale=None, row_scale_
                                           float(row_scale_bias), bool(with_argmax))
 
 
+_LOOP_DTYPES = {torch.float16: _lib.F16, torch.float64: _lib.F64}
+
+
+def _roi_loop_pool_dtype(input, rois, spatial_scale, pooled_h, pooled_w, row_scale, row_scale_bias, with_argmax):
+    """half / double ROILoopPool (ROILoopPool_cuda.cu:294: the reference dispatches float, double and half): rois carry
+    the input's dtype as `rois.data_ptr<scalar_t>()` demands; the row scale, which the reference applies as a separate
+    multiply in that dtype (roi_heads.py:733-739), stays a separate multiply."""
+    if rois.dtype != input.dtype:
+        raise RuntimeError("expected scalar type %s but found %s" % (input.dtype, rois.dtype))
+    input, rois = input.contiguous(), rois.contiguous()
+    N, C, H, W = input.shape
+    R = rois.size(0)
+    with torch.cuda.device(input.device):
+        out = torch.empty((3 * R, C, pooled_h, pooled_w), dtype=input.dtype, device=input.device)
+        arg = torch.empty((3 * R, C, pooled_h, pooled_w) if with_argmax else (0,), dtype=torch.int32, device=input.device)
+        L = _lib.lib()
+        ws = _workspace(L.wsovod_b200_roi_loop_pool_dtype_workspace(N, R, pooled_h, pooled_w), input.device)
+        rc = L.wsovod_b200_roi_loop_pool_dtype_fwd(_LOOP_DTYPES[input.dtype], _ptr(input), N, C, H, W, _ptr(rois), R,
+                                                   spatial_scale, pooled_h, pooled_w, _ptr(out),
+                                                   _ptr(arg if with_argmax else None), _ptr(ws), ws.numel(), _stream(input))
+    _lib.check(rc, "roi_loop_pool_dtype_fwd")
+    if row_scale is not None:
+        s = row_scale.to(input.dtype) + row_scale_bias
+        out = out * torch.cat([s, s, s]).view(-1, 1, 1, 1)
+    return out, arg
+
+
 @torch.library.custom_op("wsovod_b200::roi_loop_pool", mutates_args=())
 def _roi_loop_pool(input: torch.Tensor, rois: torch.Tensor, spatial_scale: float, pooled_h: int,
                    pooled_w: int, row_scale: Optional[torch.Tensor], row_scale_bias: float,
                    with_argmax: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     _need_cuda(input, rois, row_scale)
-    input, rois = _f32c(input), _f32c(rois)
     if rois.dim() != 2 or rois.size(1) != 5 or input.dim() != 4:
         raise RuntimeError("wsovod_b200::roi_loop_pool expects input NCHW and rois (R,5)")
+    if input.dtype in _LOOP_DTYPES:
+        return _roi_loop_pool_dtype(input, rois, spatial_scale, pooled_h, pooled_w, row_scale, row_scale_bias, with_argmax)
+    input, rois = _f32c(input), _f32c(rois)
     N, C, H, W = input.shape
     R = rois.size(0)
     rs = None if row_scale is None else _f32c(row_scale)
