@@ -230,6 +230,22 @@ def main():
                     seed_scores=[t.gt_scores for t in mt], seed_weights=[t.gt_weights for t in mt]),
                os.path.join(GOLD, "mist.pt"))
 
+    # ---- (3'') get_pgt_top_k with top_k != 1 / thres > 0 (roi_heads.py:1043-1343), on the MIST inputs: an integer
+    # count with a threshold, a fraction without one, and per-class boxes (num_classes * 4 columns, :1066-1069)
+    g4 = torch.Generator().manual_seed(20261021)
+    per_class_boxes = [b.unsqueeze(1).repeat(1, K, 1) + torch.rand(b.size(0), K, 1, generator=g4) * 2.0 for b in mb_l]
+    per_class_boxes = [b.reshape(b.size(0), K * 4) for b in per_class_boxes]
+    topk_cases = {}
+    for name, (bx, tk, th) in dict(count3_thres=(mb_l, 3, 0.02), frac=(mb_l, 0.05, 0), count5_perclass=(per_class_boxes, 5, 0.3),
+                                   huge=(mb_l, 10000, 0.5)).items():
+        tt = rh.WSOVODROIHeads.get_pgt_top_k(mself, bx, ms_l, mp, top_k=tk, thres=th)
+        topk_cases[name] = dict(boxes=bx, top_k=tk, thres=th, seed_boxes=[t.gt_boxes.tensor for t in tt],
+                                seed_classes=[t.gt_classes for t in tt], seed_scores=[t.gt_scores for t in tt],
+                                seed_weights=[t.gt_weights for t in tt])
+    torch.save(dict(scores=ms_l, sizes=list(mist_sizes), shapes=mist_shapes, num_classes=K,
+                    gt_classes_img=[t.clone() for t in self.gt_classes_img_int], img_scores=self.pred_class_img_logits,
+                    cases=topk_cases), os.path.join(GOLD, "pgt_topk.pt"))
+
     # ---- (3b) weighted refinement losses: InstanceRefinementOutputLayers.losses verbatim ---
     cases = {}
     for name, (dcols_per, beta, reg) in dict(agnostic=(1, 0.0, True), specific=(K, 0.5, True), noreg=(1, 0.0, False)).items():

@@ -195,6 +195,26 @@ def _mist_check(golden, device, **kw):
     assert seeds["seed_offsets"].tolist()[-1] == sum(len(t.gt_classes) for t in targets)
 
 
+def test_get_pgt_top_k_general_selection_vs_reference(golden):
+    """WSOVODROIHeads.get_pgt_top_k with top_k != 1 / thres > 0 (roi_heads.py:1043-1343): an integer count with a
+    threshold, a fraction, per-class boxes, a count larger than the image -- bit-exact against the reference's method
+    (golden generated by oracle/make_golden.py from the verbatim reference), fallback seed of the empty image included"""
+    from wsovod_b200.modeling.roi_heads import get_pgt_top_k
+    from wsovod_b200.structures import Boxes, Instances
+    f = golden("pgt_topk")
+    for name, c in f["cases"].items():
+        props = [Instances(tuple(s), proposal_boxes=Boxes(b.reshape(b.size(0), -1)[:, :4])) for b, s in zip(c["boxes"], f["shapes"])]
+        targets, seeds = get_pgt_top_k(c["boxes"], f["scores"], props, f["gt_classes_img"], f["img_scores"], f["num_classes"],
+                                       top_k=c["top_k"], thres=c["thres"])
+        for n, t in enumerate(targets):
+            assert torch.equal(t.gt_boxes.tensor, c["seed_boxes"][n]), (name, n)
+            assert torch.equal(t.gt_classes, c["seed_classes"][n]), (name, n)
+            assert torch.equal(t.gt_scores, c["seed_scores"][n]), (name, n)
+            assert torch.equal(t.gt_weights, c["seed_weights"][n]), (name, n)
+        assert seeds["seed_offsets"].tolist()[-1] == sum(len(t.gt_classes) for t in targets)
+        assert seeds["seed_boxes"].size(0) == seeds["seed_offsets"].tolist()[-1]
+
+
 def test_get_pgt_mist_vs_reference_with_oracle_nms(golden):
     """WSOVODROIHeads.get_pgt_mist (roi_heads.py:910-1040) mirror: top 15 % per class, 0.05 threshold, class-agnostic
     NMS at 0.2 -- with the oracle's NMS in place of the kernel (CPU)"""

@@ -317,13 +317,85 @@ def get_image_level_gt(targets, num_classes):
 
 
 @torch.no_grad()
-def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits,
-                  num_classes, build_targets=True):
-    """roi_heads.py:1043-1343 with top_k=1, thres=0, need_weight=True, sam=None: one seed per image-level
-    class.  Returns (targets: list[Instances{gt_boxes, gt_classes, gt_scores, gt_weights}], flat seeds).
-    ``build_targets=False`` returns (None, seeds): slicing the per-image Instances needs the seed counts on the
-    host (one device->host read); the assignment kernel only takes the flat seeds."""
+def pgt_candidates(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits, top_k=1, thres=0):
+    """The general selection of roi_heads.py:1043-1207 (any ``top_k`` / ``thres``; the callers that leave the default
+    are ``get_pgt_mist`` with top_k = 0.15, thres = 0.05 and the visualisation hooks, :919-928,1442-1449), in PyTorch:
+    per image the boxes of area > 20 (:1090-1111), per image-level class the ``top_k`` best (an integer count, a
+    fraction of the surviving proposals, :1114-1125), rank 0 always and the others only with score >= thres
+    (:1148-1175), flattened rank-major like ``masked_select`` / ``reshape(-1)`` do; the fallback seed for an image without
+    a candidate (:1181-1207).  Returns per-image lists (scores, boxes, classes, weights); weights are the image-level
+    score of the class (:1140-1146)."""
     dev = prev_pred_boxes[0].device
+    sizes = [len(p) for p in proposals]
+    scores = prev_pred_scores.split(sizes, 0) if isinstance(prev_pred_scores, torch.Tensor) else list(prev_pred_scores)
+    out_s, out_b, out_c, out_w = [], [], [], []
+    for n, (b, s, gt) in enumerate(zip(prev_pred_boxes, scores, gt_classes_img_int)):
+        G = gt.numel()
+        if b.dim() == 2 and b.size(1) == 4:
+            b = b.unsqueeze(1).expand(b.size(0), G, 4)                       # class-agnostic boxes (:1060-1064)
+        else:
+            b = b.reshape(b.size(0), -1, 4)[:, gt]                            # per-class boxes (:1066-1069,1087-1090)
+        s = s[:, gt]
+        if G > 0:
+            keep = ((b[:, :, 2] - b[:, :, 0]) * (b[:, :, 3] - b[:, :, 1])) > 20      # (num, G)
+            # the reference's masked_select(...).view(-1, G, 4) needs the same number of survivors in every column
+            if not bool((keep == keep[:, :1]).all()):
+                raise RuntimeError("shape '[-1, %d, 4]' is invalid: the area filter keeps different rows per class" % G)
+            b, s = b[keep[:, 0]], s[keep[:, 0]]
+        num = b.size(0)
+        if G == 0:
+            out_s.append(torch.ones(1, dtype=s.dtype, device=dev))
+            out_b.append(torch.tensor([[-10000.0, -10000.0, 10000.0, 10000.0]], dtype=b.dtype, device=dev))
+            out_c.append(torch.zeros(1, dtype=gt.dtype, device=dev))
+            out_w.append(torch.ones(1, dtype=pred_class_img_logits.dtype, device=dev))
+            continue
+        if top_k >= 1:
+            k = min(num, int(top_k))
+        elif 0 < top_k < 1:
+            k = max(int(num * top_k), 1)
+        else:
+            k = min(num, 1)
+        if k > num:
+            # upstream asks topk for max(int(0 * top_k), 1) = 1 row of an empty matrix (:1116-1125) and fails
+            raise RuntimeError("selected index k out of range (image %d has no proposal with box area > 20)" % n)
+        v, i = torch.topk(s, k, dim=0)                                        # (k, G)
+        m = v.ge(thres) if thres > 0 else torch.ones_like(v, dtype=torch.bool)
+        if k > 0:
+            m[0] = True
+        bb = torch.gather(b, 0, i.unsqueeze(2).expand(k, G, 4))
+        w = pred_class_img_logits[n:n + 1, gt].expand(k, G)
+        cs, cb, cc, cw = v[m], bb[m], gt.unsqueeze(0).expand(k, G)[m], w[m]
+        if cs.numel() == 0:                                                   # :1181-1207
+            cs = torch.ones(1, dtype=s.dtype, device=dev)
+            cb = torch.tensor([[-10000.0, -10000.0, 10000.0, 10000.0]], dtype=b.dtype, device=dev)
+            cc = torch.zeros(1, dtype=gt.dtype, device=dev)
+            cw = torch.ones(1, dtype=w.dtype, device=dev)
+        out_s.append(cs); out_b.append(cb); out_c.append(cc); out_w.append(cw)
+    return out_s, out_b, out_c, out_w
+
+
+@torch.no_grad()
+def get_pgt_top_k(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits,
+                  num_classes, build_targets=True, top_k=1, thres=0):
+    """roi_heads.py:1043-1343 with need_weight=True, sam=None.  The default (top_k=1, thres=0: one seed per image-level
+    class, what every ``_forward_box`` call asks for, :801,872) is one kernel for the batch; any other ``top_k`` /
+    ``thres`` goes through ``pgt_candidates``.  Returns (targets: list[Instances{gt_boxes, gt_classes, gt_scores,
+    gt_weights}], flat seeds).  ``build_targets=False`` returns (None, seeds): slicing the per-image Instances needs
+    the seed counts on the host (one device->host read); the assignment kernel only takes the flat seeds."""
+    dev = prev_pred_boxes[0].device
+    if top_k != 1 or thres > 0:
+        cs, cb, cc, cw = pgt_candidates(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int,
+                                        pred_class_img_logits, top_k, thres)
+        goff = [0]
+        for c in cs:
+            goff.append(goff[-1] + c.numel())
+        seeds = dict(seed_boxes=torch.cat(cb), seed_classes=torch.cat(cc), seed_scores=torch.cat(cs), seed_weights=torch.cat(cw),
+                     seed_offsets=torch.tensor(goff, dtype=torch.int64, device=dev), seed_count=None)
+        if not build_targets:
+            return None, seeds
+        targets = [Instances(p.image_size, gt_boxes=Boxes(b), gt_classes=c, gt_scores=s, gt_weights=w)
+                   for p, s, b, c, w in zip(proposals, cs, cb, cc, cw)]
+        return targets, seeds
     off, sizes = _offsets(proposals, dev)
     scores = prev_pred_scores if isinstance(prev_pred_scores, torch.Tensor) else torch.cat(list(prev_pred_scores), 0)
     boxes = torch.cat([b.reshape(-1, 4) for b in prev_pred_boxes], 0)

@@ -23,7 +23,7 @@ from torch import nn
 
 from .. import ops
 from ..structures import Boxes, Instances
-from .roi_heads import get_image_level_gt, get_pgt_top_k, label_proposals_wsl
+from .roi_heads import get_image_level_gt, get_pgt_top_k, label_proposals_wsl, pgt_candidates
 
 
 @torch.no_grad()
@@ -35,32 +35,9 @@ def get_pgt_mist(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_in
     images in one ``batched_nms`` call (group = image).  Returns (targets, flat seeds) like ``get_pgt_top_k``;
     ``gt_weights`` are the seed scores, as the reference's no-SAM branch zips them (:1035-1037)."""
     dev = prev_pred_boxes[0].device
-    sizes = [len(p) for p in proposals]
-    scores = prev_pred_scores.split(sizes, 0) if isinstance(prev_pred_scores, torch.Tensor) else list(prev_pred_scores)
-    cb, cs, cc, cg, per_img = [], [], [], [], []
-    for n, (b, s, gt) in enumerate(zip(prev_pred_boxes, scores, gt_classes_img_int)):
-        b = b.reshape(-1, 4)
-        keep = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])) > 20
-        b, s = b[keep], s[keep][:, gt]
-        num = b.size(0)
-        G = gt.numel()
-        if G == 0:                      # no image-level class: the reference's fallback seed (:1188-1207)
-            cb.append(torch.tensor([[-10000.0, -10000.0, 10000.0, 10000.0]], device=dev))
-            cs.append(torch.ones(1, device=dev))
-            cc.append(torch.zeros(1, dtype=gt.dtype, device=dev))
-        elif num == 0:
-            # upstream asks topk for max(int(0 * top_pro), 1) = 1 row of an empty matrix (:1116-1125) and fails
-            raise RuntimeError("selected index k out of range (image %d has no proposal with box area > 20)" % n)
-        else:
-            k = max(int(num * top_pro), 1) if 0 < top_pro < 1 else min(num, max(int(top_pro), 1))
-            v, i = torch.topk(s, k, dim=0)                                   # (k, G), scores descending per class
-            m = v.ge(thres)
-            m[0] = True
-            cs.append(v[m])                                                   # rank-major, then class: masked_select order
-            cb.append(b[i[m]])
-            cc.append(gt.unsqueeze(0).expand(k, G)[m])
-        cg.append(torch.full((cs[-1].numel(),), n, dtype=torch.int64, device=dev))
-        per_img.append(cs[-1].numel())
+    cs, cb, cc, _ = pgt_candidates(prev_pred_boxes, prev_pred_scores, proposals, gt_classes_img_int, pred_class_img_logits,
+                                   top_pro, thres)
+    cg = [torch.full((c.numel(),), n, dtype=torch.int64, device=dev) for n, c in enumerate(cs)]
     B, S, C, Gr = torch.cat(cb), torch.cat(cs), torch.cat(cc), torch.cat(cg)
     if nms_fn is None:
         keep, num_keep = torch.ops.wsovod_b200.batched_nms(B, S, Gr, len(proposals), float(nms_thresh), int(iou_mode))
