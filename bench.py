@@ -308,7 +308,13 @@ def extra_kernels(w2, st2, peaks, it, dev):
     k["roi_loop_pool"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, st2.rois, sc, 7, st2.obj, 1.0, False), max(it // 3, 2)),
                               "algorithmic_bytes": 3 * out_bytes + fixed}, peaks)
     k["roi_align"] = hbm({"ms": ktime(lambda: ops.roi_align(st2.feat, st2.rois, sc, 7, 0, True, st2.obj, 1.0), max(it // 3, 2)),
-                          "algorithmic_bytes": out_bytes + fixed}, peaks)
+                          "algorithmic_bytes": out_bytes + fixed}, peaks)      # separable tap tables (roi_align_sep.cu)
+    k["roi_align"]["kernel"] = "roi_align7_sep_kernel"
+    # the reference's half dispatch of ROILoopPool (ROILoopPool_cuda.cu:294), values + argmax: 3 x (2 + 4) bytes per output
+    f16, r16 = st2.feat.half(), st2.rois.half()
+    k["roi_loop_pool_f16+argmax"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(f16, r16, sc, 7, None, 0.0, True), max(it // 3, 2)),
+                                         "algorithmic_bytes": 3 * (out_bytes // 2 + out_bytes) + fixed // 2}, peaks)
+    del f16, r16
     # training kernels: one image of 5024 proposals (c3), K = 80, D = 768
     g = synth.gen(99)
     M, K, D = 5024, 80, 768

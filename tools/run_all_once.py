@@ -44,7 +44,13 @@ for _ in range(reps):
     torch.ops.wsovod_b200.roi_pool_backward(out[:4000], rois[:4000], arg[:4000], 8, 512, 86, 128, False)
     del out, arg
     ops.roi_loop_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)
-    ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)
+    ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)             # roi_align7_sep_kernel + roi_align_tables_kernel
+    _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+    ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)                  # the per-sample kernel it replaced (roi_plane_kernel)
+    _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
+    f16, r16 = feat.half(), rois.half()
+    ops.roi_loop_pool(f16, r16, 1 / 8, 7, None, 0.0, True)                  # loop_prepare_kernel<half> + loop_plane_kernel<half, 2>
+    del f16, r16
     torch.ops.wsovod_b200.roi_align_backward(ra[:4000].contiguous(), rois[:4000].contiguous(), 1 / 8, 0, True, 8, 512, 86, 128)
     del ra
     _, probs = ops.align(x, t, 50.0, 1, True, None, ops.ALIGN_TF32, False, True)

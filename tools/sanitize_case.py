@@ -29,8 +29,17 @@ _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
 vb, ib = ops.roi_pool(feat, rois, 1 / 8, 7, obj, 1.0, True)                  # (value, index) planes
 _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
 assert torch.equal(va, vb) and torch.equal(ia, ib)
-ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)
+ra = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)                  # separable tap tables (+ their prologue)
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+rb = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)                  # per-sample kernel
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
+assert torch.allclose(ra, rb, rtol=1e-5, atol=1e-5)
 ops.roi_loop_pool(feat, rois, 1 / 8, 7, with_argmax=False)
+# half / double ROILoopPool (roi_loop_dtype.cu): staged planes (two channels, one channel) and the backward atomics
+for dt in (torch.float16, torch.float64):
+    o3, a3 = ops.roi_loop_pool(feat.to(dt), rois.to(dt), 1 / 8, 7, with_argmax=True)
+    torch.ops.wsovod_b200.roi_pool_backward(torch.ones_like(o3), rois.to(dt), a3, N, C, H, W, True)
+ops.roi_loop_pool(feat[:, :1].double().contiguous(), rois.double(), 1 / 8, 7, with_argmax=True)
 x, t = synth.region_embeddings(N * R, D, g).to(DEV), synth.text_embeddings(K, D, g).to(DEV)
 _, probs = ops.align(x, t, 50.0, True, True, None, ops.ALIGN_TF32, False, True)
 ops.align(x, t, 50.0, True, True, None, ops.ALIGN_FP32, True, True)
