@@ -63,6 +63,23 @@ def test_c2_roi_align_separable_kernel_full_size(c2):
     assert torch.equal(out2, out * (d["objectness"] + 1).view(-1, 1, 1, 1))
 
 
+def test_c2_roi_loop_pool_blockmax_equals_scan_kernel(c2):
+    """3-way ROILoopPool at c2 (9.6 GB of output): the block-max path the library picks at 4000 proposals per image
+    against the scan kernel, bit for bit, with the objectness scale folded in"""
+    from wsovod_b200 import _lib
+    d = c2["d"]
+    out, _ = ops.roi_loop_pool(d["features"], d["rois"], 1 / 8, 7, d["objectness"], 1.0, False)
+    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+    try:
+        ref, _ = ops.roi_loop_pool(d["features"], d["rois"], 1 / 8, 7, d["objectness"], 1.0, False)
+    finally:
+        _lib.tune(_lib.TUNE_POOL_PATH, old)
+    assert torch.equal(out, ref)
+    R = d["rois"].size(0)
+    plain, _ = ops.roi_pool(d["features"], d["rois"], 1 / 8, 7, d["objectness"], 1.0, False)
+    assert torch.equal(out[:R], plain.clamp_(min=0))         # stream 0 is the max-pool with maxima starting at 0
+
+
 def test_c2_alignment_and_detections_properties(c2):
     import torchvision
     d = c2["d"]

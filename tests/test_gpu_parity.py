@@ -830,3 +830,54 @@ def test_roi_align_backward_vs_torchvision(sr, aligned):
     err = (x1.grad - x2.grad).abs().max().item()
     print(f"roi_align backward: max |d grad| {err:.3e} at gradient scale {scale:.3e}")
     assert err <= 5e-5 * scale
+
+
+@pytest.mark.parametrize("N,C,H,W,R,seed", [(2, 9, 60, 80, 900, 1), (1, 3, 86, 128, 1500, 2), (3, 6, 100, 152, 700, 3),
+                                             (2, 2, 7, 5, 300, 5), (1, 4, 1, 1, 50, 6), (1, 12, 86, 128, 2500, 9),
+                                             (1, 8, 40, 56, 3300, 10)])
+def test_roi_loop_pool_blockmax_path(N, C, H, W, R, seed):
+    """values-only 3-way ROILoopPool through the block-max planes: three floor-0 pooling passes on the integer boxes of
+    the ROI / outer grid + the fix-up kernel for the bins the excluded interior touches -- bit-exact against the oracle
+    (ROILoopPool_cuda.cu restated on the CPU), against the scan kernel and, where it is built, the reference's own
+    extension; negative, NaN and -inf cells (maxima start at 0), whole-map / out-of-image / inverted / integer-grid
+    boxes, proposals in arbitrary batch order, the objectness scale."""
+    from oracle import ref as oref
+    g = synth.gen(1900 + seed)
+    feat = synth.features(N, C, H, W, g, relu=False)
+    flat = feat.view(-1)
+    idx = torch.randint(0, flat.numel(), (max(flat.numel() // 50, 1),), generator=g)
+    flat[idx[::2]] = float("nan")
+    flat[idx[1::2]] = float("-inf")
+    boxes = []
+    for _ in range(N):
+        b = synth.proposals(R, H * 8, W * 8, g)
+        k = R // 8
+        b[:k, :2] = torch.rand(k, 2, generator=g) * 40 - 20
+        b[:k, 2] = W * 8 - torch.rand(k, generator=g) * 40 + 20
+        b[:k, 3] = H * 8 - torch.rand(k, generator=g) * 40 + 20
+        b[k:2 * k] += torch.randn(k, 4, generator=g) * 150
+        b[2 * k:3 * k] = (b[2 * k:3 * k] / 8).round() * 8
+        boxes.append(b)
+    rois, _ = synth.rois_from(boxes)
+    rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    obj = torch.rand(rois.size(0), generator=g)
+    ref, _ = oracle.roi_loop_pool(feat, rois, 1 / 8, 7)
+    fd, rd, od = feat.to(DEV), rois.to(DEV), obj.to(DEV)
+    with _pool_variant(scan=True):
+        scan = ops.roi_loop_pool(fd, rd, 1 / 8, 7, with_argmax=False)[0]
+    from wsovod_b200 import _lib
+    with _pool_variant(scan=False):
+        n0 = _lib.launch_count()
+        out, arg = ops.roi_loop_pool(fd, rd, 1 / 8, 7, with_argmax=False)
+        launches = _lib.launch_count() - n0
+        out_s, _ = ops.roi_loop_pool(fd, rd, 1 / 8, 7, od, 1.0, False)
+    assert arg.numel() == 0
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(scan, out)
+    s3 = torch.cat([obj, obj, obj]) + 1
+    assert torch.equal(out_s.cpu(), ref * s3.view(-1, 1, 1, 1))
+    if C >= 2 and H * W * 8 <= 227 * 1024:
+        assert launches >= 12            # 3 x (classify, order, bins, pool) + prologue + order + fix-up: the planes ran
+    m = oref.cuda()
+    if m is not None:
+        assert torch.equal(out, m.roi_loop_pool_forward(fd, rd, 1 / 8, 7, 7)[0])

@@ -26,7 +26,7 @@ size_t pool7_pyr_workspace(int64_t N, int64_t R);
 int pool7_pyr_cb(int64_t C, int64_t H, int64_t W, int64_t R, bool with_argmax);
 int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, const float* rois, int64_t R,
               float scale, const float* row_scale, float row_scale_bias, float* output, int32_t* argmax, void* workspace,
-              cudaStream_t st);
+              cudaStream_t st, float floor_v = -FLT_MAX);
 
 // roi_align_sep.cu: ROIAlign 7x7, adaptive sample grid, separable tap tables
 size_t align7_sep_workspace(int64_t R, int64_t H, int64_t W);
@@ -200,9 +200,11 @@ __global__ void roi_bins7_kernel(const float* __restrict__ rois, int64_t R, int 
 // grid, bins[2*i+1] = bin of the outer (x1.8) box's grid; rects[2*r] = inner (/1.8) box, rects[2*r+1] =
 // the ROI, both as (h_lo | h_hi << 16, w_lo | w_hi << 16) with int16 fields (exclusion tests are strict).
 // Geometry: ROILoopPool_cuda.cu:34-103,144-166, same expressions as roi_prepare_kernel<MODE_LOOP>.
+// iboxes (optional): [2, R, 5] float rois holding the INTEGER boxes (batch, rsw, rsh, rew, reh) of the ROI and of the outer
+// box -- fed to the block-max pooling path with spatial_scale 1, whose round(x * 1) gives the same integers back.
 __global__ void roi_loopbins7_kernel(const float* __restrict__ rois, int64_t R, int N, int H, int W, float scale,
                                      int32_t* __restrict__ bidx, int32_t* __restrict__ counts,
-                                     uint2* __restrict__ bins, uint2* __restrict__ rects) {
+                                     uint2* __restrict__ bins, uint2* __restrict__ rects, float* __restrict__ iboxes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * 49) return;
   const int64_t r = i / 49;
@@ -233,8 +235,16 @@ __global__ void roi_loopbins7_kernel(const float* __restrict__ rois, int64_t R, 
     return make_uint2((uint32_t)hs | ((uint32_t)he << 16), (uint32_t)ws | ((uint32_t)we << 16));
   };
   const int rsw = round_i(x1 * scale), rsh = round_i(y1 * scale), rew = round_i(x2 * scale), reh = round_i(y2 * scale);
+  const int osh = round_i(y1o * scale), osw = round_i(x1o * scale), oeh = round_i(y2o * scale), oew = round_i(x2o * scale);
   bins[2 * i] = one(rsh, rsw, reh, rew);
-  bins[2 * i + 1] = one(round_i(y1o * scale), round_i(x1o * scale), round_i(y2o * scale), round_i(x2o * scale));
+  bins[2 * i + 1] = one(osh, osw, oeh, oew);
+  if (bin == 0 && iboxes) {
+    float* a = iboxes + r * 5;
+    float* b = iboxes + (R + r) * 5;
+    a[0] = b[0] = roi[0];
+    a[1] = (float)rsw; a[2] = (float)rsh; a[3] = (float)rew; a[4] = (float)reh;
+    b[1] = (float)osw; b[2] = (float)osh; b[3] = (float)oew; b[4] = (float)oeh;
+  }
   if (bin == 0) {
     auto sat = [](int v) { return (uint32_t)(uint16_t)(int16_t)min(max(v, -32768), 32767); };
     rects[2 * r] = make_uint2(sat(round_i(y1i * scale)) | (sat(round_i(y2i * scale)) << 16),
@@ -765,6 +775,149 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
   }
 }
 
+// ROILoopPool on the block-max planes, second half.  The three streams are maxima (starting at 0) over a bin, over a
+// bin minus the inner box's open interior, and over a bin of the outer grid minus the ROI's open interior.  The
+// block-max pooling kernel (roi_pool_pyr.cu, floor 0) writes plain bin maxima for all three -- right for stream 0, and
+// right for every bin of streams 1 / 2 that does not meet the excluded interior (the outer ring of the grid: typically
+// 24 of 49).  This kernel rewrites the others: a bin wholly inside the interior becomes 0 without a load, a bin cut
+// by it is scanned on the raw plane in row segments left and right of the hole, like roi_loop7_kernel does for every
+// bin.  Lanes = consecutive (proposal, bin); a lane serves that bin in both grids.
+template <int CB>
+__global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams p, const uint2* __restrict__ bins,
+                                                                 const uint2* __restrict__ rects) {
+  using V = typename Vec<CB>::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int BINS = 49;
+  constexpr uint32_t CS = 4u * CB;
+  const int H = p.H, W = p.W, HW = H * W;
+  const int bid = blockIdx.x;
+  const int cg = bid % p.CG;
+  const int sidx = (bid / p.CG) % p.S;
+  const int n = bid / (p.CG * p.S);
+  const int c0 = cg * CB;
+  const int nc = min(CB, p.C - c0);
+  int start = 0;
+  for (int m = 0; m < n; ++m) start += __ldg(p.counts + m);
+  const int cnt = __ldg(p.counts + n);
+  const int per = (cnt + p.S - 1) / p.S;
+  const int pos0 = sidx * per;
+  const int nroi = min(cnt, pos0 + per) - pos0;
+  if (nroi <= 0) return;
+  {
+    const float* src = p.input + ((int64_t)n * p.C + c0) * HW;
+    V* sp = reinterpret_cast<V*>(smem_raw);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float f[CB];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
+      sp[i] = pack<CB>(f);
+    }
+  }
+  __syncthreads();
+  uint32_t sbase;
+  {
+    unsigned long long s64;
+    asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
+    sbase = (uint32_t)s64;
+  }
+  const uint32_t pitch = (uint32_t)W * CS;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int total = nroi * BINS;
+  const int32_t* order = p.order + start + pos0;
+  const int64_t block_stride = p.R * (int64_t)p.C * BINS;
+  // Only ~16 of a grid's 49 bins are CUT by the hole, so lanes that walked consecutive bins would mostly idle next to
+  // one that scans.  Each warp therefore compacts its cut bins into a small queue (behind the planes in shared memory)
+  // and scans them 32 at a time: every lane of a scanning pass has a bin, and a pass holds bins of one grid (similar
+  // sizes).  Bins wholly inside the hole are zeroed on the spot.
+  uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + (size_t)CB * HW * sizeof(float)) + wid * 64;
+
+  auto geometry = [&](int r, int bin, int g, int& hs, int& he, int& ws, int& we, int& l1, int& r0, int& t1, int& b0) {
+    const uint2 e = __ldg(bins + 2 * ((int64_t)r * BINS + bin) + g);
+    const uint2 x = __ldg(rects + 2 * (int64_t)r + g);
+    hs = e.x & 0xffff; he = e.x >> 16; ws = e.y & 0xffff; we = e.y >> 16;
+    const int ish = (int16_t)(x.x & 0xffff), ieh = (int16_t)(x.x >> 16);
+    const int isw = (int16_t)(x.y & 0xffff), iew = (int16_t)(x.y >> 16);
+    l1 = min(we, max(ws, isw + 1));        // [ws, l1) left of / on the hole's left edge
+    r0 = max(l1, min(we, iew));            // [r0, we) on / right of its right edge
+    t1 = min(he, max(hs, ish + 1));        // rows [hs, t1) above / on its top edge
+    b0 = max(t1, min(he, ieh));            // rows [b0, he) on / below its bottom edge
+  };
+  auto scan_item = [&](uint32_t item) {
+    const int g = item & 1, bin = (item >> 1) & 63, rpos = item >> 7;
+    const int r = __ldg(order + rpos);
+    int hs, he, ws, we, l1, r0, t1, b0;
+    geometry(r, bin, g, hs, he, ws, we, l1, r0, t1, b0);
+    float acc[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) acc[k] = 0.f;
+    uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+    for (int h = hs; h < he; ++h, row += pitch) {
+      if (h >= t1 && h < b0) {
+        scan_seg<CB>(acc, row, ws, l1);
+        scan_seg<CB>(acc, row, r0, we);
+      } else {
+        scan_seg<CB>(acc, row, ws, we);
+      }
+    }
+    float scale = 1.f;
+    if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
+    const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin + (g + 1) * block_stride;
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+      if (k < nc) __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(acc[k], scale) : acc[k]);
+  };
+
+  const int per_warp = (total + nw - 1) / nw;                      // a contiguous run of (proposal, bin) slots per warp
+  const int f0 = wid * per_warp, f1 = min(total, f0 + per_warp);
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {     // 0: ROI grid without the inner box (frame), 1: outer grid without the ROI (context)
+    int qn = 0;
+#pragma unroll 1
+    for (int base = f0; base < f1; base += 32) {
+      const int flat = base + lane;
+      bool cut = false;
+      uint32_t item = 0;
+      if (flat < f1) {
+        const int rpos = flat / BINS;
+        const int bin = flat - rpos * BINS;
+        const int r = __ldg(order + rpos);
+        int hs, he, ws, we, l1, r0, t1, b0;
+        geometry(r, bin, g, hs, he, ws, we, l1, r0, t1, b0);
+        if (t1 < b0 && l1 < r0) {                                   // the bin meets the interior
+          if (t1 == hs && b0 == he && l1 == ws && r0 == we) {       // ... and lies inside it: nothing is left, 0
+            const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin + (g + 1) * block_stride;
+#pragma unroll
+            for (int k = 0; k < CB; ++k)
+              if (k < nc) __stcs(p.output + o + k * BINS, 0.f);
+          } else {
+            cut = true;
+            item = ((uint32_t)rpos << 7) | ((uint32_t)bin << 1) | (uint32_t)g;
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, cut);
+      if (cut) queue[qn + __popc(bal & ((1u << lane) - 1))] = item;
+      qn += __popc(bal);
+      __syncwarp();
+      if (qn >= 32) {
+        const uint32_t it = queue[lane];
+        const uint32_t rest = lane < qn - 32 ? queue[32 + lane] : 0u;
+        __syncwarp();
+        if (lane < qn - 32) queue[lane] = rest;
+        qn -= 32;
+        __syncwarp();
+        scan_item(it);
+      }
+    }
+    if (qn > 0) {
+      const uint32_t it = queue[lane];
+      __syncwarp();
+      if (lane < qn) scan_item(it);
+    }
+    __syncwarp();
+  }
+}
+
 // backward: grad_input[b, c, argmax] += grad_output (ROILoopPool_cuda.cu:206-248)
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
                                     const int32_t* __restrict__ argmax, int64_t total, int64_t R, int N,
@@ -848,7 +1001,7 @@ static bool pool_use_blockmax(int64_t N, int64_t R, int64_t C, bool with_argmax)
 
 struct PoolWs {
   int32_t* counts; int32_t* bidx; int32_t* order; int16_t* edges; float* alignp; uint2* bins; uint2* rects;
-  void* pyr; void* asep; size_t bytes;
+  void* pyr; void* asep; float* iboxes; size_t bytes;
 };
 
 // H, W > 0 (ROIAlign only): room for the separable tap tables of roi_align_sep.cu behind the common part
@@ -867,7 +1020,8 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW, in
   size_t o_bins = take(seven && mode == MODE_POOL ? sizeof(uint2) * 49 * (size_t)R
                        : seven && mode == MODE_LOOP ? sizeof(uint2) * 98 * (size_t)R : 0);
   size_t o_rects = take(seven && mode == MODE_LOOP ? sizeof(uint2) * 2 * (size_t)R : 0);
-  size_t o_pyr = take(seven && mode == MODE_POOL ? pool7_pyr_workspace(N, R) : 0);
+  size_t o_pyr = take(seven && (mode == MODE_POOL || mode == MODE_LOOP) ? pool7_pyr_workspace(N, R) : 0);
+  size_t o_iboxes = take(seven && mode == MODE_LOOP ? sizeof(float) * 10 * (size_t)R : 0);
   size_t o_asep = take(seven && mode == MODE_ALIGN && H > 0 && W > 0 ? align7_sep_workspace(R, H, W) : 0);
   w.counts = (int32_t*)(base + o_counts);
   w.bidx = (int32_t*)(base + o_bidx);
@@ -878,6 +1032,7 @@ static PoolWs carve(void* ws, int mode, int64_t N, int64_t R, int PH, int PW, in
   w.rects = (uint2*)(base + o_rects);
   w.pyr = base + o_pyr;
   w.asep = base + o_asep;
+  w.iboxes = (float*)(base + o_iboxes);
   w.bytes = off;
   return w;
 }
@@ -956,9 +1111,12 @@ static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, c
   return after_launch();
 }
 
-template <int CB>
+constexpr size_t kLoopFixQueueBytes = 32 * 64 * sizeof(uint32_t);
+
+template <int CB, bool FIX>
 static int launch_loop7(PoolParams& p, const uint2* bins, const uint2* rects, int64_t R, cudaStream_t st) {
-  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float);
+  // FIX: + the per-warp queues of cut bins (32 warps x 64 entries)
+  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float) + (FIX ? kLoopFixQueueBytes : 0);
   p.CG = (int)ceil_div(p.C, CB);
   int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
   per_sm = std::max(per_sm, 1);
@@ -969,7 +1127,7 @@ static int launch_loop7(PoolParams& p, const uint2* bins, const uint2* rects, in
   S = std::max<int64_t>(1, std::min<int64_t>(S, ceil_div(avg, 96)));
   p.S = (int)S;
   if ((int64_t)p.N * p.S * p.CG > 0x7fffffffLL) return WSOVOD_B200_ETOOBIG;
-  auto kern = roi_loop7_kernel<CB>;
+  auto kern = FIX ? roi_loop7_fix_kernel<CB> : roi_loop7_kernel<CB>;
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1006,10 +1164,19 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   // 3-way fast path: values only (an argmax request -- trainable backbone -- takes the generic kernel)
   const bool loop7 = mode == MODE_LOOP && PH == 7 && PW == 7 && !argmax && C >= 2 && 2 * plane_bytes <= (size_t)kMaxSmemOptin;
   const bool loop7_cb4 = loop7 && C >= 3 && 4 * plane_bytes <= (size_t)kMaxSmemOptin;
+  // ... and on the block-max planes where they pay (same crossover as the plain max-pool): three pooling passes with
+  // floor 0 (ROI grid twice, outer grid once) + roi_loop7_fix_kernel for the bins the excluded interior touches
+  const int fix_cb = (C >= 3 && 4 * plane_bytes + kLoopFixQueueBytes <= (size_t)kMaxSmemOptin) ? 4
+                     : (2 * plane_bytes + kLoopFixQueueBytes <= (size_t)kMaxSmemOptin) ? 2 : 0;
+  // measured (tools/kbench_loop_pool.py): 8 x 4000 proposals 9.5 vs 10.5 ms, 1 x 5000 on a 100x152 map 2.95 vs 3.42 ms,
+  // 1 x 2000 on a 60x80 map 0.66 vs 0.51 ms -- four launches' worth of prologues and rebuilds need >= 3000 proposals per image
+  const int pv = tune(TUNE_POOL_PATH);
+  const bool loop7_pyr = loop7 && fix_cb && pv != 1 && (pv == 2 || R >= 3000 * N) && pool7_pyr_cb(C, H, W, R, false);
   if (fast7)
     roi_bins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins);
   else if (loop7)
-    roi_loopbins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins, w.rects);
+    roi_loopbins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins, w.rects,
+                                                                          loop7_pyr ? w.iboxes : nullptr);
   else if (mode == MODE_POOL)
     roi_prepare_kernel<MODE_POOL><<<pg, pt, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, PH, PW, 0, 0, w.bidx, w.counts, w.edges, w.alignp, fast7 ? w.bins : nullptr);
   else if (mode == MODE_LOOP)
@@ -1035,7 +1202,16 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
     const PoolWs w2 = carve(workspace, mode, N, R, PH, PW, H, W);
     return align7_sep(input, N, C, H, W, R, w.counts, w.order, w.alignp, row_scale, row_scale_bias, output, w2.asep, st);
   }
-  if (loop7) return loop7_cb4 ? launch_loop7<4>(p, w.bins, w.rects, R, st) : launch_loop7<2>(p, w.bins, w.rects, R, st);
+  if (loop7_pyr) {
+    const int64_t block_stride = R * C * (int64_t)49;
+    for (int s = 0; s < 3; ++s) {
+      rc = pool7_pyr(input, N, C, H, W, w.iboxes + (s == 2 ? 5 * R : 0), R, 1.0f, row_scale, row_scale_bias, output + s * block_stride,
+                     nullptr, w.pyr, st, 0.f);
+      if (rc) return rc;
+    }
+    return fix_cb == 4 ? launch_loop7<4, true>(p, w.bins, w.rects, R, st) : launch_loop7<2, true>(p, w.bins, w.rects, R, st);
+  }
+  if (loop7) return loop7_cb4 ? launch_loop7<4, false>(p, w.bins, w.rects, R, st) : launch_loop7<2, false>(p, w.bins, w.rects, R, st);
   if (fast7) return fast7_cb4 ? launch_pool7<4>(p, w.bins, R, argmax != nullptr, st)
                              : launch_pool7<2>(p, w.bins, R, argmax != nullptr, st);
   if (mode == MODE_POOL) return argmax ? dispatch_plane<MODE_POOL, true>(p, R, st) : dispatch_plane<MODE_POOL, false>(p, R, st);

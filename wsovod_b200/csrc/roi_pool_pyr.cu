@@ -265,6 +265,8 @@ struct PyrParams {
   const float* input;
   const float* rois;
   float scale;
+  float floor_v;        // values-only flavours: cells are staged as max(cell, floor_v); -FLT_MAX = torchvision roi_pool,
+                        // 0 = the maxima "starting at 0" of ROILoopPool (ROILoopPool_cuda.cu:107-113)
   float* output;
   int32_t* argmax;      // ARG flavour only
   const int32_t* img_start;
@@ -330,7 +332,7 @@ template <int CB, bool ARG> __device__ __forceinline__ void p_copy(float* m, int
 // 32 at a time: addresses are (row pointer of the channel) + column, the only predicates are the row /
 // column borders, and up to 8 x CB loads per lane are in flight.
 template <int CB, int MODE, bool ARG>
-__device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W) {
+__device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__ src, int nc, int H, int W, float floor_v) {
   constexpr uint32_t CS = CellT<CB, ARG>::CS;
   const int WP = W + kPad, HP = H + kPad, HW = H * W;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -371,7 +373,7 @@ __device__ __noinline__ void pyr_stage(uint32_t sbase, const float* __restrict__
             p_max<CB, ARG>(f[u], fa, g[u], ga);
           } else {
 #pragma unroll
-            for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), -FLT_MAX);
+            for (int k = 0; k < CB; ++k) f[u][k] = fmaxf(fmaxf(f[u][k], g[u][k]), floor_v);
           }
           p_sts<CB, ARG>(srow + (uint32_t)ww * CS, f[u], fa);
         }
@@ -652,15 +654,15 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_pyr_kernel(const PyrParams 
     if (rem > 0 && phase != PH_FALLBACK) {
       __syncthreads();                                                 // everyone is done reading the old plane
       switch (phase) {
-        case PH_11: pyr_stage<CB, 0, ARG>(sbase, src, nc, H, W); __syncthreads(); break;
+        case PH_11: pyr_stage<CB, 0, ARG>(sbase, src, nc, H, W, p.floor_v); __syncthreads(); break;
         case PH_21: pyr_double_v<CB, 1, ARG>(sbase, H + kPad, WP); break;
         case PH_22: pyr_double_h<CB, 1, ARG>(sbase, ncell); break;
         case PH_42: pyr_double_v<CB, 2, ARG>(sbase, H + kPad, WP); break;
         case PH_44: pyr_double_h<CB, 2, ARG>(sbase, ncell); break;
-        case PH_12: pyr_stage<CB, 1, ARG>(sbase, src, nc, H, W); __syncthreads(); break;
+        case PH_12: pyr_stage<CB, 1, ARG>(sbase, src, nc, H, W, p.floor_v); __syncthreads(); break;
         case PH_14: pyr_double_h<CB, 2, ARG>(sbase, ncell); break;
         case PH_24: pyr_double_v<CB, 1, ARG>(sbase, H + kPad, WP); break;
-        default:    pyr_stage<CB, 2, ARG>(sbase, src, nc, H, W); __syncthreads();
+        default:    pyr_stage<CB, 2, ARG>(sbase, src, nc, H, W, p.floor_v); __syncthreads();
                     pyr_double_v<CB, 2, ARG>(sbase, H + kPad, WP); break;   // PH_41
       }
     }
@@ -776,7 +778,7 @@ static int pyr_launch_main(PyrParams& p, int64_t R, cudaStream_t st) {
 // ROI max-pool 7x7 through the block-max planes (argmax: optional); `workspace` holds pool7_pyr_workspace() bytes
 int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, const float* rois, int64_t R,
               float scale, const float* row_scale, float row_scale_bias, float* output, int32_t* argmax, void* workspace,
-              cudaStream_t st) {
+              cudaStream_t st, float floor_v) {
   const int cb = pool7_pyr_cb(C, H, W, R, argmax != nullptr);
   if (!cb) return WSOVOD_B200_EINVAL;
   const bool cell16 = cb == 4 || argmax;            // 16-byte cells: 64 lane slots per proposal
@@ -800,7 +802,7 @@ int pool7_pyr(const float* input, int64_t N, int64_t C, int64_t H, int64_t W, co
                                                                                   row_scale_bias, w.pinfo, w.desc);
   if ((rc = after_launch())) return rc;
   PyrParams p;
-  p.input = input; p.rois = rois; p.scale = scale;
+  p.input = input; p.rois = rois; p.scale = scale; p.floor_v = floor_v;
   p.output = output; p.argmax = argmax; p.img_start = w.img_start; p.bucket_off = w.bucket_off; p.pinfo = w.pinfo; p.desc = w.desc;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.CG = 0; p.S = 1;
   if (argmax) return pyr_launch_main<2, true>(p, R, st);
