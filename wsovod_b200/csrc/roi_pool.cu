@@ -53,6 +53,8 @@ struct PoolParams {
   int32_t CG;              // channel groups  = ceil(C / CB)
   int32_t S;               // proposal chunks per image
   int32_t sampling_ratio, aligned;
+  int32_t P;               // 7x7 scan kernels: cells per staged row = W | 1 (odd: equal columns of different rows fall into
+                           // different bank groups; simulated conflict wavefronts -8 % with four channels, -27 % with two)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -563,7 +565,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
       float f[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
-      sp[i] = pack<CB>(f);
+      sp[i + (i / W) * (p.P - W)] = pack<CB>(f);
     }
   }
   __syncthreads();
@@ -573,7 +575,8 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  const uint32_t pitch = (uint32_t)W * CS;
+  const int P = p.P;
+  const uint32_t pitch = (uint32_t)P * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
 #pragma unroll
     for (int k = 0; k < CB; ++k) { m[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
     if (!empty) {
-      const int cell0 = hs * W + ws;
+      const int cell0 = hs * P + ws;
       if (!ARG) {
         int rot = ((lane & (G - 1)) - cell0) & (G - 1);
         if (bw < G) {
@@ -631,8 +634,8 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
           }
         }
       } else {
-        int rowi = cell0;
-        uint32_t lo = sbase + (uint32_t)rowi * CS;
+        int rowi = hs * W + ws;                                   // the argmax is an index into the H x W map
+        uint32_t lo = sbase + (uint32_t)cell0 * CS;
         for (int h = hs; h < he; ++h, lo += pitch, rowi += W) {
           uint32_t a = lo;
           int idx = rowi;
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
       float f[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
-      sp[i] = pack<CB>(f);
+      sp[i + (i / W) * (p.P - W)] = pack<CB>(f);
     }
   }
   __syncthreads();
@@ -712,7 +715,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  const uint32_t pitch = (uint32_t)W * CS;
+  const uint32_t pitch = (uint32_t)p.P * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
       const int isw = (int16_t)(ri.y & 0xffff), iew = (int16_t)(ri.y >> 16);
       const int l1 = min(we, max(ws, isw + 1));        // [ws, l1) left of / on the inner box's left edge
       const int r0 = max(l1, min(we, iew));            // [r0, we) on / right of its right edge
-      uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+      uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
       for (int h = hs; h < he; ++h, row += pitch) {
         if (h > ish && h < ieh) {
           scan_seg<CB>(com, row, ws, l1);
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
       const int isw = (int16_t)(rr.y & 0xffff), iew = (int16_t)(rr.y >> 16);
       const int l1 = min(we, max(ws, isw + 1));
       const int r0 = max(l1, min(we, iew));
-      uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+      uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
       for (int h = hs; h < he; ++h, row += pitch) {
         if (h > ish && h < ieh) {
           scan_seg<CB>(ctx, row, ws, l1);
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams
       float f[CB];
 #pragma unroll
       for (int k = 0; k < CB; ++k) f[k] = k < nc ? __ldg(src + (int64_t)k * HW + i) : 0.f;
-      sp[i] = pack<CB>(f);
+      sp[i + (i / W) * (p.P - W)] = pack<CB>(f);
     }
   }
   __syncthreads();
@@ -820,7 +823,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams
     asm volatile("cvta.to.shared.u64 %0, %1;" : "=l"(s64) : "l"((unsigned long long)(uintptr_t)smem_raw));
     sbase = (uint32_t)s64;
   }
-  const uint32_t pitch = (uint32_t)W * CS;
+  const uint32_t pitch = (uint32_t)p.P * CS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams
   // one that scans.  Each warp therefore compacts its cut bins into a small queue (behind the planes in shared memory)
   // and scans them 32 at a time: every lane of a scanning pass has a bin, and a pass holds bins of one grid (similar
   // sizes).  Bins wholly inside the hole are zeroed on the spot.
-  uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + (size_t)CB * HW * sizeof(float)) + wid * 64;
+  uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + (size_t)CB * H * p.P * sizeof(float)) + wid * 64;
 
   auto geometry = [&](int r, int bin, int g, int& hs, int& he, int& ws, int& we, int& l1, int& r0, int& t1, int& b0) {
     const uint2 e = __ldg(bins + 2 * ((int64_t)r * BINS + bin) + g);
@@ -850,7 +853,7 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams
     float acc[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) acc[k] = 0.f;
-    uint32_t row = sbase + (uint32_t)(hs * W) * CS;
+    uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
     for (int h = hs; h < he; ++h, row += pitch) {
       if (h >= t1 && h < b0) {
         scan_seg<CB>(acc, row, ws, l1);
@@ -1090,7 +1093,7 @@ static int dispatch_plane(PoolParams& p, int64_t R, cudaStream_t st) {
 
 template <int CB>
 static int launch_pool7(PoolParams& p, const uint2* bins, int64_t R, bool arg, cudaStream_t st) {
-  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float);
+  const size_t smem = CB * (size_t)p.H * p.P * sizeof(float);
   p.CG = (int)ceil_div(p.C, CB);
   int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
   per_sm = std::max(per_sm, 1);
@@ -1116,7 +1119,7 @@ constexpr size_t kLoopFixQueueBytes = 32 * 64 * sizeof(uint32_t);
 template <int CB, bool FIX>
 static int launch_loop7(PoolParams& p, const uint2* bins, const uint2* rects, int64_t R, cudaStream_t st) {
   // FIX: + the per-warp queues of cut bins (32 warps x 64 entries)
-  const size_t smem = CB * (size_t)p.H * p.W * sizeof(float) + (FIX ? kLoopFixQueueBytes : 0);
+  const size_t smem = CB * (size_t)p.H * p.P * sizeof(float) + (FIX ? kLoopFixQueueBytes : 0);
   p.CG = (int)ceil_div(p.C, CB);
   int per_sm = (int)std::min<size_t>(4, (size_t)kMaxSmemOptin / (smem + 1024));
   per_sm = std::max(per_sm, 1);
@@ -1158,7 +1161,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   const int pt = 128;
   const unsigned pg = (unsigned)ceil_div(R, pt);
   // specialised kernel: 7x7 bins, four interleaved planes fit shared memory, at least 3 channels
-  const size_t plane_bytes = (size_t)H * W * sizeof(float);
+  const size_t plane_bytes = (size_t)H * (W | 1) * sizeof(float);     // the 7x7 scan kernels stage rows at an odd pitch
   const bool fast7 = mode == MODE_POOL && PH == 7 && PW == 7 && C >= 2 && 2 * plane_bytes <= (size_t)kMaxSmemOptin;
   const bool fast7_cb4 = fast7 && C >= 3 && 4 * plane_bytes <= (size_t)kMaxSmemOptin;
   // 3-way fast path: values only (an argmax request -- trainable backbone -- takes the generic kernel)
@@ -1194,7 +1197,7 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   p.output = output; p.argmax = argmax;
   p.counts = w.counts; p.order = w.order; p.edges = w.edges; p.alignp = w.alignp;
   p.N = (int)N; p.C = (int)C; p.H = (int)H; p.W = (int)W; p.R = R; p.PH = PH; p.PW = PW;
-  p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+  p.CG = 0; p.S = 1; p.sampling_ratio = sampling_ratio; p.aligned = aligned; p.P = (int)(W | 1);
   // ROIAlign 7x7 with the adaptive grid: separable tap tables when the caller's workspace has room for them
   // (wsovod_b200_roi_align_workspace_hw) and the scan kernels are not forced
   if (mode == MODE_ALIGN && PH == 7 && PW == 7 && sampling_ratio <= 0 && tune(TUNE_POOL_PATH) != 1 &&
