@@ -677,6 +677,44 @@ __device__ __forceinline__ void scan_seg(float* acc, uint32_t row, int w0, int w
   }
 }
 
+// One bin minus a hole (an open rectangle): `out` collects the cells outside it and, with ALL, `all` every cell.  ONE
+// loop nest for every lane with the hole as a per-cell predicate: a warp's lanes hold bins of the same grid, so their
+// trip counts differ by a cell, and they stay converged whatever the hole cuts.  (The segment form -- up to three
+// scan_seg calls per row, chosen per row -- serialised the lanes over its call sites: ncu counted 12 of 32 threads
+// active per instruction and 8.1 G warp instructions for the 3-way pool at c2.)
+template <int CB, bool ALL>
+__device__ __forceinline__ void scan_holed(float* all, float* out, uint32_t sbase, uint32_t pitch, int P, const uint2 e,
+                                           const uint2 x) {
+  constexpr uint32_t CS = 4u * CB;
+  const int hs = e.x & 0xffff, he = e.x >> 16, ws = e.y & 0xffff, we = e.y >> 16;
+  const int ish = (int16_t)(x.x & 0xffff), ieh = (int16_t)(x.x >> 16);
+  const int isw = (int16_t)(x.y & 0xffff), iew = (int16_t)(x.y >> 16);
+  const int l1 = min(we, max(ws, isw + 1));        // hole columns of this bin: [l1, r0)
+  const int r0 = max(l1, min(we, iew));
+  const int t1 = min(he, max(hs, ish + 1));        // hole rows of this bin: [t1, b0)
+  const int b0 = max(t1, min(he, ieh));
+  if (!ALL && t1 == hs && b0 == he && l1 == ws && r0 == we) return;   // the bin lies inside the hole: nothing to collect
+  const uint32_t hole_w = (uint32_t)(r0 - l1);
+  uint32_t row = sbase + (uint32_t)(hs * P + ws) * CS;
+  for (int h = hs; h < he; ++h, row += pitch) {
+    const uint32_t hw = (h >= t1 && h < b0) ? hole_w : 0u;            // 0: no cell of this row is inside
+    uint32_t a = row;
+#pragma unroll 2
+    for (int w = ws; w < we; ++w, a += CS) {
+      const bool inside = (uint32_t)(w - l1) < hw;
+      if (ALL || !inside) {
+        float f[CB];
+        lds_cell<CB>(a, f);
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+          if (ALL) all[k] = fmaxf(all[k], f[k]);
+          if (!inside) out[k] = fmaxf(out[k], f[k]);
+        }
+      }
+    }
+  }
+}
+
 template <int CB>
 __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, const uint2* __restrict__ bins,
                                                              const uint2* __restrict__ rects) {
@@ -730,47 +768,16 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
     const uint2 rr = __ldg(rects + 2 * (int64_t)r + 1);
     float scale = 1.f;
     if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
-    float com[CB], mid[CB], ctx[CB];
+    float roi[CB], com[CB], ctx[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) { com[k] = 0.f; mid[k] = 0.f; ctx[k] = 0.f; }
-    {  // ROI grid: `com` = cells outside the inner box (the frame), `mid` = cells strictly inside it
-      const int hs = ea.x & 0xffff, he = ea.x >> 16, ws = ea.y & 0xffff, we = ea.y >> 16;
-      const int ish = (int16_t)(ri.x & 0xffff), ieh = (int16_t)(ri.x >> 16);
-      const int isw = (int16_t)(ri.y & 0xffff), iew = (int16_t)(ri.y >> 16);
-      const int l1 = min(we, max(ws, isw + 1));        // [ws, l1) left of / on the inner box's left edge
-      const int r0 = max(l1, min(we, iew));            // [r0, we) on / right of its right edge
-      uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
-      for (int h = hs; h < he; ++h, row += pitch) {
-        if (h > ish && h < ieh) {
-          scan_seg<CB>(com, row, ws, l1);
-          scan_seg<CB>(mid, row, l1, r0);
-          scan_seg<CB>(com, row, r0, we);
-        } else {
-          scan_seg<CB>(com, row, ws, we);
-        }
-      }
-    }
-    {  // outer-box grid: cells strictly inside the ROI are excluded (and never loaded)
-      const int hs = eb.x & 0xffff, he = eb.x >> 16, ws = eb.y & 0xffff, we = eb.y >> 16;
-      const int ish = (int16_t)(rr.x & 0xffff), ieh = (int16_t)(rr.x >> 16);
-      const int isw = (int16_t)(rr.y & 0xffff), iew = (int16_t)(rr.y >> 16);
-      const int l1 = min(we, max(ws, isw + 1));
-      const int r0 = max(l1, min(we, iew));
-      uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
-      for (int h = hs; h < he; ++h, row += pitch) {
-        if (h > ish && h < ieh) {
-          scan_seg<CB>(ctx, row, ws, l1);
-          scan_seg<CB>(ctx, row, r0, we);
-        } else {
-          scan_seg<CB>(ctx, row, ws, we);
-        }
-      }
-    }
+    for (int k = 0; k < CB; ++k) { roi[k] = 0.f; com[k] = 0.f; ctx[k] = 0.f; }
+    scan_holed<CB, true>(roi, com, sbase, pitch, p.P, ea, ri);     // ROI grid: every cell, and the cells outside the inner box
+    scan_holed<CB, false>(nullptr, ctx, sbase, pitch, p.P, eb, rr); // outer grid without the ROI's interior (never loaded)
     const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin;
 #pragma unroll
     for (int k = 0; k < CB; ++k)
       if (k < nc) {
-        const float vr = fmaxf(com[k], mid[k]);
+        const float vr = roi[k];
         __stcs(p.output + o + k * BINS, p.row_scale ? __fmul_rn(vr, scale) : vr);
         __stcs(p.output + o + k * BINS + block_stride, p.row_scale ? __fmul_rn(com[k], scale) : com[k]);
         __stcs(p.output + o + k * BINS + 2 * block_stride, p.row_scale ? __fmul_rn(ctx[k], scale) : ctx[k]);
@@ -848,20 +855,11 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_fix_kernel(const PoolParams
   auto scan_item = [&](uint32_t item) {
     const int g = item & 1, bin = (item >> 1) & 63, rpos = item >> 7;
     const int r = __ldg(order + rpos);
-    int hs, he, ws, we, l1, r0, t1, b0;
-    geometry(r, bin, g, hs, he, ws, we, l1, r0, t1, b0);
     float acc[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) acc[k] = 0.f;
-    uint32_t row = sbase + (uint32_t)(hs * p.P) * CS;
-    for (int h = hs; h < he; ++h, row += pitch) {
-      if (h >= t1 && h < b0) {
-        scan_seg<CB>(acc, row, ws, l1);
-        scan_seg<CB>(acc, row, r0, we);
-      } else {
-        scan_seg<CB>(acc, row, ws, we);
-      }
-    }
+    scan_holed<CB, false>(nullptr, acc, sbase, pitch, p.P, __ldg(bins + 2 * ((int64_t)r * BINS + bin) + g),
+                          __ldg(rects + 2 * (int64_t)r + g));
     float scale = 1.f;
     if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
     const int64_t o = ((int64_t)r * p.C + c0) * BINS + bin + (g + 1) * block_stride;
