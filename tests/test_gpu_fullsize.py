@@ -64,12 +64,12 @@ def test_c2_roi_align_separable_kernel_full_size(c2):
 
 
 def test_c2_roi_loop_pool_blockmax_equals_scan_kernel(c2):
-    """3-way ROILoopPool at c2 (9.6 GB of output): the block-max path the library picks at 4000 proposals per image
-    against the scan kernel, bit for bit, with the objectness scale folded in"""
+    """3-way ROILoopPool at c2 (9.6 GB of output): the scan kernel the library picks against the block-max path (three
+    floor-0 pooling passes + fix-up, forced through the tune switch), bit for bit, with the objectness scale folded in"""
     from wsovod_b200 import _lib
     d = c2["d"]
     out, _ = ops.roi_loop_pool(d["features"], d["rois"], 1 / 8, 7, d["objectness"], 1.0, False)
-    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
+    old = _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
     try:
         ref, _ = ops.roi_loop_pool(d["features"], d["rois"], 1 / 8, 7, d["objectness"], 1.0, False)
     finally:

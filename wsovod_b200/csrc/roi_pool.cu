@@ -1169,10 +1169,11 @@ static int pool_common(int mode, const float* input, int64_t N, int64_t C, int64
   // floor 0 (ROI grid twice, outer grid once) + roi_loop7_fix_kernel for the bins the excluded interior touches
   const int fix_cb = (C >= 3 && 4 * plane_bytes + kLoopFixQueueBytes <= (size_t)kMaxSmemOptin) ? 4
                      : (2 * plane_bytes + kLoopFixQueueBytes <= (size_t)kMaxSmemOptin) ? 2 : 0;
-  // measured (tools/kbench_loop_pool.py): 8 x 4000 proposals 9.5 vs 10.5 ms, 1 x 5000 on a 100x152 map 2.95 vs 3.42 ms,
-  // 1 x 2000 on a 60x80 map 0.66 vs 0.51 ms -- four launches' worth of prologues and rebuilds need >= 3000 proposals per image
-  const int pv = tune(TUNE_POOL_PATH);
-  const bool loop7_pyr = loop7 && fix_cb && pv != 1 && (pv == 2 || R >= 3000 * N) && pool7_pyr_cb(C, H, W, R, false);
+  // measured (tools/kbench_loop_pool.py, after the scan kernel's loops were made convergent): 8 x 4000 proposals 8.8 vs
+  // 7.7 ms, 1 x 5000 on a 100x152 map 2.64 vs 2.19 ms, 1 x 2000 on a 60x80 map 0.62 vs 0.36 ms -- the scan kernel wins
+  // everywhere (the fix-up's partial-sector stores are DRAM read-modify-writes), so this path runs only when forced
+  // (wsovod_b200_tune(WSOVOD_B200_TUNE_POOL_PATH, 2): tests, tools/kbench_loop_pool.py)
+  const bool loop7_pyr = loop7 && fix_cb && tune(TUNE_POOL_PATH) == 2 && pool7_pyr_cb(C, H, W, R, false);
   if (fast7)
     roi_bins7_kernel<<<(unsigned)ceil_div(R * 49, 256), 256, 0, st>>>(rois, R, (int)N, (int)H, (int)W, scale, w.bidx, w.counts, w.bins);
   else if (loop7)
