@@ -660,27 +660,12 @@ __global__ void __launch_bounds__(1024, 1) roi_pool7_kernel(const PoolParams p, 
   }
 }
 
-// ROILoopPool fast path (values only; argmax requests use the generic kernel): roi | frame | context.
-// Rows are cut into left / middle / right segments against the excluded rectangle, so there is no
-// per-cell predicate and the context scan never loads the excluded interior.  All maxima start at 0
-// ("assum all input is >=0", ROILoopPool_cuda.cu:107-113).
-template <int CB>
-__device__ __forceinline__ void scan_seg(float* acc, uint32_t row, int w0, int w1) {
-  constexpr uint32_t CS = 4u * CB;
-  uint32_t a = row + (uint32_t)w0 * CS;
-#pragma unroll 2
-  for (int w = w0; w < w1; ++w, a += CS) {
-    float f[CB];
-    lds_cell<CB>(a, f);
-#pragma unroll
-    for (int k = 0; k < CB; ++k) acc[k] = fmaxf(acc[k], f[k]);
-  }
-}
-
+// ROILoopPool fast path (values only; argmax requests use the generic kernel): roi | frame | context.  All maxima start
+// at 0 ("assum all input is >=0", ROILoopPool_cuda.cu:107-113).
 // One bin minus a hole (an open rectangle): `out` collects the cells outside it and, with ALL, `all` every cell.  ONE
 // loop nest for every lane with the hole as a per-cell predicate: a warp's lanes hold bins of the same grid, so their
 // trip counts differ by a cell, and they stay converged whatever the hole cuts.  (The segment form -- up to three
-// scan_seg calls per row, chosen per row -- serialised the lanes over its call sites: ncu counted 12 of 32 threads
+// scan loops per row, chosen per row -- serialised the lanes over its call sites: ncu counted 12 of 32 threads
 // active per instruction and 8.1 G warp instructions for the 3-way pool at c2.)
 template <int CB, bool ALL>
 __device__ __forceinline__ void scan_holed(float* all, float* out, uint32_t sbase, uint32_t pitch, int P, const uint2 e,
