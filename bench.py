@@ -307,6 +307,12 @@ def extra_kernels(w2, st2, peaks, it, dev):
                                      "algorithmic_bytes": 6 * out_bytes + fixed}, peaks)
     k["roi_loop_pool"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, st2.rois, sc, 7, st2.obj, 1.0, False), max(it // 3, 2)),
                               "algorithmic_bytes": 3 * out_bytes + fixed}, peaks)
+    # what an MRRP config asks for (roi_heads.py:723-730: three branches, proposals split by level id): one branch's call,
+    # every third proposal of each image
+    r3, o3 = st2.rois[::3].contiguous(), st2.obj[::3].contiguous()
+    k["roi_loop_pool_mrrp_branch"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, r3, sc, 7, o3, 1.0, False), max(it // 3, 2)),
+                                          "algorithmic_bytes": 3 * r3.size(0) * C2 * 49 * 4 + st2.feat.numel() * 4 + r3.size(0) * 20,
+                                          "proposals": int(r3.size(0))}, peaks)
     k["roi_align"] = hbm({"ms": ktime(lambda: ops.roi_align(st2.feat, st2.rois, sc, 7, 0, True, st2.obj, 1.0), max(it // 3, 2)),
                           "algorithmic_bytes": out_bytes + fixed}, peaks)      # separable tap tables (roi_align_sep.cu)
     k["roi_align"]["kernel"] = "roi_align7_sep_kernel"

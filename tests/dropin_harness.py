@@ -34,7 +34,7 @@ def reference_modules():
 
 def build_reference(device, *, C=16, K=20, D=32, width=48, pooler_type="ROIPool", refine_K=1, refine_reg=True,
                     batch_size=4096, positive_fraction=1.0, weight_path="rand", seed=0, topk=100, score_thresh=1e-5,
-                    mods=None):
+                    mods=None, mrrp=False):
     """the reference WSOVODROIHeads built through its own constructors (keyword path of @configurable)"""
     d2_shim, rh, fr, poolers = mods or reference_modules()
     from oracle.d2_shim import Box2BoxTransform, Matcher, ShapeSpec
@@ -50,8 +50,10 @@ def build_reference(device, *, C=16, K=20, D=32, width=48, pooler_type="ROIPool"
             shape, box2box_transform=b2b(), num_classes=K, class_head=ovc, test_score_thresh=score_thresh, test_nms_thresh=0.3,
             test_topk_per_image=topk, smooth_l1_beta=0.0, box_reg_loss_type="smooth_l1_weighted", loss_weight={},
             refine_k=k, refine_reg=[refine_reg] * refine_K, cross_entropy_weighted=True))
-    pooler = rh.ROIPooler(output_size=7, scales=(1.0 / synth.STRIDE,), sampling_ratio=0, pooler_type=pooler_type)
+    # MRRP (roi_heads.py:567-573): three dilation branches = three pooler "levels" at one scale
+    pooler = rh.ROIPooler(output_size=7, scales=(1.0 / synth.STRIDE,) * (3 if mrrp else 1), sampling_ratio=0, pooler_type=pooler_type)
     heads = rh.WSOVODROIHeads(
+        mrrp_on=mrrp, mrrp_num_branch=3,
         num_classes=K, batch_size_per_image=512, positive_fraction=0.25, proposal_matcher=Matcher([0.5], [0, 1]),
         proposal_append_gt=False, pixel_mean=(103.53, 116.28, 123.675), pixel_std=(1.0, 1.0, 1.0),
         box_in_features=["res5"], box_pooler=pooler, box_head=head, object_miner=miner, sam=None, refine_K=refine_K,
@@ -61,7 +63,7 @@ def build_reference(device, *, C=16, K=20, D=32, width=48, pooler_type="ROIPool"
     return heads.to(device)
 
 
-def build_ours(ref_heads, device, *, precision, pooler_type="ROIPool"):
+def build_ours(ref_heads, device, *, precision, pooler_type="ROIPool", mrrp=False):
     """this package's WSOVODROIHeads holding copies of the reference head's weights (same state_dict keys)"""
     from wsovod_b200 import ops  # noqa: F401
     from wsovod_b200.modeling import (InstanceRefinementOutputLayers, ObjectMiningOutputLayers, OpenVocabularyClassifier,
@@ -83,19 +85,19 @@ def build_ours(ref_heads, device, *, precision, pooler_type="ROIPool"):
                                            refine_reg=reg)
         m.load_state_dict(r.state_dict())
         refinery.append(m)
-    pooler = ROIPooler(7, (1.0 / synth.STRIDE,), 0, pooler_type)
-    ours = WSOVODROIHeads(num_classes=K, box_in_features=["res5"], box_pooler=pooler, box_head=head, object_miner=miner,
+    pooler = ROIPooler(7, (1.0 / synth.STRIDE,) * (3 if mrrp else 1), 0, pooler_type)
+    ours = WSOVODROIHeads(mrrp_on=mrrp, mrrp_num_branch=3, num_classes=K, box_in_features=["res5"], box_pooler=pooler, box_head=head, object_miner=miner,
                           box_refinery=refinery, refine_reg=[bool(r.refine_reg[r.refine_k]) for r in ref_heads.box_refinery],
                           sampling_on=True, batch_size_per_images=list(ref_heads.batch_size_per_images),
                           positive_sample_fractions=list(ref_heads.positive_sample_fractions), pooler_type=pooler_type)
     return ours.to(device)
 
 
-def make_inputs(device, *, N=2, C=16, H=30, W=40, R=300, K=20, D=32, seed=1, max_labels=3):
+def make_inputs(device, *, N=2, C=16, H=30, W=40, R=300, K=20, D=32, seed=1, max_labels=3, mrrp=False):
     """features dict, proposals (the reference's own Instances / Boxes carriers), image-level targets, text matrix"""
     from oracle.d2_shim import Boxes, Instances
     g = synth.gen(seed)
-    feat = synth.features(N, C, H, W, g).to(device)
+    feat = synth.features(3 * N if mrrp else N, C, H, W, g).to(device)     # MRRP: the three branches stacked on the batch axis
     img_h, img_w = H * synth.STRIDE, W * synth.STRIDE
     proposals, targets = [], []
     labels = synth.image_labels(N, K, g, max_labels)
@@ -104,6 +106,8 @@ def make_inputs(device, *, N=2, C=16, H=30, W=40, R=300, K=20, D=32, seed=1, max
         p = Instances((img_h, img_w))
         p.proposal_boxes = Boxes(b.to(device))
         p.objectness_logits = synth.objectness(R, g).to(device)
+        if mrrp:   # roi_heads.py:730: branch = level_ids // 1000
+            p.level_ids = (torch.randint(0, 3, (R,), generator=g) * 1000 + torch.randint(0, 1000, (R,), generator=g)).to(device)
         proposals.append(p)
         t = Instances((img_h, img_w))
         t.gt_classes = labels[n].to(device)

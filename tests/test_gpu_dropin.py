@@ -40,16 +40,17 @@ def _same_detections(got, ref, rel):
 
 
 @needs_ref
-@pytest.mark.parametrize("pooler_type,R,batch,frac", [("ROIPool", 1300, 4096, 1.0), ("ROIPool", 1500, 512, 0.25),
-                                                        ("ROILoopPool", 1300, 4096, 1.0)])
-def test_reference_forward_box_stock_vs_patched_vs_ours(pooler_type, R, batch, frac):
+@pytest.mark.parametrize("pooler_type,R,batch,frac,mrrp", [("ROIPool", 1300, 4096, 1.0, False), ("ROIPool", 1500, 512, 0.25, False),
+                                                             ("ROILoopPool", 1300, 4096, 1.0, False),
+                                                             ("ROILoopPool", 1300, 4096, 1.0, True)])   # a shipped MRRP config's shape
+def test_reference_forward_box_stock_vs_patched_vs_ours(pooler_type, R, batch, frac, mrrp):
     mods = H.reference_modules()
     d2, rh, fr, poolers = mods
     # score_thresh -1: every (proposal, class) is an NMS candidate, > 25 000 per image, so the stock arm takes
     # torchvision's "vanilla" per-class strategy like it does at real sizes (boxes.numel() > 100 000 on CUDA,
     # boxes.py:51-120) -- the coordinate trick of small inputs is not arithmetic-identical
-    kw = dict(pooler_type=pooler_type, batch_size=batch, positive_fraction=frac, score_thresh=-1.0)
-    feats, props, targets, text = H.make_inputs(DEV, R=R)
+    kw = dict(pooler_type=pooler_type, batch_size=batch, positive_fraction=frac, score_thresh=-1.0, mrrp=mrrp)
+    feats, props, targets, text = H.make_inputs(DEV, R=R, mrrp=mrrp)
     if pooler_type == "ROILoopPool" and not hasattr(sys.modules["wsovod"], "_C"):
         pytest.skip("oracle/_ref/wsovod_ref_C.so (the reference's own extension) not built")
 
@@ -72,7 +73,9 @@ def test_reference_forward_box_stock_vs_patched_vs_ours(pooler_type, R, batch, f
         undo()
 
     # ---- C: our own head class ---------------------------------------------------------------------------------
-    ours = H.build_ours(ref, DEV, precision=ops.ALIGN_FP32, pooler_type=pooler_type)
+    ours = H.build_ours(ref, DEV, precision=ops.ALIGN_FP32, pooler_type=pooler_type, mrrp=mrrp)
+    if mrrp:   # the three branches reach the pooler as chunks of one map: one launch for all of them
+        assert ours.box_pooler._merged_levels(list(torch.chunk(feats["res5"], 3))) is not None
     lc, gc = H.run_train(ours, rh, feats, props, targets, None)
     dc = H.run_test(ours, feats, props, text)
 

@@ -68,6 +68,32 @@ def test_roi_pooler_multi_level_mrrp():
         r = oracle.roi_loop_pool(feats[level], rois[inds], 1 / 8, 7)[0]
         ref[torch.cat([inds, inds + M, inds + 2 * M])] = r
     assert torch.equal(out.cpu(), ref)
+    # the levels as chunks of ONE batched map (what roi_heads.py:723-724 hands over): a single launch with image index
+    # level * N + image; same rows, also with a level id that matches no level (rows stay zero) and the objectness scale
+    fused = torch.cat(feats, 0).to(DEV)
+    chunks = list(torch.chunk(fused, 3))
+    assert pooler._merged_levels(chunks) is not None and pooler._merged_levels([f.to(DEV) for f in feats]) is None
+    out2 = pooler(chunks, [Boxes(b.to(DEV)) for b in boxes], level_ids=[l.to(DEV) for l in lv])
+    assert torch.equal(out2.cpu(), ref)
+    lv_bad = [l.clone() for l in lv]
+    lv_bad[0][::7] = 5
+    lv_bad[1][::5] = -1
+    obj = [synth.objectness(90, g) for _ in range(2)]
+    ref_bad = ref.clone()
+    bad = torch.cat([(l < 0) | (l > 2) for l in lv_bad])
+    ref_bad[torch.cat([bad, bad, bad])] = 0
+    sc = torch.cat(obj) + 1
+    ref_bad = ref_bad * torch.cat([sc, sc, sc]).view(-1, 1, 1, 1)
+    for feats_in in (chunks, [f.to(DEV) for f in feats]):
+        out3 = pooler(feats_in, [Boxes(b.to(DEV)) for b in boxes], level_ids=[l.to(DEV) for l in lv_bad],
+                      objectness_logits=[o.to(DEV) for o in obj])
+        assert torch.equal(out3.cpu(), ref_bad)
+    # plain max-pool and ROIAlign through the same merged launch
+    for ptype in ("ROIPool", "ROIAlignV2"):
+        pl = ROIPooler(7, (1 / 8, 1 / 8, 1 / 8), 0, ptype)
+        a = pl(chunks, [Boxes(b.to(DEV)) for b in boxes], level_ids=[l.to(DEV) for l in lv_bad])
+        b = pl([f.to(DEV) for f in feats], [Boxes(b.to(DEV)) for b in boxes], level_ids=[l.to(DEV) for l in lv_bad])
+        assert torch.equal(a, b)
 
 
 def test_classifier_and_inference_golden(golden):

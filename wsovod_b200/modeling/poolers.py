@@ -65,6 +65,22 @@ class ROIPooler(nn.Module):
         self.canonical_level, self.canonical_box_size = canonical_level, canonical_box_size
         self.valid_range = get_valid_range() if use_range else None
 
+    def _merged_levels(self, x):
+        """the (n_levels * N, C, H, W) tensor the level maps are consecutive chunks of, or None"""
+        p0 = self.level_poolers[0]
+        if any(getattr(p, "spatial_scale", None) != p0.spatial_scale for p in self.level_poolers):
+            return None
+        x0 = x[0]
+        if not x0.is_cuda or not x0.is_contiguous() or (x0.requires_grad and torch.is_grad_enabled()):
+            return None
+        step = x0.numel() * x0.element_size()
+        for level, t in enumerate(x):
+            if t.shape != x0.shape or t.dtype != x0.dtype or not t.is_contiguous() or t.device != x0.device:
+                return None
+            if t.data_ptr() != x0.data_ptr() + level * step or t.untyped_storage().data_ptr() != x0.untyped_storage().data_ptr():
+                return None
+        return torch.as_strided(x0, (len(x) * x0.size(0),) + tuple(x0.shape[1:]), x0.stride(), x0.storage_offset())
+
     def forward(self, x: List[torch.Tensor], box_lists, level_ids=None, oh_labels_list=None, superpixels=None,
                 objectness_logits=None):
         n_levels = len(self.level_poolers)
@@ -86,6 +102,20 @@ class ROIPooler(nn.Module):
                                     self.canonical_level, self.valid_range)
         if level_ids is not None:
             lv = torch.cat(list(level_ids)).to(torch.int64)
+        merged = self._merged_levels(x)
+        if merged is not None:
+            # MRRP (roi_heads.py:723-730): the levels are the chunks of ONE batched map at one scale.  The image index of a
+            # proposal becomes level * N + image and the whole thing is a single kernel launch whose rows come out in
+            # the proposals' own order -- no per-level nonzero (a host sync each), gather and index_put.  A proposal whose
+            # level id matches no level keeps the reference's zero rows: its box is moved off the map, where every bin
+            # of every stream is empty.
+            N = x[0].size(0)
+            valid = (lv >= 0) & (lv < n_levels)
+            far = torch.full_like(rois[:, 1:], 1.0e6)
+            r = torch.cat((rois[:, :1] + (lv.clamp(0, n_levels - 1) * N).to(rois.dtype).unsqueeze(1),
+                           torch.where(valid.unsqueeze(1), rois[:, 1:], far)), dim=1)
+            pooler = self.level_poolers[0]
+            return pooler(merged, r, scale, 1.0) if scale is not None else pooler(merged, r)
         M, C, P = rois.size(0), x[0].shape[1], self.output_size[0]
         out = torch.zeros(((3 * M) if three else M, C, P, P), dtype=x[0].dtype, device=x[0].device)
         for level, pooler in enumerate(self.level_poolers):
