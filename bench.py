@@ -307,12 +307,20 @@ def extra_kernels(w2, st2, peaks, it, dev):
                                      "algorithmic_bytes": 6 * out_bytes + fixed}, peaks)
     k["roi_loop_pool"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, st2.rois, sc, 7, st2.obj, 1.0, False), max(it // 3, 2)),
                               "algorithmic_bytes": 3 * out_bytes + fixed}, peaks)
-    # what an MRRP config asks for (roi_heads.py:723-730: three branches, proposals split by level id): one branch's call,
-    # every third proposal of each image
-    r3, o3 = st2.rois[::3].contiguous(), st2.obj[::3].contiguous()
-    k["roi_loop_pool_mrrp_branch"] = hbm({"ms": ktime(lambda: ops.roi_loop_pool(st2.feat, r3, sc, 7, o3, 1.0, False), max(it // 3, 2)),
-                                          "algorithmic_bytes": 3 * r3.size(0) * C2 * 49 * 4 + st2.feat.numel() * 4 + r3.size(0) * 20,
-                                          "proposals": int(r3.size(0))}, peaks)
+    # what an MRRP config asks for (roi_heads.py:723-730): the pooler over three branch maps stacked on the batch axis, every
+    # proposal assigned to one branch -- through wsovod_b200.modeling.ROIPooler, which runs it as one launch
+    from wsovod_b200.modeling import ROIPooler
+    from wsovod_b200.structures import Boxes
+    f3 = torch.cat([st2.feat, st2.feat.flip(0), st2.feat.roll(1, 0)], 0)
+    per = w2["R"]
+    bl = [Boxes(st2.rois[i * per:(i + 1) * per, 1:].contiguous()) for i in range(w2["N"])]
+    lids = [((torch.arange(per, device=dev) * 7 + i) % 3) for i in range(w2["N"])]
+    objs = [st2.obj[i * per:(i + 1) * per] for i in range(w2["N"])]
+    mp = ROIPooler(7, (sc, sc, sc), 0, "ROILoopPool")
+    chunks = list(torch.chunk(f3, 3))
+    k["roi_loop_pool_mrrp"] = hbm({"ms": ktime(lambda: mp(chunks, bl, level_ids=lids, objectness_logits=objs), max(it // 3, 2)),
+                                   "algorithmic_bytes": 3 * out_bytes + f3.numel() * 4 + M2 * 20, "branches": 3}, peaks)
+    del f3, chunks
     k["roi_align"] = hbm({"ms": ktime(lambda: ops.roi_align(st2.feat, st2.rois, sc, 7, 0, True, st2.obj, 1.0), max(it // 3, 2)),
                           "algorithmic_bytes": out_bytes + fixed}, peaks)      # separable tap tables (roi_align_sep.cu)
     k["roi_align"]["kernel"] = "roi_align7_sep_kernel"
