@@ -743,16 +743,28 @@ __global__ void __launch_bounds__(1024, 1) roi_loop7_kernel(const PoolParams p, 
   const int total = nroi * BINS;
   const int32_t* order = p.order + start + pos0;
   const int64_t block_stride = p.R * (int64_t)p.C * BINS;
-  for (int flat = wid * 32 + lane; flat < total; flat += nw * 32) {
-    const int rpos = flat / BINS;
-    const int bin = flat - rpos * BINS;
-    const int r = __ldg(order + rpos);
-    const uint2 ea = __ldg(bins + 2 * ((int64_t)r * BINS + bin));
-    const uint2 eb = __ldg(bins + 2 * ((int64_t)r * BINS + bin) + 1);
-    const uint2 ri = __ldg(rects + 2 * (int64_t)r);
-    const uint2 rr = __ldg(rects + 2 * (int64_t)r + 1);
-    float scale = 1.f;
-    if (p.row_scale) scale = __fadd_rn(__ldg(p.row_scale + r), p.row_scale_bias);
+  // the (proposal id, two bin words, two hole rectangles, scale) of the NEXT pass are fetched while this one runs
+  const int stride = nw * 32;
+  int r_n = 0, bin_n = 0;
+  uint4 e_n = make_uint4(0, 0, 0, 0), x_n = make_uint4(0, 0, 0, 0);
+  float sc_n = 1.f;
+  auto fetch = [&](int f) {
+    if (f < total) {
+      const int rpos = f / BINS;
+      bin_n = f - rpos * BINS;
+      r_n = __ldg(order + rpos);
+      e_n = __ldg(reinterpret_cast<const uint4*>(bins + 2 * ((int64_t)r_n * BINS + bin_n)));   // ROI-grid bin | outer-grid bin
+      x_n = __ldg(reinterpret_cast<const uint4*>(rects + 2 * (int64_t)r_n));                    // inner box | the ROI
+      if (p.row_scale) sc_n = __fadd_rn(__ldg(p.row_scale + r_n), p.row_scale_bias);
+    }
+  };
+  fetch(wid * 32 + lane);
+  for (int flat = wid * 32 + lane; flat < total; flat += stride) {
+    const int bin = bin_n, r = r_n;
+    const uint2 ea = make_uint2(e_n.x, e_n.y), eb = make_uint2(e_n.z, e_n.w);
+    const uint2 ri = make_uint2(x_n.x, x_n.y), rr = make_uint2(x_n.z, x_n.w);
+    const float scale = sc_n;
+    fetch(flat + stride);
     float roi[CB], com[CB], ctx[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) { roi[k] = 0.f; com[k] = 0.f; ctx[k] = 0.f; }
