@@ -34,7 +34,11 @@ _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_SCAN)
 rb = ops.roi_align(feat, rois, 1 / 8, 7, 0, True, obj, 1.0)                  # per-sample kernel
 _lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
 assert torch.allclose(ra, rb, rtol=1e-5, atol=1e-5)
-ops.roi_loop_pool(feat, rois, 1 / 8, 7, with_argmax=False)
+la = ops.roi_loop_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]              # converged scan kernel
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_BLOCKMAX)
+lb = ops.roi_loop_pool(feat, rois, 1 / 8, 7, obj, 1.0, False)[0]              # floor-0 pooling passes + fix-up kernel (queues)
+_lib.tune(_lib.TUNE_POOL_PATH, _lib.POOL_AUTO)
+assert torch.equal(la, lb)
 # half / double ROILoopPool (roi_loop_dtype.cu): staged planes (two channels, one channel) and the backward atomics
 for dt in (torch.float16, torch.float64):
     o3, a3 = ops.roi_loop_pool(feat.to(dt), rois.to(dt), 1 / 8, 7, with_argmax=True)
